@@ -1,0 +1,610 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:   D[M,N] = epi(A[M,K] . B[N,K]^T)
+//
+// Replaces every aten::addmm / mm behind the reference decoder (nn.Linear in decoder.py:124,
+// the packed in-projections of torch/nn/functional.py:5798-5875, out_proj :6690, linear1/2 of
+// torch/nn/modules/transformer.py:1197-1199) and their autograd dgrad / wgrad products.
+//
+// Design (one CTA per SM, persistent over a static round-robin tile schedule):
+//   warp 0      TMA producer: cp.async.bulk.tensor tiles of A and B into a STAGES-deep ring of
+//               128-byte-swizzled shared-memory buffers, completion on "full" mbarriers;
+//   warp 1      MMA issuer: one lane issues tcgen05.mma (128 x BLOCK_N x 16 per instruction,
+//               bf16 -> fp32) into one of two TMEM accumulator stages; tcgen05.commit releases
+//               the smem stage ("empty") and finally publishes the accumulator ("tmem_full");
+//   warp 2      allocates / frees the 2*BLOCK_N TMEM columns;
+//   warps 4-7   epilogue: tcgen05.ld the accumulator (thread = row, 32 columns at a time), apply
+//               bias / activation / ReLU mask / residual (or the fused softmax-CE / argmax math of
+//               the LM head) and store 16-byte vectors; arrive on "tmem_empty".
+// Operands may be K-major (reduction dimension contiguous) or MN-major (transposed storage):
+// the latter is what dgrad (B = W as stored) and wgrad (A = dY, B = X as stored) need, so no
+// operand is ever transposed in memory.
+#include "gemm.cuh"
+#include <math.h>
+
+namespace b200 {
+
+static constexpr int BLOCK_M = 128;
+static constexpr int BLOCK_K = 64;  // 64 bf16 = one 128-byte swizzle row
+static constexpr int UMMA_K = 16;
+static constexpr int NUM_THREADS = 256;
+static constexpr int ACC_STAGES = 2;
+
+struct GemmDev {
+  int M, N, K;
+  int num_m_tiles, num_n_tiles, split_k, kb_per_split, num_k_blocks;
+  void* D; long long ldd; int d_fp32; int accumulate;
+  const float* bias;
+  const bf16* residual; long long ldr;
+  const bf16* relu_mask; long long ldm;
+  int act;
+  const long long* targets; long long ignore_index;
+  float* part_max; float* part_sum; float* tgt_logit;
+  const float* row_lse; const float* inv_count;
+};
+
+template <int BLOCK_N>
+struct SmemLayout {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + alignment slack
+};
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                    const __grid_constant__ CUtensorMap tmap_b, const GemmDev p) {
+  using L = SmemLayout<BLOCK_N>;
+  constexpr int STAGES = L::STAGES;
+  constexpr uint32_t TMEM_COLS = ACC_STAGES * BLOCK_N;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + ACC_STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < ACC_STAGES; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int total_work = p.num_m_tiles * p.num_n_tiles * p.split_k;
+
+  if (warp == 0) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int split = w % p.split_k;
+        const int tile = w / p.split_k;
+        const int m_blk = tile % p.num_m_tiles;
+        const int n_blk = tile / p.num_m_tiles;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          if constexpr (!A_MN) {
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_M / 64; ++j)
+              tma_load_2d(sa + j * (BLOCK_K * 128), &tmap_a, &full_bar[stage],
+                          m_blk * BLOCK_M + j * 64, kb * BLOCK_K);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_N / 64; ++j)
+              tma_load_2d(sb + j * (BLOCK_K * 128), &tmap_b, &full_bar[stage],
+                          n_blk * BLOCK_N + j * 64, kb * BLOCK_K);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ==============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int split = w % p.split_k;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // K-major: 128-byte rows, 8-row groups 1024 B apart, 16 k-elements = +32 B.
+            // MN-major: 64-element (128 B) MN rows per k, 8-k groups 1024 B apart (SBO),
+            //           64-wide MN groups BLOCK_K*128 B apart (LBO), 16 k = +2048 B.
+            const uint64_t da = A_MN ? make_smem_desc_sw128(sa + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
+                                     : make_smem_desc_sw128(sa + k * (UMMA_K * 2), 16, 1024);
+            const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
+                                     : make_smem_desc_sw128(sb + k * (UMMA_K * 2), 16, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ============================ epilogue ================================
+    const int ew = warp - 4;  // TMEM lane quarter this warp may read
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const int split = w % p.split_k;
+      const int tile = w / p.split_k;
+      const int m_blk = tile % p.num_m_tiles;
+      const int n_blk = tile / p.num_m_tiles;
+      const int row = m_blk * BLOCK_M + ew * 32 + lane;
+      const bool row_ok = row < p.M;
+      const int n0 = n_blk * BLOCK_N;
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(ew * 32) << 16);
+
+      // per-row state of the fused LM-head epilogues
+      float run_max = -INFINITY, run_sum = 0.f, tgt_val = 0.f;
+      int best_idx = 0x7fffffff;
+      long long tgt = -1;
+      float lse = 0.f, gscale = 0.f;
+      if constexpr (EPI == EPI_CE_FWD || EPI == EPI_CE_BWD) {
+        if (row_ok) tgt = p.targets[row];
+      }
+      if constexpr (EPI == EPI_CE_BWD) {
+        if (row_ok) {
+          lse = p.row_lse[row];
+          gscale = (tgt != p.ignore_index) ? __ldg(p.inv_count) : 0.f;
+        }
+      }
+
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        uint32_t r[32];
+        tmem_ld_32x32(t_row + c * 32, r);  // warp-collective: executed by all lanes
+        // issue the global loads this chunk needs while the TMEM load is in flight
+        uint4 res[4], msk[4];
+        if constexpr (EPI == EPI_STD) {
+          if (p.residual != nullptr) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              if (row_ok && col0 + g * 8 < p.N)
+                res[g] = ldg_nc_v4(p.residual + static_cast<long long>(row) * p.ldr + col0 + g * 8);
+          }
+          if (p.relu_mask != nullptr) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              if (row_ok && col0 + g * 8 < p.N)
+                msk[g] = ldg_nc_v4(p.relu_mask + static_cast<long long>(row) * p.ldm + col0 + g * 8);
+          }
+        }
+        tmem_ld_wait();
+        if (col0 >= p.N) continue;  // warp-uniform
+
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        if (p.bias != nullptr && split == 0) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            if (col0 + g * 4 < p.N) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + g);
+              v[g * 4 + 0] += b4.x; v[g * 4 + 1] += b4.y; v[g * 4 + 2] += b4.z; v[g * 4 + 3] += b4.w;
+            }
+          }
+        }
+
+        if constexpr (EPI == EPI_STD) {
+          if (p.act == 1) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          } else if (p.act == 2) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+          }
+          if (p.relu_mask != nullptr) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (row_ok && col0 + g * 8 < p.N) {
+                const uint32_t m4[4] = {msk[g].x, msk[g].y, msk[g].z, msk[g].w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float2 f = unpack_bf16(m4[q]);
+                  if (!(f.x > 0.f)) v[g * 8 + q * 2] = 0.f;
+                  if (!(f.y > 0.f)) v[g * 8 + q * 2 + 1] = 0.f;
+                }
+              }
+            }
+          }
+          if (p.residual != nullptr) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (row_ok && col0 + g * 8 < p.N) {
+                const uint32_t r4[4] = {res[g].x, res[g].y, res[g].z, res[g].w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float2 f = unpack_bf16(r4[q]);
+                  v[g * 8 + q * 2] += f.x;
+                  v[g * 8 + q * 2 + 1] += f.y;
+                }
+              }
+            }
+          }
+          if (row_ok) {
+            if (!p.d_fp32) {
+              bf16* drow = reinterpret_cast<bf16*>(p.D) + static_cast<long long>(row) * p.ldd + col0;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                if (col0 + g * 8 < p.N) {
+                  uint4 o;
+                  o.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
+                  o.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
+                  o.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
+                  o.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
+                  *reinterpret_cast<uint4*>(drow + g * 8) = o;
+                }
+              }
+            } else {
+              float* drow = reinterpret_cast<float*>(p.D) + static_cast<long long>(row) * p.ldd + col0;
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                if (col0 + g * 4 < p.N) {
+                  if (p.accumulate) {
+                    red_add_v4_f32(drow + g * 4, v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+                  } else {
+                    *reinterpret_cast<float4*>(drow + g * 4) =
+                        make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+                  }
+                }
+              }
+            }
+          }
+        } else if constexpr (EPI == EPI_CE_FWD) {
+          // online softmax statistics of this row over the tile's valid columns
+          float cmax = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (col0 + i < p.N) cmax = fmaxf(cmax, v[i]);
+          const float new_max = fmaxf(run_max, cmax);
+          float s = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (col0 + i < p.N) s += __expf(v[i] - new_max);
+          run_sum = run_sum * __expf(run_max - new_max) + s;
+          run_max = new_max;
+          const long long rel = tgt - col0;
+          if (rel >= 0 && rel < 32) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i == rel) tgt_val = v[i];
+          }
+        } else if constexpr (EPI == EPI_CE_BWD) {
+          if (row_ok) {
+            bf16* drow = reinterpret_cast<bf16*>(p.D) + static_cast<long long>(row) * p.ldd + col0;
+            const long long rel = tgt - col0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float g = __expf(v[i] - lse);
+              if (i == rel) g -= 1.f;
+              v[i] = g * gscale;
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (col0 + g * 8 < p.N) {
+                uint4 o;
+                o.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
+                o.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
+                o.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
+                o.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
+                *reinterpret_cast<uint4*>(drow + g * 8) = o;
+              }
+            }
+          }
+        } else {  // EPI_ARGMAX: first index of the maximum (torch.argmax tie rule)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (col0 + i < p.N && v[i] > run_max) {
+              run_max = v[i];
+              best_idx = col0 + i;
+            }
+          }
+        }
+      }
+
+      if constexpr (EPI == EPI_CE_FWD) {
+        if (row_ok) {
+          const long long o = static_cast<long long>(row) * p.num_n_tiles + n_blk;
+          p.part_max[o] = run_max;
+          p.part_sum[o] = run_sum;
+          if (tgt >= n0 && tgt < n0 + BLOCK_N && tgt < p.N) p.tgt_logit[row] = tgt_val;
+        }
+      } else if constexpr (EPI == EPI_ARGMAX) {
+        if (row_ok) {
+          const long long o = static_cast<long long>(row) * p.num_n_tiles + n_blk;
+          p.part_max[o] = run_max;
+          p.part_sum[o] = __int_as_float(best_idx);
+        }
+      }
+
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(sym);
+  }
+  return fn;
+}
+
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
+                      uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
+  PFN_encodeTiled enc = get_encode_fn();
+  B200_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer not 16-byte aligned");
+  B200_REQUIRE((outer_stride_bytes & 15) == 0, "TMA row pitch (%llu B) not a multiple of 16",
+               (unsigned long long)outer_stride_bytes);
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {outer_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (inner %llu outer %llu pitch %llu box %u x %u)",
+               (int)r, (unsigned long long)inner, (unsigned long long)outer,
+               (unsigned long long)outer_stride_bytes, box_inner, box_outer);
+  return 0;
+}
+
+int device_sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+int gemm_num_n_tiles(int N, int block_n) { return (N + block_n - 1) / block_n; }
+
+template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
+static int launch_instance(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& d, int grid,
+                           cudaStream_t stream) {
+  auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, EPI>;
+  static bool configured = false;
+  constexpr int smem = SmemLayout<BLOCK_N>::TOTAL;
+  if (!configured) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  kern<<<grid, NUM_THREADS, smem, stream>>>(ta, tb, d);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static double wave_eff(long long work, int sms) {
+  long long waves = (work + sms - 1) / sms;
+  return static_cast<double>(work) / static_cast<double>(waves * sms);
+}
+
+int gemm_launch(const GemmProblem& q, cudaStream_t stream, int* n_tiles_out) {
+  B200_REQUIRE(q.M > 0 && q.N > 0 && q.K > 0, "gemm: empty problem %d x %d x %d", q.M, q.N, q.K);
+  B200_REQUIRE(q.A && q.B, "gemm: null operand");
+  B200_REQUIRE(q.N % 8 == 0, "gemm: N (%d) must be a multiple of 8", q.N);
+  B200_REQUIRE(q.epi == EPI_STD || (!q.a_mn && !q.b_mn), "gemm: fused LM-head epilogues need K-major operands");
+  if (q.epi == EPI_STD || q.epi == EPI_CE_BWD) {
+    B200_REQUIRE(q.D != nullptr, "gemm: null output");
+    B200_REQUIRE(q.ldd % (q.d_fp32 ? 4 : 8) == 0, "gemm: ldd (%lld) breaks 16-byte store alignment", (long long)q.ldd);
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(q.D) & 15) == 0, "gemm: D not 16-byte aligned");
+  }
+  B200_REQUIRE(!q.residual || (q.ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(q.residual) & 15) == 0), "gemm: residual misaligned");
+  B200_REQUIRE(!q.relu_mask || (q.ldm % 8 == 0 && (reinterpret_cast<uintptr_t>(q.relu_mask) & 15) == 0), "gemm: relu_mask misaligned");
+  B200_REQUIRE(!q.bias || (reinterpret_cast<uintptr_t>(q.bias) & 15) == 0, "gemm: bias misaligned");
+  B200_REQUIRE(!(q.accumulate && !q.d_fp32), "gemm: accumulate needs an fp32 output");
+
+  const int sms = device_sm_count();
+  const int num_kb = (q.K + BLOCK_K - 1) / BLOCK_K;
+  const int m_tiles = (q.M + BLOCK_M - 1) / BLOCK_M;
+
+  int block_n = q.block_n;
+  int split_k = q.split_k;
+  const bool may_split = (q.epi == EPI_STD) && q.d_fp32 && q.accumulate;
+  if (split_k > 1) B200_REQUIRE(may_split, "gemm: split_k > 1 needs d_fp32 && accumulate");
+  if (block_n == 0 || split_k == 0) {
+    // pick (block_n, split_k) maximising full-wave efficiency; prefer the wider tile and fewer
+    // splits on ties (wider tiles halve shared-memory operand traffic per flop).
+    double best = -1.0;
+    int bn_best = 256, sk_best = 1;
+    const int bn_opts[2] = {256, 128};
+    for (int bi = 0; bi < 2; ++bi) {
+      const int bn = bn_opts[bi];
+      if (q.block_n != 0 && bn != q.block_n) continue;
+      if (q.N <= 128 && bn == 256) continue;
+      const long long tiles = static_cast<long long>(m_tiles) * gemm_num_n_tiles(q.N, bn);
+      const int sk_max = (q.split_k == 0 && may_split) ? 16 : 1;
+      for (int sk = 1; sk <= sk_max; sk *= 2) {
+        if (q.split_k > 0 && sk != q.split_k) continue;
+        if (sk > 1 && num_kb / sk < 8) break;
+        const double useful = static_cast<double>(q.N) / (gemm_num_n_tiles(q.N, bn) * bn);
+        double e = wave_eff(tiles * sk, sms) * useful;
+        if (bn == 128) e *= 0.93;   // smem-bandwidth penalty of the narrow tile
+        if (sk > 1) e *= 0.98;      // atomics
+        if (e > best + 1e-9) { best = e; bn_best = bn; sk_best = sk; }
+      }
+    }
+    if (block_n == 0) block_n = bn_best;
+    if (split_k == 0) split_k = sk_best;
+  }
+  if (split_k < 1) split_k = 1;
+  B200_REQUIRE(block_n == 128 || block_n == 256, "gemm: block_n must be 128 or 256");
+  if (q.epi != EPI_STD) block_n = (q.epi == EPI_ARGMAX) ? 128 : 256;
+
+  GemmDev d;
+  d.M = q.M; d.N = q.N; d.K = q.K;
+  d.num_m_tiles = m_tiles;
+  d.num_n_tiles = gemm_num_n_tiles(q.N, block_n);
+  d.num_k_blocks = num_kb;
+  d.kb_per_split = (num_kb + split_k - 1) / split_k;
+  d.split_k = (num_kb + d.kb_per_split - 1) / d.kb_per_split;  // no empty splits
+  d.D = q.D; d.ldd = q.ldd; d.d_fp32 = q.d_fp32; d.accumulate = q.accumulate;
+  d.bias = q.bias; d.residual = q.residual; d.ldr = q.ldr; d.relu_mask = q.relu_mask; d.ldm = q.ldm;
+  d.act = q.act;
+  d.targets = reinterpret_cast<const long long*>(q.targets); d.ignore_index = q.ignore_index;
+  d.part_max = q.part_max; d.part_sum = q.part_sum; d.tgt_logit = q.tgt_logit;
+  d.row_lse = q.row_lse; d.inv_count = q.inv_count;
+  if (n_tiles_out) *n_tiles_out = d.num_n_tiles;
+
+  CUtensorMap ta, tb;
+  int rc;
+  if (!q.a_mn) rc = make_tmap_2d_bf16(&ta, q.A, q.K, q.M, q.lda * 2, BLOCK_K, BLOCK_M);
+  else         rc = make_tmap_2d_bf16(&ta, q.A, q.M, q.K, q.lda * 2, 64, BLOCK_K);
+  if (rc) return rc;
+  if (!q.b_mn) rc = make_tmap_2d_bf16(&tb, q.B, q.K, q.N, q.ldb * 2, BLOCK_K, block_n);
+  else         rc = make_tmap_2d_bf16(&tb, q.B, q.N, q.K, q.ldb * 2, 64, BLOCK_K);
+  if (rc) return rc;
+
+  const long long work = static_cast<long long>(d.num_m_tiles) * d.num_n_tiles * d.split_k;
+  const int grid = static_cast<int>(work < sms ? work : sms);
+
+#define B200_GEMM_CASE(BN, AMN, BMN, EP) return launch_instance<BN, AMN, BMN, EP>(ta, tb, d, grid, stream)
+  if (q.epi == EPI_CE_FWD) B200_GEMM_CASE(256, false, false, EPI_CE_FWD);
+  if (q.epi == EPI_CE_BWD) B200_GEMM_CASE(256, false, false, EPI_CE_BWD);
+  if (q.epi == EPI_ARGMAX) B200_GEMM_CASE(128, false, false, EPI_ARGMAX);
+  if (block_n == 256) {
+    if (!q.a_mn && !q.b_mn) B200_GEMM_CASE(256, false, false, EPI_STD);
+    if (!q.a_mn && q.b_mn) B200_GEMM_CASE(256, false, true, EPI_STD);
+    if (q.a_mn && q.b_mn) B200_GEMM_CASE(256, true, true, EPI_STD);
+    if (q.a_mn && !q.b_mn) B200_GEMM_CASE(256, true, false, EPI_STD);
+  } else {
+    if (!q.a_mn && !q.b_mn) B200_GEMM_CASE(128, false, false, EPI_STD);
+    if (!q.a_mn && q.b_mn) B200_GEMM_CASE(128, false, true, EPI_STD);
+    if (q.a_mn && q.b_mn) B200_GEMM_CASE(128, true, true, EPI_STD);
+    if (q.a_mn && !q.b_mn) B200_GEMM_CASE(128, true, false, EPI_STD);
+  }
+#undef B200_GEMM_CASE
+  B200_REQUIRE(false, "gemm: unreachable dispatch");
+}
+
+// ------------------------------------------------------------------------------------------
+// CUDA-core check kernel (test instrument only): same contract, fp32 accumulation of the
+// bf16 operands, one thread per output element.
+// ------------------------------------------------------------------------------------------
+__global__ void gemm_check_kernel(GemmDev p, const bf16* A, long long lda, int a_mn, const bf16* B,
+                                  long long ldb, int b_mn) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<long long>(p.M) * p.N) return;
+  const int m = static_cast<int>(idx / p.N), n = static_cast<int>(idx % p.N);
+  float acc = 0.f;
+  for (int k = 0; k < p.K; ++k) {
+    const float a = __bfloat162float(a_mn ? A[static_cast<long long>(k) * lda + m] : A[static_cast<long long>(m) * lda + k]);
+    const float b = __bfloat162float(b_mn ? B[static_cast<long long>(k) * ldb + n] : B[static_cast<long long>(n) * ldb + k]);
+    acc = fmaf(a, b, acc);
+  }
+  if (p.bias) acc += p.bias[n];
+  if (p.act == 1) acc = fmaxf(acc, 0.f);
+  else if (p.act == 2) acc = gelu_erf(acc);
+  if (p.relu_mask && !(__bfloat162float(p.relu_mask[static_cast<long long>(m) * p.ldm + n]) > 0.f)) acc = 0.f;
+  if (p.residual) acc += __bfloat162float(p.residual[static_cast<long long>(m) * p.ldr + n]);
+  if (p.d_fp32) {
+    float* d = reinterpret_cast<float*>(p.D) + static_cast<long long>(m) * p.ldd + n;
+    *d = p.accumulate ? (*d + acc) : acc;
+  } else {
+    reinterpret_cast<bf16*>(p.D)[static_cast<long long>(m) * p.ldd + n] = __float2bfloat16(acc);
+  }
+}
+
+int gemm_check_launch(const GemmProblem& q, cudaStream_t stream) {
+  B200_REQUIRE(q.epi == EPI_STD, "gemm_check: standard epilogue only");
+  GemmDev d = {};
+  d.M = q.M; d.N = q.N; d.K = q.K;
+  d.D = q.D; d.ldd = q.ldd; d.d_fp32 = q.d_fp32; d.accumulate = q.accumulate;
+  d.bias = q.bias; d.residual = q.residual; d.ldr = q.ldr; d.relu_mask = q.relu_mask; d.ldm = q.ldm;
+  d.act = q.act;
+  const long long total = static_cast<long long>(q.M) * q.N;
+  const int threads = 256;
+  const long long blocks = (total + threads - 1) / threads;
+  gemm_check_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(d, q.A, q.lda, q.a_mn, q.B, q.ldb, q.b_mn);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace b200

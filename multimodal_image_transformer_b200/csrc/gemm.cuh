@@ -1,0 +1,36 @@
+// Internal (C++) interface of the tcgen05 GEMM family; the C ABI in capi.cu wraps these.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+enum GemmEpi { EPI_STD = 0, EPI_CE_FWD = 1, EPI_CE_BWD = 2, EPI_ARGMAX = 3 };
+
+struct GemmProblem {
+  int M = 0, N = 0, K = 0;
+  const bf16* A = nullptr; int64_t lda = 0; bool a_mn = false;
+  const bf16* B = nullptr; int64_t ldb = 0; bool b_mn = false;
+  void* D = nullptr; int64_t ldd = 0; bool d_fp32 = false; bool accumulate = false;
+  const float* bias = nullptr;
+  const bf16* residual = nullptr; int64_t ldr = 0;
+  const bf16* relu_mask = nullptr; int64_t ldm = 0;
+  int act = 0;
+  int split_k = 1;   // 0 = auto
+  int block_n = 0;   // 0 = auto
+  // --- fused softmax-CE / argmax epilogues (LM head) ---
+  GemmEpi epi = EPI_STD;
+  const int64_t* targets = nullptr; long long ignore_index = 0;
+  float* part_max = nullptr;   // [M, n_tiles]
+  float* part_sum = nullptr;   // [M, n_tiles]   (CE_FWD)   /  argmax index as float bits (ARGMAX)
+  float* tgt_logit = nullptr;  // [M]
+  const float* row_lse = nullptr;
+  const float* inv_count = nullptr;
+};
+
+// Returns 0 / negative error. n_tiles_out (optional) = number of N tiles the launch used.
+int gemm_launch(const GemmProblem& p, cudaStream_t stream, int* n_tiles_out = nullptr);
+int gemm_check_launch(const GemmProblem& p, cudaStream_t stream);
+int gemm_num_n_tiles(int N, int block_n);
+int device_sm_count();
+
+}  // namespace b200

@@ -1,0 +1,305 @@
+"""CPU oracle of the caption-decoder hot path — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module, and only as the checker or as the timed CPU baseline.  The product path
+(multimodal_image_transformer_b200/) never imports it and has no CPU fallback.
+
+It is a plain-tensor fp32 restatement (torch CPU ops as the arithmetic library, because the
+reference's own arithmetic IS torch: decoder.py:105-124 builds nn.Embedding /
+nn.TransformerDecoderLayer / nn.Linear and train.py:319-327 uses torch.optim.AdamW and
+nn.CrossEntropyLoss) of:
+
+  decoder.PositionalEncodingBatchFirst           /root/reference/decoder.py:16-72
+  decoder.TransformerDecoder.forward              /root/reference/decoder.py:134-193
+  utils.generate_square_subsequent_mask           /root/reference/utils.py:11-37
+  utils.create_padding_mask                       /root/reference/utils.py:47-70
+  torch TransformerDecoderLayer post-LN branch    torch/nn/modules/transformer.py:1143-1199
+  F.multi_head_attention_forward                  torch/nn/functional.py:6244-6700
+  CrossEntropyLoss(ignore_index) + clip + AdamW   /root/reference/train.py:90-100,319-327
+  ImageToTextModel.generate greedy loop           /root/reference/model.py:216-242
+
+Parity pin: tests/golden/*.pt are produced by tests/golden/make_golden.py, which imports the
+UNMODIFIED reference from /root/reference in the build container and records its outputs; the
+not-gpu tests check this restatement against those files (and against the live reference when
+/root/reference is present).  The reference ships no tests or golden vectors of its own
+(SURVEY.md §4), so that is the strongest pin available.
+
+Parameters are passed as a dict keyed by the reference's state_dict names relative to the
+decoder module ("token_embedding.weight", "transformer_decoder.layers.0.self_attn.in_proj_weight",
+..., "fc_out.bias").
+"""
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Params = Dict[str, torch.Tensor]
+
+
+# ------------------------------------------------------------------------------------------------
+# masks and positional table
+# ------------------------------------------------------------------------------------------------
+def causal_mask(sz: int) -> torch.Tensor:
+    """utils.py:30-36 — float (sz,sz): 0 where key j <= query i, -inf above the diagonal."""
+    m = torch.zeros(sz, sz)
+    m.masked_fill_(torch.ones(sz, sz, dtype=torch.bool).triu(1), float("-inf"))
+    return m
+
+
+def padding_mask(seq: torch.Tensor, pad_idx: int = 0) -> torch.Tensor:
+    """utils.py:66 — True where the token is padding."""
+    return seq == pad_idx
+
+
+def sinusoid_table(max_len: int, d_model: int) -> torch.Tensor:
+    """decoder.py:34-51 — (1,max_len,d_model); even columns sin, odd columns cos."""
+    position = torch.arange(max_len).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, d_model, 2) * (-math.log(10000.0) / d_model))
+    pe = torch.zeros(max_len, d_model)
+    pe[:, 0::2] = torch.sin(position * div_term)
+    pe[:, 1::2] = torch.cos(position * div_term)
+    return pe.unsqueeze(0)
+
+
+# ------------------------------------------------------------------------------------------------
+# forward
+# ------------------------------------------------------------------------------------------------
+def _layer_norm(x, w, b, eps=1e-5):
+    mu = x.mean(-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(-1, keepdim=True)          # biased variance
+    return (x - mu) / torch.sqrt(var + eps) * w + b
+
+
+def _attention(q, k, v, num_heads, add_mask):
+    """q (B,Tq,E), k/v (B,Tk,E), add_mask broadcastable to (B,H,Tq,Tk) or None.
+    functional.py:6682 — softmax(q k^T / sqrt(hd) + mask) v, heads = column blocks of width hd."""
+    B, Tq, E = q.shape
+    Tk = k.shape[1]
+    hd = E // num_heads
+    qh = q.view(B, Tq, num_heads, hd).transpose(1, 2)
+    kh = k.view(B, Tk, num_heads, hd).transpose(1, 2)
+    vh = v.view(B, Tk, num_heads, hd).transpose(1, 2)
+    s = qh @ kh.transpose(-1, -2) / math.sqrt(hd)
+    if add_mask is not None:
+        s = s + add_mask
+    a = torch.softmax(s, dim=-1)
+    return (a @ vh).transpose(1, 2).reshape(B, Tq, E)
+
+
+def decoder_hidden(p: Params, tokens: torch.Tensor, memory: torch.Tensor,
+                   memory_padding_mask: Optional[torch.Tensor], num_heads: int,
+                   pad_idx: int = 0, act: str = "relu") -> torch.Tensor:
+    """Everything of decoder.py:134-186 up to (not including) fc_out; returns (B,T,E)."""
+    B, T = tokens.shape
+    E = p["token_embedding.weight"].shape[1]
+    L = 0
+    while f"transformer_decoder.layers.{L}.norm1.weight" in p:
+        L += 1
+    # decoder.py:168-170 (dropout is identity in eval / p=0, which is what parity runs use)
+    x = p["token_embedding.weight"][tokens] * math.sqrt(E) + p["positional_encoding.pe"][:, :T]
+    # decoder.py:158,162 -> functional.py:6608-6621: float causal + bool key padding, merged
+    self_mask = causal_mask(T).view(1, 1, T, T) + torch.zeros(B, 1, 1, T).masked_fill(
+        padding_mask(tokens, pad_idx).view(B, 1, 1, T), float("-inf"))
+    cross_mask = None
+    if memory_padding_mask is not None:
+        S = memory.shape[1]
+        cross_mask = torch.zeros(B, 1, 1, S).masked_fill(
+            memory_padding_mask.bool().view(B, 1, 1, S), float("-inf"))
+    fact = F.relu if act == "relu" else F.gelu
+    for l in range(L):
+        pre = f"transformer_decoder.layers.{l}."
+        # self-attention block, transformer.py:1158-1175
+        qkv = x @ p[pre + "self_attn.in_proj_weight"].t() + p[pre + "self_attn.in_proj_bias"]
+        q, k, v = qkv.split(E, dim=-1)
+        sa = _attention(q, k, v, num_heads, self_mask)
+        sa = sa @ p[pre + "self_attn.out_proj.weight"].t() + p[pre + "self_attn.out_proj.bias"]
+        x = _layer_norm(x + sa, p[pre + "norm1.weight"], p[pre + "norm1.bias"])
+        # cross-attention block, transformer.py:1177-1195 ; functional.py:5847-5864
+        w, b = p[pre + "multihead_attn.in_proj_weight"], p[pre + "multihead_attn.in_proj_bias"]
+        q = x @ w[:E].t() + b[:E]
+        kv = memory @ w[E:].t() + b[E:]
+        k, v = kv.split(E, dim=-1)
+        ca = _attention(q, k, v, num_heads, cross_mask)
+        ca = ca @ p[pre + "multihead_attn.out_proj.weight"].t() + p[pre + "multihead_attn.out_proj.bias"]
+        x = _layer_norm(x + ca, p[pre + "norm2.weight"], p[pre + "norm2.bias"])
+        # feed-forward block, transformer.py:1197-1199
+        h = fact(x @ p[pre + "linear1.weight"].t() + p[pre + "linear1.bias"])
+        ff = h @ p[pre + "linear2.weight"].t() + p[pre + "linear2.bias"]
+        x = _layer_norm(x + ff, p[pre + "norm3.weight"], p[pre + "norm3.bias"])
+    return x
+
+
+def decoder_forward(p: Params, tokens, memory, memory_padding_mask=None, num_heads: int = 8,
+                    pad_idx: int = 0, act: str = "relu") -> torch.Tensor:
+    """decoder.TransformerDecoder.forward (decoder.py:134-193): logits (B,T,V), fp32."""
+    x = decoder_hidden(p, tokens, memory, memory_padding_mask, num_heads, pad_idx, act)
+    return x @ p["fc_out.weight"].t() + p["fc_out.bias"]
+
+
+def project_memory(features: torch.Tensor, proj_w: Optional[torch.Tensor],
+                   proj_b: Optional[torch.Tensor]) -> torch.Tensor:
+    """model.py:145 — nn.Linear when encoder width != decoder width, else Identity."""
+    if proj_w is None:
+        return features
+    return features @ proj_w.t() + proj_b
+
+
+def cross_entropy(logits: torch.Tensor, targets: torch.Tensor, ignore_index: int = 0) -> torch.Tensor:
+    """train.py:90,327 — mean over targets != ignore_index of -log_softmax(logits)[target]."""
+    V = logits.shape[-1]
+    lg = logits.reshape(-1, V)
+    tg = targets.reshape(-1)
+    lse = torch.logsumexp(lg, dim=-1)
+    picked = lg.gather(1, tg.clamp(min=0).unsqueeze(1)).squeeze(1)
+    valid = tg != ignore_index
+    return ((lse - picked) * valid).sum() / valid.sum()
+
+
+def loss_and_grads(p: Params, tokens, targets, memory, memory_padding_mask=None, num_heads=8,
+                   pad_idx=0, ignore_index=0, proj: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+                   ) -> Tuple[torch.Tensor, Params]:
+    """train.py:83-93 for the decoder (+ optional projection): loss and d loss / d every
+    floating-point parameter, by autograd over the restatement.  The embedding's padding row gets
+    a zero gradient (nn.Embedding padding_idx, decoder.py:105)."""
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in p.items()
+              if v.is_floating_point() and k != "positional_encoding.pe"}
+    q = dict(p)
+    q.update(leaves)
+    mem = memory
+    proj_leaves = None
+    if proj is not None:
+        proj_leaves = tuple(t.detach().clone().requires_grad_(True) for t in proj)
+        mem = project_memory(memory, *proj_leaves)
+    loss = cross_entropy(decoder_forward(q, tokens, mem, memory_padding_mask, num_heads, pad_idx),
+                         targets, ignore_index)
+    loss.backward()
+    grads = {k: v.grad for k, v in leaves.items()}
+    grads["token_embedding.weight"][pad_idx].zero_()
+    if proj_leaves is not None:
+        grads["projection.weight"], grads["projection.bias"] = (t.grad for t in proj_leaves)
+    return loss.detach(), grads
+
+
+# ------------------------------------------------------------------------------------------------
+# optimizer step: clip_grad_norm_(5.0) + AdamW  (train.py:96-100, 319-325)
+# ------------------------------------------------------------------------------------------------
+def clip_coefficient(grads: Params, max_norm: float) -> Tuple[float, float]:
+    total = math.sqrt(sum(float((g.double() ** 2).sum()) for g in grads.values()))
+    coef = min(1.0, max_norm / (total + 1e-6)) if max_norm > 0 else 1.0
+    return total, coef
+
+
+def adamw_step(p: Params, grads: Params, state: dict, lr=1e-4, betas=(0.9, 0.98), eps=1e-9,
+               weight_decay=1e-5, max_norm=5.0) -> float:
+    """In-place on p and state; returns the pre-clip global gradient norm."""
+    total, coef = clip_coefficient(grads, max_norm)
+    state["step"] = state.get("step", 0) + 1
+    t = state["step"]
+    b1, b2 = betas
+    for k, g in grads.items():
+        g = g * coef
+        m = state.setdefault("m." + k, torch.zeros_like(g))
+        v = state.setdefault("v." + k, torch.zeros_like(g))
+        p[k].mul_(1 - lr * weight_decay)
+        m.mul_(b1).add_(g, alpha=1 - b1)
+        v.mul_(b2).addcmul_(g, g, value=1 - b2)
+        denom = v.sqrt() / math.sqrt(1 - b2 ** t) + eps
+        p[k].addcdiv_(m, denom, value=-lr / (1 - b1 ** t))
+    return total
+
+
+# ------------------------------------------------------------------------------------------------
+# generation
+# ------------------------------------------------------------------------------------------------
+def greedy_generate(p: Params, memory: torch.Tensor, start_id: int, end_id: int, max_len: int,
+                    num_heads: int, pad_idx: int = 0) -> List[List[int]]:
+    """model.py:216-242 per image (full-prefix recompute, argmax of the last position, stop on END),
+    run independently for every row of `memory` (B,S,E).  Returns token lists incl. START/END."""
+    out = []
+    for b in range(memory.shape[0]):
+        ids = torch.tensor([[start_id]], dtype=torch.long)
+        mem = memory[b:b + 1]
+        for _ in range(max_len - 1):
+            logits = decoder_forward(p, ids, mem, None, num_heads, pad_idx)
+            nxt = int(torch.argmax(logits[0, -1]))
+            ids = torch.cat([ids, torch.tensor([[nxt]])], dim=1)
+            if nxt == end_id:
+                break
+        out.append(ids[0].tolist())
+    return out
+
+
+def beam_generate(p: Params, memory: torch.Tensor, start_id: int, end_id: int, max_len: int,
+                  num_heads: int, beam_size: int, pad_idx: int = 0) -> List[List[int]]:
+    """The reference's beam search is a stub that falls back to greedy (model.py:245-252), so there
+    is no reference behaviour to restate.  This is the specification the CUDA path implements:
+    score = sum of token log-probabilities, no length penalty; a hypothesis that emitted END is
+    frozen (it competes with its final score and can only be extended by END at cost 0); ties are
+    broken towards the lower flat index (beam-major, then token id); after max_len-1 steps the
+    highest-scoring hypothesis is returned, cut after its first END."""
+    results = []
+    for b in range(memory.shape[0]):
+        mem = memory[b:b + 1]
+        seqs = [[start_id]]
+        scores = torch.zeros(1)
+        finished = [False]
+        for _ in range(max_len - 1):
+            cand = []
+            for i, s in enumerate(seqs):
+                if finished[i]:
+                    lp = torch.full((p["fc_out.bias"].shape[0],), float("-inf"))
+                    lp[end_id] = 0.0
+                else:
+                    logits = decoder_forward(p, torch.tensor([s]), mem, None, num_heads, pad_idx)
+                    lp = torch.log_softmax(logits[0, -1], dim=-1)
+                cand.append(scores[i] + lp)
+            flat = torch.cat(cand)
+            k = min(beam_size, flat.numel())
+            top = torch.topk(flat, k)
+            # torch.topk does not define tie order: enforce lowest-flat-index-first explicitly
+            order = sorted(range(k), key=lambda j: (-float(top.values[j]), int(top.indices[j])))
+            V = p["fc_out.bias"].shape[0]
+            new_seqs, new_scores, new_fin = [], [], []
+            for j in order:
+                idx = int(top.indices[j])
+                bi, tok = idx // V, idx % V
+                new_seqs.append(seqs[bi] + [tok])
+                new_scores.append(float(top.values[j]))
+                new_fin.append(finished[bi] or tok == end_id)
+            seqs, scores, finished = new_seqs, torch.tensor(new_scores), new_fin
+            if all(finished):
+                break
+        best = seqs[int(torch.argmax(scores))]
+        if end_id in best[1:]:
+            best = best[:best.index(end_id, 1) + 1]
+        results.append(best)
+    return results
+
+
+# ------------------------------------------------------------------------------------------------
+# reference-compatible random initialisation (decoder.py:105-132) without the reference classes
+# ------------------------------------------------------------------------------------------------
+def init_params(vocab_size, embed_dim, num_heads, num_layers, ff_dim, max_seq_len, seed=42,
+                pad_idx=0) -> Params:
+    """Builds the same torch.nn modules, in the same order, that decoder.py:105-124 builds, then
+    applies the Xavier pass of decoder.py:128-132, so that for one seed the values are bit-identical
+    to the reference's (checked in tests/test_oracle.py when /root/reference is present)."""
+    import torch.nn as nn
+    torch.manual_seed(seed)
+    emb = nn.Embedding(vocab_size, embed_dim, padding_idx=pad_idx)
+    nn.Dropout(p=0.0)
+    layer = nn.TransformerDecoderLayer(d_model=embed_dim, nhead=num_heads, dim_feedforward=ff_dim,
+                                       dropout=0.0, batch_first=True)
+    dec = nn.TransformerDecoder(layer, num_layers=num_layers)
+    fc = nn.Linear(embed_dim, vocab_size)
+    for q in list(emb.parameters()) + list(dec.parameters()) + list(fc.parameters()):
+        if q.dim() > 1:
+            nn.init.xavier_uniform_(q)
+    p = {"token_embedding.weight": emb.weight.detach().clone(),
+         "positional_encoding.pe": sinusoid_table(max_seq_len, embed_dim)}
+    for k, v in dec.state_dict().items():
+        p["transformer_decoder." + k] = v.detach().clone()
+    p["fc_out.weight"] = fc.weight.detach().clone()
+    p["fc_out.bias"] = fc.bias.detach().clone()
+    return p
