@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""Benchmark of the caption-decoder hot path (BASELINE.json metric: decoder train tokens/sec at
+1/2/4/8 B200; captions/sec KV-cached greedy decode).
+
+  python bench.py --gpus N --steps K --warmup W            # B200 arm (torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...   # reference CPU arm (rank 0 only)
+
+A "step" is one optimisation step of the decoder (zero_grad, forward, fused LM-head + CE, backward,
+gradient all-reduce when N > 1, global-norm clip, AdamW) on one synthetic batch of BASELINE
+configs[1]: ViT-B/16 features (197 x 768) + 6-layer d=768 decoder, batch 256 per GPU, caption
+length 48 (47 decoder positions), V=10000, random-init weights (reference _init_weights, seed 42).
+One JSON line is printed by rank 0; see DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CFG2 = dict(V=10000, E=768, H=12, L=6, F=3072, ML=100, B=256, T=47, S=197)
+METRIC = "decoder train tokens/sec"
+UNIT = "tokens/s"
+
+
+def train_flops_per_sample(c):
+    """forward flops per sample, x3 for training."""
+    T, S, E, F, L, V = c["T"], c["S"], c["E"], c["F"], c["L"], c["V"]
+    fwd = T * (L * (12 * E * E + 4 * E * F + 4 * T * E + 4 * S * E) + 2 * E * V) + L * 4 * S * E * E
+    return 3 * fwd
+
+
+def synth_batch(c, seed, full_length=True):
+    """tokens uniform in [4,V), START(1) first, no padding for the headline;
+    memory ~ N(0,1) in fp32 (the dtype the reference's encoder hands over)."""
+    g = torch.Generator().manual_seed(seed)
+    B, T, S, V, E = c["B"], c["T"], c["S"], c["V"], c["E"]
+    tok = torch.randint(4, V, (B, T), generator=g)
+    tok[:, 0] = 1
+    tgt = torch.randint(4, V, (B, T), generator=g)
+    if not full_length:
+        for b in range(B):
+            ln = int(torch.randint(12, T + 1, (1,), generator=g))
+            tok[b, ln:] = 0
+            tgt[b, max(ln - 1, 1):] = 0
+    mem = torch.randn(B, S, E, generator=g)
+    return tok, tgt, mem
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.proc, self.lines, self.idx = None, [], str(gpu_index)
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.idx, "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d, "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# reference / CPU arm: the oracle port of the reference decoder train step on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_train_tokens_per_s(c, sample_B, steps, warmup, threads):
+    from oracle import decoder_oracle as O
+    torch.set_num_threads(threads)
+    cs = dict(c, B=sample_B)
+    p = O.init_params(c["V"], c["E"], c["H"], c["L"], c["F"], c["ML"], seed=42)
+    tok, tgt, mem = synth_batch(cs, 1234)
+    state = {}
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        _, grads = O.loss_and_grads(p, tok, tgt, mem, None, c["H"])
+        O.adamw_step(p, grads, state, lr=1e-4, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-5, max_norm=5.0)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    return sample_B * c["T"] / (ms / 1e3), ms
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    c = CFG2
+    threads = os.cpu_count() or 1
+    sample_B = 8
+    steps = max(1, min(args.steps, 5))
+    warmup = max(1, min(args.warmup, 1))
+    val, ms = cpu_train_tokens_per_s(c, sample_B, steps, warmup, threads)
+    sample = (f"oracle port of the reference train step (fp32 torch CPU ops, {threads} threads) on B={sample_B} of the "
+              f"{c['B']}-sample batch, same T/S/E/L/V; {warmup} warm-up + {steps} timed steps")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp32", "data": "synthetic",
+        "config": workload_config(c, args.gpus, dropout=0.0),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(c, n_gpus, dropout):
+    return {"workload": "BASELINE configs[1]: ViT-B/16 features (197x768) + 6-layer d=768 decoder train step, "
+                        "batch 256 per GPU, caption len 48 (T=47), V=10000",
+            "batch_per_gpu": c["B"], "global_batch": c["B"] * n_gpus, "T": c["T"], "S": c["S"], "embed_dim": c["E"],
+            "heads": c["H"], "ff_dim": c["F"], "layers": c["L"], "vocab": c["V"], "dropout": dropout,
+            "padding": "none (full-length captions)", "parallelism": f"dp{n_gpus}",
+            "l2": "working set per step (~3 GB activations + 0.9 GB parameter/optimizer state) exceeds the 126 MB L2; no flush needed"}
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    from multimodal_image_transformer_b200 import _lib as L
+    from multimodal_image_transformer_b200.decoder import TransformerDecoder
+    from multimodal_image_transformer_b200.dp import DataParallel
+    from multimodal_image_transformer_b200.train import B200AdamW, fused_train_step
+
+    rank, local, world = DataParallel.init_from_env("nccl")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = L.lib()
+    c = CFG2
+    torch.manual_seed(42)
+    dec = TransformerDecoder(c["V"], c["E"], c["H"], c["L"], c["F"], c["ML"], dropout=0.0, pad_idx=0, device=dev)
+    dec.train()
+    opt = B200AdamW(dec, lr=1e-4, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-5)
+    dp = DataParallel(dec.engine) if world > 1 else None
+    if dp is not None:
+        dp.broadcast_parameters()
+
+    n_batches = 4
+    host = [synth_batch(c, 1000 + 17 * rank + i) for i in range(n_batches)]
+    dev_batches = [tuple(t.to(dev) for t in b) for b in host]
+
+    def step(batch):
+        tok, tgt, mem = batch
+        return fused_train_step(dec, mem, tok, tgt, opt, 0, 5.0, dp)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        out = step(dev_batches[i % n_batches])
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM (value) ----------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.b200_launch_count()
+    L.check(lib.b200_gemm_profile_begin(min(1 << 20, 400 * args.steps + 64)), "profile_begin")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        out = step(dev_batches[i % n_batches])
+    e1.record()
+    barrier()
+    launches = lib.b200_launch_count() - launches0
+    n_l, tot_ms, tot_fl = C.c_int32(), C.c_double(), C.c_double()
+    L.check(lib.b200_gemm_profile_end(C.byref(n_l), C.byref(tot_ms), C.byref(tot_fl), None, None, 0), "profile_end")
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1) / args.steps
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    last_loss = float(out[0].item())
+    tokens_per_step = c["B"] * c["T"] * world
+    value = tokens_per_step / (ms / 1e3)
+
+    # ---- timed region 2: end to end through the public API from pinned host buffers (e2e) -----
+    pinned = [tuple(t.pin_memory() for t in b) for b in host]
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [tuple(torch.empty_like(t, device=dev) for t in pinned[0]) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    loss_host = torch.zeros(2, 2).pin_memory()
+
+    def upload(i):
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[s])
+            for d, h in zip(slots[s], pinned[i % n_batches]):
+                d.copy_(h, non_blocking=True)
+            ready[s].record(copy_stream)
+
+    def e2e_loop(n):
+        losses = []
+        for s in range(2):
+            consumed[s].record()
+        upload(0)
+        for i in range(n):
+            if i + 1 < n:
+                upload(i + 1)                     # next batch streams in while this one computes
+            s = i % 2
+            torch.cuda.current_stream().wait_event(ready[s])
+            o = step(slots[s])
+            consumed[s].record()
+            loss_host[s].copy_(o, non_blocking=True)   # device -> host read of the step's loss
+            if i >= 1:
+                losses.append(float(loss_host[(i - 1) % 2][0]))   # read one step late: no pipeline stall
+            torch.cuda.current_stream().synchronize() if i + 1 == n else None
+        return losses
+
+    e2e_loop(min(3, args.warmup))
+    barrier()
+    t0 = time.perf_counter()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    e2e_loop(args.steps)
+    e3.record()
+    barrier()
+    e2e_ms_dev = e2.elapsed_time(e3) / args.steps
+    e2e_ms_wall = 1e3 * (time.perf_counter() - t0) / args.steps
+    t = torch.tensor([max(e2e_ms_dev, e2e_ms_wall)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    h2d = sum(x.numel() * x.element_size() for x in pinned[0])
+    e2e = {"value": tokens_per_step / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 8 * world,
+           "api": "train.fused_train_step(TransformerDecoder, B200AdamW) on pinned host fp32 features + int64 tokens, "
+                  "double-buffered H2D on a copy stream, loss read back every step"}
+
+    if rank != 0:
+        return
+
+    peaks, peak_src = measured_peaks()
+    peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+    gemm_ms_per_step = tot_ms.value / args.steps
+    achieved_tf = (tot_fl.value / 1e12) / (tot_ms.value / 1e3) if tot_ms.value > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all instantiations: fwd, dgrad, wgrad, LM-head/CE)",
+                "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                "peak_source": peak_src + ", bf16_tflops_sustained (kernel timed inside a long step)",
+                "launches_per_step": n_l.value / args.steps, "gemm_ms_per_step": gemm_ms_per_step,
+                "gemm_share_of_step": gemm_ms_per_step / ms,
+                "algorithmic_flops_per_step": tot_fl.value / args.steps,
+                "how": "2*M*N*K per launch summed over every GEMM launch of the timed steps / sum of their CUDA-event "
+                       "durations on the launching stream",
+                "traffic": None}
+    step_tf = train_flops_per_sample(c) * c["B"] / (ms / 1e3) / 1e12
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic", "config": workload_config(c, world, dropout=0.0),
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+        "step_model_tflops_per_gpu": step_tf, "step_model_frac_of_peak": step_tf / peak_tf,
+        "last_loss": last_loss,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        val, cms = cpu_train_tokens_per_s(c, 8, 3, 1, threads)
+        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "ms_per_step": cms,
+                                "sample": f"oracle port of the reference train step, fp32, B=8 of the 256-sample batch "
+                                          f"(same T/S/E/L/V), 1 warm-up + 3 timed steps, {threads} threads"}
+    if world == 1 and not args.no_decode:
+        line["decode"] = bench_decode(dec, c, dev, peaks, peak_src)
+    print(json.dumps(line))
+
+
+def bench_decode(dec, c, dev, peaks, peak_src):
+    """BASELINE configs[3]: KV-cached greedy generation, batch 512, max_len 48, END suppressed
+    (fixed 47 steps), cross-attention K/V computed once per image (time included)."""
+    eng = dec.engine
+    B, S, E, L, H, F, V = 512, c["S"], c["E"], c["L"], c["H"], c["F"], c["V"]
+    max_len = 48
+    mem = torch.randn(B, S, E, device=dev)
+    end_never = V + 7           # no token equals it: every row runs all 47 steps
+
+    def run():
+        eng.decode_begin(mem, None, beam=1, max_len=max_len)
+        return eng.generate_greedy(1, end_never, max_len, 0)
+
+    for _ in range(2):
+        run()
+    torch.cuda.synchronize()
+    reps = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        toks, lens = run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    # algorithmic bytes, bf16
+    w = 2 * (L * (6 * E * E + 2 * E * F) + E * V)
+    total = 0
+    for t in range(1, max_len):
+        total += w + 2 * B * L * 2 * t * E + 2 * B * L * 2 * S * E + 2 * B * L * 2 * E
+    hbm = float(peaks["hbm_gbs"])
+    gbs = total / (ms / 1e3) / 1e9
+    return {"metric": "captions/sec KV-cached greedy decode", "value": B / (ms / 1e3), "unit": "captions/s",
+            "ms_per_batch": ms, "config": {"workload": "BASELINE configs[3]: greedy, batch 512, max_len 48 (47 steps, END "
+                                                       "suppressed), cfg2 decoder, S=197, cross K/V precompute included",
+                                           "batch": B, "max_len": max_len},
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                         "algorithmic_bytes": total, "peak_source": peak_src, "traffic": None}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-decode", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

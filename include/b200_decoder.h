@@ -33,6 +33,15 @@ int b200_version(void);
 const char* b200_last_error(void);
 /* 0 when device `dev` is an sm_100 part and the kernels can run on it. */
 int b200_check_device(int dev);
+/* number of kernels this library has launched in the calling process (bench.py "gpu_launches"). */
+long long b200_launch_count(void);
+/* per-launch device timing of the tcgen05 GEMM family (bench.py "roofline"): between begin and
+ * end every GEMM launch is bracketed by two CUDA events on its own stream; end (after the caller
+ * has synchronised) returns the launch count, summed milliseconds and summed algorithmic flops
+ * (2*M*N*K per launch), optionally per launch. */
+int b200_gemm_profile_begin(int32_t max_launches);
+int b200_gemm_profile_end(int32_t* n_launches, double* total_ms, double* total_flops,
+                          float* per_launch_ms, double* per_launch_flops, int32_t cap);
 
 /* ---- GEMM: D[M,N] = epi(A[M,K] . B[N,K]^T)  (replaces aten::addmm behind nn.Linear,
  *      torch/nn/functional.py:5798-5875 in-projections, decoder.py:191 fc_out and their
@@ -84,8 +93,8 @@ int b200_lmhead_argmax(const void* x, int64_t ldx, const void* w, int64_t ldw, c
                        float* scratch, void* stream);
 
 /* ---- elementwise / normalisation kernels ---------------------------------------------------- */
-/* x[b,t,:] = emb[tok[b,t],:] * scale + pe[t,:]   (decoder.py:168-170, 71-72). emb fp32 or bf16. */
-int b200_embed_pe_fwd(const int64_t* tokens, const void* emb_bf16, const float* pe, void* x_bf16,
+/* x[b,t,:] = emb[tok[b,t],:] * scale + pe[t,:]   (decoder.py:168-170, 71-72); fp32 table. */
+int b200_embed_pe_fwd(const int64_t* tokens, const float* emb, const float* pe, void* x_bf16,
                       int32_t B, int32_t T, int32_t E, int32_t V, float scale, void* stream);
 /* demb[tok,:] += scale * dx[b,t,:]  for tok != pad_idx (nn.Embedding padding_idx, decoder.py:105) */
 int b200_embed_bwd(const int64_t* tokens, const void* dx_bf16, float* demb, int32_t B, int32_t T,
@@ -167,59 +176,66 @@ int32_t b200_engine_num_params(const b200_engine* e);
 /* params_f32/grads_f32/params_bf16: arenas of b200_engine_param_count() elements. */
 int b200_engine_bind(b200_engine* e, float* params_f32, void* params_bf16, float* grads_f32,
                      const float* pe_f32);
+/* `mem_dim` is the width of the memory rows handed to the forward calls: embed_dim (already
+ * projected, the decoder.TransformerDecoder.forward contract) or enc_dim (the engine applies
+ * model.py:145's projection itself).  training = 1 keeps every activation backward needs. */
 int64_t b200_engine_workspace_bytes(const b200_engine* e, int32_t B, int32_t T, int32_t S,
-                                    int32_t training);
+                                    int32_t mem_dim, int32_t training);
 int b200_engine_set_workspace(b200_engine* e, void* ws, int64_t bytes);
 
 /* decoder.TransformerDecoder.forward (decoder.py:134-193): tokens [B,T] int64, memory
- * [B,S,enc_dim] fp32, mem_pad [B,S] uint8 or NULL -> logits [B,T,V] fp32. */
+ * [B,S,mem_dim] fp32, mem_pad [B,S] uint8 (1 = padded) or NULL -> logits [B,T,V] fp32. */
 int b200_engine_forward_logits(b200_engine* e, const int64_t* tokens, const float* memory,
                                const uint8_t* mem_pad, int32_t B, int32_t T, int32_t S,
-                               float* logits, void* stream);
-/* forward + fused CE (train.py:83-90 / train.py:142-145): loss_out[0] = mean CE over targets !=
- * ignore_index, loss_out[1] = number of such targets.  keep_for_backward = 1 retains activations.
- * inv_count_dev: optional device scalar overriding 1/valid_count (data-parallel global mean). */
+                               int32_t mem_dim, int32_t training, float* logits, void* stream);
+/* forward + fused LM-head/CE (train.py:83-90, 142-145), logits never materialised:
+ * loss_out[0] = mean CE over targets != ignore_index, loss_out[1] = number of such targets. */
 int b200_engine_forward_loss(b200_engine* e, const int64_t* tokens, const int64_t* targets,
                              const float* memory, const uint8_t* mem_pad, int32_t B, int32_t T,
-                             int32_t S, int64_t ignore_index, int32_t keep_for_backward,
+                             int32_t S, int32_t mem_dim, int64_t ignore_index, int32_t training,
                              float* loss_out, void* stream);
-/* backward of the last forward_loss(keep_for_backward=1) into the bound gradient arena
- * (accumulating: caller zero-fills).  events: optional array of cudaEvent_t recorded on
- * `stream` after the last gradient write of each bucket; bucket_end[i] is the arena offset at
- * which bucket i ends, in reverse-execution order (see DESIGN.md "gradient buckets"). */
+/* backward of the last forward_loss(training=1) into the bound gradient arena (accumulating:
+ * the caller zero-fills, as optimizer.zero_grad() does in train.py:80).
+ * inv_count_dev: optional device scalar replacing 1/valid_count (data-parallel global mean).
+ * dmemory: optional [B,S,embed_dim] fp32 gradient w.r.t. memory (mem_dim == embed_dim only).
+ * bucket_events: optional array of cudaEvent_t, one per gradient bucket (see
+ * b200_engine_grad_buckets), recorded on `stream` right after the bucket's last write. */
 int b200_engine_backward(b200_engine* e, const float* inv_count_dev, float* dmemory,
                          void* const* bucket_events, int32_t num_bucket_events, void* stream);
-/* backward from an explicit dlogits [B,T,V] fp32 (autograd compatibility path of
- * decoder.TransformerDecoder.forward). */
+/* backward of the last forward_logits(training=1) from an explicit dlogits [B,T,V] fp32: the
+ * autograd-compatibility path behind decoder.TransformerDecoder.forward + loss.backward(). */
 int b200_engine_backward_from_dlogits(b200_engine* e, const float* dlogits, float* dmemory,
                                       void* stream);
-/* bucket description for the data-parallel all-reduce: fills up to `cap` (offset,count) pairs in
- * the order their gradients become final during backward; returns the number of buckets. */
+/* gradient buckets for the data-parallel all-reduce, in the order they become final during
+ * backward: fc_out, layer L-1 .. layer 0, embedding(+projection).  Fills up to `cap`
+ * (offset,count) pairs in arena elements; returns the number of buckets (L + 2). */
 int32_t b200_engine_grad_buckets(const b200_engine* e, int64_t* offsets, int64_t* counts,
                                  int32_t cap);
 
-/* ---- KV-cached generation (model.py:216-242, batched) --------------------------------------
- * begin: projects memory once per image into per-layer cross K/V, resets the self cache.
- * step: consumes tokens_in [B*beam] at position `pos`, returns greedy ids (and their
- * log-probabilities when logprob != NULL).  Workspace from b200_engine_decode_workspace_bytes. */
-int64_t b200_engine_decode_workspace_bytes(const b200_engine* e, int32_t B, int32_t beam,
-                                           int32_t S, int32_t max_len);
-int b200_engine_decode_begin(b200_engine* e, const float* memory, const uint8_t* mem_pad,
-                             int32_t B, int32_t beam, int32_t S, int32_t max_len, void* ws,
+/* ---- KV-cached generation (replaces the full-prefix recompute loop of model.py:216-242) ------
+ * decode_begin projects the image memory ONCE per image into per-layer cross-attention K/V
+ * (head-major, shared by all beams of an image) and carves the self-attention cache from `ws`
+ * (b200_engine_decode_workspace_bytes, 256-byte aligned).  Rows are image-major: row = b*beam+k. */
+int64_t b200_engine_decode_workspace_bytes(const b200_engine* e, int32_t B, int32_t beam, int32_t S,
+                                           int32_t mem_dim, int32_t max_len);
+int b200_engine_decode_begin(b200_engine* e, const float* memory, const uint8_t* mem_pad, int32_t B,
+                             int32_t beam, int32_t S, int32_t mem_dim, int32_t max_len, void* ws,
                              int64_t ws_bytes, void* stream);
-int b200_engine_decode_step(b200_engine* e, const int64_t* tokens_in, int32_t pos,
-                            int64_t* next_ids, float* next_logprob, void* stream);
-/* beam search support: top-`beam` continuations per image over (beam x V) log-probs of the last
- * step, and re-indexing of the self-attention cache by the chosen parent beams. */
-int b200_engine_decode_step_topk(b200_engine* e, const int64_t* tokens_in, int32_t pos,
-                                 const float* beam_scores, const uint8_t* finished,
-                                 int64_t end_id, int64_t* out_tokens, int32_t* out_parent,
-                                 float* out_scores, void* stream);
-int b200_engine_decode_reorder(b200_engine* e, const int32_t* parent, int32_t pos, void* stream);
-/* whole greedy loop on device, END handling included: out_tokens [B,max_len] int64 (START first,
- * PAD after END), out_len [B]. */
+/* one position for every row: tokens_in [B*beam] at position pos -> argmax ids [B*beam]
+ * (first index on ties, torch.argmax, model.py:233). */
+int b200_engine_decode_step(b200_engine* e, const int64_t* tokens_in, int32_t pos, int64_t* next_ids,
+                            void* stream);
+/* the whole greedy loop without host round trips: out_tokens [B,max_len] int64 holds START, the
+ * generated ids up to and including END, then PAD; out_len [B] counts START..END.  With
+ * stop_check_interval = n > 0 the host checks every n steps whether every row has emitted END
+ * (the reference's early exit, model.py:239-240); 0 = always run max_len-1 steps. */
 int b200_engine_generate_greedy(b200_engine* e, int64_t start_id, int64_t end_id, int32_t max_len,
-                                int64_t* out_tokens, int32_t* out_len, void* stream);
+                                int32_t stop_check_interval, int64_t* out_tokens, int32_t* out_len,
+                                void* stream);
+/* beam search (the reference's is a stub, model.py:245-252; semantics in DESIGN.md): sum of
+ * log-probabilities, no length penalty, finished hypotheses frozen, lower index wins ties. */
+int b200_engine_generate_beam(b200_engine* e, int64_t start_id, int64_t end_id, int32_t max_len,
+                              int64_t* out_tokens, int32_t* out_len, float* out_score, void* stream);
 
 #ifdef __cplusplus
 }

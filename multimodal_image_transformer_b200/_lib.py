@@ -58,6 +58,55 @@ class EngineConfig(C.Structure):
     ]
 
 
+_P, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+# name -> (restype, argtypes); mirrors include/b200_decoder.h one to one (checked by
+# tests/test_abi.py against the header text and the built library's export table).
+SIGNATURES = {
+    "b200_version": (C.c_int, []),
+    "b200_last_error": (C.c_char_p, []),
+    "b200_check_device": (C.c_int, [C.c_int]),
+    "b200_launch_count": (C.c_longlong, []),
+    "b200_gemm_profile_begin": (C.c_int, [_I32]),
+    "b200_gemm_profile_end": (C.c_int, [_P, _P, _P, _P, _P, _I32]),
+    "b200_gemm": (C.c_int, [C.POINTER(GemmArgs), _P]),
+    "b200_gemm_check": (C.c_int, [C.POINTER(GemmArgs), _P]),
+    "b200_lmhead_ce_fwd": (C.c_int, [_P, _I64, _P, _I64, _P, _P, _I32, _I32, _I32, _I64, _P, _P, _P, _P, _P, _P]),
+    "b200_lmhead_ce_bwd": (C.c_int, [_P, _I64, _P, _I64, _P, _P, _I32, _I32, _I32, _I64, _P, _P, _P, _I64, _P]),
+    "b200_lmhead_argmax": (C.c_int, [_P, _I64, _P, _I64, _P, _I32, _I32, _I32, _P, _P, _P, _P]),
+    "b200_embed_pe_fwd": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _F, _P]),
+    "b200_embed_bwd": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I64, _F, _P]),
+    "b200_layernorm_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I32, _F, _P]),
+    "b200_layernorm_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _P]),
+    "b200_colsum": (C.c_int, [_P, _I64, _P, _I32, _I32, _P]),
+    "b200_cast_f32_to_bf16": (C.c_int, [_P, _P, _I64, _P]),
+    "b200_cast_bf16_to_f32": (C.c_int, [_P, _P, _I64, _P]),
+    "b200_attn_fwd": (C.c_int, [C.POINTER(AttnFwdArgs), _P]),
+    "b200_attn_bwd": (C.c_int, [C.POINTER(AttnBwdArgs), _P]),
+    "b200_grad_sumsq": (C.c_int, [_P, _I64, _P, _P]),
+    "b200_adamw_step": (C.c_int, [_P, _P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _F, _F, _I32, _P]),
+    "b200_engine_create": (C.c_int, [C.POINTER(EngineConfig), C.POINTER(C.c_void_p)]),
+    "b200_engine_destroy": (None, [_P]),
+    "b200_engine_param_count": (_I64, [_P]),
+    "b200_engine_param_offset": (_I64, [_P, C.c_char_p, C.POINTER(C.c_int64)]),
+    "b200_engine_param_name": (C.c_int, [_P, _I32, C.c_char_p, _I32]),
+    "b200_engine_num_params": (_I32, [_P]),
+    "b200_engine_bind": (C.c_int, [_P, _P, _P, _P, _P]),
+    "b200_engine_workspace_bytes": (_I64, [_P, _I32, _I32, _I32, _I32, _I32]),
+    "b200_engine_set_workspace": (C.c_int, [_P, _P, _I64]),
+    "b200_engine_forward_logits": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P, _P]),
+    "b200_engine_forward_loss": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I64, _I32, _P, _P]),
+    "b200_engine_backward": (C.c_int, [_P, _P, _P, _P, _I32, _P]),
+    "b200_engine_backward_from_dlogits": (C.c_int, [_P, _P, _P, _P]),
+    "b200_engine_grad_buckets": (_I32, [_P, _P, _P, _I32]),
+    "b200_engine_decode_workspace_bytes": (_I64, [_P, _I32, _I32, _I32, _I32, _I32]),
+    "b200_engine_decode_begin": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P, _I64, _P]),
+    "b200_engine_decode_step": (C.c_int, [_P, _P, _I32, _P, _P]),
+    "b200_engine_generate_greedy": (C.c_int, [_P, _I64, _I64, _I32, _I32, _P, _P, _P]),
+    "b200_engine_generate_beam": (C.c_int, [_P, _I64, _I64, _I32, _P, _P, _P, _P]),
+}
+
+
 def lib():
     """Load (once) and return the CDLL; raises if the library has not been built."""
     global _lib
@@ -67,11 +116,10 @@ def lib():
                 "b200 decoder library not built: %s is missing (run `python __graft_entry__.py`); "
                 "there is no CPU fallback" % LIB_PATH)
         _lib = C.CDLL(LIB_PATH)
-        _lib.b200_last_error.restype = C.c_char_p
-        for name in ("b200_engine_param_count", "b200_engine_param_offset",
-                     "b200_engine_workspace_bytes", "b200_engine_decode_workspace_bytes"):
-            if hasattr(_lib, name):
-                getattr(_lib, name).restype = C.c_int64
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(_lib, name)   # AttributeError here = header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
     return _lib
 
 
@@ -84,7 +132,7 @@ def check(rc, what="b200 call"):
 def ptr(t):
     """Device pointer of a torch tensor (or None) as c_void_p."""
     if t is None:
-        return C.c_void_p(0)
+        return None
     return C.c_void_p(t.data_ptr())
 
 

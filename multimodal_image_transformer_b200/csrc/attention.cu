@@ -1,0 +1,484 @@
+// Fused attention for the caption decoder (replaces F.scaled_dot_product_attention reached from
+// torch/nn/functional.py:6682 via nn.MultiheadAttention):
+//   self attention : causal (key j <= query i, utils.py:30-36) + key padding taken straight from
+//                    the token ids (utils.py:66, decoder.py:158-162), never materialised as a mask;
+//   cross attention: every query sees all S image tokens (model.py:158), optional key padding.
+// One CTA per (image, head).  The whole K and V of that (image, head) — 50..257 ViT/CLIP tokens or
+// <= 99 caption positions — are loaded ONCE into shared memory and stay resident while every
+// query tile is processed; scores/probabilities live in registers (flash-style online softmax),
+// products run on the warp-level tensor-core path (mma.sync m16n8k16 bf16, fp32 accumulate;
+// the problems are 47x47..47x257 per head, far below one tcgen05 tile).
+// Backward recomputes P from the saved log-sum-exp: phase 1 produces dQ per query tile, phase 2
+// produces dK/dV per key tile (no atomics, deterministic).
+#include "attention.cuh"
+#include <math.h>
+
+namespace b200 {
+
+static constexpr float LOG2E = 1.4426950408889634f;
+static constexpr float LN2 = 0.6931471805599453f;
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(saddr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(saddr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
+struct AttnDev {
+  const bf16 *q, *k, *v, *o_in, *d_o;
+  bf16 *o, *dq, *dk, *dv;
+  long long q_bs, q_ts, k_bs, k_ts, v_bs, v_ts, o_bs, o_ts, do_bs, do_ts, dq_bs, dq_ts, dk_bs, dk_ts, dv_bs, dv_ts;
+  float* lse;
+  int B, H, Tq, Tk, TQP, TKP;
+  int causal;
+  const long long* key_tokens; long long pad_idx;
+  const unsigned char* key_pad_mask;
+  float scale;
+};
+
+// cooperative copy of `rows` x HD bf16 (row stride ts elements) into padded smem, zero-filling
+// rows [rows, rows_padded)
+template <int HD>
+__device__ __forceinline__ void load_rows(bf16* dst, const bf16* src, long long ts, int rows, int rows_padded) {
+  constexpr int LD = HD + 8;
+  constexpr int VPR = HD / 8;
+  for (int i = threadIdx.x; i < rows_padded * VPR; i += blockDim.x) {
+    const int r = i / VPR, c = (i % VPR) * 8;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (r < rows) val = ldg_nc_v4(src + r * ts + c);
+    *reinterpret_cast<uint4*>(dst + r * LD + c) = val;
+  }
+}
+
+// C[16 x (NT*8)] += A[16 x HD] * B^T, A rows at a_row0 of sA, B rows (the "n" index) at b_row0 of
+// sB, both stored [row][HD+8] (dimension contiguous).
+template <int HD, int NT>
+__device__ __forceinline__ void mma_abt(float (&c)[NT][4], const bf16* sA, int a_row0, const bf16* sB,
+                                        int b_row0, int b_rows_avail) {
+  constexpr int LD = HD + 8;
+  const int lane = threadIdx.x & 31;
+  const int mi = lane >> 3, r8 = lane & 7;
+#pragma unroll
+  for (int ks = 0; ks < HD / 16; ++ks) {
+    uint32_t a[4];
+    ldsm_x4(a, smem_u32(sA + (a_row0 + (mi & 1) * 8 + r8) * LD + ks * 16 + (mi >> 1) * 8));
+#pragma unroll
+    for (int j = 0; j < NT; j += 2) {
+      if (j * 8 < b_rows_avail) {   // warp-uniform
+        uint32_t b[4];
+        ldsm_x4(b, smem_u32(sB + (b_row0 + (j + (mi >> 1)) * 8 + r8) * LD + ks * 16 + (mi & 1) * 8));
+        mma16816(c[j], a, b[0], b[1]);
+        mma16816(c[j + 1], a, b[2], b[3]);
+      }
+    }
+  }
+}
+
+// C[16 x HD] += P[16 x (NT*8)] * B, P given as fp32 accumulator fragments (converted to bf16),
+// B rows (the reduction index) at b_row0 of sB stored [row][HD+8].
+template <int HD, int NT>
+__device__ __forceinline__ void mma_pb(float (&c)[HD / 8][4], const float (&p)[NT][4], const bf16* sB,
+                                       int b_row0, int b_rows_avail) {
+  constexpr int LD = HD + 8;
+  const int lane = threadIdx.x & 31;
+  const int mi = lane >> 3, r8 = lane & 7;
+#pragma unroll
+  for (int kk = 0; kk < NT / 2; ++kk) {
+    if (kk * 16 < b_rows_avail) {   // warp-uniform
+      uint32_t a[4];
+      a[0] = pack_bf16(p[2 * kk][0], p[2 * kk][1]);
+      a[1] = pack_bf16(p[2 * kk][2], p[2 * kk][3]);
+      a[2] = pack_bf16(p[2 * kk + 1][0], p[2 * kk + 1][1]);
+      a[3] = pack_bf16(p[2 * kk + 1][2], p[2 * kk + 1][3]);
+#pragma unroll
+      for (int dn = 0; dn < HD / 8; dn += 2) {
+        uint32_t b[4];
+        ldsm_x4_t(b, smem_u32(sB + (b_row0 + kk * 16 + (mi & 1) * 8 + r8) * LD + (dn + (mi >> 1)) * 8));
+        mma16816(c[dn], a, b[0], b[1]);
+        mma16816(c[dn + 1], a, b[2], b[3]);
+      }
+    }
+  }
+}
+
+template <int HD>
+struct AttnSmem {
+  static constexpr int LD = HD + 8;
+  static size_t fwd_bytes(int TQP, int TKP) {
+    return static_cast<size_t>(TQP + 2 * TKP) * LD * 2 + TKP * sizeof(float) + 16;
+  }
+  static size_t bwd_bytes(int TQP, int TKP) {
+    return static_cast<size_t>(2 * TQP + 2 * TKP) * LD * 2 + (TKP + 2 * TQP) * sizeof(float) + 16;
+  }
+};
+
+__device__ __forceinline__ void fill_key_bias(float* sBias, const AttnDev& p, int b) {
+  for (int j = threadIdx.x; j < p.TKP; j += blockDim.x) {
+    bool masked = j >= p.Tk;
+    if (!masked && p.key_tokens) masked = p.key_tokens[static_cast<long long>(b) * p.Tk + j] == p.pad_idx;
+    if (!masked && p.key_pad_mask) masked = p.key_pad_mask[static_cast<long long>(b) * p.Tk + j] != 0;
+    sBias[j] = masked ? -INFINITY : 0.f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------
+template <int HD, int NT>
+__global__ void __launch_bounds__(128)
+attn_fwd_kernel(const AttnDev p) {
+  constexpr int LD = HD + 8;
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  bf16* sQ = reinterpret_cast<bf16*>(smem_attn);
+  bf16* sK = sQ + p.TQP * LD;
+  bf16* sV = sK + p.TKP * LD;
+  float* sBias = reinterpret_cast<float*>(sV + p.TKP * LD);
+
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+
+  load_rows<HD>(sQ, p.q + b * p.q_bs + h * HD, p.q_ts, p.Tq, p.TQP);
+  load_rows<HD>(sK, p.k + b * p.k_bs + h * HD, p.k_ts, p.Tk, p.TKP);
+  load_rows<HD>(sV, p.v + b * p.v_bs + h * HD, p.v_ts, p.Tk, p.TKP);
+  fill_key_bias(sBias, p, b);
+  __syncthreads();
+
+  const float sl2 = p.scale * LOG2E;
+  for (int mt = warp; mt * 16 < p.TQP; mt += 4) {
+    const int row0 = mt * 16;
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+    float o[HD / 8][4];
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+    const int kend = p.causal ? min(p.TKP, row0 + 16) : p.TKP;
+    for (int kb0 = 0; kb0 < kend; kb0 += NT * 8) {
+      float s[NT][4];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
+      const int avail = kend - kb0;
+      mma_abt<HD, NT>(s, sQ, row0, sK, kb0, avail);
+      float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int key = kb0 + j * 8 + 2 * t + (e & 1);
+          const int row = row0 + g + (e >> 1) * 8;
+          float val = -INFINITY;
+          if (j * 8 < avail && key < p.TKP && !(p.causal && key > row)) val = s[j][e] * sl2 + sBias[key];
+          s[j][e] = val;
+          mx[e >> 1] = fmaxf(mx[e >> 1], val);
+        }
+      }
+      float alpha[2], m_new[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        m_new[r] = fmaxf(m_run[r], quad_max(mx[r]));
+        alpha[r] = (m_run[r] == -INFINITY) ? 0.f : exp2f(m_run[r] - m_new[r]);
+        m_run[r] = m_new[r];
+      }
+      float ps[2] = {0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float mm = m_new[e >> 1];
+          const float pv = (mm == -INFINITY) ? 0.f : exp2f(s[j][e] - mm);
+          s[j][e] = pv;
+          ps[e >> 1] += pv;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) l_run[r] = l_run[r] * alpha[r] + ps[r];
+#pragma unroll
+      for (int i = 0; i < HD / 8; ++i) {
+        o[i][0] *= alpha[0]; o[i][1] *= alpha[0]; o[i][2] *= alpha[1]; o[i][3] *= alpha[1];
+      }
+      mma_pb<HD, NT>(o, s, sV, kb0, avail);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const float l = quad_sum(l_run[r]);
+      const int row = row0 + g + r * 8;
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      if (row < p.Tq) {
+        bf16* orow = p.o + b * p.o_bs + row * p.o_ts + h * HD;
+#pragma unroll
+        for (int i = 0; i < HD / 8; ++i)
+          *reinterpret_cast<uint32_t*>(orow + i * 8 + 2 * t) = pack_bf16(o[i][2 * r] * inv, o[i][2 * r + 1] * inv);
+        if (p.lse && t == 0)
+          p.lse[(static_cast<long long>(b) * p.H + h) * p.Tq + row] = (l > 0.f) ? m_run[r] * LN2 + logf(l) : -INFINITY;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------
+template <int HD, int NT>
+__global__ void __launch_bounds__(128)
+attn_bwd_kernel(const AttnDev p) {
+  constexpr int LD = HD + 8;
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  bf16* sQ = reinterpret_cast<bf16*>(smem_attn);
+  bf16* sdO = sQ + p.TQP * LD;
+  bf16* sK = sdO + p.TQP * LD;
+  bf16* sV = sK + p.TKP * LD;
+  float* sBias = reinterpret_cast<float*>(sV + p.TKP * LD);
+  float* sLse = sBias + p.TKP;   // already multiplied by log2(e); +inf on padded query rows
+  float* sD = sLse + p.TQP;
+
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+
+  load_rows<HD>(sQ, p.q + b * p.q_bs + h * HD, p.q_ts, p.Tq, p.TQP);
+  load_rows<HD>(sdO, p.d_o + b * p.do_bs + h * HD, p.do_ts, p.Tq, p.TQP);
+  load_rows<HD>(sK, p.k + b * p.k_bs + h * HD, p.k_ts, p.Tk, p.TKP);
+  load_rows<HD>(sV, p.v + b * p.v_bs + h * HD, p.v_ts, p.Tk, p.TKP);
+  fill_key_bias(sBias, p, b);
+  // D_i = sum_d dO[i,d] * O[i,d]; one warp per row
+  for (int row = warp; row < p.TQP; row += 4) {
+    float acc = 0.f;
+    if (row < p.Tq) {
+      const bf16* orow = p.o_in + b * p.o_bs + row * p.o_ts + h * HD;
+      const bf16* drow = p.d_o + b * p.do_bs + row * p.do_ts + h * HD;
+      for (int c = lane * 2; c < HD; c += 64) {
+        const float2 a = unpack_bf16(*reinterpret_cast<const uint32_t*>(orow + c));
+        const float2 d = unpack_bf16(*reinterpret_cast<const uint32_t*>(drow + c));
+        acc += a.x * d.x + a.y * d.y;
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      sD[row] = acc;
+      float l = INFINITY;
+      if (row < p.Tq) {
+        l = p.lse[(static_cast<long long>(b) * p.H + h) * p.Tq + row];
+        l = (l == -INFINITY) ? INFINITY : l * LOG2E;   // fully masked row: P = 0
+      }
+      sLse[row] = l;
+    }
+  }
+  __syncthreads();
+
+  const float sl2 = p.scale * LOG2E;
+
+  // ---- phase 1: dQ, one 16-query tile per warp iteration
+  for (int mt = warp; mt * 16 < p.TQP; mt += 4) {
+    const int row0 = mt * 16;
+    float dq[HD / 8][4];
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) { dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f; }
+    const float lse0 = sLse[row0 + g], lse1 = sLse[row0 + g + 8];
+    const float d0 = sD[row0 + g], d1 = sD[row0 + g + 8];
+    const int kend = p.causal ? min(p.TKP, row0 + 16) : p.TKP;
+    for (int kb0 = 0; kb0 < kend; kb0 += NT * 8) {
+      float s[NT][4], dp[NT][4];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+        dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
+      }
+      const int avail = kend - kb0;
+      mma_abt<HD, NT>(s, sQ, row0, sK, kb0, avail);
+      mma_abt<HD, NT>(dp, sdO, row0, sV, kb0, avail);
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int key = kb0 + j * 8 + 2 * t + (e & 1);
+          const int row = row0 + g + (e >> 1) * 8;
+          float ds = 0.f;
+          if (j * 8 < avail && key < p.TKP && !(p.causal && key > row)) {
+            const float pv = exp2f(s[j][e] * sl2 + sBias[key] - ((e >> 1) ? lse1 : lse0));
+            ds = pv * (dp[j][e] - ((e >> 1) ? d1 : d0)) * p.scale;
+          }
+          s[j][e] = ds;
+        }
+      }
+      mma_pb<HD, NT>(dq, s, sK, kb0, avail);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int row = row0 + g + r * 8;
+      if (row < p.Tq) {
+        bf16* drow = p.dq + b * p.dq_bs + row * p.dq_ts + h * HD;
+#pragma unroll
+        for (int i = 0; i < HD / 8; ++i)
+          *reinterpret_cast<uint32_t*>(drow + i * 8 + 2 * t) = pack_bf16(dq[i][2 * r], dq[i][2 * r + 1]);
+      }
+    }
+  }
+
+  // ---- phase 2: dK, dV, one 16-key tile per warp iteration (scores computed transposed)
+  for (int kt = warp; kt * 16 < p.TKP; kt += 4) {
+    const int key0 = kt * 16;
+    float dk[HD / 8][4], dv[HD / 8][4];
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) {
+      dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
+      dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
+    }
+    const float kb_0 = sBias[key0 + g], kb_1 = sBias[key0 + g + 8];
+    // causal: only queries >= key contribute; start at the 16-aligned query tile holding key0
+    const int qstart = p.causal ? min(key0, p.TQP) : 0;
+    for (int q0 = qstart; q0 < p.TQP; q0 += NT * 8) {
+      float st[NT][4], dpt[NT][4];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        st[j][0] = st[j][1] = st[j][2] = st[j][3] = 0.f;
+        dpt[j][0] = dpt[j][1] = dpt[j][2] = dpt[j][3] = 0.f;
+      }
+      const int avail = p.TQP - q0;
+      mma_abt<HD, NT>(st, sK, key0, sQ, q0, avail);
+      mma_abt<HD, NT>(dpt, sV, key0, sdO, q0, avail);
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int qi = q0 + j * 8 + 2 * t + (e & 1);
+          const int key = key0 + g + (e >> 1) * 8;
+          float pv = 0.f, ds = 0.f;
+          if (j * 8 < avail && qi < p.TQP && !(p.causal && key > qi)) {
+            pv = exp2f(st[j][e] * sl2 + ((e >> 1) ? kb_1 : kb_0) - sLse[qi]);
+            ds = pv * (dpt[j][e] - sD[qi]) * p.scale;
+          }
+          st[j][e] = pv;
+          dpt[j][e] = ds;
+        }
+      }
+      mma_pb<HD, NT>(dv, st, sdO, q0, avail);
+      mma_pb<HD, NT>(dk, dpt, sQ, q0, avail);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int key = key0 + g + r * 8;
+      if (key < p.Tk) {
+        bf16* krow = p.dk + b * p.dk_bs + key * p.dk_ts + h * HD;
+        bf16* vrow = p.dv + b * p.dv_bs + key * p.dv_ts + h * HD;
+#pragma unroll
+        for (int i = 0; i < HD / 8; ++i) {
+          *reinterpret_cast<uint32_t*>(krow + i * 8 + 2 * t) = pack_bf16(dk[i][2 * r], dk[i][2 * r + 1]);
+          *reinterpret_cast<uint32_t*>(vrow + i * 8 + 2 * t) = pack_bf16(dv[i][2 * r], dv[i][2 * r + 1]);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------
+static int check_common(const AttnArgs& a) {
+  B200_REQUIRE(a.B > 0 && a.H > 0 && a.Tq > 0 && a.Tk > 0, "attention: empty problem");
+  B200_REQUIRE(a.hd == 32 || a.hd == 64 || a.hd == 96 || a.hd == 128, "attention: head dim %d not in {32,64,96,128}", a.hd);
+  B200_REQUIRE(a.Tq <= 512 && a.Tk <= 512, "attention: Tq/Tk (%d/%d) above the 512 resident-tile limit", a.Tq, a.Tk);
+  auto ok = [](const void* ptr, long long bs, long long ts) {
+    return ptr != nullptr && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && bs % 8 == 0 && ts % 8 == 0;
+  };
+  B200_REQUIRE(ok(a.q, a.q_bs, a.q_ts) && ok(a.k, a.k_bs, a.k_ts) && ok(a.v, a.v_bs, a.v_ts) && ok(a.o, a.o_bs, a.o_ts),
+               "attention: q/k/v/o must be non-null, 16-byte aligned, strides multiples of 8");
+  return 0;
+}
+
+static void fill_dev(const AttnArgs& a, AttnDev* d) {
+  memset(d, 0, sizeof(*d));
+  d->q = a.q; d->k = a.k; d->v = a.v; d->o = a.o; d->o_in = a.o;
+  d->q_bs = a.q_bs; d->q_ts = a.q_ts; d->k_bs = a.k_bs; d->k_ts = a.k_ts;
+  d->v_bs = a.v_bs; d->v_ts = a.v_ts; d->o_bs = a.o_bs; d->o_ts = a.o_ts;
+  d->lse = a.lse;
+  d->B = a.B; d->H = a.H; d->Tq = a.Tq; d->Tk = a.Tk;
+  d->TQP = (a.Tq + 15) / 16 * 16; d->TKP = (a.Tk + 15) / 16 * 16;
+  d->causal = a.causal;
+  d->key_tokens = reinterpret_cast<const long long*>(a.key_tokens); d->pad_idx = a.pad_idx;
+  d->key_pad_mask = a.key_pad_mask;
+  d->scale = a.scale;
+}
+
+template <int HD, int NT>
+static int launch_fwd(const AttnDev& d, cudaStream_t s) {
+  const size_t smem = AttnSmem<HD>::fwd_bytes(d.TQP, d.TKP);
+  B200_REQUIRE(smem <= 227 * 1024, "attention fwd: %zu B of shared memory needed (> 227 KB)", smem);
+  static size_t configured = 0;
+  if (smem > configured) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<HD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = smem;
+  }
+  attn_fwd_kernel<HD, NT><<<dim3(d.H, d.B), 128, smem, s>>>(d);
+  note_launch();
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+template <int HD, int NT>
+static int launch_bwd(const AttnDev& d, cudaStream_t s) {
+  const size_t smem = AttnSmem<HD>::bwd_bytes(d.TQP, d.TKP);
+  B200_REQUIRE(smem <= 227 * 1024, "attention bwd: %zu B of shared memory needed (> 227 KB)", smem);
+  static size_t configured = 0;
+  if (smem > configured) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<HD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = smem;
+  }
+  attn_bwd_kernel<HD, NT><<<dim3(d.H, d.B), 128, smem, s>>>(d);
+  note_launch();
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int attn_fwd(const AttnArgs& a, cudaStream_t s) {
+  if (int rc = check_common(a)) return rc;
+  AttnDev d;
+  fill_dev(a, &d);
+  switch (a.hd) {
+    case 32: return launch_fwd<32, 8>(d, s);
+    case 64: return launch_fwd<64, 8>(d, s);
+    case 96: return launch_fwd<96, 8>(d, s);
+    default: return launch_fwd<128, 8>(d, s);
+  }
+}
+
+int attn_bwd(const AttnArgs& a, const AttnGrads& gr, cudaStream_t s) {
+  if (int rc = check_common(a)) return rc;
+  B200_REQUIRE(a.lse != nullptr, "attention bwd: lse is required");
+  auto ok = [](const void* ptr, long long bs, long long ts) {
+    return ptr != nullptr && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && bs % 8 == 0 && ts % 8 == 0;
+  };
+  B200_REQUIRE(ok(gr.d_o, gr.do_bs, gr.do_ts) && ok(gr.dq, gr.dq_bs, gr.dq_ts) && ok(gr.dk, gr.dk_bs, gr.dk_ts) && ok(gr.dv, gr.dv_bs, gr.dv_ts),
+               "attention bwd: dO/dQ/dK/dV must be non-null, 16-byte aligned, strides multiples of 8");
+  AttnDev d;
+  fill_dev(a, &d);
+  d.d_o = gr.d_o; d.do_bs = gr.do_bs; d.do_ts = gr.do_ts;
+  d.dq = gr.dq; d.dq_bs = gr.dq_bs; d.dq_ts = gr.dq_ts;
+  d.dk = gr.dk; d.dk_bs = gr.dk_bs; d.dk_ts = gr.dk_ts;
+  d.dv = gr.dv; d.dv_bs = gr.dv_bs; d.dv_ts = gr.dv_ts;
+  switch (a.hd) {
+    case 32: return launch_bwd<32, 8>(d, s);
+    case 64: return launch_bwd<64, 8>(d, s);
+    case 96: return launch_bwd<96, 4>(d, s);
+    default: return launch_bwd<128, 4>(d, s);
+  }
+}
+
+}  // namespace b200

@@ -30,6 +30,14 @@ void set_last_error(const char* fmt, ...);
     }                                                                                     \
   } while (0)
 
+// ------------------------------------------------------------------ launch accounting
+// every launcher calls note_launch(); bench.py reports the count as "gpu_launches".
+void note_launch(int n = 1);
+// optional per-launch timing of the GEMM family (bench.py roofline): when enabled, gemm_launch
+// brackets its kernel with two events from a pool and remembers the algorithmic flops.
+bool gemm_profile_enabled();
+void gemm_profile_record(cudaStream_t s, bool begin, double flops);
+
 // ------------------------------------------------------------------ small utils
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -1,0 +1,39 @@
+// Internal (C++) launchers of the memory-bound kernels of KV-cached caption generation.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+// cross K/V from the projection GEMM's [B*S, 2E] layout into head-major [B][H][S][hd] K and V
+// planes (contiguous per (image, head): what the decode kernel streams).
+int kv_to_head_major(const bf16* kv, bf16* k_hm, bf16* v_hm, int B, int S, int H, int hd, cudaStream_t s);
+// append this step's K/V (columns [E,2E) and [2E,3E) of qkv [R,3E]) to the self cache at `pos`
+// cache layout [R][H][max_len][hd]
+int kv_append(const bf16* qkv, bf16* kcache, bf16* vcache, int R, int H, int hd, int max_len, int pos, cudaStream_t s);
+// single-query attention: for every group g (image) and head h, NQ query rows (beams) attend
+// over the same nkeys keys.  q/o: [groups*nq, H*hd] rows; K/V: [groups][H][kv_len][hd], reading
+// the first nkeys rows.  key_pad: optional [groups, nkeys] uint8.
+int attn_decode(const bf16* q, long long q_rs, const bf16* k, const bf16* v, int kv_len, int nkeys,
+                bf16* o, long long o_rs, int groups, int nq, int H, int hd, const unsigned char* key_pad,
+                float scale, cudaStream_t s);
+// greedy bookkeeping after a step: finished rows emit pad_id, END marks a row finished
+int greedy_update(const int64_t* next_ids, int64_t* cur_tokens, int64_t* out_tokens, int* out_len,
+                  unsigned char* finished, int* n_finished, int R, int max_len, int pos, long long end_id,
+                  long long pad_id, cudaStream_t s);
+// beam search: per image top-`beam` of (beam x V) candidate scores = score[beam] + log_softmax(logits)
+int beam_topk(const float* logits, const float* beam_scores, const unsigned char* finished, int B, int beam,
+              int V, long long end_id, int first_step, int64_t* out_tokens, int* out_parent,
+              float* out_scores, cudaStream_t s);
+int beam_advance(const int64_t* seq_in, int64_t* seq_out, const unsigned char* fin_in, unsigned char* fin_out,
+                 const int64_t* tokens, const int* parent, int R, int beam, int max_len, int pos, long long end_id,
+                 cudaStream_t s);
+int beam_finalize(const int64_t* seqs, const float* scores, int B, int beam, int max_len, int n_tok,
+                  long long end_id, long long pad_id, int64_t* out_tokens, int* out_len, float* out_score,
+                  cudaStream_t s);
+int fill_i64(int64_t* p, long long n, long long v, cudaStream_t s);
+int fill_col_i64(int64_t* p, long long n, long long stride, long long v, cudaStream_t s);
+// cache[dst row] = cache[parent row] for positions [0,pos]
+int cache_reorder(const bf16* src_k, const bf16* src_v, bf16* dst_k, bf16* dst_v, const int* parent, int B,
+                  int beam, int H, int hd, int max_len, int pos, cudaStream_t s);
+
+}  // namespace b200

@@ -1,0 +1,776 @@
+// Decoder engine: the launch sequence of decoder.TransformerDecoder.forward (decoder.py:134-193,
+// post-LN nn.TransformerDecoderLayer, torch/nn/modules/transformer.py:1143-1199), of the fused
+// loss (train.py:90,327) and of their backward, expressed as calls into the sm_100a kernels.
+// The engine owns no memory: parameters/gradients are caller-bound flat arenas, activations live
+// in a caller-provided workspace carved by a deterministic bump plan.
+#include "../../include/b200_decoder.h"
+#include "attention.cuh"
+#include "common.cuh"
+#include "decode.cuh"
+#include "gemm.cuh"
+#include "kernels.cuh"
+#include <math.h>
+#include <string>
+#include <vector>
+
+using namespace b200;
+
+namespace {
+
+struct ParamInfo {
+  std::string name;
+  int64_t offset, numel;
+};
+
+struct LayerOff {
+  int64_t sa_w, sa_b, sa_ow, sa_ob, ca_w, ca_b, ca_ow, ca_ob, l1_w, l1_b, l2_w, l2_b;
+  int64_t n1_w, n1_b, n2_w, n2_b, n3_w, n3_b;
+  int64_t begin;
+};
+
+struct LayerAct {   // activations of one layer kept for backward
+  bf16 *qkv, *attn_o, *y1, *x1, *qc, *kvc, *attn_c, *y2, *x2, *h, *y3;
+  float *lse_s, *lse_c, *mean1, *rstd1, *mean2, *rstd2, *mean3, *rstd3;
+};
+
+struct Plan {
+  int B = 0, T = 0, S = 0, mem_dim = 0, training = 0;
+  int64_t bytes = 0;
+  bf16* mem16 = nullptr;      // [B*S, mem_dim]
+  bf16* memp = nullptr;       // [B*S, E] projected memory (== mem16 when no projection)
+  std::vector<LayerAct> act;  // L entries when training, 1 otherwise
+  std::vector<bf16*> xs;      // xs[l] = input of layer l, xs[L] = decoder output
+  bf16* x_final = nullptr;    // [M, E]
+  float *row_lse = nullptr, *row_loss = nullptr, *ce_scratch = nullptr, *scalars = nullptr;
+  // backward temporaries
+  bf16 *dlogits = nullptr, *dxa = nullptr, *dxb = nullptr, *dxc = nullptr, *dh = nullptr,
+       *dqkv = nullptr, *dkv = nullptr, *dattn = nullptr, *dqc = nullptr, *dmemp16 = nullptr;
+  float* dmemp = nullptr;     // [B*S, E] fp32 accumulator of d(projected memory)
+};
+
+struct Bump {
+  uint8_t* base;
+  int64_t off = 0;
+  explicit Bump(uint8_t* b) : base(b) {}
+  template <class Tp>
+  Tp* take(int64_t n) {
+    off = (off + 255) & ~static_cast<int64_t>(255);
+    Tp* p = base ? reinterpret_cast<Tp*>(base + off) : nullptr;
+    off += n * static_cast<int64_t>(sizeof(Tp));
+    return p;
+  }
+};
+
+}  // namespace
+
+struct b200_engine {
+  b200_engine_config cfg;
+  std::vector<ParamInfo> params;
+  std::vector<LayerOff> lo;
+  int64_t total = 0;
+  int64_t proj_w = -1, proj_b = -1, emb = -1, fc_w = -1, fc_b = -1;
+  float* pf = nullptr;
+  bf16* ph = nullptr;
+  float* gf = nullptr;
+  const float* pe = nullptr;
+  uint8_t* ws = nullptr;
+  int64_t ws_bytes = 0;
+  Plan plan;   // of the last forward
+  const int64_t* last_tokens = nullptr;
+  const int64_t* last_targets = nullptr;
+  const uint8_t* last_mem_pad = nullptr;
+  long long last_ignore = 0;
+  bool have_saved = false;
+  // decode state (carved from the caller's decode workspace by decode_begin)
+  struct Decode {
+    int B = 0, beam = 0, R = 0, S = 0, max_len = 0;
+    bf16 *mem16 = nullptr, *memp = nullptr, *kv_tmp = nullptr;
+    bf16 *kc = nullptr, *vc = nullptr;           // [L][B][H][S][hd] cross K/V, once per image
+    bf16 *kcache[2] = {nullptr, nullptr}, *vcache[2] = {nullptr, nullptr};   // [L][R][H][max_len][hd]
+    int cur = 0;                                 // which self-cache copy is live (beam ping-pong)
+    bf16 *xa = nullptr, *xb = nullptr, *qkv = nullptr, *attn = nullptr, *y = nullptr, *x1 = nullptr,
+         *qc = nullptr, *x2 = nullptr, *h = nullptr;
+    float *scratch = nullptr, *logits = nullptr, *scores[2] = {nullptr, nullptr}, *best = nullptr;
+    int64_t *ids = nullptr, *cur_tok = nullptr, *seq[2] = {nullptr, nullptr};
+    int *parent = nullptr, *out_len = nullptr, *n_finished = nullptr;
+    unsigned char* fin[2] = {nullptr, nullptr};
+    const uint8_t* mem_pad = nullptr;
+    int64_t bytes = 0;
+    bool ready = false;
+  } dec;
+};
+
+namespace {
+
+int64_t add_param(b200_engine* e, const std::string& name, int64_t numel) {
+  const int64_t off = (e->total + 63) & ~static_cast<int64_t>(63);
+  e->params.push_back({name, off, numel});
+  e->total = off + numel;
+  return off;
+}
+
+void build_plan(const b200_engine* e, Plan* pl, uint8_t* base, int B, int T, int S, int mem_dim, int training) {
+  const auto& c = e->cfg;
+  const int64_t E = c.embed_dim, F = c.ff_dim, V = c.vocab_size, H = c.num_heads, L = c.num_layers;
+  const int64_t M = static_cast<int64_t>(B) * T, Ms = static_cast<int64_t>(B) * S;
+  Bump b(base);
+  pl->B = B; pl->T = T; pl->S = S; pl->mem_dim = mem_dim; pl->training = training;
+  pl->mem16 = b.take<bf16>(Ms * mem_dim);
+  pl->memp = (mem_dim != E) ? b.take<bf16>(Ms * E) : pl->mem16;
+  // residual stream: training keeps every layer input (xs[l]) for backward, inference ping-pongs
+  pl->xs.resize(L + 1);
+  if (training) {
+    for (int l = 0; l <= L; ++l) pl->xs[l] = b.take<bf16>(M * E);
+  } else {
+    bf16* xa = b.take<bf16>(M * E);
+    bf16* xb = b.take<bf16>(M * E);
+    for (int l = 0; l <= L; ++l) pl->xs[l] = (l & 1) ? xb : xa;
+  }
+  const int slots = training ? static_cast<int>(L) : 1;
+  pl->act.resize(slots);
+  for (int l = 0; l < slots; ++l) {
+    LayerAct& a = pl->act[l];
+    a.qkv = b.take<bf16>(M * 3 * E);
+    a.attn_o = b.take<bf16>(M * E);
+    a.y1 = b.take<bf16>(M * E);
+    a.x1 = b.take<bf16>(M * E);
+    a.qc = b.take<bf16>(M * E);
+    a.kvc = b.take<bf16>(Ms * 2 * E);
+    a.attn_c = b.take<bf16>(M * E);
+    a.y2 = b.take<bf16>(M * E);
+    a.x2 = b.take<bf16>(M * E);
+    a.h = b.take<bf16>(M * F);
+    a.y3 = b.take<bf16>(M * E);
+    a.lse_s = b.take<float>(static_cast<int64_t>(B) * H * T);
+    a.lse_c = b.take<float>(static_cast<int64_t>(B) * H * T);
+    a.mean1 = b.take<float>(M); a.rstd1 = b.take<float>(M);
+    a.mean2 = b.take<float>(M); a.rstd2 = b.take<float>(M);
+    a.mean3 = b.take<float>(M); a.rstd3 = b.take<float>(M);
+  }
+  pl->x_final = pl->xs[L];
+  const int64_t n_tiles = (V + 127) / 128;
+  pl->row_lse = b.take<float>(M);
+  pl->row_loss = b.take<float>(M);
+  pl->ce_scratch = b.take<float>(3 * M * n_tiles + M);
+  pl->scalars = b.take<float>(16);
+  if (training) {
+    pl->dlogits = b.take<bf16>(M * V);
+    pl->dxa = b.take<bf16>(M * E);
+    pl->dxb = b.take<bf16>(M * E);
+    pl->dxc = b.take<bf16>(M * E);
+    pl->dh = b.take<bf16>(M * F);
+    pl->dqkv = b.take<bf16>(M * 3 * E);
+    pl->dkv = b.take<bf16>(Ms * 2 * E);
+    pl->dattn = b.take<bf16>(M * E);
+    pl->dqc = b.take<bf16>(M * E);
+    pl->dmemp = b.take<float>(Ms * E);
+    pl->dmemp16 = b.take<bf16>(Ms * E);
+  }
+  pl->bytes = (b.off + 255) & ~static_cast<int64_t>(255);
+}
+
+// y = x W^T + b  with optional activation / residual; W rows [row0,row0+N) of a [*,K] matrix
+int linear_fwd(const bf16* x, int64_t ldx, const bf16* W, const float* bias, bf16* y, int64_t ldy, int M,
+               int N, int K, int act, const bf16* residual, int64_t ldr, cudaStream_t s) {
+  GemmProblem g;
+  g.M = M; g.N = N; g.K = K;
+  g.A = x; g.lda = ldx; g.B = W; g.ldb = K;
+  g.D = y; g.ldd = ldy; g.bias = bias; g.act = act; g.residual = residual; g.ldr = ldr;
+  g.split_k = 1;
+  return gemm_launch(g, s);
+}
+// dx = dy W (+ residual) (* relu mask);  W is [N_out, K_in] as stored
+int linear_dgrad(const bf16* dy, int64_t lddy, const bf16* W, int N_out, int K_in, bf16* dx, int64_t lddx,
+                 int M, const bf16* residual, int64_t ldr, const bf16* relu_mask, int64_t ldm, cudaStream_t s) {
+  GemmProblem g;
+  g.M = M; g.N = K_in; g.K = N_out;
+  g.A = dy; g.lda = lddy; g.B = W; g.ldb = K_in; g.b_mn = true;
+  g.D = dx; g.ldd = lddx; g.residual = residual; g.ldr = ldr; g.relu_mask = relu_mask; g.ldm = ldm;
+  g.split_k = 1;
+  return gemm_launch(g, s);
+}
+// dW[N_out,K_in] += dy^T x ; db[N_out] += colsum(dy)
+int linear_wgrad(const bf16* dy, int64_t lddy, const bf16* x, int64_t ldx, float* dW, float* db, int M,
+                 int N_out, int K_in, cudaStream_t s) {
+  GemmProblem g;
+  g.M = N_out; g.N = K_in; g.K = M;
+  g.A = dy; g.lda = lddy; g.a_mn = true; g.B = x; g.ldb = ldx; g.b_mn = true;
+  g.D = dW; g.ldd = K_in; g.d_fp32 = true; g.accumulate = true; g.split_k = 0;
+  if (int rc = gemm_launch(g, s)) return rc;
+  if (db) return colsum(dy, lddy, db, M, N_out, s);
+  return 0;
+}
+
+#define RC(expr) do { if (int _rc = (expr)) return _rc; } while (0)
+
+int run_forward(b200_engine* e, const int64_t* tokens, const float* memory, const uint8_t* mem_pad, int B,
+                int T, int S, int mem_dim, int training, cudaStream_t s) {
+  const auto& c = e->cfg;
+  const int E = c.embed_dim, F = c.ff_dim, H = c.num_heads, L = c.num_layers, hd = E / H;
+  B200_REQUIRE(e->pf && e->ph, "engine: parameters not bound");
+  B200_REQUIRE(B > 0 && T > 0 && S > 0, "engine: empty batch (B=%d T=%d S=%d)", B, T, S);
+  B200_REQUIRE(T <= c.max_seq_len, "engine: T=%d exceeds max_seq_len=%d (positional table too short, decoder.py:71)", T, c.max_seq_len);
+  B200_REQUIRE(mem_dim == E || (mem_dim == c.enc_dim && e->proj_w >= 0), "engine: memory width %d matches neither embed_dim %d nor enc_dim %d", mem_dim, E, c.enc_dim);
+  Plan probe;
+  build_plan(e, &probe, nullptr, B, T, S, mem_dim, training);
+  B200_REQUIRE(e->ws && probe.bytes <= e->ws_bytes, "engine: workspace too small (%lld needed, %lld bound)", (long long)probe.bytes, (long long)e->ws_bytes);
+  build_plan(e, &e->plan, e->ws, B, T, S, mem_dim, training);
+  Plan& pl = e->plan;
+  const int M = B * T, Ms = B * S;
+  const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+
+  RC(cast_f32_to_bf16(memory, pl.mem16, static_cast<long long>(Ms) * mem_dim, s));
+  if (mem_dim != E)
+    RC(linear_fwd(pl.mem16, mem_dim, e->ph + e->proj_w, e->pf + e->proj_b, pl.memp, E, Ms, E, mem_dim, 0, nullptr, 0, s));
+
+  RC(embed_pe_fwd(tokens, e->pf + e->emb, e->pe, pl.xs[0], B, T, E, c.vocab_size, sqrtf(static_cast<float>(E)), s));
+
+  for (int l = 0; l < L; ++l) {
+    const LayerOff& o = e->lo[l];
+    LayerAct& a = pl.act[training ? l : 0];
+    const bf16* x = pl.xs[l];
+    bf16* x_out = pl.xs[l + 1];
+    // --- self-attention block
+    RC(linear_fwd(x, E, e->ph + o.sa_w, e->pf + o.sa_b, a.qkv, 3 * E, M, 3 * E, E, 0, nullptr, 0, s));
+    AttnArgs sa;
+    sa.q = a.qkv; sa.k = a.qkv + E; sa.v = a.qkv + 2 * E;
+    sa.q_bs = sa.k_bs = sa.v_bs = static_cast<long long>(T) * 3 * E; sa.q_ts = sa.k_ts = sa.v_ts = 3 * E;
+    sa.o = a.attn_o; sa.o_bs = static_cast<long long>(T) * E; sa.o_ts = E;
+    sa.lse = a.lse_s; sa.B = B; sa.H = H; sa.Tq = T; sa.Tk = T; sa.hd = hd; sa.causal = 1;
+    sa.key_tokens = tokens; sa.pad_idx = c.pad_idx; sa.scale = scale;
+    RC(attn_fwd(sa, s));
+    RC(linear_fwd(a.attn_o, E, e->ph + o.sa_ow, e->pf + o.sa_ob, a.y1, E, M, E, E, 0, x, E, s));
+    RC(layernorm_fwd(a.y1, e->pf + o.n1_w, e->pf + o.n1_b, a.x1, a.mean1, a.rstd1, M, E, c.ln_eps, s));
+    // --- cross-attention block
+    RC(linear_fwd(a.x1, E, e->ph + o.ca_w, e->pf + o.ca_b, a.qc, E, M, E, E, 0, nullptr, 0, s));
+    RC(linear_fwd(pl.memp, E, e->ph + o.ca_w + static_cast<int64_t>(E) * E, e->pf + o.ca_b + E, a.kvc, 2 * E, Ms, 2 * E, E, 0, nullptr, 0, s));
+    AttnArgs ca;
+    ca.q = a.qc; ca.q_bs = static_cast<long long>(T) * E; ca.q_ts = E;
+    ca.k = a.kvc; ca.v = a.kvc + E; ca.k_bs = ca.v_bs = static_cast<long long>(S) * 2 * E; ca.k_ts = ca.v_ts = 2 * E;
+    ca.o = a.attn_c; ca.o_bs = static_cast<long long>(T) * E; ca.o_ts = E;
+    ca.lse = a.lse_c; ca.B = B; ca.H = H; ca.Tq = T; ca.Tk = S; ca.hd = hd; ca.causal = 0;
+    ca.key_pad_mask = mem_pad; ca.scale = scale;
+    RC(attn_fwd(ca, s));
+    RC(linear_fwd(a.attn_c, E, e->ph + o.ca_ow, e->pf + o.ca_ob, a.y2, E, M, E, E, 0, a.x1, E, s));
+    RC(layernorm_fwd(a.y2, e->pf + o.n2_w, e->pf + o.n2_b, a.x2, a.mean2, a.rstd2, M, E, c.ln_eps, s));
+    // --- feed-forward block
+    RC(linear_fwd(a.x2, E, e->ph + o.l1_w, e->pf + o.l1_b, a.h, F, M, F, E, c.act, nullptr, 0, s));
+    RC(linear_fwd(a.h, F, e->ph + o.l2_w, e->pf + o.l2_b, a.y3, E, M, E, F, 0, a.x2, E, s));
+    RC(layernorm_fwd(a.y3, e->pf + o.n3_w, e->pf + o.n3_b, x_out, a.mean3, a.rstd3, M, E, c.ln_eps, s));
+  }
+  return 0;
+}
+
+int run_backward(b200_engine* e, bool have_dlogits, float* dmemory, void* const* events, int n_events, cudaStream_t s) {
+  const auto& c = e->cfg;
+  const int E = c.embed_dim, F = c.ff_dim, H = c.num_heads, L = c.num_layers, hd = E / H, V = c.vocab_size;
+  Plan& pl = e->plan;
+  B200_REQUIRE(e->have_saved && pl.training, "engine: backward needs a preceding training forward");
+  B200_REQUIRE(e->gf, "engine: gradient arena not bound");
+  B200_REQUIRE(c.act == B200_ACT_RELU, "engine: backward is implemented for the reference activation (ReLU) only");
+  const int B = pl.B, T = pl.T, S = pl.S;
+  const int M = B * T, Ms = B * S;
+  const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+  const bool need_dmemp = (pl.mem_dim != E) || dmemory != nullptr;
+  B200_REQUIRE(!(dmemory && pl.mem_dim != E), "engine: dmemory is only available when memory is already embed_dim wide");
+  (void)have_dlogits;
+  int ev = 0;
+  auto mark = [&](void) {
+    if (events && ev < n_events && events[ev]) cudaEventRecord(static_cast<cudaEvent_t>(events[ev]), s);
+    ++ev;
+  };
+
+  if (need_dmemp) B200_CHECK_CUDA(cudaMemsetAsync(pl.dmemp, 0, static_cast<size_t>(Ms) * E * sizeof(float), s));
+
+  // --- LM head
+  RC(linear_wgrad(pl.dlogits, V, pl.x_final, E, e->gf + e->fc_w, e->gf + e->fc_b, M, V, E, s));
+  bf16* dx = pl.dxa;
+  RC(linear_dgrad(pl.dlogits, V, e->ph + e->fc_w, V, E, dx, E, M, nullptr, 0, nullptr, 0, s));
+  mark();
+
+  bf16* spare1 = pl.dxb;
+  bf16* spare2 = pl.dxc;
+  for (int l = L - 1; l >= 0; --l) {
+    const LayerOff& o = e->lo[l];
+    LayerAct& a = pl.act[l];
+    float* g = e->gf;
+    // LN3
+    bf16* dy3 = spare1;
+    RC(layernorm_bwd(dx, a.y3, e->pf + o.n3_w, a.mean3, a.rstd3, dy3, g + o.n3_w, g + o.n3_b, M, E, s));
+    // FFN
+    RC(linear_wgrad(dy3, E, a.h, F, g + o.l2_w, g + o.l2_b, M, E, F, s));
+    RC(linear_dgrad(dy3, E, e->ph + o.l2_w, E, F, pl.dh, F, M, nullptr, 0, a.h, F, s));
+    RC(linear_wgrad(pl.dh, F, a.x2, E, g + o.l1_w, g + o.l1_b, M, F, E, s));
+    bf16* dx2 = spare2;
+    RC(linear_dgrad(pl.dh, F, e->ph + o.l1_w, F, E, dx2, E, M, dy3, E, nullptr, 0, s));
+    // LN2
+    bf16* dy2 = dx;   // dx (grad of layer output) is dead now
+    RC(layernorm_bwd(dx2, a.y2, e->pf + o.n2_w, a.mean2, a.rstd2, dy2, g + o.n2_w, g + o.n2_b, M, E, s));
+    // cross-attention
+    RC(linear_wgrad(dy2, E, a.attn_c, E, g + o.ca_ow, g + o.ca_ob, M, E, E, s));
+    RC(linear_dgrad(dy2, E, e->ph + o.ca_ow, E, E, pl.dattn, E, M, nullptr, 0, nullptr, 0, s));
+    AttnArgs ca;
+    ca.q = a.qc; ca.q_bs = static_cast<long long>(T) * E; ca.q_ts = E;
+    ca.k = a.kvc; ca.v = a.kvc + E; ca.k_bs = ca.v_bs = static_cast<long long>(S) * 2 * E; ca.k_ts = ca.v_ts = 2 * E;
+    ca.o = a.attn_c; ca.o_bs = static_cast<long long>(T) * E; ca.o_ts = E;
+    ca.lse = a.lse_c; ca.B = B; ca.H = H; ca.Tq = T; ca.Tk = S; ca.hd = hd; ca.causal = 0;
+    ca.key_pad_mask = e->last_mem_pad; ca.scale = scale;
+    AttnGrads cg;
+    cg.d_o = pl.dattn; cg.do_bs = static_cast<long long>(T) * E; cg.do_ts = E;
+    cg.dq = pl.dqc; cg.dq_bs = static_cast<long long>(T) * E; cg.dq_ts = E;
+    cg.dk = pl.dkv; cg.dv = pl.dkv + E; cg.dk_bs = cg.dv_bs = static_cast<long long>(S) * 2 * E; cg.dk_ts = cg.dv_ts = 2 * E;
+    RC(attn_bwd(ca, cg, s));
+    RC(linear_wgrad(pl.dqc, E, a.x1, E, g + o.ca_w, g + o.ca_b, M, E, E, s));
+    RC(linear_wgrad(pl.dkv, 2 * E, pl.memp, E, g + o.ca_w + static_cast<int64_t>(E) * E, g + o.ca_b + E, Ms, 2 * E, E, s));
+    if (need_dmemp) {
+      GemmProblem gp;
+      gp.M = Ms; gp.N = E; gp.K = 2 * E;
+      gp.A = pl.dkv; gp.lda = 2 * E; gp.B = e->ph + o.ca_w + static_cast<int64_t>(E) * E; gp.ldb = E; gp.b_mn = true;
+      gp.D = pl.dmemp; gp.ldd = E; gp.d_fp32 = true; gp.accumulate = true; gp.split_k = 1;
+      RC(gemm_launch(gp, s));
+    }
+    bf16* dx1 = spare1;   // dy3 is dead
+    RC(linear_dgrad(pl.dqc, E, e->ph + o.ca_w, E, E, dx1, E, M, dy2, E, nullptr, 0, s));
+    // LN1
+    bf16* dy1 = spare2;   // dx2 is dead
+    RC(layernorm_bwd(dx1, a.y1, e->pf + o.n1_w, a.mean1, a.rstd1, dy1, g + o.n1_w, g + o.n1_b, M, E, s));
+    // self-attention
+    RC(linear_wgrad(dy1, E, a.attn_o, E, g + o.sa_ow, g + o.sa_ob, M, E, E, s));
+    RC(linear_dgrad(dy1, E, e->ph + o.sa_ow, E, E, pl.dattn, E, M, nullptr, 0, nullptr, 0, s));
+    AttnArgs sa;
+    sa.q = a.qkv; sa.k = a.qkv + E; sa.v = a.qkv + 2 * E;
+    sa.q_bs = sa.k_bs = sa.v_bs = static_cast<long long>(T) * 3 * E; sa.q_ts = sa.k_ts = sa.v_ts = 3 * E;
+    sa.o = a.attn_o; sa.o_bs = static_cast<long long>(T) * E; sa.o_ts = E;
+    sa.lse = a.lse_s; sa.B = B; sa.H = H; sa.Tq = T; sa.Tk = T; sa.hd = hd; sa.causal = 1;
+    sa.key_tokens = e->last_tokens; sa.pad_idx = c.pad_idx; sa.scale = scale;
+    AttnGrads sg;
+    sg.d_o = pl.dattn; sg.do_bs = static_cast<long long>(T) * E; sg.do_ts = E;
+    sg.dq = pl.dqkv; sg.dk = pl.dqkv + E; sg.dv = pl.dqkv + 2 * E;
+    sg.dq_bs = sg.dk_bs = sg.dv_bs = static_cast<long long>(T) * 3 * E; sg.dq_ts = sg.dk_ts = sg.dv_ts = 3 * E;
+    RC(attn_bwd(sa, sg, s));
+    RC(linear_wgrad(pl.dqkv, 3 * E, pl.xs[l], E, g + o.sa_w, g + o.sa_b, M, 3 * E, E, s));
+    bf16* dx_in = dx;     // dy2 is dead
+    RC(linear_dgrad(pl.dqkv, 3 * E, e->ph + o.sa_w, 3 * E, E, dx_in, E, M, dy1, E, nullptr, 0, s));
+    dx = dx_in;
+    mark();
+  }
+  RC(embed_bwd(e->last_tokens, dx, e->gf + e->emb, B, T, E, V, c.pad_idx, sqrtf(static_cast<float>(E)), s));
+  if (pl.mem_dim != E) {
+    RC(cast_f32_to_bf16(pl.dmemp, pl.dmemp16, static_cast<long long>(Ms) * E, s));
+    RC(linear_wgrad(pl.dmemp16, E, pl.mem16, pl.mem_dim, e->gf + e->proj_w, e->gf + e->proj_b, Ms, E, pl.mem_dim, s));
+  } else if (dmemory) {
+    B200_CHECK_CUDA(cudaMemcpyAsync(dmemory, pl.dmemp, static_cast<size_t>(Ms) * E * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+  mark();
+  return 0;
+}
+
+
+void build_decode_plan(const b200_engine* e, b200_engine::Decode* d, uint8_t* base, int B, int beam, int S,
+                       int mem_dim, int max_len) {
+  const auto& c = e->cfg;
+  const int64_t E = c.embed_dim, F = c.ff_dim, V = c.vocab_size, L = c.num_layers;
+  const int64_t R = static_cast<int64_t>(B) * beam, Ms = static_cast<int64_t>(B) * S;
+  Bump b(base);
+  d->B = B; d->beam = beam; d->R = static_cast<int>(R); d->S = S; d->max_len = max_len;
+  d->mem16 = b.take<bf16>(Ms * mem_dim);
+  d->memp = (mem_dim != E) ? b.take<bf16>(Ms * E) : d->mem16;
+  d->kv_tmp = b.take<bf16>(Ms * 2 * E);
+  d->kc = b.take<bf16>(L * Ms * E);
+  d->vc = b.take<bf16>(L * Ms * E);
+  const int copies = beam > 1 ? 2 : 1;
+  for (int i = 0; i < 2; ++i) {
+    d->kcache[i] = i < copies ? b.take<bf16>(L * R * max_len * E) : nullptr;
+    d->vcache[i] = i < copies ? b.take<bf16>(L * R * max_len * E) : nullptr;
+    d->seq[i] = b.take<int64_t>(R * max_len);
+    d->scores[i] = b.take<float>(R);
+    d->fin[i] = b.take<unsigned char>(R);
+  }
+  d->xa = b.take<bf16>(R * E); d->xb = b.take<bf16>(R * E);
+  d->qkv = b.take<bf16>(R * 3 * E); d->attn = b.take<bf16>(R * E); d->y = b.take<bf16>(R * E);
+  d->x1 = b.take<bf16>(R * E); d->qc = b.take<bf16>(R * E); d->x2 = b.take<bf16>(R * E);
+  d->h = b.take<bf16>(R * F);
+  d->scratch = b.take<float>(2 * R * ((V + 127) / 128));
+  d->logits = beam > 1 ? b.take<float>(R * V) : nullptr;
+  d->best = b.take<float>(R);
+  d->ids = b.take<int64_t>(R); d->cur_tok = b.take<int64_t>(R);
+  d->parent = b.take<int>(R); d->out_len = b.take<int>(R); d->n_finished = b.take<int>(4);
+  d->bytes = (b.off + 255) & ~static_cast<int64_t>(255);
+}
+
+// one decode position for every row: tokens [R] at position pos -> final hidden in *x_out
+int decode_hidden(b200_engine* e, const int64_t* tokens, int pos, bf16** x_out, cudaStream_t s) {
+  const auto& c = e->cfg;
+  auto& d = e->dec;
+  const int E = c.embed_dim, F = c.ff_dim, H = c.num_heads, L = c.num_layers, hd = E / H;
+  const int R = d.R, B = d.B, S = d.S;
+  const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+  B200_REQUIRE(pos >= 0 && pos < d.max_len && pos < c.max_seq_len, "decode: position %d out of range", pos);
+  bf16* x = d.xa;
+  bf16* xn = d.xb;
+  RC(embed_pe_fwd(tokens, e->pf + e->emb, e->pe, x, R, 1, E, c.vocab_size, sqrtf(static_cast<float>(E)), s, pos));
+  const int64_t self_stride = static_cast<int64_t>(R) * d.max_len * E;
+  const int64_t cross_stride = static_cast<int64_t>(B) * S * E;
+  for (int l = 0; l < L; ++l) {
+    const LayerOff& o = e->lo[l];
+    bf16* kc_l = d.kcache[d.cur] + l * self_stride;
+    bf16* vc_l = d.vcache[d.cur] + l * self_stride;
+    RC(linear_fwd(x, E, e->ph + o.sa_w, e->pf + o.sa_b, d.qkv, 3 * E, R, 3 * E, E, 0, nullptr, 0, s));
+    RC(kv_append(d.qkv, kc_l, vc_l, R, H, hd, d.max_len, pos, s));
+    RC(attn_decode(d.qkv, 3 * E, kc_l, vc_l, d.max_len, pos + 1, d.attn, E, R, 1, H, hd, nullptr, scale, s));
+    RC(linear_fwd(d.attn, E, e->ph + o.sa_ow, e->pf + o.sa_ob, d.y, E, R, E, E, 0, x, E, s));
+    RC(layernorm_fwd(d.y, e->pf + o.n1_w, e->pf + o.n1_b, d.x1, nullptr, nullptr, R, E, c.ln_eps, s));
+    RC(linear_fwd(d.x1, E, e->ph + o.ca_w, e->pf + o.ca_b, d.qc, E, R, E, E, 0, nullptr, 0, s));
+    RC(attn_decode(d.qc, E, d.kc + l * cross_stride, d.vc + l * cross_stride, S, S, d.attn, E, B, d.beam, H, hd,
+                   d.mem_pad, scale, s));
+    RC(linear_fwd(d.attn, E, e->ph + o.ca_ow, e->pf + o.ca_ob, d.y, E, R, E, E, 0, d.x1, E, s));
+    RC(layernorm_fwd(d.y, e->pf + o.n2_w, e->pf + o.n2_b, d.x2, nullptr, nullptr, R, E, c.ln_eps, s));
+    RC(linear_fwd(d.x2, E, e->ph + o.l1_w, e->pf + o.l1_b, d.h, F, R, F, E, c.act, nullptr, 0, s));
+    RC(linear_fwd(d.h, F, e->ph + o.l2_w, e->pf + o.l2_b, d.y, E, R, E, F, 0, d.x2, E, s));
+    RC(layernorm_fwd(d.y, e->pf + o.n3_w, e->pf + o.n3_b, xn, nullptr, nullptr, R, E, c.ln_eps, s));
+    bf16* t = x; x = xn; xn = t;
+  }
+  *x_out = x;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200_engine_create(const b200_engine_config* cfg, b200_engine** out) {
+  B200_REQUIRE(cfg && out, "engine_create: null argument");
+  const int E = cfg->embed_dim, H = cfg->num_heads, F = cfg->ff_dim, V = cfg->vocab_size, L = cfg->num_layers;
+  B200_REQUIRE(E > 0 && H > 0 && F > 0 && V > 0 && L > 0 && cfg->max_seq_len > 0, "engine_create: non-positive dimension");
+  B200_REQUIRE(E % H == 0, "engine_create: embed_dim %d not divisible by num_heads %d", E, H);
+  const int hd = E / H;
+  B200_REQUIRE(hd == 32 || hd == 64 || hd == 96 || hd == 128, "engine_create: head dim %d not in {32,64,96,128}", hd);
+  B200_REQUIRE(E % 64 == 0 && F % 64 == 0 && V % 8 == 0, "engine_create: embed_dim/ff_dim must be multiples of 64 and vocab_size of 8 (got %d/%d/%d)", E, F, V);
+  B200_REQUIRE(cfg->enc_dim % 8 == 0, "engine_create: enc_dim %d must be a multiple of 8", cfg->enc_dim);
+  b200_engine* e = new b200_engine();
+  e->cfg = *cfg;
+  if (e->cfg.ln_eps <= 0.f) e->cfg.ln_eps = 1e-5f;
+  if (cfg->enc_dim != E) {
+    e->proj_w = add_param(e, "projection.weight", static_cast<int64_t>(E) * cfg->enc_dim);
+    e->proj_b = add_param(e, "projection.bias", E);
+  }
+  e->emb = add_param(e, "token_embedding.weight", static_cast<int64_t>(V) * E);
+  e->lo.resize(L);
+  for (int l = 0; l < L; ++l) {
+    const std::string p = "transformer_decoder.layers." + std::to_string(l) + ".";
+    LayerOff& o = e->lo[l];
+    o.sa_w = add_param(e, p + "self_attn.in_proj_weight", 3LL * E * E);
+    o.begin = o.sa_w;
+    o.sa_b = add_param(e, p + "self_attn.in_proj_bias", 3LL * E);
+    o.sa_ow = add_param(e, p + "self_attn.out_proj.weight", 1LL * E * E);
+    o.sa_ob = add_param(e, p + "self_attn.out_proj.bias", E);
+    o.ca_w = add_param(e, p + "multihead_attn.in_proj_weight", 3LL * E * E);
+    o.ca_b = add_param(e, p + "multihead_attn.in_proj_bias", 3LL * E);
+    o.ca_ow = add_param(e, p + "multihead_attn.out_proj.weight", 1LL * E * E);
+    o.ca_ob = add_param(e, p + "multihead_attn.out_proj.bias", E);
+    o.l1_w = add_param(e, p + "linear1.weight", 1LL * F * E);
+    o.l1_b = add_param(e, p + "linear1.bias", F);
+    o.l2_w = add_param(e, p + "linear2.weight", 1LL * E * F);
+    o.l2_b = add_param(e, p + "linear2.bias", E);
+    o.n1_w = add_param(e, p + "norm1.weight", E);
+    o.n1_b = add_param(e, p + "norm1.bias", E);
+    o.n2_w = add_param(e, p + "norm2.weight", E);
+    o.n2_b = add_param(e, p + "norm2.bias", E);
+    o.n3_w = add_param(e, p + "norm3.weight", E);
+    o.n3_b = add_param(e, p + "norm3.bias", E);
+  }
+  e->fc_w = add_param(e, "fc_out.weight", static_cast<int64_t>(V) * E);
+  e->fc_b = add_param(e, "fc_out.bias", V);
+  e->total = (e->total + 63) & ~static_cast<int64_t>(63);
+  *out = e;
+  return 0;
+}
+
+void b200_engine_destroy(b200_engine* e) { delete e; }
+
+int64_t b200_engine_param_count(const b200_engine* e) { return e ? e->total : -1; }
+int32_t b200_engine_num_params(const b200_engine* e) { return e ? static_cast<int32_t>(e->params.size()) : -1; }
+
+int64_t b200_engine_param_offset(const b200_engine* e, const char* name, int64_t* numel) {
+  if (!e || !name) return -1;
+  for (const auto& p : e->params)
+    if (p.name == name) {
+      if (numel) *numel = p.numel;
+      return p.offset;
+    }
+  return -1;
+}
+
+int b200_engine_param_name(const b200_engine* e, int32_t index, char* buf, int32_t buflen) {
+  B200_REQUIRE(e && buf && index >= 0 && index < static_cast<int32_t>(e->params.size()), "param_name: bad index");
+  snprintf(buf, buflen, "%s", e->params[index].name.c_str());
+  return 0;
+}
+
+int b200_engine_bind(b200_engine* e, float* params_f32, void* params_bf16, float* grads_f32, const float* pe_f32) {
+  B200_REQUIRE(e && params_f32 && params_bf16 && pe_f32, "engine_bind: null argument");
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(params_f32) & 255) == 0 && (reinterpret_cast<uintptr_t>(params_bf16) & 255) == 0 &&
+               (reinterpret_cast<uintptr_t>(grads_f32) & 255) == 0, "engine_bind: arenas must be 256-byte aligned");
+  e->pf = params_f32; e->ph = static_cast<bf16*>(params_bf16); e->gf = grads_f32; e->pe = pe_f32;
+  return 0;
+}
+
+int64_t b200_engine_workspace_bytes(const b200_engine* e, int32_t B, int32_t T, int32_t S, int32_t mem_dim, int32_t training) {
+  if (!e) return -1;
+  Plan pl;
+  build_plan(e, &pl, nullptr, B, T, S, mem_dim, training);
+  return pl.bytes;
+}
+
+int b200_engine_set_workspace(b200_engine* e, void* ws, int64_t bytes) {
+  B200_REQUIRE(e && ws && (reinterpret_cast<uintptr_t>(ws) & 255) == 0, "set_workspace: null or misaligned workspace");
+  e->ws = static_cast<uint8_t*>(ws);
+  e->ws_bytes = bytes;
+  e->have_saved = false;
+  return 0;
+}
+
+int b200_engine_forward_logits(b200_engine* e, const int64_t* tokens, const float* memory, const uint8_t* mem_pad,
+                               int32_t B, int32_t T, int32_t S, int32_t mem_dim, int32_t training, float* logits, void* stream) {
+  B200_REQUIRE(e && tokens && memory && logits, "forward_logits: null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  RC(run_forward(e, tokens, memory, mem_pad, B, T, S, mem_dim, training, s));
+  e->last_tokens = tokens; e->last_targets = nullptr; e->last_mem_pad = mem_pad;
+  e->have_saved = training != 0;
+  const int E = e->cfg.embed_dim, V = e->cfg.vocab_size;
+  GemmProblem g;
+  g.M = B * T; g.N = V; g.K = E;
+  g.A = e->plan.x_final; g.lda = E; g.B = e->ph + e->fc_w; g.ldb = E;
+  g.D = logits; g.ldd = V; g.d_fp32 = true; g.bias = e->pf + e->fc_b; g.split_k = 1;
+  return gemm_launch(g, s);
+}
+
+int b200_engine_forward_loss(b200_engine* e, const int64_t* tokens, const int64_t* targets, const float* memory,
+                             const uint8_t* mem_pad, int32_t B, int32_t T, int32_t S, int32_t mem_dim,
+                             int64_t ignore_index, int32_t training, float* loss_out, void* stream) {
+  B200_REQUIRE(e && tokens && targets && memory && loss_out, "forward_loss: null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  RC(run_forward(e, tokens, memory, mem_pad, B, T, S, mem_dim, training, s));
+  e->last_tokens = tokens; e->last_targets = targets; e->last_mem_pad = mem_pad; e->last_ignore = ignore_index;
+  e->have_saved = training != 0;
+  Plan& pl = e->plan;
+  const int E = e->cfg.embed_dim, V = e->cfg.vocab_size, M = B * T;
+  B200_CHECK_CUDA(cudaMemsetAsync(pl.scalars, 0, 16 * sizeof(float), s));
+  RC(b200_lmhead_ce_fwd(pl.x_final, E, e->ph + e->fc_w, E, e->pf + e->fc_b, targets, M, V, E, ignore_index,
+                        pl.row_lse, pl.row_loss, pl.scalars, pl.scalars + 1, pl.ce_scratch, stream));
+  RC(ce_mean(pl.scalars, pl.scalars + 1, pl.scalars + 4, s));
+  B200_CHECK_CUDA(cudaMemcpyAsync(loss_out, pl.scalars + 4, 2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+int b200_engine_backward(b200_engine* e, const float* inv_count_dev, float* dmemory, void* const* bucket_events,
+                         int32_t num_bucket_events, void* stream) {
+  B200_REQUIRE(e, "backward: null engine");
+  B200_REQUIRE(e->have_saved && e->last_targets, "backward: call forward_loss(training=1) first");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Plan& pl = e->plan;
+  const int E = e->cfg.embed_dim, V = e->cfg.vocab_size, M = pl.B * pl.T;
+  const float* inv = inv_count_dev ? inv_count_dev : pl.scalars + 6;
+  RC(b200_lmhead_ce_bwd(pl.x_final, E, e->ph + e->fc_w, E, e->pf + e->fc_b, e->last_targets, M, V, E, e->last_ignore,
+                        pl.row_lse, inv, pl.dlogits, V, stream));
+  return run_backward(e, false, dmemory, bucket_events, num_bucket_events, s);
+}
+
+int b200_engine_backward_from_dlogits(b200_engine* e, const float* dlogits, float* dmemory, void* stream) {
+  B200_REQUIRE(e && dlogits, "backward_from_dlogits: null argument");
+  B200_REQUIRE(e->have_saved, "backward_from_dlogits: call forward_logits(training=1) first");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Plan& pl = e->plan;
+  const long long n = static_cast<long long>(pl.B) * pl.T * e->cfg.vocab_size;
+  RC(cast_f32_to_bf16(dlogits, pl.dlogits, n, s));
+  return run_backward(e, true, dmemory, nullptr, 0, s);
+}
+
+int32_t b200_engine_grad_buckets(const b200_engine* e, int64_t* offsets, int64_t* counts, int32_t cap) {
+  if (!e) return -1;
+  const int L = e->cfg.num_layers;
+  const int n = L + 2;
+  if (offsets && counts) {
+    int i = 0;
+    auto put = [&](int64_t off, int64_t end) {
+      if (i < cap) { offsets[i] = off; counts[i] = end - off; }
+      ++i;
+    };
+    put(e->fc_w, e->total);
+    for (int l = L - 1; l >= 0; --l) put(e->lo[l].begin, (l + 1 < L) ? e->lo[l + 1].begin : e->fc_w);
+    put(0, e->lo[0].begin);
+  }
+  return n;
+}
+
+// ---- LM head entry points (also used stand-alone by the tests)
+int b200_lmhead_ce_fwd(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias,
+                       const int64_t* targets, int32_t M, int32_t V, int32_t E, int64_t ignore_index,
+                       float* row_lse, float* row_loss, float* loss_sum, float* valid_count, float* scratch,
+                       void* stream) {
+  B200_REQUIRE(x && w && targets && row_lse && loss_sum && valid_count && scratch, "lmhead_ce_fwd: null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int n_tiles = gemm_num_n_tiles(V, 256);
+  GemmProblem g;
+  g.M = M; g.N = V; g.K = E;
+  g.A = static_cast<const bf16*>(x); g.lda = ldx; g.B = static_cast<const bf16*>(w); g.ldb = ldw;
+  g.bias = bias; g.epi = EPI_CE_FWD; g.targets = targets; g.ignore_index = ignore_index;
+  g.part_max = scratch;
+  g.part_sum = scratch + static_cast<int64_t>(M) * n_tiles;
+  g.tgt_logit = scratch + 2 * static_cast<int64_t>(M) * n_tiles;
+  g.split_k = 1;
+  RC(gemm_launch(g, s));
+  return ce_finalize(g.part_max, g.part_sum, g.tgt_logit, targets, M, n_tiles, ignore_index, row_lse, row_loss,
+                     loss_sum, valid_count, s);
+}
+
+int b200_lmhead_ce_bwd(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias,
+                       const int64_t* targets, int32_t M, int32_t V, int32_t E, int64_t ignore_index,
+                       const float* row_lse, const float* inv_count, void* dlogits, int64_t ldd, void* stream) {
+  B200_REQUIRE(x && w && targets && row_lse && inv_count && dlogits, "lmhead_ce_bwd: null argument");
+  GemmProblem g;
+  g.M = M; g.N = V; g.K = E;
+  g.A = static_cast<const bf16*>(x); g.lda = ldx; g.B = static_cast<const bf16*>(w); g.ldb = ldw;
+  g.bias = bias; g.epi = EPI_CE_BWD; g.targets = targets; g.ignore_index = ignore_index;
+  g.row_lse = row_lse; g.inv_count = inv_count; g.D = dlogits; g.ldd = ldd; g.split_k = 1;
+  return gemm_launch(g, static_cast<cudaStream_t>(stream));
+}
+
+int b200_lmhead_argmax(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias, int32_t M,
+                       int32_t V, int32_t E, int64_t* out_ids, float* out_max, float* scratch, void* stream) {
+  B200_REQUIRE(x && w && out_ids && scratch, "lmhead_argmax: null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int n_tiles = gemm_num_n_tiles(V, 128);
+  GemmProblem g;
+  g.M = M; g.N = V; g.K = E;
+  g.A = static_cast<const bf16*>(x); g.lda = ldx; g.B = static_cast<const bf16*>(w); g.ldb = ldw;
+  g.bias = bias; g.epi = EPI_ARGMAX;
+  g.part_max = scratch; g.part_sum = scratch + static_cast<int64_t>(M) * n_tiles; g.split_k = 1;
+  RC(gemm_launch(g, s));
+  return argmax_finalize(g.part_max, g.part_sum, M, n_tiles, out_ids, out_max, s);
+}
+
+
+// ---- KV-cached generation ------------------------------------------------------------------
+int64_t b200_engine_decode_workspace_bytes(const b200_engine* e, int32_t B, int32_t beam, int32_t S,
+                                           int32_t mem_dim, int32_t max_len) {
+  if (!e || B <= 0 || beam <= 0 || S <= 0 || max_len <= 0) return -1;
+  b200_engine::Decode d;
+  build_decode_plan(e, &d, nullptr, B, beam, S, mem_dim, max_len);
+  return d.bytes;
+}
+
+int b200_engine_decode_begin(b200_engine* e, const float* memory, const uint8_t* mem_pad, int32_t B, int32_t beam,
+                             int32_t S, int32_t mem_dim, int32_t max_len, void* ws, int64_t ws_bytes, void* stream) {
+  B200_REQUIRE(e && memory && ws, "decode_begin: null argument");
+  B200_REQUIRE(e->pf && e->ph, "decode_begin: parameters not bound");
+  const auto& c = e->cfg;
+  const int E = c.embed_dim, H = c.num_heads, L = c.num_layers, hd = E / H;
+  B200_REQUIRE(B > 0 && S > 0 && beam >= 1 && beam <= 4, "decode_begin: B=%d S=%d beam=%d (beam must be 1..4)", B, S, beam);
+  B200_REQUIRE(max_len >= 2 && max_len <= c.max_seq_len, "decode_begin: max_len %d outside [2, max_seq_len=%d] (decoder.py:71)", max_len, c.max_seq_len);
+  B200_REQUIRE(mem_dim == E || (mem_dim == c.enc_dim && e->proj_w >= 0), "decode_begin: memory width %d matches neither embed_dim nor enc_dim", mem_dim);
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "decode_begin: workspace must be 256-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  auto& d = e->dec;
+  d.ready = false;
+  build_decode_plan(e, &d, static_cast<uint8_t*>(ws), B, beam, S, mem_dim, max_len);
+  B200_REQUIRE(d.bytes <= ws_bytes, "decode_begin: workspace too small (%lld needed, %lld given)", (long long)d.bytes, (long long)ws_bytes);
+  d.mem_pad = mem_pad;
+  d.cur = 0;
+  const int Ms = B * S;
+  RC(cast_f32_to_bf16(memory, d.mem16, static_cast<long long>(Ms) * mem_dim, s));
+  if (mem_dim != E)
+    RC(linear_fwd(d.mem16, mem_dim, e->ph + e->proj_w, e->pf + e->proj_b, d.memp, E, Ms, E, mem_dim, 0, nullptr, 0, s));
+  // image-side K/V: projected ONCE per image and layer (the reference redoes this every token)
+  for (int l = 0; l < L; ++l) {
+    const LayerOff& o = e->lo[l];
+    RC(linear_fwd(d.memp, E, e->ph + o.ca_w + static_cast<int64_t>(E) * E, e->pf + o.ca_b + E, d.kv_tmp, 2 * E, Ms, 2 * E, E, 0, nullptr, 0, s));
+    RC(kv_to_head_major(d.kv_tmp, d.kc + static_cast<int64_t>(l) * Ms * E, d.vc + static_cast<int64_t>(l) * Ms * E, B, S, H, hd, s));
+  }
+  d.ready = true;
+  return 0;
+}
+
+int b200_engine_decode_step(b200_engine* e, const int64_t* tokens_in, int32_t pos, int64_t* next_ids, void* stream) {
+  B200_REQUIRE(e && tokens_in && next_ids, "decode_step: null argument");
+  B200_REQUIRE(e->dec.ready, "decode_step: call decode_begin first");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  bf16* x = nullptr;
+  RC(decode_hidden(e, tokens_in, pos, &x, s));
+  const int E = e->cfg.embed_dim, V = e->cfg.vocab_size;
+  return b200_lmhead_argmax(x, E, e->ph + e->fc_w, E, e->pf + e->fc_b, e->dec.R, V, E, next_ids, e->dec.best,
+                            e->dec.scratch, stream);
+}
+
+int b200_engine_generate_greedy(b200_engine* e, int64_t start_id, int64_t end_id, int32_t max_len,
+                                int32_t stop_check_interval, int64_t* out_tokens, int32_t* out_len, void* stream) {
+  B200_REQUIRE(e && out_tokens && out_len, "generate_greedy: null argument");
+  auto& d = e->dec;
+  B200_REQUIRE(d.ready && d.beam == 1, "generate_greedy: call decode_begin(beam=1) first");
+  B200_REQUIRE(max_len >= 2 && max_len <= d.max_len, "generate_greedy: max_len %d exceeds the decode plan's %d", max_len, d.max_len);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int R = d.R;
+  const long long pad = e->cfg.pad_idx;
+  RC(fill_i64(out_tokens, static_cast<long long>(R) * max_len, pad, s));
+  RC(fill_col_i64(out_tokens, R, max_len, start_id, s));
+  RC(fill_i64(d.cur_tok, R, start_id, s));
+  B200_CHECK_CUDA(cudaMemsetAsync(d.fin[0], 0, R, s));
+  B200_CHECK_CUDA(cudaMemsetAsync(d.n_finished, 0, sizeof(int), s));
+  B200_CHECK_CUDA(cudaMemsetAsync(out_len, 0, sizeof(int) * R, s));   // overwritten below; rows start at length 1
+  for (int pos = 0; pos + 1 < max_len; ++pos) {
+    RC(b200_engine_decode_step(e, d.cur_tok, pos, d.ids, stream));
+    RC(greedy_update(d.ids, d.cur_tok, out_tokens, out_len, d.fin[0], d.n_finished, R, max_len, pos, end_id, pad, s));
+    if (stop_check_interval > 0 && (pos + 1) % stop_check_interval == 0) {
+      int nf = 0;
+      B200_CHECK_CUDA(cudaMemcpyAsync(&nf, d.n_finished, sizeof(int), cudaMemcpyDeviceToHost, s));
+      B200_CHECK_CUDA(cudaStreamSynchronize(s));
+      if (nf >= R) break;
+    }
+  }
+  return 0;
+}
+
+int b200_engine_generate_beam(b200_engine* e, int64_t start_id, int64_t end_id, int32_t max_len, int64_t* out_tokens,
+                              int32_t* out_len, float* out_score, void* stream) {
+  B200_REQUIRE(e && out_tokens && out_len, "generate_beam: null argument");
+  auto& d = e->dec;
+  B200_REQUIRE(d.ready && d.beam >= 1, "generate_beam: call decode_begin first");
+  B200_REQUIRE(d.beam == 1 || d.logits != nullptr, "generate_beam: decode plan has no logits buffer");
+  B200_REQUIRE(max_len >= 2 && max_len <= d.max_len, "generate_beam: max_len %d exceeds the decode plan's %d", max_len, d.max_len);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const auto& c = e->cfg;
+  const int E = c.embed_dim, V = c.vocab_size, H = c.num_heads, L = c.num_layers, hd = E / H;
+  const int R = d.R, B = d.B, beam = d.beam;
+  float* logits = d.logits;
+  B200_REQUIRE(logits != nullptr, "generate_beam: decode_begin was called with beam=1; use generate_greedy");
+  int cs = 0;   // live copy of seq / scores / finished flags
+  RC(fill_i64(d.seq[0], static_cast<long long>(R) * d.max_len, c.pad_idx, s));
+  RC(fill_col_i64(d.seq[0], R, d.max_len, start_id, s));
+  RC(fill_i64(d.cur_tok, R, start_id, s));
+  B200_CHECK_CUDA(cudaMemsetAsync(d.fin[0], 0, R, s));
+  B200_CHECK_CUDA(cudaMemsetAsync(d.scores[0], 0, sizeof(float) * R, s));
+  int n_tok = 1;
+  for (int pos = 0; pos + 1 < max_len; ++pos) {
+    bf16* x = nullptr;
+    RC(decode_hidden(e, d.cur_tok, pos, &x, s));
+    GemmProblem g;
+    g.M = R; g.N = V; g.K = E;
+    g.A = x; g.lda = E; g.B = e->ph + e->fc_w; g.ldb = E;
+    g.D = logits; g.ldd = V; g.d_fp32 = true; g.bias = e->pf + e->fc_b; g.split_k = 1;
+    RC(gemm_launch(g, s));
+    RC(beam_topk(logits, d.scores[cs], d.fin[cs], B, beam, V, end_id, pos == 0, d.cur_tok, d.parent, d.scores[cs ^ 1], s));
+    RC(beam_advance(d.seq[cs], d.seq[cs ^ 1], d.fin[cs], d.fin[cs ^ 1], d.cur_tok, d.parent, R, beam, d.max_len, pos, end_id, s));
+    // the self-attention cache follows the surviving hypotheses
+    for (int l = 0; l < L; ++l) {
+      const int64_t off = static_cast<int64_t>(l) * R * d.max_len * E;
+      RC(cache_reorder(d.kcache[d.cur] + off, d.vcache[d.cur] + off, d.kcache[d.cur ^ 1] + off, d.vcache[d.cur ^ 1] + off,
+                       d.parent, B, beam, H, hd, d.max_len, pos, s));
+    }
+    d.cur ^= 1;
+    cs ^= 1;
+    ++n_tok;
+  }
+  return beam_finalize(d.seq[cs], d.scores[cs], B, beam, d.max_len, n_tok, end_id, c.pad_idx, out_tokens, out_len, out_score, s);
+}
+
+}  // extern "C"

@@ -456,7 +456,11 @@ static int launch_instance(const CUtensorMap& ta, const CUtensorMap& tb, const G
     B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
+  const bool prof = gemm_profile_enabled();
+  if (prof) gemm_profile_record(stream, true, 2.0 * d.M * static_cast<double>(d.N) * d.K);
   kern<<<grid, NUM_THREADS, smem, stream>>>(ta, tb, d);
+  if (prof) gemm_profile_record(stream, false, 0.0);
+  note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -603,6 +607,7 @@ int gemm_check_launch(const GemmProblem& q, cudaStream_t stream) {
   const int threads = 256;
   const long long blocks = (total + threads - 1) / threads;
   gemm_check_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(d, q.A, q.lda, q.a_mn, q.B, q.ldb, q.b_mn);
+  note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1,0 +1,550 @@
+// Memory-bound kernels of the caption decoder: every one is a single pass over its operands with
+// 128-bit global accesses; reductions use warp shuffles (one warp per row for LayerNorm).
+#include "kernels.cuh"
+#include <math.h>
+
+namespace b200 {
+
+static inline int cdiv(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------
+// token embedding * sqrt(E) + sinusoidal PE   (decoder.py:168-170, 71-72)
+// ------------------------------------------------------------------------------------------
+__global__ void embed_pe_fwd_kernel(const int64_t* __restrict__ tokens, const float* __restrict__ emb,
+                                    const float* __restrict__ pe, bf16* __restrict__ x, int rows,
+                                    int T, int E, int V, float scale, int t0) {
+  const int vec_per_row = E >> 3;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<long long>(rows) * vec_per_row) return;
+  const int row = static_cast<int>(idx / vec_per_row);
+  const int c = static_cast<int>(idx % vec_per_row) << 3;
+  long long tok = tokens[row];
+  tok = tok < 0 ? 0 : (tok >= V ? V - 1 : tok);
+  const int t = row % T + t0;
+  const float4* e4 = reinterpret_cast<const float4*>(emb + tok * E + c);
+  const float4* p4 = reinterpret_cast<const float4*>(pe + static_cast<long long>(t) * E + c);
+  const float4 e0 = __ldg(e4), e1 = __ldg(e4 + 1), p0 = __ldg(p4), p1 = __ldg(p4 + 1);
+  uint4 o;
+  o.x = pack_bf16(fmaf(e0.x, scale, p0.x), fmaf(e0.y, scale, p0.y));
+  o.y = pack_bf16(fmaf(e0.z, scale, p0.z), fmaf(e0.w, scale, p0.w));
+  o.z = pack_bf16(fmaf(e1.x, scale, p1.x), fmaf(e1.y, scale, p1.y));
+  o.w = pack_bf16(fmaf(e1.z, scale, p1.z), fmaf(e1.w, scale, p1.w));
+  *reinterpret_cast<uint4*>(x + static_cast<long long>(row) * E + c) = o;
+}
+
+int embed_pe_fwd(const int64_t* tokens, const float* emb, const float* pe, bf16* x, int B, int T,
+                 int E, int V, float scale, cudaStream_t s, int t0) {
+  B200_REQUIRE(E % 8 == 0, "embed: E (%d) must be a multiple of 8", E);
+  const long long n = static_cast<long long>(B) * T * (E / 8);
+  embed_pe_fwd_kernel<<<cdiv(n, 256), 256, 0, s>>>(tokens, emb, pe, x, B * T, T, E, V, scale, t0);
+  note_launch();
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// scatter-add into the embedding gradient; the padding row receives nothing (decoder.py:105)
+__global__ void embed_bwd_kernel(const int64_t* __restrict__ tokens, const bf16* __restrict__ dx,
+                                 float* __restrict__ demb, int rows, int E, int V, long long pad_idx,
+                                 float scale) {
+  const int vec_per_row = E >> 3;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<long long>(rows) * vec_per_row) return;
+  const int row = static_cast<int>(idx / vec_per_row);
+  const int c = static_cast<int>(idx % vec_per_row) << 3;
+  const long long tok = tokens[row];
+  if (tok == pad_idx || tok < 0 || tok >= V) return;
+  const uint4 g = ldg_nc_v4(dx + static_cast<long long>(row) * E + c);
+  const float2 a = unpack_bf16(g.x), b = unpack_bf16(g.y), cc = unpack_bf16(g.z), d = unpack_bf16(g.w);
+  float* dst = demb + tok * E + c;
+  red_add_v4_f32(dst, a.x * scale, a.y * scale, b.x * scale, b.y * scale);
+  red_add_v4_f32(dst + 4, cc.x * scale, cc.y * scale, d.x * scale, d.y * scale);
+}
+
+int embed_bwd(const int64_t* tokens, const bf16* dx, float* demb, int B, int T, int E, int V,
+              long long pad_idx, float scale, cudaStream_t s) {
+  B200_REQUIRE(E % 8 == 0, "embed_bwd: E (%d) must be a multiple of 8", E);
+  const long long n = static_cast<long long>(B) * T * (E / 8);
+  embed_bwd_kernel<<<cdiv(n, 256), 256, 0, s>>>(tokens, dx, demb, B * T, E, V, pad_idx, scale);
+  note_launch();
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm (torch.nn.LayerNorm: biased variance, eps inside the sqrt), one warp per row
+// ------------------------------------------------------------------------------------------
+static constexpr int LN_MAXV = 8;  // 8 x (8 bf16) x 32 lanes = E up to 2048
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 o;
+  o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
+  o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+  return o;
+}
+
+template <int NV>
+__global__ void __launch_bounds__(128)
+layernorm_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, bf16* __restrict__ y, float* __restrict__ mean,
+                     float* __restrict__ rstd, int rows, int E, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 4 + warp;
+  if (row >= rows) return;
+  const int nvec = E >> 3;
+  const bf16* xr = x + static_cast<long long>(row) * E;
+  float v[NV][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      unpack8(ldg_nc_v4(xr + vi * 8), v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += v[i][j];
+    }
+  }
+  const float mu = warp_sum(sum) / E;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (lane + i * 32 < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mu; sq += d * d; }
+    }
+  }
+  const float rs = rsqrtf(warp_sum(sq) / E + eps);
+  if (lane == 0) {
+    if (mean) mean[row] = mu;
+    if (rstd) rstd[row] = rs;
+  }
+  bf16* yr = y + static_cast<long long>(row) * E;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8) + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8) + 1);
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mu) * rs * g[j] + b[j];
+      *reinterpret_cast<uint4*>(yr + vi * 8) = pack8(o);
+    }
+  }
+}
+
+int layernorm_fwd(const bf16* x, const float* gamma, const float* beta, bf16* y, float* mean,
+                  float* rstd, int rows, int E, float eps, cudaStream_t s) {
+  B200_REQUIRE(E % 8 == 0 && E <= LN_MAXV * 256, "layernorm: E (%d) must be a multiple of 8 and <= %d", E, LN_MAXV * 256);
+  if (rows == 0) return 0;
+  const int nv = cdiv(E / 8, 32);
+#define B200_LN_FWD(NV) layernorm_fwd_kernel<NV><<<cdiv(rows, 4), 128, 0, s>>>(x, gamma, beta, y, mean, rstd, rows, E, eps)
+  if (nv <= 1) B200_LN_FWD(1); else if (nv == 2) B200_LN_FWD(2); else if (nv == 3) B200_LN_FWD(3);
+  else if (nv == 4) B200_LN_FWD(4); else B200_LN_FWD(8);
+#undef B200_LN_FWD
+  note_launch();
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// dx = rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*gamma;  dgamma += dy*xhat, dbeta += dy.
+// Each warp walks rows with a grid stride keeping its column slice of dgamma/dbeta in registers;
+// the 4 warps of a block combine through shared memory and issue one atomic per column.
+template <int NV>
+__global__ void __launch_bounds__(128)
+layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                     const float* __restrict__ gamma, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, bf16* __restrict__ dx,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int E) {
+  extern __shared__ float sm_red[];  // [2][4][E]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = E >> 3;
+  float gam[NV][8], dg[NV][8], db[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + i * 32;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { dg[i][j] = 0.f; db[i][j] = 0.f; gam[i][j] = 0.f; }
+    if (vi < nvec) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8) + 1);
+      gam[i][0] = g0.x; gam[i][1] = g0.y; gam[i][2] = g0.z; gam[i][3] = g0.w;
+      gam[i][4] = g1.x; gam[i][5] = g1.y; gam[i][6] = g1.z; gam[i][7] = g1.w;
+    }
+  }
+  for (int row = blockIdx.x * 4 + warp; row < rows; row += gridDim.x * 4) {
+    const float mu = mean[row], rs = rstd[row];
+    const bf16* xr = x + static_cast<long long>(row) * E;
+    const bf16* dyr = dy + static_cast<long long>(row) * E;
+    float xh[NV][8], g[NV][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        float xv[8], dv[8];
+        unpack8(ldg_nc_v4(xr + vi * 8), xv);
+        unpack8(ldg_nc_v4(dyr + vi * 8), dv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[i][j] = (xv[j] - mu) * rs;
+          g[i][j] = dv[j] * gam[i][j];
+          s1 += g[i][j];
+          s2 += g[i][j] * xh[i][j];
+          dg[i][j] += dv[j] * xh[i][j];
+          db[i][j] += dv[j];
+        }
+      }
+    }
+    const float c1 = warp_sum(s1) / E, c2 = warp_sum(s2) / E;
+    bf16* dxr = dx + static_cast<long long>(row) * E;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rs * (g[i][j] - c1 - xh[i][j] * c2);
+        *reinterpret_cast<uint4*>(dxr + vi * 8) = pack8(o);
+      }
+    }
+  }
+  float* sg = sm_red;
+  float* sb = sm_red + 4 * E;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sg[warp * E + vi * 8 + j] = dg[i][j];
+        sb[warp * E + vi * 8 + j] = db[i][j];
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < E; c += blockDim.x) {
+    const float a = sg[c] + sg[E + c] + sg[2 * E + c] + sg[3 * E + c];
+    const float b = sb[c] + sb[E + c] + sb[2 * E + c] + sb[3 * E + c];
+    atomicAdd(dgamma + c, a);
+    atomicAdd(dbeta + c, b);
+  }
+}
+
+int layernorm_bwd(const bf16* dy, const bf16* x, const float* gamma, const float* mean,
+                  const float* rstd, bf16* dx, float* dgamma, float* dbeta, int rows, int E,
+                  cudaStream_t s) {
+  B200_REQUIRE(E % 8 == 0 && E <= LN_MAXV * 256, "layernorm_bwd: E (%d) must be a multiple of 8 and <= %d", E, LN_MAXV * 256);
+  if (rows == 0) return 0;
+  int blocks = cdiv(rows, 4);
+  const int cap = 2 * 148;
+  if (blocks > cap) blocks = cap;
+  const size_t smem = static_cast<size_t>(8) * E * sizeof(float);
+  const int nv = cdiv(E / 8, 32);
+#define B200_LN_BWD(NV)                                                                              \
+  do {                                                                                               \
+    static bool configured = false;                                                                  \
+    if (!configured) {                                                                               \
+      B200_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * NV * 256 * 4)); \
+      configured = true;                                                                             \
+    }                                                                                                \
+    layernorm_bwd_kernel<NV><<<blocks, 128, smem, s>>>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, rows, E); \
+  } while (0)
+  if (nv <= 1) B200_LN_BWD(1); else if (nv == 2) B200_LN_BWD(2); else if (nv == 3) B200_LN_BWD(3);
+  else if (nv == 4) B200_LN_BWD(4); else B200_LN_BWD(8);
+#undef B200_LN_BWD
+  note_launch();
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// column sums (bias gradients): out[n] += sum_m x[m,n]
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+colsum_kernel(const bf16* __restrict__ x, long long ldx, float* __restrict__ out, int M, int N) {
+  __shared__ float red[8][256];
+  const int cv = threadIdx.x & 31;   // column vector within the block's 256-column strip
+  const int rl = threadIdx.x >> 5;   // row lane 0..7
+  const int col = blockIdx.x * 256 + cv * 8;
+  const int r0 = blockIdx.y * 128;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (col < N) {
+    const int r1 = min(r0 + 128, M);
+    for (int r = r0 + rl; r < r1; r += 8) {
+      float f[8];
+      unpack8(ldg_nc_v4(x + static_cast<long long>(r) * ldx + col), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[rl][cv * 8 + j] = acc[j];
+  __syncthreads();
+  const int c = threadIdx.x;
+  if (blockIdx.x * 256 + c < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) s += red[r][c];
+    atomicAdd(out + blockIdx.x * 256 + c, s);
+  }
+}
+
+int colsum(const bf16* x, long long ldx, float* out, int M, int N, cudaStream_t s) {
+  B200_REQUIRE(N % 8 == 0 && ldx % 8 == 0, "colsum: N (%d) and ldx (%lld) must be multiples of 8", N, ldx);
+  if (M == 0) return 0;
+  dim3 grid(cdiv(N, 256), cdiv(M, 128));
+  colsum_kernel<<<grid, 256, 0, s>>>(x, ldx, out, M, N);
+  note_launch();
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// casts
+// ------------------------------------------------------------------------------------------
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
+  const long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src + i));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src + i) + 1);
+    uint4 o;
+    o.x = pack_bf16(a.x, a.y); o.y = pack_bf16(a.z, a.w);
+    o.z = pack_bf16(b.x, b.y); o.w = pack_bf16(b.z, b.w);
+    *reinterpret_cast<uint4*>(dst + i) = o;
+  } else {
+    for (long long j = i; j < n; ++j) dst[j] = __float2bfloat16(src[j]);
+  }
+}
+__global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, long long n) {
+  const long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(src + i), f);
+    *reinterpret_cast<float4*>(dst + i) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(dst + i + 4) = make_float4(f[4], f[5], f[6], f[7]);
+  } else {
+    for (long long j = i; j < n; ++j) dst[j] = __bfloat162float(src[j]);
+  }
+}
+int cast_f32_to_bf16(const float* src, bf16* dst, long long n, cudaStream_t s) {
+  if (n == 0) return 0;
+  B200_REQUIRE(((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0), "cast: pointers must be 16-byte aligned");
+  cast_f32_bf16_kernel<<<cdiv(cdiv(n, 8), 256), 256, 0, s>>>(src, dst, n);
+  note_launch();
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int cast_bf16_to_f32(const bf16* src, float* dst, long long n, cudaStream_t s) {
+  if (n == 0) return 0;
+  B200_REQUIRE(((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0), "cast: pointers must be 16-byte aligned");
+  cast_bf16_f32_kernel<<<cdiv(cdiv(n, 8), 256), 256, 0, s>>>(src, dst, n);
+  note_launch();
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// softmax-CE finalisation
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ce_finalize_kernel(const float* __restrict__ part_max, const float* __restrict__ part_sum,
+                   const float* __restrict__ tgt_logit, const int64_t* __restrict__ targets, int M,
+                   int n_tiles, long long ignore_index, float* __restrict__ row_lse,
+                   float* __restrict__ row_loss, float* __restrict__ loss_sum,
+                   float* __restrict__ valid_count) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  float loss = 0.f, cnt = 0.f;
+  if (row < M) {
+    const float* pm = part_max + static_cast<long long>(row) * n_tiles;
+    const float* ps = part_sum + static_cast<long long>(row) * n_tiles;
+    float m = -INFINITY;
+    for (int i = 0; i < n_tiles; ++i) m = fmaxf(m, pm[i]);
+    float s = 0.f;
+    for (int i = 0; i < n_tiles; ++i) s += ps[i] * expf(pm[i] - m);
+    const float lse = m + logf(s);
+    row_lse[row] = lse;
+    const long long t = targets[row];
+    if (t != ignore_index) {
+      loss = lse - tgt_logit[row];
+      cnt = 1.f;
+    }
+    if (row_loss) row_loss[row] = loss;
+  }
+  loss = warp_sum(loss);
+  cnt = warp_sum(cnt);
+  __shared__ float sl[8], sc[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sl[warp] = loss; sc[warp] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < 8; ++i) { a += sl[i]; b += sc[i]; }
+    atomicAdd(loss_sum, a);
+    atomicAdd(valid_count, b);
+  }
+}
+
+int ce_finalize(const float* part_max, const float* part_sum, const float* tgt_logit,
+                const int64_t* targets, int M, int n_tiles, long long ignore_index, float* row_lse,
+                float* row_loss, float* loss_sum, float* valid_count, cudaStream_t s) {
+  ce_finalize_kernel<<<cdiv(M, 256), 256, 0, s>>>(part_max, part_sum, tgt_logit, targets, M, n_tiles,
+                                                 ignore_index, row_lse, row_loss, loss_sum, valid_count);
+  note_launch();
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void ce_mean_kernel(const float* loss_sum, const float* valid_count, float* out) {
+  const float c = *valid_count;
+  out[0] = *loss_sum / c;   // 0/0 -> NaN, as nn.CrossEntropyLoss does when every target is ignored
+  out[1] = c;
+  out[2] = 1.f / c;
+}
+int ce_mean(const float* loss_sum, const float* valid_count, float* out, cudaStream_t s) {
+  ce_mean_kernel<<<1, 1, 0, s>>>(loss_sum, valid_count, out);
+  note_launch();
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void argmax_finalize_kernel(const float* __restrict__ part_max, const float* __restrict__ part_idx,
+                                       int M, int n_tiles, int64_t* __restrict__ out_ids,
+                                       float* __restrict__ out_max) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= M) return;
+  const float* pm = part_max + static_cast<long long>(row) * n_tiles;
+  const float* pi = part_idx + static_cast<long long>(row) * n_tiles;
+  float best = -INFINITY;
+  int idx = 0;
+  for (int i = 0; i < n_tiles; ++i) {   // increasing column order + strict '>' = first index on ties
+    if (pm[i] > best) { best = pm[i]; idx = __float_as_int(pi[i]); }
+  }
+  out_ids[row] = idx;
+  if (out_max) out_max[row] = best;
+}
+int argmax_finalize(const float* part_max, const float* part_idx, int M, int n_tiles, int64_t* out_ids,
+                    float* out_max, cudaStream_t s) {
+  argmax_finalize_kernel<<<cdiv(M, 128), 128, 0, s>>>(part_max, part_idx, M, n_tiles, out_ids, out_max);
+  note_launch();
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// optimizer: global grad norm + clip + AdamW (train.py:96-100, 319-325)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+grad_sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ sumsq) {
+  float acc = 0.f;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 4;
+  for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 4 <= n) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(g + i));
+      acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    } else {
+      for (long long j = i; j < n; ++j) acc += g[j] * g[j];
+    }
+  }
+  acc = warp_sum(acc);
+  __shared__ float sw[8];
+  if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += sw[i];
+    atomicAdd(sumsq, t);
+  }
+}
+int grad_sumsq(const float* g, long long n, float* sumsq, cudaStream_t s) {
+  if (n == 0) return 0;
+  int blocks = cdiv(n, 256 * 4 * 8);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  grad_sumsq_kernel<<<blocks, 256, 0, s>>>(g, n, sumsq);
+  note_launch();
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void __launch_bounds__(256)
+adamw_kernel(float* __restrict__ p, bf16* __restrict__ p16, const float* __restrict__ g,
+             float* __restrict__ m, float* __restrict__ v, long long n, const float* __restrict__ sumsq,
+             float max_norm, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt) {
+  float coef = 1.f;
+  if (max_norm > 0.f && sumsq != nullptr) {
+    const float total = sqrtf(*sumsq);
+    coef = fminf(1.f, max_norm / (total + 1e-6f));
+  }
+  const float step_size = lr / bc1;
+  const long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4;
+  if (i >= n) return;
+  float pv[4], gv[4], mv[4], vv[4];
+  const int cnt = (i + 4 <= n) ? 4 : static_cast<int>(n - i);
+  if (cnt == 4) {
+    const float4 a = *reinterpret_cast<const float4*>(p + i);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(g + i));
+    const float4 c = *reinterpret_cast<const float4*>(m + i);
+    const float4 d = *reinterpret_cast<const float4*>(v + i);
+    pv[0] = a.x; pv[1] = a.y; pv[2] = a.z; pv[3] = a.w;
+    gv[0] = b.x; gv[1] = b.y; gv[2] = b.z; gv[3] = b.w;
+    mv[0] = c.x; mv[1] = c.y; mv[2] = c.z; mv[3] = c.w;
+    vv[0] = d.x; vv[1] = d.y; vv[2] = d.z; vv[3] = d.w;
+  } else {
+    for (int j = 0; j < 4; ++j) {
+      const bool ok = j < cnt;
+      pv[j] = ok ? p[i + j] : 0.f; gv[j] = ok ? g[i + j] : 0.f;
+      mv[j] = ok ? m[i + j] : 0.f; vv[j] = ok ? v[i + j] : 0.f;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float gg = gv[j] * coef;
+    pv[j] *= (1.f - lr * wd);
+    mv[j] = b1 * mv[j] + (1.f - b1) * gg;
+    vv[j] = b2 * vv[j] + (1.f - b2) * gg * gg;
+    const float denom = sqrtf(vv[j]) / bc2_sqrt + eps;
+    pv[j] -= step_size * (mv[j] / denom);
+  }
+  if (cnt == 4) {
+    *reinterpret_cast<float4*>(p + i) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+    *reinterpret_cast<float4*>(m + i) = make_float4(mv[0], mv[1], mv[2], mv[3]);
+    *reinterpret_cast<float4*>(v + i) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    if (p16) {
+      uint2 o;
+      o.x = pack_bf16(pv[0], pv[1]); o.y = pack_bf16(pv[2], pv[3]);
+      *reinterpret_cast<uint2*>(p16 + i) = o;
+    }
+  } else {
+    for (int j = 0; j < cnt; ++j) {
+      p[i + j] = pv[j]; m[i + j] = mv[j]; v[i + j] = vv[j];
+      if (p16) p16[i + j] = __float2bfloat16(pv[j]);
+    }
+  }
+}
+
+int adamw_step(float* p, bf16* p16, const float* g, float* m, float* v, long long n,
+               const float* sumsq, float max_norm, float lr, float b1, float b2, float eps, float wd,
+               int step, cudaStream_t s) {
+  if (n == 0) return 0;
+  B200_REQUIRE(step >= 1, "adamw: step must be >= 1");
+  const float bc1 = 1.f - powf(b1, static_cast<float>(step));
+  const float bc2 = 1.f - powf(b2, static_cast<float>(step));
+  const double bc1d = 1.0 - pow(static_cast<double>(b1), step);
+  const double bc2d = 1.0 - pow(static_cast<double>(b2), step);
+  (void)bc1; (void)bc2;
+  adamw_kernel<<<cdiv(cdiv(n, 4), 256), 256, 0, s>>>(p, p16, g, m, v, n, sumsq, max_norm, lr, b1, b2, eps,
+                                                      wd, static_cast<float>(bc1d),
+                                                      static_cast<float>(sqrt(bc2d)));
+  note_launch();
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace b200

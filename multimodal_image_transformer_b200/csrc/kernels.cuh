@@ -1,0 +1,36 @@
+// Internal (C++) launchers of the memory-bound kernels: embedding, LayerNorm, reductions,
+// softmax-CE finalisation, optimizer.  All take raw device pointers and a stream.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+// position of row r is (r % T) + t0  (t0 > 0: single-position decode steps)
+int embed_pe_fwd(const int64_t* tokens, const float* emb, const float* pe, bf16* x, int B, int T,
+                 int E, int V, float scale, cudaStream_t s, int t0 = 0);
+int embed_bwd(const int64_t* tokens, const bf16* dx, float* demb, int B, int T, int E, int V,
+              long long pad_idx, float scale, cudaStream_t s);
+int layernorm_fwd(const bf16* x, const float* gamma, const float* beta, bf16* y, float* mean,
+                  float* rstd, int rows, int E, float eps, cudaStream_t s);
+int layernorm_bwd(const bf16* dy, const bf16* x, const float* gamma, const float* mean,
+                  const float* rstd, bf16* dx, float* dgamma, float* dbeta, int rows, int E,
+                  cudaStream_t s);
+int colsum(const bf16* x, long long ldx, float* out, int M, int N, cudaStream_t s);
+int cast_f32_to_bf16(const float* src, bf16* dst, long long n, cudaStream_t s);
+int cast_bf16_to_f32(const bf16* src, float* dst, long long n, cudaStream_t s);
+
+// softmax-CE finalisation of the LM-head partials written by the EPI_CE_FWD GEMM epilogue
+int ce_finalize(const float* part_max, const float* part_sum, const float* tgt_logit,
+                const int64_t* targets, int M, int n_tiles, long long ignore_index, float* row_lse,
+                float* row_loss, float* loss_sum, float* valid_count, cudaStream_t s);
+// out[0] = loss_sum/valid_count, out[1] = valid_count, out[2] = 1/valid_count
+int ce_mean(const float* loss_sum, const float* valid_count, float* out, cudaStream_t s);
+int argmax_finalize(const float* part_max, const float* part_idx, int M, int n_tiles,
+                    int64_t* out_ids, float* out_max, cudaStream_t s);
+// dlogits (fp32 [M,V]) -> bf16 copy (autograd compatibility path)
+int grad_sumsq(const float* g, long long n, float* sumsq, cudaStream_t s);
+int adamw_step(float* p, bf16* p16, const float* g, float* m, float* v, long long n,
+               const float* sumsq, float max_norm, float lr, float b1, float b2, float eps,
+               float wd, int step, cudaStream_t s);
+
+}  // namespace b200

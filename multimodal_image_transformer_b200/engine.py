@@ -1,0 +1,282 @@
+"""Python handle on the C-ABI decoder engine (include/b200_decoder.h).
+
+PyTorch is used here for device memory (the flat parameter / gradient / optimizer arenas and the
+activation workspace are torch allocations), streams and torch.distributed — nothing else.  All
+arithmetic happens in libb200decoder.so; there is no CPU or eager fallback.
+"""
+import ctypes as C
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+
+def sinusoid_table(max_len: int, d_model: int) -> torch.Tensor:
+    """The `pe` buffer of decoder.PositionalEncodingBatchFirst (reference decoder.py:34-51)."""
+    position = torch.arange(max_len).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, d_model, 2) * (-math.log(10000.0) / d_model))
+    pe = torch.zeros(max_len, d_model)
+    pe[:, 0::2] = torch.sin(position * div_term)
+    pe[:, 1::2] = torch.cos(position * div_term)
+    return pe.unsqueeze(0)
+
+
+class DecoderEngine:
+    """Owns the flat arenas and the workspace; one instance per model replica (one per GPU)."""
+
+    def __init__(self, vocab_size: int, embed_dim: int, num_heads: int, num_layers: int, ff_dim: int,
+                 max_seq_len: int, pad_idx: int = 0, enc_dim: Optional[int] = None,
+                 act: str = "relu", device="cuda"):
+        self.lib = L.lib()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("b200 decoder engine needs a CUDA device (sm_100a); there is no CPU fallback")
+        L.check(self.lib.b200_check_device(self.device.index or 0), "b200_check_device")
+        self.cfg = L.EngineConfig()
+        self.cfg.vocab_size, self.cfg.embed_dim, self.cfg.num_heads = vocab_size, embed_dim, num_heads
+        self.cfg.num_layers, self.cfg.ff_dim, self.cfg.max_seq_len = num_layers, ff_dim, max_seq_len
+        self.cfg.enc_dim = enc_dim if enc_dim is not None else embed_dim
+        self.cfg.pad_idx = pad_idx
+        self.cfg.ln_eps = 1e-5
+        self.cfg.act = {"relu": 1, "gelu": 2}[act]
+        self.handle = C.c_void_p()
+        L.check(self.lib.b200_engine_create(C.byref(self.cfg), C.byref(self.handle)), "engine_create")
+        self.vocab_size, self.embed_dim, self.num_heads = vocab_size, embed_dim, num_heads
+        self.num_layers, self.ff_dim, self.max_seq_len = num_layers, ff_dim, max_seq_len
+        self.enc_dim = self.cfg.enc_dim
+        self.pad_idx = pad_idx
+
+        self.total = int(self.lib.b200_engine_param_count(self.handle))
+        self.layout: Dict[str, Tuple[int, int]] = {}
+        buf = C.create_string_buffer(256)
+        for i in range(self.lib.b200_engine_num_params(self.handle)):
+            L.check(self.lib.b200_engine_param_name(self.handle, i, buf, 256), "param_name")
+            name = buf.value.decode()
+            numel = C.c_int64()
+            off = self.lib.b200_engine_param_offset(self.handle, name.encode(), C.byref(numel))
+            self.layout[name] = (int(off), int(numel.value))
+
+        with torch.cuda.device(self.device):
+            self.params = torch.zeros(self.total, device=self.device, dtype=torch.float32)
+            self.params_bf16 = torch.zeros(self.total, device=self.device, dtype=torch.bfloat16)
+            self.grads = torch.zeros(self.total, device=self.device, dtype=torch.float32)
+            self.pe = sinusoid_table(max_seq_len, embed_dim).to(self.device).contiguous()
+            self._scal = torch.zeros(8, device=self.device, dtype=torch.float32)
+        self.exp_avg = None
+        self.exp_avg_sq = None
+        self.opt_step = 0
+        self._ws = None
+        self._ws_key = None
+        self._shadow_version = -1
+        L.check(self.lib.b200_engine_bind(self.handle, L.ptr(self.params), L.ptr(self.params_bf16),
+                                          L.ptr(self.grads), L.ptr(self.pe)), "engine_bind")
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.b200_engine_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ arenas
+    def shapes(self) -> Dict[str, Tuple[int, ...]]:
+        E, F, V = self.embed_dim, self.ff_dim, self.vocab_size
+        sh: Dict[str, Tuple[int, ...]] = {}
+        if self.enc_dim != E:
+            sh["projection.weight"] = (E, self.enc_dim)
+            sh["projection.bias"] = (E,)
+        sh["token_embedding.weight"] = (V, E)
+        for l in range(self.num_layers):
+            p = f"transformer_decoder.layers.{l}."
+            sh[p + "self_attn.in_proj_weight"] = (3 * E, E)
+            sh[p + "self_attn.in_proj_bias"] = (3 * E,)
+            sh[p + "self_attn.out_proj.weight"] = (E, E)
+            sh[p + "self_attn.out_proj.bias"] = (E,)
+            sh[p + "multihead_attn.in_proj_weight"] = (3 * E, E)
+            sh[p + "multihead_attn.in_proj_bias"] = (3 * E,)
+            sh[p + "multihead_attn.out_proj.weight"] = (E, E)
+            sh[p + "multihead_attn.out_proj.bias"] = (E,)
+            sh[p + "linear1.weight"] = (F, E)
+            sh[p + "linear1.bias"] = (F,)
+            sh[p + "linear2.weight"] = (E, F)
+            sh[p + "linear2.bias"] = (E,)
+            for n in ("norm1", "norm2", "norm3"):
+                sh[p + n + ".weight"] = (E,)
+                sh[p + n + ".bias"] = (E,)
+        sh["fc_out.weight"] = (V, E)
+        sh["fc_out.bias"] = (V,)
+        return sh
+
+    def view(self, name: str, arena: Optional[torch.Tensor] = None) -> torch.Tensor:
+        off, n = self.layout[name]
+        a = self.params if arena is None else arena
+        return a[off:off + n].view(self.shapes()[name])
+
+    def load(self, tensors: Dict[str, torch.Tensor]) -> None:
+        """Copy named fp32 tensors (reference state_dict names relative to the decoder) in."""
+        with torch.no_grad():
+            for k, v in tensors.items():
+                if k in self.layout:
+                    self.view(k).copy_(v.to(self.device, torch.float32))
+        self.sync_shadow(force=True)
+
+    def sync_shadow(self, force: bool = False) -> None:
+        """Refresh the bf16 weight shadow if the fp32 master was modified through torch."""
+        ver = self.params._version
+        if force or ver != self._shadow_version:
+            L.check(self.lib.b200_cast_f32_to_bf16(L.ptr(self.params), L.ptr(self.params_bf16),
+                                                   C.c_int64(self.total), L.cur_stream()), "cast")
+            self._shadow_version = ver
+
+    def zero_grad(self) -> None:
+        self.grads.zero_()
+
+    # ------------------------------------------------------------------ workspace
+    def _ensure_ws(self, B: int, T: int, S: int, mem_dim: int, training: bool) -> None:
+        need = int(self.lib.b200_engine_workspace_bytes(self.handle, B, T, S, mem_dim, int(training)))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, device=self.device, dtype=torch.uint8)
+            L.check(self.lib.b200_engine_set_workspace(self.handle, L.ptr(self._ws), C.c_int64(self._ws.numel())),
+                    "set_workspace")
+
+    @staticmethod
+    def _prep(tokens, memory, mem_pad):
+        assert tokens.dtype == torch.int64 and tokens.is_cuda and tokens.dim() == 2
+        tokens = tokens.contiguous()
+        memory = memory.to(torch.float32).contiguous()
+        assert memory.dim() == 3 and memory.shape[0] == tokens.shape[0]
+        if mem_pad is not None:
+            mem_pad = mem_pad.to(torch.uint8).contiguous()
+        return tokens, memory, mem_pad
+
+    # ------------------------------------------------------------------ whole-model calls
+    def forward_logits(self, tokens, memory, mem_pad=None, training: bool = False) -> torch.Tensor:
+        tokens, memory, mem_pad = self._prep(tokens, memory, mem_pad)
+        B, T = tokens.shape
+        S, mem_dim = memory.shape[1], memory.shape[2]
+        self.sync_shadow()
+        self._ensure_ws(B, T, S, mem_dim, training)
+        logits = torch.empty(B, T, self.vocab_size, device=self.device, dtype=torch.float32)
+        self._keep = (tokens, memory, mem_pad)
+        L.check(self.lib.b200_engine_forward_logits(self.handle, L.ptr(tokens), L.ptr(memory), L.ptr(mem_pad),
+                                                    B, T, S, mem_dim, int(training), L.ptr(logits),
+                                                    L.cur_stream()), "forward_logits")
+        return logits
+
+    def forward_loss(self, tokens, targets, memory, mem_pad=None, ignore_index: int = 0,
+                     training: bool = False) -> torch.Tensor:
+        """Returns a device tensor [mean_loss, n_valid_targets]."""
+        tokens, memory, mem_pad = self._prep(tokens, memory, mem_pad)
+        targets = targets.contiguous()
+        B, T = tokens.shape
+        S, mem_dim = memory.shape[1], memory.shape[2]
+        self.sync_shadow()
+        self._ensure_ws(B, T, S, mem_dim, training)
+        out = torch.empty(2, device=self.device, dtype=torch.float32)
+        self._keep = (tokens, memory, mem_pad, targets)
+        L.check(self.lib.b200_engine_forward_loss(self.handle, L.ptr(tokens), L.ptr(targets), L.ptr(memory),
+                                                  L.ptr(mem_pad), B, T, S, mem_dim, C.c_int64(ignore_index),
+                                                  int(training), L.ptr(out), L.cur_stream()), "forward_loss")
+        return out
+
+    def backward(self, inv_count: Optional[torch.Tensor] = None, want_dmemory: bool = False,
+                 events: Optional[List[torch.cuda.Event]] = None) -> Optional[torch.Tensor]:
+        dmem = None
+        if want_dmemory:
+            _, memory = self._keep[0], self._keep[1]
+            dmem = torch.empty_like(memory)
+        ev_arr, n_ev = None, 0
+        if events:
+            n_ev = len(events)
+            ev_arr = (C.c_void_p * n_ev)(*[C.c_void_p(e.cuda_event) for e in events])
+        L.check(self.lib.b200_engine_backward(self.handle, L.ptr(inv_count), L.ptr(dmem), ev_arr, n_ev,
+                                              L.cur_stream()), "backward")
+        return dmem
+
+    def backward_from_dlogits(self, dlogits: torch.Tensor, want_dmemory: bool = False) -> Optional[torch.Tensor]:
+        dlogits = dlogits.to(torch.float32).contiguous()
+        dmem = None
+        if want_dmemory:
+            dmem = torch.empty_like(self._keep[1])
+        L.check(self.lib.b200_engine_backward_from_dlogits(self.handle, L.ptr(dlogits), L.ptr(dmem),
+                                                           L.cur_stream()), "backward_from_dlogits")
+        return dmem
+
+    def grad_buckets(self) -> List[Tuple[int, int]]:
+        n = self.lib.b200_engine_grad_buckets(self.handle, None, None, 0)
+        offs = (C.c_int64 * n)()
+        cnts = (C.c_int64 * n)()
+        self.lib.b200_engine_grad_buckets(self.handle, offs, cnts, n)
+        return [(int(offs[i]), int(cnts[i])) for i in range(n)]
+
+    # ------------------------------------------------------------------ optimizer
+    def adamw_step(self, lr=1e-4, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-5, max_norm=5.0) -> torch.Tensor:
+        """clip_grad_norm_(max_norm) + AdamW over the whole arena (train.py:96-100, 319-325).
+        Returns the device scalar holding the squared global gradient norm (pre-clip)."""
+        if self.exp_avg is None:
+            self.exp_avg = torch.zeros_like(self.params)
+            self.exp_avg_sq = torch.zeros_like(self.params)
+        self.opt_step += 1
+        sumsq = self._scal[0:1]
+        sumsq.zero_()
+        st = L.cur_stream()
+        L.check(self.lib.b200_grad_sumsq(L.ptr(self.grads), C.c_int64(self.total), L.ptr(sumsq), st), "grad_sumsq")
+        L.check(self.lib.b200_adamw_step(L.ptr(self.params), L.ptr(self.params_bf16), L.ptr(self.grads),
+                                         L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq), C.c_int64(self.total),
+                                         L.ptr(sumsq), C.c_float(max_norm), C.c_float(lr), C.c_float(betas[0]),
+                                         C.c_float(betas[1]), C.c_float(eps), C.c_float(weight_decay),
+                                         self.opt_step, st), "adamw_step")
+        # the kernel wrote both the fp32 master and the bf16 shadow: nothing to re-sync
+        return sumsq
+
+    # ------------------------------------------------------------------ KV-cached generation
+    def decode_begin(self, memory: torch.Tensor, mem_pad: Optional[torch.Tensor] = None, beam: int = 1,
+                     max_len: int = 100) -> None:
+        """Project the image memory once per image into per-layer cross K/V and reset the caches."""
+        memory = memory.to(self.device, torch.float32).contiguous()
+        if mem_pad is not None:
+            mem_pad = mem_pad.to(self.device, torch.uint8).contiguous()
+        B, S, mem_dim = memory.shape
+        self.sync_shadow()
+        need = int(self.lib.b200_engine_decode_workspace_bytes(self.handle, B, beam, S, mem_dim, max_len))
+        if need < 0:
+            raise RuntimeError("decode_begin: invalid shape")
+        if getattr(self, "_dws", None) is None or self._dws.numel() < need:
+            self._dws = None
+            self._dws = torch.empty(need, device=self.device, dtype=torch.uint8)
+        self._dkeep = (memory, mem_pad)
+        self._dshape = (B, beam, max_len)
+        L.check(self.lib.b200_engine_decode_begin(self.handle, L.ptr(memory), L.ptr(mem_pad), B, beam, S, mem_dim,
+                                                  max_len, L.ptr(self._dws), self._dws.numel(), L.cur_stream()),
+                "decode_begin")
+
+    def decode_step(self, tokens_in: torch.Tensor, pos: int) -> torch.Tensor:
+        tokens_in = tokens_in.to(self.device, torch.int64).contiguous()
+        out = torch.empty_like(tokens_in)
+        L.check(self.lib.b200_engine_decode_step(self.handle, L.ptr(tokens_in), pos, L.ptr(out), L.cur_stream()),
+                "decode_step")
+        return out
+
+    def generate_greedy(self, start_id: int, end_id: int, max_len: int, stop_check_interval: int = 0):
+        """Returns (tokens [B,max_len] int64: START .. END then PAD, lengths [B] int32) on device."""
+        B, beam, plan_len = self._dshape
+        assert beam == 1
+        toks = torch.empty(B, max_len, device=self.device, dtype=torch.int64)
+        lens = torch.empty(B, device=self.device, dtype=torch.int32)
+        L.check(self.lib.b200_engine_generate_greedy(self.handle, start_id, end_id, max_len, stop_check_interval,
+                                                     L.ptr(toks), L.ptr(lens), L.cur_stream()), "generate_greedy")
+        return toks, lens
+
+    def generate_beam(self, start_id: int, end_id: int, max_len: int):
+        """Returns (tokens [B,plan max_len], lengths [B], scores [B]) of the best hypothesis."""
+        B, beam, plan_len = self._dshape
+        toks = torch.empty(B, plan_len, device=self.device, dtype=torch.int64)
+        lens = torch.empty(B, device=self.device, dtype=torch.int32)
+        score = torch.empty(B, device=self.device, dtype=torch.float32)
+        L.check(self.lib.b200_engine_generate_beam(self.handle, start_id, end_id, max_len, L.ptr(toks), L.ptr(lens),
+                                                   L.ptr(score), L.cur_stream()), "generate_beam")
+        return toks, lens, score

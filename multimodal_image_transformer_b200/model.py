@@ -1,0 +1,174 @@
+"""Drop-in for the reference's model.py (reference model.py:12-255): a frozen Hugging Face vision
+encoder feeding the B200 caption decoder.  Same constructor, forward and generate signatures and
+the same state_dict keys (`encoder.*`, `projection.*`, `decoder.*`).  The encoder stays stock
+PyTorch (frozen, no_grad, out of the hot path's scope); projection + decoder run in the engine."""
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import config
+from .decoder import TransformerDecoder, _Holder
+
+
+def _load_encoder(name: str):
+    """Vision tower + hidden size, as reference model.py:34-66 resolves them."""
+    from transformers import AutoModel
+    full = AutoModel.from_pretrained(name)
+    enc = full.vision_model if hasattr(full, "vision_model") else full
+    hidden = getattr(enc.config, "hidden_size", None)
+    if hidden is None and hasattr(full.config, "vision_config"):
+        hidden = full.config.vision_config.hidden_size
+    if hidden is None:
+        raise AttributeError(f"cannot determine the encoder output width of {name}")
+    return enc, int(hidden)
+
+
+class _Projection(_Holder):
+    """nn.Linear(enc_dim, embed_dim) whose weight/bias live in the decoder engine's arena
+    (reference model.py:97-99); callable for API compatibility, fused into the engine's forward."""
+
+    def __init__(self, decoder: TransformerDecoder):
+        super().__init__()
+        eng = decoder.engine
+        self._eng = [eng]      # list: keep the engine out of nn.Module's attribute registry
+        self.weight = nn.Parameter(eng.view("projection.weight"))
+        self.bias = nn.Parameter(eng.view("projection.bias"))
+        self.weight.grad = eng.view("projection.weight", eng.grads)
+        self.bias.grad = eng.view("projection.bias", eng.grads)
+        self.in_features, self.out_features = eng.enc_dim, eng.embed_dim
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        from . import ops
+        return ops.linear(x, self.weight, self.bias)
+
+
+class ImageToTextModel(nn.Module):
+    def __init__(self, decoder_vocab_size: int, decoder_embed_dim: int, decoder_heads: int,
+                 decoder_layers: int, decoder_ff_dim: int, decoder_max_seq_len: int,
+                 decoder_dropout: float, decoder_pad_idx: int, *, encoder: Optional[nn.Module] = None,
+                 encoder_output_dim: Optional[int] = None, image_processor=None,
+                 memory_mode: Optional[str] = None, device=None):
+        super().__init__()
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if encoder is None:
+            encoder, encoder_output_dim = _load_encoder(config.ENCODER_MODEL_NAME)
+        self.encoder = encoder.to(dev)
+        self.encoder_output_dim = int(encoder_output_dim)
+        if image_processor is None:
+            from transformers import AutoImageProcessor
+            image_processor = AutoImageProcessor.from_pretrained(config.IMAGE_PROCESSOR_NAME)
+        self.image_processor = image_processor
+        for p in self.encoder.parameters():      # frozen feature extractor (reference model.py:87-89)
+            p.requires_grad = False
+        self.encoder.eval()
+        self.decoder_embed_dim = decoder_embed_dim
+        self.decoder_pad_idx = decoder_pad_idx
+        self.memory_mode = memory_mode or config.MEMORY_MODE
+        # RNG order of the reference: projection (nn.Linear default init) before the decoder
+        proj_init = None
+        if self.encoder_output_dim != decoder_embed_dim:
+            lin = nn.Linear(self.encoder_output_dim, decoder_embed_dim)
+            proj_init = {"projection.weight": lin.weight.detach(), "projection.bias": lin.bias.detach()}
+        self.decoder = TransformerDecoder(decoder_vocab_size, decoder_embed_dim, decoder_heads, decoder_layers,
+                                          decoder_ff_dim, decoder_max_seq_len, decoder_dropout, decoder_pad_idx,
+                                          enc_dim=self.encoder_output_dim, device=dev)
+        if proj_init is not None:
+            self.decoder.engine.load(proj_init)
+            self.projection = _Projection(self.decoder)
+        else:
+            self.projection = nn.Identity()
+
+    def train(self, mode: bool = True):
+        super().train(mode)
+        return self
+
+    # ------------------------------------------------------------------ features
+    @torch.no_grad()
+    def encode(self, image_tensors: torch.Tensor) -> torch.Tensor:
+        """Frozen encoder -> (B, S, enc_dim) memory before projection: the CLS token only in the
+        reference's mode (model.py:141,151), every patch token in "patch" mode."""
+        hs = self.encoder(pixel_values=image_tensors.to(self.decoder.engine.device)).last_hidden_state
+        return hs[:, :1, :] if self.memory_mode == "cls" else hs
+
+    # ------------------------------------------------------------------ reference API
+    def forward(self, image_tensors: torch.Tensor, tgt_tokens: torch.Tensor) -> torch.Tensor:
+        memory = self.encode(image_tensors)
+        if isinstance(self.projection, nn.Identity):
+            return self.decoder(tgt_tokens, memory, None)
+        return _forward_with_projection(self, tgt_tokens, memory)
+
+    def loss(self, image_tensors, tgt_tokens, target_tokens, ignore_index: int = 0, training=None) -> torch.Tensor:
+        """Fused path: encoder -> (projection + decoder + LM head + CE) without logits."""
+        memory = self.encode(image_tensors)
+        return self.decoder.loss(tgt_tokens.to(memory.device), target_tokens.to(memory.device), memory, None,
+                                 ignore_index, training)
+
+    @torch.no_grad()
+    def generate(self, image, start_token_id, end_token_id, max_len=100, method="greedy", beam_size=3) -> List[int]:
+        """One PIL image -> token ids incl. START (and END if produced), as reference model.py:171-255;
+        KV-cached on the GPU.  `beam` is a real beam search here (the reference falls back to greedy)."""
+        self.eval()
+        dev = self.decoder.engine.device
+        pixel_values = self.image_processor(images=image, return_tensors="pt")["pixel_values"].to(dev)
+        return self.generate_batch(pixel_values, start_token_id, end_token_id, max_len, method, beam_size)[0]
+
+    @torch.no_grad()
+    def generate_batch(self, pixel_values: torch.Tensor, start_token_id: int, end_token_id: int, max_len: int = 100,
+                       method: str = "greedy", beam_size: int = 3) -> List[List[int]]:
+        memory = self.encode(pixel_values)
+        return generate_from_memory(self.decoder, memory, start_token_id, end_token_id, max_len, method, beam_size)
+
+
+def generate_from_memory(decoder: TransformerDecoder, memory: torch.Tensor, start_token_id: int, end_token_id: int,
+                         max_len: int = 100, method: str = "greedy", beam_size: int = 3,
+                         memory_padding_mask=None, stop_check_interval: int = 8) -> List[List[int]]:
+    """Batched caption generation from image memory (B,S,mem_dim): lists of ids, START first, cut
+    after END (the list contract of reference model.py:242)."""
+    eng = decoder.engine
+    if method == "greedy" or (method == "beam" and beam_size == 1):
+        eng.decode_begin(memory, memory_padding_mask, beam=1, max_len=max_len)
+        toks, lens = eng.generate_greedy(start_token_id, end_token_id, max_len, stop_check_interval)
+    elif method == "beam":
+        eng.decode_begin(memory, memory_padding_mask, beam=beam_size, max_len=max_len)
+        toks, lens, _ = eng.generate_beam(start_token_id, end_token_id, max_len)
+    else:
+        raise ValueError(f"Unsupported generation method: {method}. Choose 'greedy' or 'beam'.")
+    toks, lens = toks.cpu(), lens.cpu()
+    return [toks[b, :int(lens[b])].tolist() for b in range(toks.shape[0])]
+
+
+class _ProjectedDecoderFunction(torch.autograd.Function):
+    """Autograd bridge of ImageToTextModel.forward when the projection lives inside the engine."""
+
+    @staticmethod
+    def forward(ctx, model, tokens, memory, *params):
+        eng = model.decoder.engine
+        logits = eng.forward_logits(tokens, memory, None, training=True)
+        eng._generation = getattr(eng, "_generation", 0) + 1
+        ctx.model, ctx.generation = model, eng._generation
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        model = ctx.model
+        eng = model.decoder.engine
+        if eng._generation != ctx.generation:
+            raise RuntimeError("b200 decoder: activations of this forward were overwritten by a later forward")
+        saved = eng.grads.clone()
+        eng.grads.zero_()
+        eng.backward_from_dlogits(dlogits)
+        names = ["projection.weight", "projection.bias"] + model.decoder._param_names
+        grads = tuple(eng.view(n, eng.grads).clone() for n in names)
+        eng.grads.copy_(saved)
+        return (None, None, None) + grads
+
+
+def _forward_with_projection(model: ImageToTextModel, tgt_tokens, memory):
+    dec = model.decoder
+    dec._warn_dropout()
+    tgt_tokens = tgt_tokens.to(dec.engine.device)
+    params = [model.projection.weight, model.projection.bias] + dec._flat_params()
+    if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+        return _ProjectedDecoderFunction.apply(model, tgt_tokens, memory, *params)
+    return dec.engine.forward_logits(tgt_tokens, memory, None, training=False)

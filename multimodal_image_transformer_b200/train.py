@@ -1,0 +1,123 @@
+"""Drop-in for the train / eval steps of the reference's train.py (reference train.py:62-151):
+same function names, argument lists and return values.  With a B200 model + B200AdamW the step is
+the fused path (forward + LM-head/CE without logits + backward + bucketed gradient all-reduce +
+global-norm clip + AdamW, no per-step host sync except the loss read the reference also does);
+with any other optimizer / criterion it degrades to the reference's own loop over the
+autograd-compatible forward."""
+from typing import Optional
+
+import torch
+
+from . import config
+from .dp import DataParallel
+
+
+class B200AdamW:
+    """torch.optim.AdamW-compatible facade over the engine's fused clip + AdamW kernel
+    (reference train.py:96-100, 319-325; torch AdamW semantics)."""
+
+    def __init__(self, model, lr=config.LEARNING_RATE, betas=(config.ADAM_BETA1, config.ADAM_BETA2),
+                 eps=config.ADAM_EPS, weight_decay=config.WEIGHT_DECAY, max_grad_norm: float = 0.0):
+        self.decoder = model.decoder if hasattr(model, "decoder") else model
+        self.engine = self.decoder.engine
+        self.param_groups = [dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
+                                  params=[p for p in model.parameters() if p.requires_grad])]
+        self.max_grad_norm = max_grad_norm
+        self.last_grad_sumsq: Optional[torch.Tensor] = None
+
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        self.engine.zero_grad()          # the arena stays allocated; .grad views keep pointing at it
+
+    def step(self, max_grad_norm: Optional[float] = None) -> None:
+        g = self.param_groups[0]
+        mn = self.max_grad_norm if max_grad_norm is None else max_grad_norm
+        self.last_grad_sumsq = self.engine.adamw_step(lr=g["lr"], betas=g["betas"], eps=g["eps"],
+                                                      weight_decay=g["weight_decay"], max_norm=mn)
+
+    def state_dict(self):
+        e = self.engine
+        return {"step": e.opt_step, "exp_avg": None if e.exp_avg is None else e.exp_avg.clone(),
+                "exp_avg_sq": None if e.exp_avg_sq is None else e.exp_avg_sq.clone(),
+                "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]}
+
+    def load_state_dict(self, sd) -> None:
+        e = self.engine
+        e.opt_step = int(sd["step"])
+        if sd["exp_avg"] is not None:
+            e.exp_avg = sd["exp_avg"].to(e.device).clone()
+            e.exp_avg_sq = sd["exp_avg_sq"].to(e.device).clone()
+        for g, s in zip(self.param_groups, sd["param_groups"]):
+            g.update(s)
+
+
+def _ignore_index(criterion) -> int:
+    return int(getattr(criterion, "ignore_index", config.PAD_TOKEN_ID))
+
+
+def fused_train_step(model, images, decoder_input_tokens, target_tokens, optimizer: B200AdamW, ignore_index: int,
+                     grad_clip_value: float, dp: Optional[DataParallel] = None) -> torch.Tensor:
+    """One optimisation step; returns the device tensor [loss, n_valid] (no host sync)."""
+    decoder = model.decoder if hasattr(model, "decoder") else model
+    optimizer.zero_grad()
+    if hasattr(model, "decoder"):
+        out = model.loss(images, decoder_input_tokens, target_tokens, ignore_index, training=True)
+    else:   # a bare decoder: `images` is the memory
+        out = decoder.loss(decoder_input_tokens, target_tokens, images, None, ignore_index, training=True)
+    if dp is not None and dp.world_size > 1:
+        inv = dp.global_inv_count(out)                 # 1 / (non-PAD targets over all ranks)
+        decoder.backward(inv_count=inv, events=dp.events)
+        dp.allreduce_buckets()
+        out = dp.global_loss(out, inv)
+    else:
+        decoder.backward()
+    optimizer.step(max_grad_norm=grad_clip_value)
+    return out
+
+
+def train_one_epoch(model, dataloader, optimizer, criterion, device, grad_clip_value, scheduler, epoch,
+                    log_interval, wandb_run, dp: Optional[DataParallel] = None):
+    """Mean training loss of one epoch (reference train.py:62-123)."""
+    model.train()
+    total_loss, num_batches = 0.0, len(dataloader)
+    fused = isinstance(optimizer, B200AdamW)
+    for i, batch in enumerate(dataloader):
+        images = batch["images"].to(device, non_blocking=True)
+        tokens = batch["decoder_input_tokens"].to(device, non_blocking=True)
+        targets = batch["target_tokens"].to(device, non_blocking=True)
+        if fused:
+            out = fused_train_step(model, images, tokens, targets, optimizer, _ignore_index(criterion),
+                                   grad_clip_value, dp)
+            batch_loss = float(out[0].item())
+        else:
+            optimizer.zero_grad()
+            logits = model(images, tokens)
+            loss = criterion(logits.view(-1, logits.size(-1)), targets.reshape(-1))
+            loss.backward()
+            if grad_clip_value > 0:
+                torch.nn.utils.clip_grad_norm_(model.parameters(), grad_clip_value)
+            optimizer.step()
+            batch_loss = loss.item()
+        if scheduler:
+            current_lr = scheduler.get_last_lr()[0]
+            scheduler.step()
+        else:
+            current_lr = optimizer.param_groups[0]["lr"]
+        total_loss += batch_loss
+        if wandb_run and (epoch * num_batches + i + 1) % log_interval == 0:
+            wandb_run.log({"train_batch_loss": batch_loss, "learning_rate": current_lr,
+                           "global_step": epoch * num_batches + i + 1})
+    return total_loss / max(num_batches, 1)
+
+
+def evaluate(model, dataloader, criterion, device):
+    """Mean evaluation loss (reference train.py:125-151); fused LM-head + CE, no logits."""
+    model.eval()
+    total_loss, num_batches = 0.0, len(dataloader)
+    ii = _ignore_index(criterion)
+    with torch.no_grad():
+        for batch in dataloader:
+            images = batch["images"].to(device, non_blocking=True)
+            tokens = batch["decoder_input_tokens"].to(device, non_blocking=True)
+            targets = batch["target_tokens"].to(device, non_blocking=True)
+            total_loss += float(model.loss(images, tokens, targets, ii, training=False)[0].item())
+    return total_loss / max(num_batches, 1)

@@ -71,7 +71,16 @@ def _layer_norm(x, w, b, eps=1e-5):
     return (x - mu) / torch.sqrt(var + eps) * w + b
 
 
-def _attention(q, k, v, num_heads, add_mask):
+def _ste_bf16(t: torch.Tensor) -> torch.Tensor:
+    """Round to bf16 and back (straight-through for autograd): emulates a bf16 storage point."""
+    return t + (t.bfloat16().float() - t).detach()
+
+
+def _ident(t):
+    return t
+
+
+def _attention(q, k, v, num_heads, add_mask, r=_ident):
     """q (B,Tq,E), k/v (B,Tk,E), add_mask broadcastable to (B,H,Tq,Tk) or None.
     functional.py:6682 — softmax(q k^T / sqrt(hd) + mask) v, heads = column blocks of width hd."""
     B, Tq, E = q.shape
@@ -83,21 +92,31 @@ def _attention(q, k, v, num_heads, add_mask):
     s = qh @ kh.transpose(-1, -2) / math.sqrt(hd)
     if add_mask is not None:
         s = s + add_mask
-    a = torch.softmax(s, dim=-1)
+    a = r(torch.softmax(s, dim=-1))
     return (a @ vh).transpose(1, 2).reshape(B, Tq, E)
 
 
 def decoder_hidden(p: Params, tokens: torch.Tensor, memory: torch.Tensor,
                    memory_padding_mask: Optional[torch.Tensor], num_heads: int,
-                   pad_idx: int = 0, act: str = "relu") -> torch.Tensor:
-    """Everything of decoder.py:134-186 up to (not including) fc_out; returns (B,T,E)."""
+                   pad_idx: int = 0, act: str = "relu", emulate_bf16: bool = False) -> torch.Tensor:
+    """Everything of decoder.py:134-186 up to (not including) fc_out; returns (B,T,E).
+
+    emulate_bf16=True rounds GEMM weights and every tensor the CUDA path stores to bf16 at the
+    same points (fp32 accumulation, fp32 biases / LayerNorm parameters / embedding table).  It is
+    NOT the reference's arithmetic; tests use it to separate kernel-math errors from the
+    expected bf16 storage noise (e.g. ReLU-mask flips of near-zero pre-activations)."""
+    r = _ste_bf16 if emulate_bf16 else _ident
+    if emulate_bf16:
+        p = {k: (r(v) if (v.is_floating_point() and v.dim() == 2 and k != "token_embedding.weight"
+                          and not k.startswith("positional_encoding")) else v) for k, v in p.items()}
+        memory = r(memory)
     B, T = tokens.shape
     E = p["token_embedding.weight"].shape[1]
     L = 0
     while f"transformer_decoder.layers.{L}.norm1.weight" in p:
         L += 1
     # decoder.py:168-170 (dropout is identity in eval / p=0, which is what parity runs use)
-    x = p["token_embedding.weight"][tokens] * math.sqrt(E) + p["positional_encoding.pe"][:, :T]
+    x = r(p["token_embedding.weight"][tokens] * math.sqrt(E) + p["positional_encoding.pe"][:, :T])
     # decoder.py:158,162 -> functional.py:6608-6621: float causal + bool key padding, merged
     self_mask = causal_mask(T).view(1, 1, T, T) + torch.zeros(B, 1, 1, T).masked_fill(
         padding_mask(tokens, pad_idx).view(B, 1, 1, T), float("-inf"))
@@ -110,31 +129,32 @@ def decoder_hidden(p: Params, tokens: torch.Tensor, memory: torch.Tensor,
     for l in range(L):
         pre = f"transformer_decoder.layers.{l}."
         # self-attention block, transformer.py:1158-1175
-        qkv = x @ p[pre + "self_attn.in_proj_weight"].t() + p[pre + "self_attn.in_proj_bias"]
+        qkv = r(x @ p[pre + "self_attn.in_proj_weight"].t() + p[pre + "self_attn.in_proj_bias"])
         q, k, v = qkv.split(E, dim=-1)
-        sa = _attention(q, k, v, num_heads, self_mask)
+        sa = r(_attention(q, k, v, num_heads, self_mask, r))
         sa = sa @ p[pre + "self_attn.out_proj.weight"].t() + p[pre + "self_attn.out_proj.bias"]
-        x = _layer_norm(x + sa, p[pre + "norm1.weight"], p[pre + "norm1.bias"])
+        x = r(_layer_norm(r(x + sa), p[pre + "norm1.weight"], p[pre + "norm1.bias"]))
         # cross-attention block, transformer.py:1177-1195 ; functional.py:5847-5864
         w, b = p[pre + "multihead_attn.in_proj_weight"], p[pre + "multihead_attn.in_proj_bias"]
-        q = x @ w[:E].t() + b[:E]
-        kv = memory @ w[E:].t() + b[E:]
+        q = r(x @ w[:E].t() + b[:E])
+        kv = r(memory @ w[E:].t() + b[E:])
         k, v = kv.split(E, dim=-1)
-        ca = _attention(q, k, v, num_heads, cross_mask)
+        ca = r(_attention(q, k, v, num_heads, cross_mask, r))
         ca = ca @ p[pre + "multihead_attn.out_proj.weight"].t() + p[pre + "multihead_attn.out_proj.bias"]
-        x = _layer_norm(x + ca, p[pre + "norm2.weight"], p[pre + "norm2.bias"])
+        x = r(_layer_norm(r(x + ca), p[pre + "norm2.weight"], p[pre + "norm2.bias"]))
         # feed-forward block, transformer.py:1197-1199
-        h = fact(x @ p[pre + "linear1.weight"].t() + p[pre + "linear1.bias"])
+        h = r(fact(x @ p[pre + "linear1.weight"].t() + p[pre + "linear1.bias"]))
         ff = h @ p[pre + "linear2.weight"].t() + p[pre + "linear2.bias"]
-        x = _layer_norm(x + ff, p[pre + "norm3.weight"], p[pre + "norm3.bias"])
+        x = r(_layer_norm(r(x + ff), p[pre + "norm3.weight"], p[pre + "norm3.bias"]))
     return x
 
 
 def decoder_forward(p: Params, tokens, memory, memory_padding_mask=None, num_heads: int = 8,
-                    pad_idx: int = 0, act: str = "relu") -> torch.Tensor:
+                    pad_idx: int = 0, act: str = "relu", emulate_bf16: bool = False) -> torch.Tensor:
     """decoder.TransformerDecoder.forward (decoder.py:134-193): logits (B,T,V), fp32."""
-    x = decoder_hidden(p, tokens, memory, memory_padding_mask, num_heads, pad_idx, act)
-    return x @ p["fc_out.weight"].t() + p["fc_out.bias"]
+    x = decoder_hidden(p, tokens, memory, memory_padding_mask, num_heads, pad_idx, act, emulate_bf16)
+    w = _ste_bf16(p["fc_out.weight"]) if emulate_bf16 else p["fc_out.weight"]
+    return x @ w.t() + p["fc_out.bias"]
 
 
 def project_memory(features: torch.Tensor, proj_w: Optional[torch.Tensor],
@@ -157,8 +177,8 @@ def cross_entropy(logits: torch.Tensor, targets: torch.Tensor, ignore_index: int
 
 
 def loss_and_grads(p: Params, tokens, targets, memory, memory_padding_mask=None, num_heads=8,
-                   pad_idx=0, ignore_index=0, proj: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
-                   ) -> Tuple[torch.Tensor, Params]:
+                   pad_idx=0, ignore_index=0, proj: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+                   emulate_bf16: bool = False) -> Tuple[torch.Tensor, Params]:
     """train.py:83-93 for the decoder (+ optional projection): loss and d loss / d every
     floating-point parameter, by autograd over the restatement.  The embedding's padding row gets
     a zero gradient (nn.Embedding padding_idx, decoder.py:105)."""
@@ -170,9 +190,12 @@ def loss_and_grads(p: Params, tokens, targets, memory, memory_padding_mask=None,
     proj_leaves = None
     if proj is not None:
         proj_leaves = tuple(t.detach().clone().requires_grad_(True) for t in proj)
-        mem = project_memory(memory, *proj_leaves)
-    loss = cross_entropy(decoder_forward(q, tokens, mem, memory_padding_mask, num_heads, pad_idx),
-                         targets, ignore_index)
+        if emulate_bf16:
+            mem = _ste_bf16(project_memory(_ste_bf16(memory), _ste_bf16(proj_leaves[0]), proj_leaves[1]))
+        else:
+            mem = project_memory(memory, *proj_leaves)
+    loss = cross_entropy(decoder_forward(q, tokens, mem, memory_padding_mask, num_heads, pad_idx,
+                                         emulate_bf16=emulate_bf16), targets, ignore_index)
     loss.backward()
     grads = {k: v.grad for k, v in leaves.items()}
     grads["token_embedding.weight"][pad_idx].zero_()

@@ -1,0 +1,279 @@
+"""Whole-path parity on the B200: the CUDA engine (through the C ABI) and the drop-in modules
+against the CPU oracle and the committed golden vectors of the unmodified reference.
+
+Tolerances (BASELINE.json north_star / SURVEY 8c):
+  logits  <= 2e-2 max-relative per row (bf16 storage, fp32 accumulate)
+  loss    <= 1e-3 relative
+  grads   per tensor: relative L2 <= 1e-1 and cosine >= 0.995 against BOTH the fp32 oracle and
+          the bf16-emulating oracle.  Why not tighter: a ReLU unit whose pre-activation is within
+          bf16 rounding of zero flips its mask and perturbs the gradient by O(sqrt(flip fraction)).
+          Measured on the B200 (profiles/r01_grad_noise.log): engine-vs-fp32, engine-vs-emulated and
+          emulated-vs-fp32 all sit at 2-7e-2 (cosine 0.998-0.9999), i.e. two bf16 evaluations of the
+          reference differ from each other as much as the engine differs from either; tensors next
+          to the loss (fc_out, last layer's linear2/norm3), which see no mask flips, agree to <= 7e-3.
+          The tight (4e-3) checks of the backward MATH are the per-kernel tests in
+          test_gpu_kernels.py (attention / LayerNorm / GEMM dgrad+wgrad / CE on identical inputs).
+  greedy  identical token ids on >= 99 % of samples
+"""
+import pytest
+import torch
+
+from oracle import decoder_oracle as O
+from tests.helpers import CFGS, golden_params, load_golden, make_engine, rel_l2, row_max_rel, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _grad_close(got, ref, rel=1e-1, cos=0.995):
+    got = got.detach().float().cpu().flatten()
+    ref = ref.detach().float().cpu().flatten()
+    c = torch.nn.functional.cosine_similarity(got, ref, dim=0).item()
+    return rel_l2(got, ref) < rel and c > cos
+
+
+def _case(name, seed=42):
+    c = CFGS[name]
+    p = O.init_params(c["V"], c["E"], c["H"], c["L"], c["F"], c["ML"], seed=seed)
+    return c, p, synth(c, seed + 1)
+
+
+@pytest.mark.parametrize("name", ["nano", "tiny", "hd96", "cfg1", "cfg2s"])
+def test_forward_logits_and_loss_vs_oracle(cuda_dev, name):
+    c, p, (tok, tgt, mem, mpm) = _case(name)
+    eng = make_engine(c, p, cuda_dev)
+    with torch.no_grad():
+        ref = O.decoder_forward(p, tok, mem, None, c["H"])
+        ref_m = O.decoder_forward(p, tok, mem, mpm, c["H"])
+    got = eng.forward_logits(tok.to(cuda_dev), mem.to(cuda_dev), None, training=False)
+    assert row_max_rel(got, ref) < 2e-2
+    got_t = eng.forward_logits(tok.to(cuda_dev), mem.to(cuda_dev), None, training=True)
+    assert torch.equal(got, got_t)                     # same kernels, different workspace plan
+    got_m = eng.forward_logits(tok.to(cuda_dev), mem.to(cuda_dev), mpm.to(cuda_dev), training=False)
+    assert row_max_rel(got_m, ref_m) < 2e-2
+    lref = O.cross_entropy(ref, tgt, 0).item()
+    lg = eng.forward_loss(tok.to(cuda_dev), tgt.to(cuda_dev), mem.to(cuda_dev), None, 0, training=False).cpu()
+    assert abs(lg[0].item() - lref) < 1e-3 * lref
+    assert lg[1].item() == (tgt != 0).sum().item()
+
+
+@pytest.mark.parametrize("name", ["nano", "cfg1"])
+def test_forward_vs_reference_golden(cuda_dev, name):
+    g = load_golden(name)
+    c = g["config"]
+    eng = make_engine(c, golden_params(g), cuda_dev)
+    tok, mem = g["tokens"].to(cuda_dev), g["memory"].to(cuda_dev)
+    got = eng.forward_logits(tok, mem, None).cpu()
+    got_m = eng.forward_logits(tok, mem, g["mem_pad"].to(cuda_dev)).cpu()
+    if c["full"]:
+        assert row_max_rel(got, g["logits"]) < 2e-2 and row_max_rel(got_m, g["logits_mem_pad"]) < 2e-2
+    else:
+        err = (got[:, :, ::97] - g["logits_sub"]).abs().amax(-1) / g["logits_rowmax"]
+        assert err.max().item() < 2e-2
+    loss = eng.forward_loss(tok, g["targets"].to(cuda_dev), mem, None, 0).cpu()[0].item()
+    assert abs(loss - g["loss"]) < 1e-3 * g["loss"]
+
+
+@pytest.mark.parametrize("name", ["nano", "tiny", "hd96", "cfg1"])
+def test_gradients_vs_oracle(cuda_dev, name):
+    c, p, (tok, tgt, mem, _) = _case(name)
+    eng = make_engine(c, p, cuda_dev)
+    lref, g32 = O.loss_and_grads(p, tok, tgt, mem, None, c["H"])
+    _, g16 = O.loss_and_grads(p, tok, tgt, mem, None, c["H"], emulate_bf16=True)
+    eng.zero_grad()
+    out = eng.forward_loss(tok.to(cuda_dev), tgt.to(cuda_dev), mem.to(cuda_dev), None, 0, training=True)
+    dmem = eng.backward(want_dmemory=True)
+    torch.cuda.synchronize()
+    assert abs(out[0].item() - lref.item()) < 1e-3 * lref.item()
+    for k in g32:
+        got = eng.view(k, eng.grads)
+        assert _grad_close(got, g16[k]), (k, rel_l2(got, g16[k]))
+        assert _grad_close(got, g32[k]), (k, rel_l2(got, g32[k]))
+        if k.startswith("fc_out"):
+            assert rel_l2(got, g32[k]) < 1.5e-2, (k, rel_l2(got, g32[k]))   # no ReLU between it and the loss
+    assert float(eng.view("token_embedding.weight", eng.grads)[0].abs().max()) == 0.0
+    memr = mem.clone().requires_grad_(True)
+    O.cross_entropy(O.decoder_forward(p, tok, memr, None, c["H"], emulate_bf16=True), tgt, 0).backward()
+    assert _grad_close(dmem, memr.grad)
+    # backward accumulates (optimizer.zero_grad() semantics of train.py:80): a second pass doubles
+    first = eng.grads.clone()
+    eng.forward_loss(tok.to(cuda_dev), tgt.to(cuda_dev), mem.to(cuda_dev), None, 0, training=True)
+    eng.backward()
+    assert rel_l2(eng.grads, 2 * first) < 1e-3
+
+
+def test_projection_path_cfg1(cuda_dev):
+    """BASELINE cfg1: 768-wide CLIP features projected to the 512-wide decoder inside the engine."""
+    c = CFGS["cfg1"]
+    p = O.init_params(c["V"], c["E"], c["H"], c["L"], c["F"], c["ML"], seed=42)
+    tok, tgt, _, _ = synth(c, 43)
+    gen = torch.Generator().manual_seed(9)
+    feat = torch.randn(c["B"], c["S"], 768, generator=gen)
+    lin = torch.nn.Linear(768, c["E"])
+    pw, pb = lin.weight.detach().clone(), lin.bias.detach().clone()
+    eng = make_engine(c, dict(p, **{"projection.weight": pw, "projection.bias": pb}), cuda_dev, enc_dim=768)
+    lref, g16 = O.loss_and_grads(p, tok, tgt, feat, None, c["H"], proj=(pw, pb), emulate_bf16=True)
+    with torch.no_grad():
+        ref_logits = O.decoder_forward(p, tok, O.project_memory(feat, pw, pb), None, c["H"])
+    assert row_max_rel(eng.forward_logits(tok.to(cuda_dev), feat.to(cuda_dev), None), ref_logits) < 2e-2
+    eng.zero_grad()
+    out = eng.forward_loss(tok.to(cuda_dev), tgt.to(cuda_dev), feat.to(cuda_dev), None, 0, training=True)
+    eng.backward()
+    assert abs(out[0].item() - lref.item()) < 1e-3 * lref.item()
+    for k in ("projection.weight", "projection.bias", "transformer_decoder.layers.0.multihead_attn.in_proj_weight"):
+        assert _grad_close(eng.view(k, eng.grads), g16[k]), (k, rel_l2(eng.view(k, eng.grads), g16[k]))
+
+
+def test_train_trajectory_vs_reference_golden(cuda_dev):
+    """3 steps of zero_grad / fwd / CE / bwd / clip(5.0) / AdamW exactly as train.py:80-100."""
+    g = load_golden("nano")
+    c = g["config"]
+    eng = make_engine(c, golden_params(g), cuda_dev)
+    tok, tgt, mem = (g[k].to(cuda_dev) for k in ("tokens", "targets", "memory"))
+    losses = []
+    for _ in range(3):
+        eng.zero_grad()
+        out = eng.forward_loss(tok, tgt, mem, None, 0, training=True)
+        eng.backward()
+        eng.adamw_step(lr=g["train_lr"], betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-5, max_norm=5.0)
+        losses.append(out[0].item())
+    for a, b in zip(losses, g["train_losses"]):
+        assert abs(a - b) < 2e-3 * b, (losses, g["train_losses"])
+    for k, v in g["params_after"].items():
+        d = (eng.view(k).cpu() - v).abs()
+        assert d.max() <= 2 * 3 * g["train_lr"] + 1e-6, k        # Adam sign sensitivity, see test_oracle.py
+        if "in_proj_bias" not in k:                              # key-bias gradients are exactly zero: pure sign noise
+            assert d.mean() < 0.35 * g["train_lr"], k
+
+
+def test_dropin_module_state_dict_and_autograd(cuda_dev):
+    """decoder.TransformerDecoder: reference constructor signature, bit-identical seeded init,
+    reference state_dict keys/shapes, and the logits -> criterion -> backward() loop of train.py."""
+    from multimodal_image_transformer_b200.decoder import TransformerDecoder
+    c = CFGS["nano"]
+    torch.manual_seed(42)
+    dec = TransformerDecoder(c["V"], c["E"], c["H"], c["L"], c["F"], c["ML"], dropout=0.0, pad_idx=0)
+    p = O.init_params(c["V"], c["E"], c["H"], c["L"], c["F"], c["ML"], seed=42)
+    sd = dec.state_dict()
+    assert list(sd.keys()) == list(p.keys()) or set(sd.keys()) == set(p.keys())
+    for k in p:
+        assert sd[k].shape == p[k].shape and torch.equal(sd[k].cpu(), p[k]), k
+    tok, tgt, mem, mpm = synth(c, 43)
+    dec.eval()
+    with torch.no_grad():
+        lg = dec(tok.to(cuda_dev), mem.to(cuda_dev), mpm.to(cuda_dev))
+        ref = O.decoder_forward(p, tok, mem, mpm, c["H"])
+    assert lg.shape == (c["B"], c["T"], c["V"]) and row_max_rel(lg, ref) < 2e-2
+    dec.train()
+    logits = dec(tok.to(cuda_dev), mem.to(cuda_dev))
+    loss = torch.nn.CrossEntropyLoss(ignore_index=0)(logits.view(-1, c["V"]), tgt.to(cuda_dev).reshape(-1))
+    for q in dec.parameters():
+        q.grad = None
+    loss.backward()
+    _, g16 = O.loss_and_grads(p, tok, tgt, mem, None, c["H"], emulate_bf16=True)
+    named = dict(dec.named_parameters())
+    assert set(named) == set(g16)
+    for k, v in g16.items():
+        assert _grad_close(named[k].grad, v), (k, rel_l2(named[k].grad, v))
+    # load_state_dict round trip with perturbed reference-format tensors
+    sd2 = {k: (v + 0.01 if v.is_floating_point() and k != "positional_encoding.pe" else v) for k, v in p.items()}
+    dec.load_state_dict(sd2, strict=True)
+    with torch.no_grad():
+        lg2 = dec.eval()(tok.to(cuda_dev), mem.to(cuda_dev))
+        ref2 = O.decoder_forward(sd2, tok, mem, None, c["H"])
+    assert row_max_rel(lg2, ref2) < 2e-2
+
+
+def test_greedy_vs_reference_golden_and_oracle(cuda_dev):
+    from multimodal_image_transformer_b200.decoder import TransformerDecoder  # noqa: F401
+    for name in ("nano", "cfg1"):
+        g = load_golden(name)
+        c = g["config"]
+        eng = make_engine(c, golden_params(g), cuda_dev)
+        n = len(g["greedy"])
+        eng.decode_begin(g["memory"][:n].to(cuda_dev), None, beam=1, max_len=g["greedy_max_len"])
+        toks, lens = eng.generate_greedy(1, 2, g["greedy_max_len"], stop_check_interval=0)
+        got = [toks[b, :int(lens[b])].tolist() for b in range(n)]
+        same = sum(a == b for a, b in zip(got, g["greedy"]))
+        assert same >= 0.99 * n, (got, g["greedy"])
+
+
+def test_greedy_batch_vs_oracle_and_early_stop(cuda_dev):
+    c = dict(CFGS["tiny"], B=24)
+    p = O.init_params(c["V"], c["E"], c["H"], c["L"], c["F"], c["ML"], seed=3)
+    p["fc_out.bias"][2] += 1.5          # make END likely enough that some rows stop early
+    mem = torch.randn(c["B"], c["S"], c["E"], generator=torch.Generator().manual_seed(4))
+    with torch.no_grad():
+        ref = O.greedy_generate(p, mem, 1, 2, 14, c["H"])
+    eng = make_engine(c, p, cuda_dev)
+    eng.decode_begin(mem.to(cuda_dev), None, beam=1, max_len=14)
+    for interval in (0, 4):
+        toks, lens = eng.generate_greedy(1, 2, 14, stop_check_interval=interval)
+        got = [toks[b, :int(lens[b])].tolist() for b in range(c["B"])]
+        same = sum(a == b for a, b in zip(got, ref))
+        assert same >= 0.95 * c["B"], (same, got[:3], ref[:3])     # 24 rows: allow one bf16 near-tie
+        for b in range(c["B"]):
+            assert toks[b, int(lens[b]):].eq(0).all()              # PAD after END
+        eng.decode_begin(mem.to(cuda_dev), None, beam=1, max_len=14)
+
+
+def test_kv_cache_step_equals_full_recompute(cuda_dev):
+    """decode_step logits-argmax at position t == argmax of the full forward on the prefix."""
+    c, p, (tok, _, mem, mpm) = _case("tiny")
+    tok = tok.clone()
+    tok[tok == 0] = 7
+    eng = make_engine(c, p, cuda_dev)
+    full = eng.forward_logits(tok.to(cuda_dev), mem.to(cuda_dev), mpm.to(cuda_dev)).argmax(-1).cpu()
+    eng.decode_begin(mem.to(cuda_dev), mpm.to(cuda_dev), beam=1, max_len=c["T"] + 1)
+    agree = 0
+    for t in range(c["T"]):
+        nxt = eng.decode_step(tok[:, t].to(cuda_dev), t).cpu()
+        agree += int((nxt == full[:, t]).sum())
+    assert agree >= 0.98 * tok.numel()
+
+
+def test_beam_search_vs_oracle_spec(cuda_dev):
+    c = dict(CFGS["nano"], B=6)
+    p = O.init_params(c["V"], c["E"], c["H"], c["L"], c["F"], c["ML"], seed=5)
+    p["fc_out.bias"][2] += 1.0
+    mem = torch.randn(c["B"], c["S"], c["E"], generator=torch.Generator().manual_seed(6))
+    eng = make_engine(c, p, cuda_dev)
+    with torch.no_grad():
+        ref3 = O.beam_generate(p, mem, 1, 2, 10, c["H"], beam_size=3)
+        greedy = O.greedy_generate(p, mem, 1, 2, 10, c["H"])
+    eng.decode_begin(mem.to(cuda_dev), None, beam=3, max_len=10)
+    toks, lens, score = eng.generate_beam(1, 2, 10)
+    got = [toks[b, :int(lens[b])].tolist() for b in range(c["B"])]
+    assert sum(a == b for a, b in zip(got, ref3)) >= c["B"] - 1, (got, ref3)
+    assert torch.isfinite(score).all()
+    # beam = 1 through the model-level API degenerates to greedy
+    from multimodal_image_transformer_b200.model import generate_from_memory
+
+    class _D:      # minimal stand-in exposing .engine
+        engine = eng
+    out = generate_from_memory(_D, mem.to(cuda_dev), 1, 2, 10, method="beam", beam_size=1)
+    assert sum(a == b for a, b in zip(out, greedy)) >= c["B"] - 1
+
+
+def test_full_size_properties_cfg2(cuda_dev):
+    """BASELINE cfg2 (B=256, T=47, S=197, E=768, H=12, F=3072, L=6, V=10000): too big for the CPU
+    oracle, so check size-independent properties: loss at init ~ ln V, gradient norms finite, padding
+    row untouched, batch-permutation invariance of the loss, and equality of the fused loss with
+    the loss computed from materialised logits."""
+    c = dict(V=10000, E=768, H=12, L=6, F=3072, ML=100, B=256, T=47, S=197)
+    p = O.init_params(c["V"], c["E"], c["H"], c["L"], c["F"], c["ML"], seed=42)
+    tok, tgt, mem, _ = synth(c, 43)
+    eng = make_engine(c, p, cuda_dev)
+    tokd, tgtd, memd = tok.to(cuda_dev), tgt.to(cuda_dev), mem.to(cuda_dev)
+    eng.zero_grad()
+    out = eng.forward_loss(tokd, tgtd, memd, None, 0, training=True)
+    eng.backward()
+    loss = out[0].item()
+    assert abs(loss - 9.21) < 0.35 and out[1].item() == (tgt != 0).sum().item()
+    assert torch.isfinite(eng.grads).all() and eng.grads.norm().item() > 0
+    assert float(eng.view("token_embedding.weight", eng.grads)[0].abs().max()) == 0.0
+    logits = eng.forward_logits(tokd, memd, None)
+    lref = torch.nn.functional.cross_entropy(logits.view(-1, c["V"]), tgtd.view(-1), ignore_index=0).item()
+    assert abs(loss - lref) < 2e-4 * lref
+    perm = torch.randperm(c["B"], generator=torch.Generator().manual_seed(1))
+    out_p = eng.forward_loss(tokd[perm], tgtd[perm], memd[perm], None, 0, training=False)
+    assert abs(out_p[0].item() - loss) < 1e-5 * loss

@@ -1,0 +1,53 @@
+"""Host-side logic that needs no GPU: sharding, bucket planning, id post-processing, mask helpers,
+and the guarantee that the product path refuses to run without CUDA (no CPU fallback)."""
+import pytest
+import torch
+
+from multimodal_image_transformer_b200 import dp, inference, utils
+from oracle import decoder_oracle as O
+
+
+def test_shard_range_partitions_batch():
+    for n in (0, 1, 7, 256, 513):
+        for w in (1, 2, 4, 8):
+            spans = [dp.shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [e - b for b, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_plan_buckets_merges_in_readiness_order():
+    segs = [(900, 100), (600, 300), (300, 300), (0, 300)]          # fc_out, layer1, layer0, embedding
+    assert dp.plan_buckets(segs, 400) == [(600, 400), (300, 300), (0, 300)]
+    assert dp.plan_buckets(segs, 10) == segs                       # nothing fits: one bucket per segment
+    assert dp.plan_buckets(segs, 10 ** 9) == [(0, 1000)]
+    covered = sum(c for _, c in dp.plan_buckets(segs, 650))
+    assert covered == 1000
+
+
+def test_postprocess_ids_matches_reference_rules():
+    # reference inference.py:98-107: cut at first END, drop one leading START
+    assert inference.postprocess_ids([1, 7, 8, 2, 9, 2], 1, 2) == [7, 8]
+    assert inference.postprocess_ids([1, 7, 8], 1, 2) == [7, 8]
+    assert inference.postprocess_ids([7, 1, 2], 1, 2) == [7, 1]
+    assert inference.postprocess_ids([1, 2], 1, 2) == []
+    assert inference.postprocess_ids([], 1, 2) == []
+    assert inference.clean_caption("  a <UNK>  dog <UNK>runs  ") == "a dog runs"
+
+
+def test_mask_helpers_match_oracle():
+    for sz in (1, 5, 31):
+        assert torch.equal(utils.generate_square_subsequent_mask(sz), O.causal_mask(sz))
+    seq = torch.tensor([[1, 5, 0, 0], [1, 0, 7, 2]])
+    assert torch.equal(utils.create_padding_mask(seq, 0), O.padding_mask(seq, 0))
+
+
+def test_no_cpu_fallback():
+    from multimodal_image_transformer_b200.engine import DecoderEngine
+    with pytest.raises(RuntimeError):
+        DecoderEngine(264, 64, 2, 2, 128, 40, device="cpu")
+    if not torch.cuda.is_available():
+        from multimodal_image_transformer_b200.decoder import TransformerDecoder
+        with pytest.raises(Exception):
+            TransformerDecoder(264, 64, 2, 2, 128, 40, dropout=0.0)
