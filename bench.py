@@ -221,7 +221,16 @@ def run_b200(args):
     barrier()
     launches = lib.b200_launch_count() - launches0
     n_l, tot_ms, tot_fl = C.c_int32(), C.c_double(), C.c_double()
-    L.check(lib.b200_gemm_profile_end(C.byref(n_l), C.byref(tot_ms), C.byref(tot_fl), None, None, 0), "profile_end")
+    cap = 400 * args.steps + 64
+    pl_ms, pl_fl = (C.c_float * cap)(), (C.c_double * cap)()
+    L.check(lib.b200_gemm_profile_end(C.byref(n_l), C.byref(tot_ms), C.byref(tot_fl), pl_ms, pl_fl, cap), "profile_end")
+    if args.gemm_detail and rank == 0:
+        per = n_l.value // args.steps
+        with open(args.gemm_detail, "w") as f:
+            f.write("idx_in_step,gflop,avg_us,tflops\n")
+            for i in range(per):
+                ms_i = sum(pl_ms[k * per + i] for k in range(args.steps)) / args.steps
+                f.write(f"{i},{pl_fl[i] / 1e9:.2f},{ms_i * 1e3:.1f},{pl_fl[i] / 1e9 / max(ms_i, 1e-9):.1f}\n")
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1) / args.steps
     t = torch.tensor([ms], device=dev)
@@ -369,6 +378,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--gemm-detail", default=None, help="write per-launch GEMM timings of one step to this CSV")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -12,6 +12,7 @@
 // produces dK/dV per key tile (no atomics, deterministic).
 #include "attention.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace b200 {
 
@@ -56,17 +57,24 @@ struct AttnDev {
   float scale;
 };
 
-// cooperative copy of `rows` x HD bf16 (row stride ts elements) into padded smem, zero-filling
-// rows [rows, rows_padded)
+// cooperative asynchronous copy (cp.async, 16 B per request, all requests in flight at once) of
+// `rows` x HD bf16 (row stride ts elements) into padded smem; rows [rows, rows_padded) are
+// zero-filled through the src-size-0 form.  Completion: cp_async_wait_all() + __syncthreads().
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
 template <int HD>
 __device__ __forceinline__ void load_rows(bf16* dst, const bf16* src, long long ts, int rows, int rows_padded) {
   constexpr int LD = HD + 8;
   constexpr int VPR = HD / 8;
   for (int i = threadIdx.x; i < rows_padded * VPR; i += blockDim.x) {
     const int r = i / VPR, c = (i % VPR) * 8;
-    uint4 val = make_uint4(0u, 0u, 0u, 0u);
-    if (r < rows) val = ldg_nc_v4(src + r * ts + c);
-    *reinterpret_cast<uint4*>(dst + r * LD + c) = val;
+    const bool ok = r < rows;
+    cp_async_16(dst + r * LD + c, src + (ok ? r * ts : 0) + c, ok ? 16 : 0);
   }
 }
 
@@ -128,7 +136,7 @@ struct AttnSmem {
     return static_cast<size_t>(TQP + 2 * TKP) * LD * 2 + TKP * sizeof(float) + 16;
   }
   static size_t bwd_bytes(int TQP, int TKP) {
-    return static_cast<size_t>(2 * TQP + 2 * TKP) * LD * 2 + (TKP + 2 * TQP) * sizeof(float) + 16;
+    return static_cast<size_t>(3 * TQP + 2 * TKP) * LD * 2 + (TKP + 2 * TQP) * sizeof(float) + 16;
   }
 };
 
@@ -162,6 +170,7 @@ attn_fwd_kernel(const AttnDev p) {
   load_rows<HD>(sK, p.k + b * p.k_bs + h * HD, p.k_ts, p.Tk, p.TKP);
   load_rows<HD>(sV, p.v + b * p.v_bs + h * HD, p.v_ts, p.Tk, p.TKP);
   fill_key_bias(sBias, p, b);
+  cp_async_wait_all();
   __syncthreads();
 
   const float sl2 = p.scale * LOG2E;
@@ -246,7 +255,8 @@ attn_bwd_kernel(const AttnDev p) {
   bf16* sdO = sQ + p.TQP * LD;
   bf16* sK = sdO + p.TQP * LD;
   bf16* sV = sK + p.TKP * LD;
-  float* sBias = reinterpret_cast<float*>(sV + p.TKP * LD);
+  bf16* sO = sV + p.TKP * LD;
+  float* sBias = reinterpret_cast<float*>(sO + p.TQP * LD);
   float* sLse = sBias + p.TKP;   // already multiplied by log2(e); +inf on padded query rows
   float* sD = sLse + p.TQP;
 
@@ -258,29 +268,28 @@ attn_bwd_kernel(const AttnDev p) {
   load_rows<HD>(sdO, p.d_o + b * p.do_bs + h * HD, p.do_ts, p.Tq, p.TQP);
   load_rows<HD>(sK, p.k + b * p.k_bs + h * HD, p.k_ts, p.Tk, p.TKP);
   load_rows<HD>(sV, p.v + b * p.v_bs + h * HD, p.v_ts, p.Tk, p.TKP);
+  load_rows<HD>(sO, p.o_in + b * p.o_bs + h * HD, p.o_ts, p.Tq, p.TQP);
   fill_key_bias(sBias, p, b);
-  // D_i = sum_d dO[i,d] * O[i,d]; one warp per row
+  for (int row = threadIdx.x; row < p.TQP; row += blockDim.x) {
+    float l = INFINITY;
+    if (row < p.Tq) {
+      l = p.lse[(static_cast<long long>(b) * p.H + h) * p.Tq + row];
+      l = (l == -INFINITY) ? INFINITY : l * LOG2E;   // fully masked row: P = 0
+    }
+    sLse[row] = l;
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  // D_i = sum_d dO[i,d] * O[i,d]; one warp per row, from shared memory
   for (int row = warp; row < p.TQP; row += 4) {
     float acc = 0.f;
-    if (row < p.Tq) {
-      const bf16* orow = p.o_in + b * p.o_bs + row * p.o_ts + h * HD;
-      const bf16* drow = p.d_o + b * p.do_bs + row * p.do_ts + h * HD;
-      for (int c = lane * 2; c < HD; c += 64) {
-        const float2 a = unpack_bf16(*reinterpret_cast<const uint32_t*>(orow + c));
-        const float2 d = unpack_bf16(*reinterpret_cast<const uint32_t*>(drow + c));
-        acc += a.x * d.x + a.y * d.y;
-      }
+    for (int c = lane * 2; c < HD; c += 64) {
+      const float2 a = unpack_bf16(*reinterpret_cast<const uint32_t*>(sO + row * LD + c));
+      const float2 d = unpack_bf16(*reinterpret_cast<const uint32_t*>(sdO + row * LD + c));
+      acc += a.x * d.x + a.y * d.y;
     }
     acc = warp_sum(acc);
-    if (lane == 0) {
-      sD[row] = acc;
-      float l = INFINITY;
-      if (row < p.Tq) {
-        l = p.lse[(static_cast<long long>(b) * p.H + h) * p.Tq + row];
-        l = (l == -INFINITY) ? INFINITY : l * LOG2E;   // fully masked row: P = 0
-      }
-      sLse[row] = l;
-    }
+    if (lane == 0) sD[row] = acc;
   }
   __syncthreads();
 
@@ -390,6 +399,228 @@ attn_bwd_kernel(const AttnDev p) {
 }
 
 // ------------------------------------------------------------------------------------------
+// backward, staged variant (the default): S and dP are computed ONCE per (query tile, key block)
+// work item, P and dS go through shared memory in bf16 so that every later product can fetch the
+// operand orientation it needs with ldmatrix(.trans):
+//   step 1   items (q-tile, key block): S = Q K^T, dP = dO V^T -> P, dS kept packed in registers
+//   step 2a  P -> smem;  dV[key tile] = P^T dO
+//   step 2b  dS -> same smem;  dK[key tile] = dS^T Q  and  dQ[q-tile, half of hd] = dS K
+// 5 products instead of 7, 8 balanced warps, <= 128 registers, two CTAs per SM.
+// ------------------------------------------------------------------------------------------
+template <int HD, int NT, int MAXI>
+__global__ void __launch_bounds__(256, 2)
+attn_bwd2_kernel(const AttnDev p) {
+  constexpr int LD = HD + 8;
+  constexpr int KB = NT * 8;
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  const int LDP = p.TKP + 8;
+  bf16* sQ = reinterpret_cast<bf16*>(smem_attn);
+  bf16* sdO = sQ + p.TQP * LD;
+  bf16* sK = sdO + p.TQP * LD;
+  bf16* sV = sK + p.TKP * LD;
+  bf16* sPS = sV + p.TKP * LD;                       // [TQP][LDP]; first holds O (for D), then P, then dS
+  const int ps_elems = p.TQP * (LDP > LD ? LDP : LD);
+  float* sBias = reinterpret_cast<float*>(sPS + ps_elems);
+  float* sLse = sBias + p.TKP;
+  float* sD = sLse + p.TQP;
+
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int mi = lane >> 3, r8 = lane & 7;
+
+  load_rows<HD>(sQ, p.q + b * p.q_bs + h * HD, p.q_ts, p.Tq, p.TQP);
+  load_rows<HD>(sdO, p.d_o + b * p.do_bs + h * HD, p.do_ts, p.Tq, p.TQP);
+  load_rows<HD>(sK, p.k + b * p.k_bs + h * HD, p.k_ts, p.Tk, p.TKP);
+  load_rows<HD>(sV, p.v + b * p.v_bs + h * HD, p.v_ts, p.Tk, p.TKP);
+  load_rows<HD>(sPS, p.o_in + b * p.o_bs + h * HD, p.o_ts, p.Tq, p.TQP);   // O, row pitch LD
+  fill_key_bias(sBias, p, b);
+  for (int row = threadIdx.x; row < p.TQP; row += blockDim.x) {
+    float l = INFINITY;
+    if (row < p.Tq) {
+      l = p.lse[(static_cast<long long>(b) * p.H + h) * p.Tq + row];
+      l = (l == -INFINITY) ? INFINITY : l * LOG2E;
+    }
+    sLse[row] = l;
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  for (int row = warp; row < p.TQP; row += 8) {
+    float acc = 0.f;
+    for (int c = lane * 2; c < HD; c += 64) {
+      const float2 a = unpack_bf16(*reinterpret_cast<const uint32_t*>(sPS + row * LD + c));
+      const float2 d = unpack_bf16(*reinterpret_cast<const uint32_t*>(sdO + row * LD + c));
+      acc += a.x * d.x + a.y * d.y;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) sD[row] = acc;
+  }
+  __syncthreads();   // O is dead from here on; sPS is free
+
+  const float sl2 = p.scale * LOG2E;
+  const int n_qt = p.TQP / 16;
+  const int NB = (p.TKP + KB - 1) / KB;
+  const int items = n_qt * NB;
+
+  // ---- step 1
+  uint32_t pP[MAXI][NT][2], pS[MAXI][NT][2];
+#pragma unroll
+  for (int ii = 0; ii < MAXI; ++ii) {
+#pragma unroll
+    for (int j = 0; j < NT; ++j) { pP[ii][j][0] = pP[ii][j][1] = 0u; pS[ii][j][0] = pS[ii][j][1] = 0u; }
+    const int item = warp + ii * 8;
+    if (item < items) {
+      const int mt = item / NB, kb = item % NB;
+      const int row0 = mt * 16, key0 = kb * KB;
+      if (!(p.causal && key0 > row0 + 15)) {
+        const int avail = min(KB, p.TKP - key0);
+        float sacc[NT][4], dp[NT][4];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          sacc[j][0] = sacc[j][1] = sacc[j][2] = sacc[j][3] = 0.f;
+          dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
+        }
+        mma_abt<HD, NT>(sacc, sQ, row0, sK, key0, avail);
+        mma_abt<HD, NT>(dp, sdO, row0, sV, key0, avail);
+        const float lse0 = sLse[row0 + g], lse1 = sLse[row0 + g + 8];
+        const float d0 = sD[row0 + g], d1 = sD[row0 + g + 8];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          float pv[4], ds[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int key = key0 + j * 8 + 2 * t + (e & 1);
+            const int row = row0 + g + (e >> 1) * 8;
+            pv[e] = 0.f; ds[e] = 0.f;
+            if (j * 8 < avail && !(p.causal && key > row)) {
+              pv[e] = exp2f(sacc[j][e] * sl2 + sBias[key] - ((e >> 1) ? lse1 : lse0));
+              ds[e] = pv[e] * (dp[j][e] - ((e >> 1) ? d1 : d0)) * p.scale;
+            }
+          }
+          pP[ii][j][0] = pack_bf16(pv[0], pv[1]); pP[ii][j][1] = pack_bf16(pv[2], pv[3]);
+          pS[ii][j][0] = pack_bf16(ds[0], ds[1]); pS[ii][j][1] = pack_bf16(ds[2], ds[3]);
+        }
+      }
+    }
+  }
+
+  auto stage = [&](const uint32_t (&src)[MAXI][NT][2]) {
+#pragma unroll
+    for (int ii = 0; ii < MAXI; ++ii) {
+      const int item = warp + ii * 8;
+      if (item < items) {
+        const int mt = item / NB, kb = item % NB;
+        const int row0 = mt * 16, key0 = kb * KB;
+        const int avail = min(KB, p.TKP - key0);
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          if (j * 8 < avail) {
+            *reinterpret_cast<uint32_t*>(sPS + (row0 + g) * LDP + key0 + j * 8 + 2 * t) = src[ii][j][0];
+            *reinterpret_cast<uint32_t*>(sPS + (row0 + g + 8) * LDP + key0 + j * 8 + 2 * t) = src[ii][j][1];
+          }
+        }
+      }
+    }
+  };
+
+  // ---- step 2a: dV[key tile] = P^T dO
+  stage(pP);
+  __syncthreads();
+  const int n_kt = p.TKP / 16;
+  for (int kt = warp; kt < n_kt; kt += 8) {
+    float acc[HD / 8][4];
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+    const int qs0 = p.causal ? min(kt, n_qt) : 0;
+    for (int qs = qs0; qs < n_qt; ++qs) {
+      uint32_t a[4];
+      ldsm_x4_t(a, smem_u32(sPS + (qs * 16 + (mi >> 1) * 8 + r8) * LDP + kt * 16 + (mi & 1) * 8));
+#pragma unroll
+      for (int dn = 0; dn < HD / 8; dn += 2) {
+        uint32_t bb[4];
+        ldsm_x4_t(bb, smem_u32(sdO + (qs * 16 + (mi & 1) * 8 + r8) * LD + (dn + (mi >> 1)) * 8));
+        mma16816(acc[dn], a, bb[0], bb[1]);
+        mma16816(acc[dn + 1], a, bb[2], bb[3]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int key = kt * 16 + g + r * 8;
+      if (key < p.Tk) {
+        bf16* vrow = p.dv + b * p.dv_bs + key * p.dv_ts + h * HD;
+#pragma unroll
+        for (int i = 0; i < HD / 8; ++i)
+          *reinterpret_cast<uint32_t*>(vrow + i * 8 + 2 * t) = pack_bf16(acc[i][2 * r], acc[i][2 * r + 1]);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- step 2b: dS -> smem; dK[key tile] = dS^T Q; dQ[q tile, hd half] = dS K
+  stage(pS);
+  __syncthreads();
+  const int n_dq = n_qt * 2;
+  for (int w = warp; w < n_dq + n_kt; w += 8) {
+    if (w < n_dq) {
+      const int mt = w >> 1, half = w & 1;
+      constexpr int NH = HD / 16;                  // n-tiles in one half of the head dim
+      float acc[NH][4];
+#pragma unroll
+      for (int i = 0; i < NH; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+      const int ks_end = p.causal ? min(n_kt, mt + 1) : n_kt;
+      for (int ks = 0; ks < ks_end; ++ks) {
+        uint32_t a[4];
+        ldsm_x4(a, smem_u32(sPS + (mt * 16 + (mi & 1) * 8 + r8) * LDP + ks * 16 + (mi >> 1) * 8));
+#pragma unroll
+        for (int dn = 0; dn < NH; dn += 2) {
+          uint32_t bb[4];
+          ldsm_x4_t(bb, smem_u32(sK + (ks * 16 + (mi & 1) * 8 + r8) * LD + (half * NH + dn + (mi >> 1)) * 8));
+          mma16816(acc[dn], a, bb[0], bb[1]);
+          mma16816(acc[dn + 1], a, bb[2], bb[3]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int row = mt * 16 + g + r * 8;
+        if (row < p.Tq) {
+          bf16* drow = p.dq + b * p.dq_bs + row * p.dq_ts + h * HD + half * (HD / 2);
+#pragma unroll
+          for (int i = 0; i < NH; ++i)
+            *reinterpret_cast<uint32_t*>(drow + i * 8 + 2 * t) = pack_bf16(acc[i][2 * r], acc[i][2 * r + 1]);
+        }
+      }
+    } else {
+      const int kt = w - n_dq;
+      float acc[HD / 8][4];
+#pragma unroll
+      for (int i = 0; i < HD / 8; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+      const int qs0 = p.causal ? min(kt, n_qt) : 0;
+      for (int qs = qs0; qs < n_qt; ++qs) {
+        uint32_t a[4];
+        ldsm_x4_t(a, smem_u32(sPS + (qs * 16 + (mi >> 1) * 8 + r8) * LDP + kt * 16 + (mi & 1) * 8));
+#pragma unroll
+        for (int dn = 0; dn < HD / 8; dn += 2) {
+          uint32_t bb[4];
+          ldsm_x4_t(bb, smem_u32(sQ + (qs * 16 + (mi & 1) * 8 + r8) * LD + (dn + (mi >> 1)) * 8));
+          mma16816(acc[dn], a, bb[0], bb[1]);
+          mma16816(acc[dn + 1], a, bb[2], bb[3]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int key = kt * 16 + g + r * 8;
+        if (key < p.Tk) {
+          bf16* krow = p.dk + b * p.dk_bs + key * p.dk_ts + h * HD;
+#pragma unroll
+          for (int i = 0; i < HD / 8; ++i)
+            *reinterpret_cast<uint32_t*>(krow + i * 8 + 2 * t) = pack_bf16(acc[i][2 * r], acc[i][2 * r + 1]);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------
 static int check_common(const AttnArgs& a) {
@@ -447,6 +678,46 @@ static int launch_bwd(const AttnDev& d, cudaStream_t s) {
   return 0;
 }
 
+template <int HD, int NT, int MAXI>
+static int launch_bwd2(const AttnDev& d, cudaStream_t s) {
+  constexpr int LD = HD + 8;
+  const int LDP = d.TKP + 8;
+  const size_t smem = static_cast<size_t>(2 * d.TQP + 2 * d.TKP) * LD * 2 + static_cast<size_t>(d.TQP) * (LDP > LD ? LDP : LD) * 2 +
+                      (d.TKP + 2 * d.TQP) * sizeof(float) + 16;
+  B200_REQUIRE(smem <= 227 * 1024, "attention bwd: %zu B of shared memory needed (> 227 KB)", smem);
+  static size_t configured = 0;
+  if (smem > configured) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd2_kernel<HD, NT, MAXI>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = smem;
+  }
+  attn_bwd2_kernel<HD, NT, MAXI><<<dim3(d.H, d.B), 256, smem, s>>>(d);
+  note_launch();
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// staged backward when its register-held work items fit (<= 8 warps x MAXI), else the two-phase one
+template <int HD>
+static int dispatch_bwd(const AttnDev& d, cudaStream_t s, int nt_fallback) {
+  static const bool force_v1 = getenv("B200_ATTN_BWD_V1") != nullptr;
+  const int n_qt = d.TQP / 16;
+  if (!force_v1) {
+    if (d.TKP > 96) {
+      const int items = n_qt * ((d.TKP + 47) / 48);
+      if (items <= 16) return launch_bwd2<HD, 6, 2>(d, s);
+      if (items <= 24) return launch_bwd2<HD, 6, 3>(d, s);
+    } else {
+      const int items = n_qt * (d.TKP / 16);
+      if (items <= 16) return launch_bwd2<HD, 2, 2>(d, s);
+      if (items <= 24) return launch_bwd2<HD, 2, 3>(d, s);
+      const int items48 = n_qt * ((d.TKP + 47) / 48);
+      if (items48 <= 16) return launch_bwd2<HD, 6, 2>(d, s);
+      if (items48 <= 24) return launch_bwd2<HD, 6, 3>(d, s);
+    }
+  }
+  return nt_fallback == 8 ? launch_bwd<HD, 8>(d, s) : launch_bwd<HD, 4>(d, s);
+}
+
 int attn_fwd(const AttnArgs& a, cudaStream_t s) {
   if (int rc = check_common(a)) return rc;
   AttnDev d;
@@ -474,10 +745,10 @@ int attn_bwd(const AttnArgs& a, const AttnGrads& gr, cudaStream_t s) {
   d.dk = gr.dk; d.dk_bs = gr.dk_bs; d.dk_ts = gr.dk_ts;
   d.dv = gr.dv; d.dv_bs = gr.dv_bs; d.dv_ts = gr.dv_ts;
   switch (a.hd) {
-    case 32: return launch_bwd<32, 8>(d, s);
-    case 64: return launch_bwd<64, 8>(d, s);
-    case 96: return launch_bwd<96, 4>(d, s);
-    default: return launch_bwd<128, 4>(d, s);
+    case 32: return dispatch_bwd<32>(d, s, 8);
+    case 64: return dispatch_bwd<64>(d, s, 8);
+    case 96: return dispatch_bwd<96>(d, s, 4);
+    default: return dispatch_bwd<128>(d, s, 4);
   }
 }
 

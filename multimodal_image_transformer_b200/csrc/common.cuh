@@ -217,7 +217,7 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, bool a_mn_m
 // ------------------------------------------------------------------ vector global access
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
   uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+  asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                : "l"(p));
   return r;

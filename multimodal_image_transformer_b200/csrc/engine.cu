@@ -10,6 +10,8 @@
 #include "gemm.cuh"
 #include "kernels.cuh"
 #include <math.h>
+#include <stdlib.h>
+#include <initializer_list>
 #include <string>
 #include <vector>
 
@@ -97,6 +99,10 @@ struct b200_engine {
     const uint8_t* mem_pad = nullptr;
     int64_t bytes = 0;
     bool ready = false;
+    // CUDA-graph cache of the whole generation loop (one per (workspace, shape, ids) key)
+    cudaGraphExec_t graph = nullptr;
+    cudaStream_t cap_stream = nullptr;
+    uint64_t graph_key = 0, seen_key = 0;
   } dec;
 };
 
@@ -434,6 +440,52 @@ int decode_hidden(b200_engine* e, const int64_t* tokens, int pos, bf16** x_out, 
   return 0;
 }
 
+uint64_t mix_key(std::initializer_list<uint64_t> v) {
+  uint64_t h = 1469598103934665603ull;
+  for (uint64_t x : v) { h ^= x + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); h *= 1099511628211ull; }
+  return h ? h : 1;
+}
+
+// Runs `body` (which only enqueues work on `s`) either eagerly or as a cached CUDA graph: the first
+// call with a given key runs eagerly (lazy one-time kernel attribute set-up happens there), the
+// second captures + instantiates, later calls replay.  A generation step is ~90 small launches, so
+// replaying removes the host launch cost that otherwise bounds batch-512 decoding.
+template <class Body>
+int run_maybe_graphed(b200_engine* e, uint64_t key, cudaStream_t s, Body body) {
+  auto& d = e->dec;
+  static const bool disabled = getenv("B200_NO_GRAPH") != nullptr;
+  if (disabled) return body(s);
+  if (d.graph && d.graph_key == key) {
+    B200_CHECK_CUDA(cudaGraphLaunch(d.graph, s));
+    return 0;
+  }
+  if (d.seen_key != key) {   // first sighting: eager
+    d.seen_key = key;
+    return body(s);
+  }
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(s, &st);
+  if (st != cudaStreamCaptureStatusNone) return body(s);   // caller is already capturing: just enqueue
+  if (d.graph) { cudaGraphExecDestroy(d.graph); d.graph = nullptr; d.graph_key = 0; }
+  // capture on a private stream (the caller's may be the legacy default stream, which cannot be
+  // captured); nothing executes during capture, the instantiated graph is launched on `s`.
+  if (!d.cap_stream) B200_CHECK_CUDA(cudaStreamCreateWithFlags(&d.cap_stream, cudaStreamNonBlocking));
+  B200_CHECK_CUDA(cudaStreamBeginCapture(d.cap_stream, cudaStreamCaptureModeRelaxed));
+  const int rc = body(d.cap_stream);
+  cudaGraph_t g = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(d.cap_stream, &g);
+  if (rc != 0) { if (g) cudaGraphDestroy(g); return rc; }
+  B200_CHECK_CUDA(ce);
+  cudaGraphExec_t ex = nullptr;
+  const cudaError_t ci = cudaGraphInstantiate(&ex, g, 0);
+  cudaGraphDestroy(g);
+  B200_CHECK_CUDA(ci);
+  d.graph = ex;
+  d.graph_key = key;
+  B200_CHECK_CUDA(cudaGraphLaunch(d.graph, s));
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -486,7 +538,11 @@ int b200_engine_create(const b200_engine_config* cfg, b200_engine** out) {
   return 0;
 }
 
-void b200_engine_destroy(b200_engine* e) { delete e; }
+void b200_engine_destroy(b200_engine* e) {
+  if (e && e->dec.graph) cudaGraphExecDestroy(e->dec.graph);
+  if (e && e->dec.cap_stream) cudaStreamDestroy(e->dec.cap_stream);
+  delete e;
+}
 
 int64_t b200_engine_param_count(const b200_engine* e) { return e ? e->total : -1; }
 int32_t b200_engine_num_params(const b200_engine* e) { return e ? static_cast<int32_t>(e->params.size()) : -1; }
@@ -711,22 +767,46 @@ int b200_engine_generate_greedy(b200_engine* e, int64_t start_id, int64_t end_id
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int R = d.R;
   const long long pad = e->cfg.pad_idx;
-  RC(fill_i64(out_tokens, static_cast<long long>(R) * max_len, pad, s));
-  RC(fill_col_i64(out_tokens, R, max_len, start_id, s));
-  RC(fill_i64(d.cur_tok, R, start_id, s));
-  B200_CHECK_CUDA(cudaMemsetAsync(d.fin[0], 0, R, s));
-  B200_CHECK_CUDA(cudaMemsetAsync(d.n_finished, 0, sizeof(int), s));
-  B200_CHECK_CUDA(cudaMemsetAsync(out_len, 0, sizeof(int) * R, s));   // overwritten below; rows start at length 1
-  for (int pos = 0; pos + 1 < max_len; ++pos) {
-    RC(b200_engine_decode_step(e, d.cur_tok, pos, d.ids, stream));
-    RC(greedy_update(d.ids, d.cur_tok, out_tokens, out_len, d.fin[0], d.n_finished, R, max_len, pos, end_id, pad, s));
-    if (stop_check_interval > 0 && (pos + 1) % stop_check_interval == 0) {
-      int nf = 0;
-      B200_CHECK_CUDA(cudaMemcpyAsync(&nf, d.n_finished, sizeof(int), cudaMemcpyDeviceToHost, s));
-      B200_CHECK_CUDA(cudaStreamSynchronize(s));
-      if (nf >= R) break;
+  int64_t* toks = d.seq[0];          // [R, d.max_len] staging inside the workspace (stable address for the graph)
+  const int ld = d.max_len;
+  auto prologue = [&](cudaStream_t ws) -> int {
+    RC(fill_i64(toks, static_cast<long long>(R) * ld, pad, ws));
+    RC(fill_col_i64(toks, R, ld, start_id, ws));
+    RC(fill_i64(d.cur_tok, R, start_id, ws));
+    B200_CHECK_CUDA(cudaMemsetAsync(d.fin[0], 0, R, ws));
+    B200_CHECK_CUDA(cudaMemsetAsync(d.n_finished, 0, sizeof(int), ws));
+    B200_CHECK_CUDA(cudaMemsetAsync(d.out_len, 0, sizeof(int) * R, ws));
+    return 0;
+  };
+  auto one_step = [&](int pos, cudaStream_t ws) -> int {
+    RC(b200_engine_decode_step(e, d.cur_tok, pos, d.ids, ws));
+    return greedy_update(d.ids, d.cur_tok, toks, d.out_len, d.fin[0], d.n_finished, R, ld, pos, end_id, pad, ws);
+  };
+  if (stop_check_interval > 0) {
+    RC(prologue(s));
+    for (int pos = 0; pos + 1 < max_len; ++pos) {
+      RC(one_step(pos, s));
+      if ((pos + 1) % stop_check_interval == 0) {   // the reference's early exit (model.py:239-240), batched
+        int nf = 0;
+        B200_CHECK_CUDA(cudaMemcpyAsync(&nf, d.n_finished, sizeof(int), cudaMemcpyDeviceToHost, s));
+        B200_CHECK_CUDA(cudaStreamSynchronize(s));
+        if (nf >= R) break;
+      }
     }
+  } else {
+    const uint64_t key = mix_key({reinterpret_cast<uint64_t>(d.kc), static_cast<uint64_t>(R), static_cast<uint64_t>(d.S),
+                                  static_cast<uint64_t>(d.max_len), static_cast<uint64_t>(max_len), static_cast<uint64_t>(start_id),
+                                  static_cast<uint64_t>(end_id), reinterpret_cast<uint64_t>(d.mem_pad), 1ull});
+    RC(run_maybe_graphed(e, key, s, [&](cudaStream_t ws) -> int {
+      RC(prologue(ws));
+      for (int pos = 0; pos + 1 < max_len; ++pos) RC(one_step(pos, ws));
+      return 0;
+    }));
   }
+  B200_CHECK_CUDA(cudaMemcpy2DAsync(out_tokens, static_cast<size_t>(max_len) * sizeof(int64_t), toks,
+                                    static_cast<size_t>(ld) * sizeof(int64_t), static_cast<size_t>(max_len) * sizeof(int64_t),
+                                    R, cudaMemcpyDeviceToDevice, s));
+  B200_CHECK_CUDA(cudaMemcpyAsync(out_len, d.out_len, sizeof(int) * R, cudaMemcpyDeviceToDevice, s));
   return 0;
 }
 
