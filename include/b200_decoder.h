@@ -102,10 +102,12 @@ int b200_embed_bwd(const int64_t* tokens, const void* dx_bf16, float* demb, int3
 /* y = LayerNorm(x) * gamma + beta, eps inside sqrt, biased variance (torch LayerNorm). */
 int b200_layernorm_fwd(const void* x_bf16, const float* gamma, const float* beta, void* y_bf16,
                        float* mean, float* rstd, int32_t rows, int32_t E, float eps, void* stream);
-/* dx (bf16), dgamma/dbeta (fp32, accumulated with atomics: caller zero-fills). */
+/* dx (bf16), dgamma/dbeta (fp32, accumulated with atomics: caller zero-fills).  dxsum (optional,
+ * fp32 [E], accumulated) receives the column sums of dx: the bias gradient of the Linear whose
+ * output (plus residual) this LayerNorm normalised. */
 int b200_layernorm_bwd(const void* dy_bf16, const void* x_bf16, const float* gamma,
                        const float* mean, const float* rstd, void* dx_bf16, float* dgamma,
-                       float* dbeta, int32_t rows, int32_t E, void* stream);
+                       float* dbeta, float* dxsum, int32_t rows, int32_t E, void* stream);
 /* out[n] += sum_m x[m,n]   (bias gradients). x bf16 [M,N]. */
 int b200_colsum(const void* x_bf16, int64_t ldx, float* out, int32_t M, int32_t N, void* stream);
 int b200_cast_f32_to_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);

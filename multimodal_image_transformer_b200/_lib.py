@@ -77,7 +77,7 @@ SIGNATURES = {
     "b200_embed_pe_fwd": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _F, _P]),
     "b200_embed_bwd": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I64, _F, _P]),
     "b200_layernorm_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I32, _F, _P]),
-    "b200_layernorm_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _P]),
+    "b200_layernorm_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _P]),
     "b200_colsum": (C.c_int, [_P, _I64, _P, _I32, _I32, _P]),
     "b200_cast_f32_to_bf16": (C.c_int, [_P, _P, _I64, _P]),
     "b200_cast_bf16_to_f32": (C.c_int, [_P, _P, _I64, _P]),

@@ -133,9 +133,9 @@ int b200_layernorm_fwd(const void* x, const float* gamma, const float* beta, voi
   return layernorm_fwd(CBF(x), gamma, beta, BF(y), mean, rstd, rows, E, eps, S_(stream));
 }
 int b200_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
-                       void* dx, float* dgamma, float* dbeta, int32_t rows, int32_t E, void* stream) {
+                       void* dx, float* dgamma, float* dbeta, float* dxsum, int32_t rows, int32_t E, void* stream) {
   B200_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta, "layernorm_bwd: null argument");
-  return layernorm_bwd(CBF(dy), CBF(x), gamma, mean, rstd, BF(dx), dgamma, dbeta, rows, E, S_(stream));
+  return layernorm_bwd(CBF(dy), CBF(x), gamma, mean, rstd, BF(dx), dgamma, dbeta, dxsum, rows, E, S_(stream));
 }
 int b200_colsum(const void* x, int64_t ldx, float* out, int32_t M, int32_t N, void* stream) {
   B200_REQUIRE(x && out, "colsum: null argument");

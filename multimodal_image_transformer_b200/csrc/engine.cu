@@ -302,18 +302,18 @@ int run_backward(b200_engine* e, bool have_dlogits, float* dmemory, void* const*
     float* g = e->gf;
     // LN3
     bf16* dy3 = spare1;
-    RC(layernorm_bwd(dx, a.y3, e->pf + o.n3_w, a.mean3, a.rstd3, dy3, g + o.n3_w, g + o.n3_b, M, E, s));
-    // FFN
-    RC(linear_wgrad(dy3, E, a.h, F, g + o.l2_w, g + o.l2_b, M, E, F, s));
+    RC(layernorm_bwd(dx, a.y3, e->pf + o.n3_w, a.mean3, a.rstd3, dy3, g + o.n3_w, g + o.n3_b, g + o.l2_b, M, E, s));
+    // FFN (linear2's bias gradient = column sums of dy3, produced by the LayerNorm backward above)
+    RC(linear_wgrad(dy3, E, a.h, F, g + o.l2_w, nullptr, M, E, F, s));
     RC(linear_dgrad(dy3, E, e->ph + o.l2_w, E, F, pl.dh, F, M, nullptr, 0, a.h, F, s));
     RC(linear_wgrad(pl.dh, F, a.x2, E, g + o.l1_w, g + o.l1_b, M, F, E, s));
     bf16* dx2 = spare2;
     RC(linear_dgrad(pl.dh, F, e->ph + o.l1_w, F, E, dx2, E, M, dy3, E, nullptr, 0, s));
     // LN2
     bf16* dy2 = dx;   // dx (grad of layer output) is dead now
-    RC(layernorm_bwd(dx2, a.y2, e->pf + o.n2_w, a.mean2, a.rstd2, dy2, g + o.n2_w, g + o.n2_b, M, E, s));
+    RC(layernorm_bwd(dx2, a.y2, e->pf + o.n2_w, a.mean2, a.rstd2, dy2, g + o.n2_w, g + o.n2_b, g + o.ca_ob, M, E, s));
     // cross-attention
-    RC(linear_wgrad(dy2, E, a.attn_c, E, g + o.ca_ow, g + o.ca_ob, M, E, E, s));
+    RC(linear_wgrad(dy2, E, a.attn_c, E, g + o.ca_ow, nullptr, M, E, E, s));
     RC(linear_dgrad(dy2, E, e->ph + o.ca_ow, E, E, pl.dattn, E, M, nullptr, 0, nullptr, 0, s));
     AttnArgs ca;
     ca.q = a.qc; ca.q_bs = static_cast<long long>(T) * E; ca.q_ts = E;
@@ -339,9 +339,9 @@ int run_backward(b200_engine* e, bool have_dlogits, float* dmemory, void* const*
     RC(linear_dgrad(pl.dqc, E, e->ph + o.ca_w, E, E, dx1, E, M, dy2, E, nullptr, 0, s));
     // LN1
     bf16* dy1 = spare2;   // dx2 is dead
-    RC(layernorm_bwd(dx1, a.y1, e->pf + o.n1_w, a.mean1, a.rstd1, dy1, g + o.n1_w, g + o.n1_b, M, E, s));
+    RC(layernorm_bwd(dx1, a.y1, e->pf + o.n1_w, a.mean1, a.rstd1, dy1, g + o.n1_w, g + o.n1_b, g + o.sa_ob, M, E, s));
     // self-attention
-    RC(linear_wgrad(dy1, E, a.attn_o, E, g + o.sa_ow, g + o.sa_ob, M, E, E, s));
+    RC(linear_wgrad(dy1, E, a.attn_o, E, g + o.sa_ow, nullptr, M, E, E, s));
     RC(linear_dgrad(dy1, E, e->ph + o.sa_ow, E, E, pl.dattn, E, M, nullptr, 0, nullptr, 0, s));
     AttnArgs sa;
     sa.q = a.qkv; sa.k = a.qkv + E; sa.v = a.qkv + 2 * E;

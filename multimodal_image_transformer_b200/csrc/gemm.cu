@@ -19,6 +19,7 @@
 // operand is ever transposed in memory.
 #include "gemm.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace b200 {
 
@@ -36,117 +37,159 @@ struct GemmDev {
   const bf16* residual; long long ldr;
   const bf16* relu_mask; long long ldm;
   int act;
+  int aux_mode;   // 0 none, 1 residual add, 2 relu mask (tile fetched by TMA through tmap_aux)
   const long long* targets; long long ignore_index;
   float* part_max; float* part_sum; float* tgt_logit;
   const float* row_lse; const float* inv_count;
 };
 
-template <int BLOCK_N>
+static constexpr int SLAB_BYTES = BLOCK_M * 128;   // epilogue staging slab: 128 rows x 128 B (64 bf16 / 32 fp32 columns)
+
+// Dynamic shared memory (1024-byte aligned base, at most MAX_SMEM):
+//   [stages x (A tile | B tile)] [2 output slabs] [2 aux slabs, only when a residual / mask is fused]
+//   [2 bias tiles] [barriers].  The stage count is whatever fits: 6 (5 with aux) for the 256-wide pair tile.
+static constexpr int MAX_SMEM = 227 * 1024;
+static constexpr int MAX_STAGES = 8;
+static constexpr int BAR_BYTES = 256;
+
+template <int BLOCK_N, int CL>
 struct SmemLayout {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int B_BYTES = (BLOCK_N / CL) * BLOCK_K * 2;     // pair mode: each CTA stages half of B
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + alignment slack
+  __host__ __device__ static constexpr int epi_bytes(bool aux) { return (aux ? 4 : 2) * SLAB_BYTES + 2 * BLOCK_N * 4; }
+  __host__ __device__ static constexpr int stages(bool aux) {
+    return (MAX_SMEM - epi_bytes(aux) - BAR_BYTES) / STAGE_BYTES > MAX_STAGES ? MAX_STAGES
+                                                                              : (MAX_SMEM - epi_bytes(aux) - BAR_BYTES) / STAGE_BYTES;
+  }
+  __host__ __device__ static constexpr int total(bool aux) { return stages(aux) * STAGE_BYTES + epi_bytes(aux) + BAR_BYTES; }
 };
 
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
+// CL = 1: one CTA per 128 x BLOCK_N tile (cta_group::1).
+// CL = 2: a CTA PAIR (cluster of 2, cta_group::2) per 256 x BLOCK_N tile.  Each CTA stages its own
+//         128 rows of A and HALF of the B tile, the leader's single MMA thread issues 256-row
+//         instructions that read both shared memories and write 128 accumulator lanes into each
+//         CTA's TMEM.  Per CTA and k-block that is 32 KB of operands instead of 48 KB for the same
+//         128 x 256 x 64 MACs: the L2 -> SM operand stream (measured bound of the CL = 1 kernel,
+//         ~38 B/cycle/SM) shrinks by a third and the tensor core reads B from shared memory once per pair.
+template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                    const __grid_constant__ CUtensorMap tmap_b, const GemmDev p) {
-  using L = SmemLayout<BLOCK_N>;
-  constexpr int STAGES = L::STAGES;
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_aux,
+                    const GemmDev p) {
+  using L = SmemLayout<BLOCK_N, CL>;
   constexpr uint32_t TMEM_COLS = ACC_STAGES * BLOCK_N;
+  constexpr int NSH = BLOCK_N / CL;            // B rows (N) staged by this CTA
+  const bool has_aux_smem = p.aux_mode != 0;
+  const int STAGES = L::stages(has_aux_smem);
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();   // 128-byte swizzle atoms need a 1024-byte aligned base
+  const int epi_offset = STAGES * L::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + epi_offset + L::epi_bytes(has_aux_smem));
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tmem_full = empty_bar + MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + ACC_STAGES;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
+  uint64_t* aux_full = tmem_empty + ACC_STAGES;      // [2] residual / mask slabs landed
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(aux_full + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CL > 1) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_d);
+    tma_prefetch_desc(&tmap_aux);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&full_bar[i], CL);    // pair: leader's expect_tx arrive + the peer producer's remote arrive
+      mbar_init(&empty_bar[i], 1);    // one tcgen05.commit arrival (multicast to both CTAs in pair mode)
     }
     for (int i = 0; i < ACC_STAGES; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128);
+      mbar_init(&tmem_empty[i], 128 * CL);   // every epilogue thread of the pair arrives on the leader's
+      mbar_init(&aux_full[i], 1);
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr_smem, TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (CL > 1) { tmem_alloc_pair(tmem_ptr_smem, TMEM_COLS); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_ptr_smem, TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();   // peer barriers must be initialised before any remote arrive
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  const int total_work = p.num_m_tiles * p.num_n_tiles * p.split_k;
+  // work items are enumerated per cluster; both CTAs of a pair walk the same sequence
+  const int num_m_groups = (p.num_m_tiles + CL - 1) / CL;
+  const int total_work = num_m_groups * p.num_n_tiles * p.split_k;
+  const int w_begin = blockIdx.x / CL, w_stride = gridDim.x / CL;
 
   if (warp == 0) {
-    // ============================ TMA producer ============================
+    // ============================ TMA producer (every CTA) ============================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      for (int w = w_begin; w < total_work; w += w_stride) {
         const int split = w % p.split_k;
         const int tile = w / p.split_k;
-        const int m_blk = tile % p.num_m_tiles;
-        const int n_blk = tile / p.num_m_tiles;
+        const int m_blk = (tile % num_m_groups) * CL + static_cast<int>(cta_rank);   // may be a ghost tile (>= num_m_tiles)
+        const int n_blk = tile / num_m_groups;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          if constexpr (CL == 1) {
+            mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          } else {
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], CL * L::STAGE_BYTES);   // both CTAs' bytes land on the leader's barrier
+            else mbar_arrive_remote(&full_bar[stage], 0);
+          }
+          const int n_row0 = n_blk * BLOCK_N + static_cast<int>(cta_rank) * NSH;
+          auto load = [&](void* dst, const CUtensorMap* m, int c0, int c1) {
+            if constexpr (CL == 1) tma_load_2d(dst, m, &full_bar[stage], c0, c1);
+            else tma_load_2d_pair(dst, m, &full_bar[stage], c0, c1);
+          };
           if constexpr (!A_MN) {
-            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+            load(sa, &tmap_a, kb * BLOCK_K, m_blk * BLOCK_M);
           } else {
 #pragma unroll
             for (int j = 0; j < BLOCK_M / 64; ++j)
-              tma_load_2d(sa + j * (BLOCK_K * 128), &tmap_a, &full_bar[stage],
-                          m_blk * BLOCK_M + j * 64, kb * BLOCK_K);
+              load(sa + j * (BLOCK_K * 128), &tmap_a, m_blk * BLOCK_M + j * 64, kb * BLOCK_K);
           }
           if constexpr (!B_MN) {
-            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+            load(sb, &tmap_b, kb * BLOCK_K, n_row0);
           } else {
 #pragma unroll
-            for (int j = 0; j < BLOCK_N / 64; ++j)
-              tma_load_2d(sb + j * (BLOCK_K * 128), &tmap_b, &full_bar[stage],
-                          n_blk * BLOCK_N + j * 64, kb * BLOCK_K);
+            for (int j = 0; j < NSH / 64; ++j)
+              load(sb + j * (BLOCK_K * 128), &tmap_b, n_row0 + j * 64, kb * BLOCK_K);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ============================ MMA issuer ==============================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
+    // ============================ MMA issuer (leader CTA only) ==============================
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M * CL, BLOCK_N, A_MN, B_MN);
+      constexpr uint16_t PAIR_MASK = static_cast<uint16_t>((1u << CL) - 1u);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      for (int w = w_begin; w < total_work; w += w_stride) {
         const int split = w % p.split_k;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
@@ -167,28 +210,65 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                      : make_smem_desc_sw128(sa + k * (UMMA_K * 2), 16, 1024);
             const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
                                      : make_smem_desc_sw128(sb + k * (UMMA_K * 2), 16, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (CL == 1) umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16_pair(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs have read it
+          // frees this smem stage (in both CTAs of a pair) once the MMAs have read it
+          if constexpr (CL == 1) umma_commit(&empty_bar[stage]);
+          else umma_commit_pair(&empty_bar[stage], PAIR_MASK);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete
+        // accumulator complete: publish to the epilogue warps (of both CTAs)
+        if constexpr (CL == 1) umma_commit(&tmem_full[acc]);
+        else umma_commit_pair(&tmem_full[acc], PAIR_MASK);
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp >= 4) {
     // ============================ epilogue ================================
-    const int ew = warp - 4;  // TMEM lane quarter this warp may read
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+    // thread = accumulator row.  Per tile: the bias slice goes to shared memory once (broadcast
+    // reads afterwards); the residual / ReLU-mask tile is fetched slab by slab with TMA (128 rows x
+    // 128 B, double-buffered, prefetched two slabs ahead); results are staged in 128-byte-swizzled
+    // shared memory and written with TMA stores (or TMA reduce-add for split-K / accumulation),
+    // which also clips the M and N tails.
+    const int ew = warp - 4;                      // TMEM lane quarter this warp may read
+    const int et = static_cast<int>(threadIdx.x) - 128;   // 0..127
+    const bool elected = et == 0;
+    uint8_t* sC = smem + epi_offset;
+    uint8_t* sR = sC + 2 * SLAB_BYTES;              // present only when a residual / mask is fused
+    float* sBias = reinterpret_cast<float*>(sC + (has_aux_smem ? 4 : 2) * SLAB_BYTES);
+    constexpr bool STORES = (EPI == EPI_STD || EPI == EPI_CE_BWD);
+    const bool out_f32 = (EPI == EPI_STD) && p.d_fp32;
+    const int slab_cols = out_f32 ? 32 : 64;
+    const int nslabs = BLOCK_N / slab_cols;
+    const bool has_aux = (EPI == EPI_STD) && p.aux_mode != 0;
+    const uint32_t sw = static_cast<uint32_t>(et & 7);          // 128-byte swizzle phase of this row
+    int acc = 0, tile_par = 0;
+    uint32_t acc_phase = 0, aux_phase[2] = {0u, 0u};
+    for (int w = w_begin; w < total_work; w += w_stride) {
       const int split = w % p.split_k;
       const int tile = w / p.split_k;
-      const int m_blk = tile % p.num_m_tiles;
-      const int n_blk = tile / p.num_m_tiles;
-      const int row = m_blk * BLOCK_M + ew * 32 + lane;
+      const int m_blk = (tile % num_m_groups) * CL + static_cast<int>(cta_rank);
+      const int n_blk = tile / num_m_groups;
+      const int m0 = m_blk * BLOCK_M;
+      const int row = m0 + et;
       const bool row_ok = row < p.M;
       const int n0 = n_blk * BLOCK_N;
+      const bool tile_live = m0 < p.M;             // ghost tiles of an odd pair do nothing but drain TMEM
+
+      float* bias_s = sBias + tile_par * BLOCK_N;
+      for (int i = et; i < BLOCK_N; i += 128)
+        bias_s[i] = (p.bias != nullptr && split == 0 && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+      if (has_aux && elected && tile_live) {
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          if (sl < nslabs && n0 + sl * 64 < p.N) {
+            mbar_arrive_expect_tx(&aux_full[sl], SLAB_BYTES);
+            tma_load_2d(sR + sl * SLAB_BYTES, &tmap_aux, &aux_full[sl], n0 + sl * 64, m0);
+          }
+        }
+      }
+      named_barrier_sync(1, 128);                  // bias tile visible to all epilogue threads
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -210,154 +290,149 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
 
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        const int col0 = n0 + c * 32;
-        uint32_t r[32];
-        tmem_ld_32x32(t_row + c * 32, r);  // warp-collective: executed by all lanes
-        // issue the global loads this chunk needs while the TMEM load is in flight
-        uint4 res[4], msk[4];
-        if constexpr (EPI == EPI_STD) {
-          if (p.residual != nullptr) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              if (row_ok && col0 + g * 8 < p.N)
-                res[g] = ldg_nc_v4(p.residual + static_cast<long long>(row) * p.ldr + col0 + g * 8);
-          }
-          if (p.relu_mask != nullptr) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              if (row_ok && col0 + g * 8 < p.N)
-                msk[g] = ldg_nc_v4(p.relu_mask + static_cast<long long>(row) * p.ldm + col0 + g * 8);
-          }
-        }
-        tmem_ld_wait();
-        if (col0 >= p.N) continue;  // warp-uniform
+      for (int slab = 0; slab < nslabs; ++slab) {
+        const int b = slab & 1;
+        const int scol0 = n0 + slab * slab_cols;
+        const bool slab_live = tile_live && scol0 < p.N && p.act != 99;   // warp-uniform (act 99: diagnostic, mainloop only)
+        uint8_t* sCb = sC + b * SLAB_BYTES;
+        const uint8_t* sRb = sR + b * SLAB_BYTES;
+        if constexpr (STORES) named_barrier_sync(2, 128);   // the TMA store that last read sC[b] has drained (see below)
 
-        float v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        if (p.bias != nullptr && split == 0) {
+        for (int half = 0; half < 2; ++half) {
+          if (half == 1 && out_f32) break;        // fp32 output: one 32-column chunk per slab
+          const int c = out_f32 ? slab : slab * 2 + half;     // 32-column chunk index within the tile
+          const int col0 = n0 + c * 32;
+          uint32_t r[32];
+          tmem_ld_32x32(t_row + c * 32, r);       // warp-collective: executed by all lanes
+          tmem_ld_wait();
+          if (slab == nslabs - 1 && (half == 1 || out_f32)) {
+            // last TMEM read of this tile is complete: hand the accumulator stage back to the MMA thread
+            tc_fence_before();
+            if constexpr (CL == 1) mbar_arrive(&tmem_empty[acc]);
+            else mbar_arrive_remote(&tmem_empty[acc], 0);
+          }
+          if (!slab_live || col0 >= p.N) continue;
+
+          float v[32];
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
-            if (col0 + g * 4 < p.N) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + g);
-              v[g * 4 + 0] += b4.x; v[g * 4 + 1] += b4.y; v[g * 4 + 2] += b4.z; v[g * 4 + 3] += b4.w;
-            }
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + g * 4);
+            v[g * 4 + 0] = __uint_as_float(r[g * 4 + 0]) + b4.x;
+            v[g * 4 + 1] = __uint_as_float(r[g * 4 + 1]) + b4.y;
+            v[g * 4 + 2] = __uint_as_float(r[g * 4 + 2]) + b4.z;
+            v[g * 4 + 3] = __uint_as_float(r[g * 4 + 3]) + b4.w;
           }
-        }
 
-        if constexpr (EPI == EPI_STD) {
-          if (p.act == 1) {
+          if constexpr (EPI == EPI_STD) {
+            if (p.act == 1) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-          } else if (p.act == 2) {
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            } else if (p.act == 2) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-          }
-          if (p.relu_mask != nullptr) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              if (row_ok && col0 + g * 8 < p.N) {
-                const uint32_t m4[4] = {msk[g].x, msk[g].y, msk[g].z, msk[g].w};
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const float2 f = unpack_bf16(m4[q]);
-                  if (!(f.x > 0.f)) v[g * 8 + q * 2] = 0.f;
-                  if (!(f.y > 0.f)) v[g * 8 + q * 2 + 1] = 0.f;
-                }
-              }
+              for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
             }
-          }
-          if (p.residual != nullptr) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              if (row_ok && col0 + g * 8 < p.N) {
-                const uint32_t r4[4] = {res[g].x, res[g].y, res[g].z, res[g].w};
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const float2 f = unpack_bf16(r4[q]);
-                  v[g * 8 + q * 2] += f.x;
-                  v[g * 8 + q * 2 + 1] += f.y;
-                }
+            if (has_aux) {
+              if (half == 0) {                    // slab b of the aux tile has landed
+                mbar_wait(&aux_full[b], aux_phase[b]);
+                aux_phase[b] ^= 1u;
               }
-            }
-          }
-          if (row_ok) {
-            if (!p.d_fp32) {
-              bf16* drow = reinterpret_cast<bf16*>(p.D) + static_cast<long long>(row) * p.ldd + col0;
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
-                if (col0 + g * 8 < p.N) {
-                  uint4 o;
-                  o.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
-                  o.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
-                  o.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
-                  o.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
-                  *reinterpret_cast<uint4*>(drow + g * 8) = o;
-                }
-              }
-            } else {
-              float* drow = reinterpret_cast<float*>(p.D) + static_cast<long long>(row) * p.ldd + col0;
+                const uint32_t u = static_cast<uint32_t>(half * 4 + g);      // 16-byte unit within the 128-byte row
+                const uint4 x = *reinterpret_cast<const uint4*>(sRb + et * 128 + ((u ^ sw) << 4));
+                const uint32_t x4[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                if (col0 + g * 4 < p.N) {
-                  if (p.accumulate) {
-                    red_add_v4_f32(drow + g * 4, v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+                for (int q = 0; q < 4; ++q) {
+                  const float2 f = unpack_bf16(x4[q]);
+                  if (p.aux_mode == 1) {
+                    v[g * 8 + q * 2] += f.x;
+                    v[g * 8 + q * 2 + 1] += f.y;
                   } else {
-                    *reinterpret_cast<float4*>(drow + g * 4) =
-                        make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+                    if (!(f.x > 0.f)) v[g * 8 + q * 2] = 0.f;
+                    if (!(f.y > 0.f)) v[g * 8 + q * 2 + 1] = 0.f;
                   }
                 }
               }
             }
-          }
-        } else if constexpr (EPI == EPI_CE_FWD) {
-          // online softmax statistics of this row over the tile's valid columns
-          float cmax = -INFINITY;
+            if (!out_f32) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (col0 + i < p.N) cmax = fmaxf(cmax, v[i]);
-          const float new_max = fmaxf(run_max, cmax);
-          float s = 0.f;
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (col0 + i < p.N) s += __expf(v[i] - new_max);
-          run_sum = run_sum * __expf(run_max - new_max) + s;
-          run_max = new_max;
-          const long long rel = tgt - col0;
-          if (rel >= 0 && rel < 32) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i == rel) tgt_val = v[i];
-          }
-        } else if constexpr (EPI == EPI_CE_BWD) {
-          if (row_ok) {
-            bf16* drow = reinterpret_cast<bf16*>(p.D) + static_cast<long long>(row) * p.ldd + col0;
-            const long long rel = tgt - col0;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float g = __expf(v[i] - lse);
-              if (i == rel) g -= 1.f;
-              v[i] = g * gscale;
-            }
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              if (col0 + g * 8 < p.N) {
+              for (int g = 0; g < 4; ++g) {
                 uint4 o;
                 o.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
                 o.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
                 o.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
                 o.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
-                *reinterpret_cast<uint4*>(drow + g * 8) = o;
+                const uint32_t u = static_cast<uint32_t>(half * 4 + g);
+                *reinterpret_cast<uint4*>(sCb + et * 128 + ((u ^ sw) << 4)) = o;
+              }
+            } else {
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                *reinterpret_cast<float4*>(sCb + et * 128 + ((static_cast<uint32_t>(g) ^ sw) << 4)) =
+                    make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+            }
+          } else if constexpr (EPI == EPI_CE_FWD) {
+            // online softmax statistics of this row over the tile's valid columns
+            float cmax = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < p.N) cmax = fmaxf(cmax, v[i]);
+            const float new_max = fmaxf(run_max, cmax);
+            float sacc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < p.N) sacc += __expf(v[i] - new_max);
+            run_sum = run_sum * __expf(run_max - new_max) + sacc;
+            run_max = new_max;
+            const long long rel = tgt - col0;
+            if (rel >= 0 && rel < 32) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i == rel) tgt_val = v[i];
+            }
+          } else if constexpr (EPI == EPI_CE_BWD) {
+            const long long rel = tgt - col0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float gq = __expf(v[i] - lse);
+              if (i == rel) gq -= 1.f;
+              v[i] = gq * gscale;
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 o;
+              o.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
+              o.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
+              o.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
+              o.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
+              const uint32_t u = static_cast<uint32_t>(half * 4 + g);
+              *reinterpret_cast<uint4*>(sCb + et * 128 + ((u ^ sw) << 4)) = o;
+            }
+          } else {  // EPI_ARGMAX: first index of the maximum (torch.argmax tie rule)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (col0 + i < p.N && v[i] > run_max) {
+                run_max = v[i];
+                best_idx = col0 + i;
               }
             }
           }
-        } else {  // EPI_ARGMAX: first index of the maximum (torch.argmax tie rule)
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (col0 + i < p.N && v[i] > run_max) {
-              run_max = v[i];
-              best_idx = col0 + i;
+        }
+
+        if constexpr (STORES) {
+          fence_proxy_async();                     // staging writes -> visible to the TMA engine
+          named_barrier_sync(3, 128);              // whole slab staged; everyone is done reading sR[b]
+          if (elected) {
+            if (slab_live) {
+              if (EPI == EPI_STD && p.accumulate) tma_reduce_add_2d(&tmap_d, sCb, scol0, m0);
+              else tma_store_2d(&tmap_d, sCb, scol0, m0);
+            }
+            bulk_commit();
+            bulk_wait_read<1>();                   // the store issued from the OTHER buffer has finished reading it
+            if (has_aux && tile_live && slab + 2 < nslabs && n0 + (slab + 2) * 64 < p.N) {
+              mbar_arrive_expect_tx(&aux_full[b], SLAB_BYTES);
+              tma_load_2d(sR + b * SLAB_BYTES, &tmap_aux, &aux_full[b], n0 + (slab + 2) * 64, m0);
             }
           }
         }
@@ -377,18 +452,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           p.part_sum[o] = __int_as_float(best_idx);
         }
       }
-
-      tc_fence_before();
-      mbar_arrive(&tmem_empty[acc]);
+      tile_par ^= 1;
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
+    if (STORES && elected) bulk_wait_all();        // shared memory must outlive the asynchronous stores
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();   // the pair shares shared memory, TMEM and barriers until here
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (CL > 1) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -413,8 +489,8 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
-                      uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
+static int make_tmap_2d(CUtensorMap* out, CUtensorMapDataType dt, const void* base, uint64_t inner, uint64_t outer,
+                        uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
   PFN_encodeTiled enc = get_encode_fn();
   B200_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
   B200_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer not 16-byte aligned");
@@ -424,13 +500,20 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64
   cuuint64_t strides[1] = {outer_stride_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
-                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   B200_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (inner %llu outer %llu pitch %llu box %u x %u)",
                (int)r, (unsigned long long)inner, (unsigned long long)outer,
                (unsigned long long)outer_stride_bytes, box_inner, box_outer);
   return 0;
+}
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
+                      uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
+  return make_tmap_2d(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, inner, outer, outer_stride_bytes, box_inner, box_outer);
+}
+int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
+                     uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
+  return make_tmap_2d(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, inner, outer, outer_stride_bytes, box_inner, box_outer);
 }
 
 int device_sm_count() {
@@ -446,19 +529,35 @@ int device_sm_count() {
 
 int gemm_num_n_tiles(int N, int block_n) { return (N + block_n - 1) / block_n; }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
-static int launch_instance(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& d, int grid,
-                           cudaStream_t stream) {
-  auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, EPI>;
+template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, int CL>
+static int launch_instance(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td,
+                           const CUtensorMap& tx, const GemmDev& d, int grid, cudaStream_t stream) {
+  auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, EPI, CL>;
   static bool configured = false;
-  constexpr int smem = SmemLayout<BLOCK_N>::TOTAL;
+  const int smem = SmemLayout<BLOCK_N, CL>::total(d.aux_mode != 0);
   if (!configured) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
     configured = true;
   }
   const bool prof = gemm_profile_enabled();
   if (prof) gemm_profile_record(stream, true, 2.0 * d.M * static_cast<double>(d.N) * d.K);
-  kern<<<grid, NUM_THREADS, smem, stream>>>(ta, tb, d);
+  if constexpr (CL == 1) {
+    kern<<<grid, NUM_THREADS, smem, stream>>>(ta, tb, td, tx, d);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B200_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, td, tx, d));
+  }
   if (prof) gemm_profile_record(stream, false, 0.0);
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
@@ -537,19 +636,45 @@ int gemm_launch(const GemmProblem& q, cudaStream_t stream, int* n_tiles_out) {
   d.row_lse = q.row_lse; d.inv_count = q.inv_count;
   if (n_tiles_out) *n_tiles_out = d.num_n_tiles;
 
+  // cluster of two CTAs sharing the B tile through TMA multicast whenever there are >= 2 M tiles
+  static const bool no_cluster = getenv("B200_GEMM_NO_CLUSTER") != nullptr;
+  const int cl = (!no_cluster && d.num_m_tiles >= 2 && sms >= 2) ? 2 : 1;
+
   CUtensorMap ta, tb;
   int rc;
   if (!q.a_mn) rc = make_tmap_2d_bf16(&ta, q.A, q.K, q.M, q.lda * 2, BLOCK_K, BLOCK_M);
   else         rc = make_tmap_2d_bf16(&ta, q.A, q.M, q.K, q.lda * 2, 64, BLOCK_K);
   if (rc) return rc;
-  if (!q.b_mn) rc = make_tmap_2d_bf16(&tb, q.B, q.K, q.N, q.ldb * 2, BLOCK_K, block_n);
+  if (!q.b_mn) rc = make_tmap_2d_bf16(&tb, q.B, q.K, q.N, q.ldb * 2, BLOCK_K, block_n / cl);
   else         rc = make_tmap_2d_bf16(&tb, q.B, q.N, q.K, q.ldb * 2, 64, BLOCK_K);
   if (rc) return rc;
+  // output and residual / mask tiles travel through 128-row x 128-byte TMA boxes
+  CUtensorMap td = ta, tx = ta;
+  if (q.epi == EPI_STD || q.epi == EPI_CE_BWD) {
+    if (q.d_fp32) rc = make_tmap_2d_f32(&td, q.D, q.N, q.M, q.ldd * 4, 32, BLOCK_M);
+    else          rc = make_tmap_2d_bf16(&td, q.D, q.N, q.M, q.ldd * 2, 64, BLOCK_M);
+    if (rc) return rc;
+  }
+  d.aux_mode = 0;
+  if (q.epi == EPI_STD && (q.residual || q.relu_mask)) {
+    B200_REQUIRE(!(q.residual && q.relu_mask), "gemm: residual and relu_mask cannot be combined in one launch");
+    B200_REQUIRE(!q.d_fp32, "gemm: residual / relu_mask need a bf16 output");
+    const bf16* aux = q.residual ? q.residual : q.relu_mask;
+    const long long lda_x = q.residual ? q.ldr : q.ldm;
+    rc = make_tmap_2d_bf16(&tx, aux, q.N, q.M, lda_x * 2, 64, BLOCK_M);
+    if (rc) return rc;
+    d.aux_mode = q.residual ? 1 : 2;
+  }
 
-  const long long work = static_cast<long long>(d.num_m_tiles) * d.num_n_tiles * d.split_k;
-  const int grid = static_cast<int>(work < sms ? work : sms);
+  const long long work = static_cast<long long>((d.num_m_tiles + cl - 1) / cl) * d.num_n_tiles * d.split_k;
+  const long long slots = sms / cl;
+  const int grid = static_cast<int>(work < slots ? work : slots) * cl;
 
-#define B200_GEMM_CASE(BN, AMN, BMN, EP) return launch_instance<BN, AMN, BMN, EP>(ta, tb, d, grid, stream)
+#define B200_GEMM_CASE(BN, AMN, BMN, EP)                                                  \
+  do {                                                                                    \
+    if (cl == 2) return launch_instance<BN, AMN, BMN, EP, 2>(ta, tb, td, tx, d, grid, stream);    \
+    return launch_instance<BN, AMN, BMN, EP, 1>(ta, tb, td, tx, d, grid, stream);                 \
+  } while (0)
   if (q.epi == EPI_CE_FWD) B200_GEMM_CASE(256, false, false, EPI_CE_FWD);
   if (q.epi == EPI_CE_BWD) B200_GEMM_CASE(256, false, false, EPI_CE_BWD);
   if (q.epi == EPI_ARGMAX) B200_GEMM_CASE(128, false, false, EPI_ARGMAX);

@@ -154,24 +154,28 @@ int layernorm_fwd(const bf16* x, const float* gamma, const float* beta, bf16* y,
   return 0;
 }
 
-// dx = rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*gamma;  dgamma += dy*xhat, dbeta += dy.
-// Each warp walks rows with a grid stride keeping its column slice of dgamma/dbeta in registers;
-// the 4 warps of a block combine through shared memory and issue one atomic per column.
+// dx = rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*gamma;  dgamma += dy*xhat, dbeta += dy,
+// and optionally dxsum += dx (the bias gradient of the Linear whose output fed this LayerNorm, so
+// that no separate column-sum pass over dx is needed).  Each warp walks rows with a grid stride,
+// two rows per iteration (both rows' loads in flight together), keeping its column slice of the
+// three column reductions in registers; the 4 warps of a block combine through shared memory and
+// issue one atomic per column.
 template <int NV>
 __global__ void __launch_bounds__(128)
 layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                      const float* __restrict__ gamma, const float* __restrict__ mean,
                      const float* __restrict__ rstd, bf16* __restrict__ dx,
-                     float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int E) {
-  extern __shared__ float sm_red[];  // [2][4][E]
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum,
+                     int rows, int E) {
+  extern __shared__ float sm_red[];  // [3][4][E]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = E >> 3;
-  float gam[NV][8], dg[NV][8], db[NV][8];
+  float gam[NV][8], dg[NV][8], db[NV][8], dsx[NV][8];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int vi = lane + i * 32;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { dg[i][j] = 0.f; db[i][j] = 0.f; gam[i][j] = 0.f; }
+    for (int j = 0; j < 8; ++j) { dg[i][j] = 0.f; db[i][j] = 0.f; dsx[i][j] = 0.f; gam[i][j] = 0.f; }
     if (vi < nvec) {
       const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
       const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8) + 1);
@@ -179,45 +183,70 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
       gam[i][4] = g1.x; gam[i][5] = g1.y; gam[i][6] = g1.z; gam[i][7] = g1.w;
     }
   }
-  for (int row = blockIdx.x * 4 + warp; row < rows; row += gridDim.x * 4) {
-    const float mu = mean[row], rs = rstd[row];
-    const bf16* xr = x + static_cast<long long>(row) * E;
-    const bf16* dyr = dy + static_cast<long long>(row) * E;
-    float xh[NV][8], g[NV][8];
-    float s1 = 0.f, s2 = 0.f;
+  const int stride = gridDim.x * 4;
+  for (int row0 = blockIdx.x * 4 + warp; row0 < rows; row0 += 2 * stride) {
+    uint4 xr[2][NV], dr[2][NV];
+    float mu[2], rs[2];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int vi = lane + i * 32;
-      if (vi < nvec) {
-        float xv[8], dv[8];
-        unpack8(ldg_nc_v4(xr + vi * 8), xv);
-        unpack8(ldg_nc_v4(dyr + vi * 8), dv);
+    for (int q = 0; q < 2; ++q) {
+      const int row = row0 + q * stride;
+      const bool ok = row < rows;
+      mu[q] = ok ? mean[row] : 0.f;
+      rs[q] = ok ? rstd[row] : 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          xh[i][j] = (xv[j] - mu) * rs;
-          g[i][j] = dv[j] * gam[i][j];
-          s1 += g[i][j];
-          s2 += g[i][j] * xh[i][j];
-          dg[i][j] += dv[j] * xh[i][j];
-          db[i][j] += dv[j];
+      for (int i = 0; i < NV; ++i) {
+        const int vi = lane + i * 32;
+        xr[q][i] = make_uint4(0u, 0u, 0u, 0u);
+        dr[q][i] = make_uint4(0u, 0u, 0u, 0u);
+        if (ok && vi < nvec) {
+          xr[q][i] = ldg_nc_v4(x + static_cast<long long>(row) * E + vi * 8);
+          dr[q][i] = ldg_nc_v4(dy + static_cast<long long>(row) * E + vi * 8);
         }
       }
     }
-    const float c1 = warp_sum(s1) / E, c2 = warp_sum(s2) / E;
-    bf16* dxr = dx + static_cast<long long>(row) * E;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int vi = lane + i * 32;
-      if (vi < nvec) {
-        float o[8];
+    for (int q = 0; q < 2; ++q) {
+      const int row = row0 + q * stride;
+      if (row >= rows) break;   // warp-uniform
+      float xh[NV][8], g[NV][8];
+      float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rs * (g[i][j] - c1 - xh[i][j] * c2);
-        *reinterpret_cast<uint4*>(dxr + vi * 8) = pack8(o);
+      for (int i = 0; i < NV; ++i) {
+        if (lane + i * 32 < nvec) {
+          float xv[8], dv[8];
+          unpack8(xr[q][i], xv);
+          unpack8(dr[q][i], dv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            xh[i][j] = (xv[j] - mu[q]) * rs[q];
+            g[i][j] = dv[j] * gam[i][j];
+            s1 += g[i][j];
+            s2 += g[i][j] * xh[i][j];
+            dg[i][j] += dv[j] * xh[i][j];
+            db[i][j] += dv[j];
+          }
+        }
+      }
+      const float c1 = warp_sum(s1) / E, c2 = warp_sum(s2) / E;
+      bf16* dxr = dx + static_cast<long long>(row) * E;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int vi = lane + i * 32;
+        if (vi < nvec) {
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            o[j] = rs[q] * (g[i][j] - c1 - xh[i][j] * c2);
+            dsx[i][j] += o[j];
+          }
+          *reinterpret_cast<uint4*>(dxr + vi * 8) = pack8(o);
+        }
       }
     }
   }
   float* sg = sm_red;
   float* sb = sm_red + 4 * E;
+  float* sx = sm_red + 8 * E;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int vi = lane + i * 32;
@@ -226,36 +255,36 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
       for (int j = 0; j < 8; ++j) {
         sg[warp * E + vi * 8 + j] = dg[i][j];
         sb[warp * E + vi * 8 + j] = db[i][j];
+        sx[warp * E + vi * 8 + j] = dsx[i][j];
       }
     }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < E; c += blockDim.x) {
-    const float a = sg[c] + sg[E + c] + sg[2 * E + c] + sg[3 * E + c];
-    const float b = sb[c] + sb[E + c] + sb[2 * E + c] + sb[3 * E + c];
-    atomicAdd(dgamma + c, a);
-    atomicAdd(dbeta + c, b);
+    atomicAdd(dgamma + c, sg[c] + sg[E + c] + sg[2 * E + c] + sg[3 * E + c]);
+    atomicAdd(dbeta + c, sb[c] + sb[E + c] + sb[2 * E + c] + sb[3 * E + c]);
+    if (dxsum) atomicAdd(dxsum + c, sx[c] + sx[E + c] + sx[2 * E + c] + sx[3 * E + c]);
   }
 }
 
 int layernorm_bwd(const bf16* dy, const bf16* x, const float* gamma, const float* mean,
-                  const float* rstd, bf16* dx, float* dgamma, float* dbeta, int rows, int E,
+                  const float* rstd, bf16* dx, float* dgamma, float* dbeta, float* dxsum, int rows, int E,
                   cudaStream_t s) {
   B200_REQUIRE(E % 8 == 0 && E <= LN_MAXV * 256, "layernorm_bwd: E (%d) must be a multiple of 8 and <= %d", E, LN_MAXV * 256);
   if (rows == 0) return 0;
-  int blocks = cdiv(rows, 4);
-  const int cap = 2 * 148;
+  int blocks = cdiv(rows, 8);          // two rows per warp iteration
+  const int cap = 4 * 148;
   if (blocks > cap) blocks = cap;
-  const size_t smem = static_cast<size_t>(8) * E * sizeof(float);
+  const size_t smem = static_cast<size_t>(12) * E * sizeof(float);
   const int nv = cdiv(E / 8, 32);
 #define B200_LN_BWD(NV)                                                                              \
   do {                                                                                               \
     static bool configured = false;                                                                  \
     if (!configured) {                                                                               \
-      B200_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * NV * 256 * 4)); \
+      B200_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * NV * 256 * 4)); \
       configured = true;                                                                             \
     }                                                                                                \
-    layernorm_bwd_kernel<NV><<<blocks, 128, smem, s>>>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, rows, E); \
+    layernorm_bwd_kernel<NV><<<blocks, 128, smem, s>>>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, dxsum, rows, E); \
   } while (0)
   if (nv <= 1) B200_LN_BWD(1); else if (nv == 2) B200_LN_BWD(2); else if (nv == 3) B200_LN_BWD(3);
   else if (nv == 4) B200_LN_BWD(4); else B200_LN_BWD(8);

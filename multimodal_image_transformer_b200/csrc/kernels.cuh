@@ -12,8 +12,9 @@ int embed_bwd(const int64_t* tokens, const bf16* dx, float* demb, int B, int T, 
               long long pad_idx, float scale, cudaStream_t s);
 int layernorm_fwd(const bf16* x, const float* gamma, const float* beta, bf16* y, float* mean,
                   float* rstd, int rows, int E, float eps, cudaStream_t s);
+// dxsum (optional): += column sums of dx, i.e. the bias gradient of the Linear feeding this LayerNorm
 int layernorm_bwd(const bf16* dy, const bf16* x, const float* gamma, const float* mean,
-                  const float* rstd, bf16* dx, float* dgamma, float* dbeta, int rows, int E,
+                  const float* rstd, bf16* dx, float* dgamma, float* dbeta, float* dxsum, int rows, int E,
                   cudaStream_t s);
 int colsum(const bf16* x, long long ldx, float* out, int M, int N, cudaStream_t s);
 int cast_f32_to_bf16(const float* src, bf16* dst, long long n, cudaStream_t s);

@@ -42,9 +42,9 @@ def test_ln():
         xd, dyd = x.to(dev), dy.to(dev)
         yd = torch.empty_like(xd); mean = torch.empty(rows, device=dev); rstd = torch.empty(rows, device=dev)
         L.check(lib.b200_layernorm_fwd(L.ptr(xd), L.ptr(gamma.to(dev)), L.ptr(beta.to(dev)), L.ptr(yd), L.ptr(mean), L.ptr(rstd), rows, E, 1e-5, L.cur_stream()))
-        dxd = torch.empty_like(xd); dg = torch.zeros(E, device=dev); db = torch.zeros(E, device=dev)
+        dxd = torch.empty_like(xd); dg = torch.zeros(E, device=dev); db = torch.zeros(E, device=dev); dsum = torch.zeros(E, device=dev)
         gd = gamma.to(dev)
-        L.check(lib.b200_layernorm_bwd(L.ptr(dyd), L.ptr(xd), L.ptr(gd), L.ptr(mean), L.ptr(rstd), L.ptr(dxd), L.ptr(dg), L.ptr(db), rows, E, L.cur_stream()))
+        L.check(lib.b200_layernorm_bwd(L.ptr(dyd), L.ptr(xd), L.ptr(gd), L.ptr(mean), L.ptr(rstd), L.ptr(dxd), L.ptr(dg), L.ptr(db), L.ptr(dsum), rows, E, L.cur_stream()))
         torch.cuda.synchronize()
         ok &= show(f"ln fwd {rows}x{E}", yd, y.detach(), 1e-2)
         ok &= show(f"ln bwd dx {rows}x{E}", dxd, xf.grad, 1e-2)

@@ -128,6 +128,20 @@ def main():
                 e1.record(); torch.cuda.synchronize()
                 ms = e0.elapsed_time(e1) / 10
                 print(f"   cuBLAS same shape: {ms*1e3:.1f} us  {2*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
+    if "noepi" in which:
+        for (M, N, K) in [(12032, 3072, 768), (12032, 768, 768), (12032, 768, 3072), (12032, 2304, 768)]:
+            A = torch.randn(M, K, device=dev).bfloat16(); B = torch.randn(N, K, device=dev).bfloat16()
+            D = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+            bias = torch.randn(N, device=dev); res = torch.randn(M, N, device=dev).bfloat16()
+            for tag, kw in [("plain", {}), ("bias", dict(bias=bias)), ("bias+res", dict(bias=bias, residual=res)), ("noepi", dict(act=99))]:
+                for _ in range(3): run_gemm(A, B, M, N, K, 0, 0, D=D, block_n=256, **kw)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(10): run_gemm(A, B, M, N, K, 0, 0, D=D, block_n=256, **kw)
+                e1.record(); torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 10
+                print(f"M{M} N{N} K{K} {tag:9s}: {ms*1e3:.1f} us {2*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
     print("ALL OK" if ok else "SOME FAILED")
 
 
