@@ -174,7 +174,7 @@ def run_b200(args):
     from multimodal_image_transformer_b200 import _lib as L
     from multimodal_image_transformer_b200.decoder import TransformerDecoder
     from multimodal_image_transformer_b200.dp import DataParallel
-    from multimodal_image_transformer_b200.train import B200AdamW, fused_train_step
+    from multimodal_image_transformer_b200.train import B200AdamW, GraphedTrainStep, fused_train_step
 
     rank, local, world = DataParallel.init_from_env("nccl")
     torch.cuda.set_device(local)
@@ -232,7 +232,29 @@ def run_b200(args):
                 ms_i = sum(pl_ms[k * per + i] for k in range(args.steps)) / args.steps
                 f.write(f"{i},{pl_fl[i] / 1e9:.2f},{ms_i * 1e3:.1f},{pl_fl[i] / 1e9 / max(ms_i, 1e-9):.1f}\n")
     clocks = sampler.stop() if rank == 0 else None
-    ms = e0.elapsed_time(e1) / args.steps
+    ms_eager = e0.elapsed_time(e1) / args.steps
+    use_graph = not args.no_graph
+    graphed = []
+    if use_graph:
+        # same step, replayed from a CUDA graph (train.GraphedTrainStep): one graph per resident batch
+        graphed = [GraphedTrainStep(dec, opt, 0, 5.0, warmup=0, dp=dp) for _ in range(2)]
+        for gi, gs in enumerate(graphed):
+            tok, tgt, mem = dev_batches[gi]
+            out = gs(mem, tok, tgt)             # captures, then replays once
+        for i in range(2):
+            tok, tgt, mem = dev_batches[i % 2]
+            out = graphed[i % 2](mem, tok, tgt)
+        barrier()
+        launches0 = lib.b200_launch_count()
+        e0.record()
+        for i in range(args.steps):
+            tok, tgt, mem = dev_batches[i % 2]
+            out = graphed[i % 2](mem, tok, tgt)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / args.steps
+    else:
+        ms = ms_eager
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -257,6 +279,8 @@ def run_b200(args):
                 d.copy_(h, non_blocking=True)
             ready[s].record(copy_stream)
 
+    e2e_graphs = [GraphedTrainStep(dec, opt, 0, 5.0, warmup=0, dp=dp) for _ in range(2)] if use_graph else None
+
     def e2e_loop(n):
         losses = []
         for s in range(2):
@@ -267,7 +291,11 @@ def run_b200(args):
                 upload(i + 1)                     # next batch streams in while this one computes
             s = i % 2
             torch.cuda.current_stream().wait_event(ready[s])
-            o = step(slots[s])
+            if e2e_graphs is not None:
+                tok_s, tgt_s, mem_s = slots[s]
+                o = e2e_graphs[s](mem_s, tok_s, tgt_s)   # graph s is bound to input slot s (no extra copy)
+            else:
+                o = step(slots[s])
             consumed[s].record()
             loss_host[s].copy_(o, non_blocking=True)   # device -> host read of the step's loss
             if i >= 1:
@@ -306,10 +334,11 @@ def run_b200(args):
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                 "peak_source": peak_src + ", bf16_tflops_sustained (kernel timed inside a long step)",
                 "launches_per_step": n_l.value / args.steps, "gemm_ms_per_step": gemm_ms_per_step,
-                "gemm_share_of_step": gemm_ms_per_step / ms,
+                "gemm_share_of_step": gemm_ms_per_step / ms_eager,
                 "algorithmic_flops_per_step": tot_fl.value / args.steps,
-                "how": "2*M*N*K per launch summed over every GEMM launch of the timed steps / sum of their CUDA-event "
-                       "durations on the launching stream",
+                "how": "2*M*N*K per launch summed over every GEMM launch of K eagerly launched timed steps / sum of their "
+                       "CUDA-event durations on the launching stream (events cannot be read back from a graph replay, so "
+                       "the roofline pass is the eager one; ms_per_step_eager is its step time)",
                 "traffic": None}
     step_tf = train_flops_per_sample(c) * c["B"] / (ms / 1e3) / 1e12
     line = {
@@ -318,6 +347,8 @@ def run_b200(args):
         "data": "synthetic", "config": workload_config(c, world, dropout=0.0),
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         "step_model_tflops_per_gpu": step_tf, "step_model_frac_of_peak": step_tf / peak_tf,
+        "launch_mode": "cuda-graph replay (train.GraphedTrainStep)" if use_graph else "eager launches",
+        "ms_per_step_eager": ms_eager,
         "last_loss": last_loss,
     }
     if world == 1 and not args.no_cpu_baseline:
@@ -378,6 +409,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time the eager launch sequence instead of the CUDA-graph replay")
     ap.add_argument("--gemm-detail", default=None, help="write per-launch GEMM timings of one step to this CSV")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

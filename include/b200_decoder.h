@@ -152,6 +152,13 @@ int b200_adamw_step(float* param, void* param_bf16, const float* grad, float* ex
                     float beta1, float beta2, float eps, float weight_decay, int32_t step,
                     void* stream);
 
+/* Same update with the step counter (incremented by the call) and the learning rate read from
+ * device memory: a CUDA graph that captured the train step stays valid across replays. */
+int b200_adamw_step_dev(float* param, void* param_bf16, const float* grad, float* exp_avg,
+                        float* exp_avg_sq, int64_t n, const float* sumsq, float max_norm,
+                        const float* lr_dev, float beta1, float beta2, float eps, float weight_decay,
+                        int32_t* step_dev, void* stream);
+
 /* ---- decoder engine: whole-model entry points ----------------------------------------------
  * The engine owns no parameters: the caller binds flat arenas whose layout is fixed by
  * b200_engine_param_offset().  Tensor names are the reference state_dict keys relative to the
@@ -204,6 +211,11 @@ int b200_engine_forward_loss(b200_engine* e, const int64_t* tokens, const int64_
  * b200_engine_grad_buckets), recorded on `stream` right after the bucket's last write. */
 int b200_engine_backward(b200_engine* e, const float* inv_count_dev, float* dmemory,
                          void* const* bucket_events, int32_t num_bucket_events, void* stream);
+/* the same backward cut into the L + 2 parts that match the gradient buckets (part 0 = LM head,
+ * part k = layer L-k, part L+1 = embedding + projection): runs parts [first_part, last_part].
+ * The data-parallel driver interleaves one all-reduce per part (capturable in a CUDA graph). */
+int b200_engine_backward_parts(b200_engine* e, const float* inv_count_dev, float* dmemory,
+                               int32_t first_part, int32_t last_part, void* stream);
 /* backward of the last forward_logits(training=1) from an explicit dlogits [B,T,V] fp32: the
  * autograd-compatibility path behind decoder.TransformerDecoder.forward + loss.backward(). */
 int b200_engine_backward_from_dlogits(b200_engine* e, const float* dlogits, float* dmemory,

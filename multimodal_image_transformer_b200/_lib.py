@@ -85,6 +85,7 @@ SIGNATURES = {
     "b200_attn_bwd": (C.c_int, [C.POINTER(AttnBwdArgs), _P]),
     "b200_grad_sumsq": (C.c_int, [_P, _I64, _P, _P]),
     "b200_adamw_step": (C.c_int, [_P, _P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _F, _F, _I32, _P]),
+    "b200_adamw_step_dev": (C.c_int, [_P, _P, _P, _P, _P, _I64, _P, _F, _P, _F, _F, _F, _F, _P, _P]),
     "b200_engine_create": (C.c_int, [C.POINTER(EngineConfig), C.POINTER(C.c_void_p)]),
     "b200_engine_destroy": (None, [_P]),
     "b200_engine_param_count": (_I64, [_P]),
@@ -97,6 +98,7 @@ SIGNATURES = {
     "b200_engine_forward_logits": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P, _P]),
     "b200_engine_forward_loss": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I64, _I32, _P, _P]),
     "b200_engine_backward": (C.c_int, [_P, _P, _P, _P, _I32, _P]),
+    "b200_engine_backward_parts": (C.c_int, [_P, _P, _P, _I32, _I32, _P]),
     "b200_engine_backward_from_dlogits": (C.c_int, [_P, _P, _P, _P]),
     "b200_engine_grad_buckets": (_I32, [_P, _P, _P, _I32]),
     "b200_engine_decode_workspace_bytes": (_I64, [_P, _I32, _I32, _I32, _I32, _I32]),

@@ -188,5 +188,12 @@ int b200_adamw_step(float* param, void* param_bf16, const float* grad, float* ex
   return adamw_step(param, BF(param_bf16), grad, exp_avg, exp_avg_sq, n, sumsq, max_norm, lr, beta1, beta2, eps,
                     weight_decay, step, S_(stream));
 }
+int b200_adamw_step_dev(float* param, void* param_bf16, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                        const float* sumsq, float max_norm, const float* lr_dev, float beta1, float beta2, float eps,
+                        float weight_decay, int32_t* step_dev, void* stream) {
+  B200_REQUIRE(param && grad && exp_avg && exp_avg_sq && lr_dev && step_dev, "adamw_step_dev: null argument");
+  return adamw_step(param, BF(param_bf16), grad, exp_avg, exp_avg_sq, n, sumsq, max_norm, 0.f, beta1, beta2, eps,
+                    weight_decay, 0, S_(stream), step_dev, lr_dev);
+}
 
 }  // extern "C"

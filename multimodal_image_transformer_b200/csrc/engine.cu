@@ -267,7 +267,11 @@ int run_forward(b200_engine* e, const int64_t* tokens, const float* memory, cons
   return 0;
 }
 
-int run_backward(b200_engine* e, bool have_dlogits, float* dmemory, void* const* events, int n_events, cudaStream_t s) {
+// Backward in L+2 parts, in the order gradients become final: part 0 = LM head (fc_out), part k in
+// [1, L] = decoder layer L-k, part L+1 = embedding (+ projection).  Parts [first, last] are run;
+// the data-parallel driver runs one part per gradient bucket and all-reduces in between.
+int run_backward(b200_engine* e, bool have_dlogits, float* dmemory, void* const* events, int n_events, cudaStream_t s,
+                 int first_part = 0, int last_part = 1 << 30) {
   const auto& c = e->cfg;
   const int E = c.embed_dim, F = c.ff_dim, H = c.num_heads, L = c.num_layers, hd = E / H, V = c.vocab_size;
   Plan& pl = e->plan;
@@ -286,17 +290,20 @@ int run_backward(b200_engine* e, bool have_dlogits, float* dmemory, void* const*
     ++ev;
   };
 
-  if (need_dmemp) B200_CHECK_CUDA(cudaMemsetAsync(pl.dmemp, 0, static_cast<size_t>(Ms) * E * sizeof(float), s));
-
-  // --- LM head
-  RC(linear_wgrad(pl.dlogits, V, pl.x_final, E, e->gf + e->fc_w, e->gf + e->fc_b, M, V, E, s));
-  bf16* dx = pl.dxa;
-  RC(linear_dgrad(pl.dlogits, V, e->ph + e->fc_w, V, E, dx, E, M, nullptr, 0, nullptr, 0, s));
-  mark();
+  bf16* dx = pl.dxa;      // gradient of the residual stream at every part boundary lives in dxa
+  if (first_part <= 0) {
+    if (need_dmemp) B200_CHECK_CUDA(cudaMemsetAsync(pl.dmemp, 0, static_cast<size_t>(Ms) * E * sizeof(float), s));
+    // --- LM head
+    RC(linear_wgrad(pl.dlogits, V, pl.x_final, E, e->gf + e->fc_w, e->gf + e->fc_b, M, V, E, s));
+    RC(linear_dgrad(pl.dlogits, V, e->ph + e->fc_w, V, E, dx, E, M, nullptr, 0, nullptr, 0, s));
+    mark();
+  }
 
   bf16* spare1 = pl.dxb;
   bf16* spare2 = pl.dxc;
   for (int l = L - 1; l >= 0; --l) {
+    const int part = L - l;
+    if (part < first_part || part > last_part) continue;
     const LayerOff& o = e->lo[l];
     LayerAct& a = pl.act[l];
     float* g = e->gf;
@@ -360,6 +367,7 @@ int run_backward(b200_engine* e, bool have_dlogits, float* dmemory, void* const*
     dx = dx_in;
     mark();
   }
+  if (last_part < L + 1) return 0;
   RC(embed_bwd(e->last_tokens, dx, e->gf + e->emb, B, T, E, V, c.pad_idx, sqrtf(static_cast<float>(E)), s));
   if (pl.mem_dim != E) {
     RC(cast_f32_to_bf16(pl.dmemp, pl.dmemp16, static_cast<long long>(Ms) * E, s));
@@ -630,6 +638,22 @@ int b200_engine_backward(b200_engine* e, const float* inv_count_dev, float* dmem
   RC(b200_lmhead_ce_bwd(pl.x_final, E, e->ph + e->fc_w, E, e->pf + e->fc_b, e->last_targets, M, V, E, e->last_ignore,
                         pl.row_lse, inv, pl.dlogits, V, stream));
   return run_backward(e, false, dmemory, bucket_events, num_bucket_events, s);
+}
+
+int b200_engine_backward_parts(b200_engine* e, const float* inv_count_dev, float* dmemory, int32_t first_part,
+                               int32_t last_part, void* stream) {
+  B200_REQUIRE(e, "backward_parts: null engine");
+  B200_REQUIRE(e->have_saved && e->last_targets, "backward_parts: call forward_loss(training=1) first");
+  B200_REQUIRE(first_part >= 0 && first_part <= last_part, "backward_parts: bad part range [%d, %d]", first_part, last_part);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Plan& pl = e->plan;
+  if (first_part == 0) {
+    const int E = e->cfg.embed_dim, V = e->cfg.vocab_size, M = pl.B * pl.T;
+    const float* inv = inv_count_dev ? inv_count_dev : pl.scalars + 6;
+    RC(b200_lmhead_ce_bwd(pl.x_final, E, e->ph + e->fc_w, E, e->pf + e->fc_b, e->last_targets, M, V, E, e->last_ignore,
+                          pl.row_lse, inv, pl.dlogits, V, stream));
+  }
+  return run_backward(e, false, dmemory, nullptr, 0, s, first_part, last_part);
 }
 
 int b200_engine_backward_from_dlogits(b200_engine* e, const float* dlogits, float* dmemory, void* stream) {

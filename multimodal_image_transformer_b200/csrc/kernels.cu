@@ -505,7 +505,14 @@ int grad_sumsq(const float* g, long long n, float* sumsq, cudaStream_t s) {
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, bf16* __restrict__ p16, const float* __restrict__ g,
              float* __restrict__ m, float* __restrict__ v, long long n, const float* __restrict__ sumsq,
-             float max_norm, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt) {
+             float max_norm, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
+             const int* __restrict__ step_dev, const float* __restrict__ lr_dev) {
+  if (step_dev != nullptr) {   // graph-replay mode: the step count (and lr) live on the device
+    const float t = static_cast<float>(*step_dev);
+    bc1 = 1.f - powf(b1, t);
+    bc2_sqrt = sqrtf(1.f - powf(b2, t));
+  }
+  if (lr_dev != nullptr) lr = *lr_dev;
   float coef = 1.f;
   if (max_norm > 0.f && sumsq != nullptr) {
     const float total = sqrtf(*sumsq);
@@ -558,11 +565,18 @@ adamw_kernel(float* __restrict__ p, bf16* __restrict__ p16, const float* __restr
   }
 }
 
+__global__ void inc_step_kernel(int* step) { *step += 1; }
+
 int adamw_step(float* p, bf16* p16, const float* g, float* m, float* v, long long n,
                const float* sumsq, float max_norm, float lr, float b1, float b2, float eps, float wd,
-               int step, cudaStream_t s) {
+               int step, cudaStream_t s, int* step_dev, const float* lr_dev) {
   if (n == 0) return 0;
-  B200_REQUIRE(step >= 1, "adamw: step must be >= 1");
+  B200_REQUIRE(step >= 1 || step_dev != nullptr, "adamw: step must be >= 1");
+  if (step_dev != nullptr) {
+    inc_step_kernel<<<1, 1, 0, s>>>(step_dev);
+    note_launch();
+    if (step < 1) step = 1;
+  }
   const float bc1 = 1.f - powf(b1, static_cast<float>(step));
   const float bc2 = 1.f - powf(b2, static_cast<float>(step));
   const double bc1d = 1.0 - pow(static_cast<double>(b1), step);
@@ -570,7 +584,7 @@ int adamw_step(float* p, bf16* p16, const float* g, float* m, float* v, long lon
   (void)bc1; (void)bc2;
   adamw_kernel<<<cdiv(cdiv(n, 4), 256), 256, 0, s>>>(p, p16, g, m, v, n, sumsq, max_norm, lr, b1, b2, eps,
                                                       wd, static_cast<float>(bc1d),
-                                                      static_cast<float>(sqrt(bc2d)));
+                                                      static_cast<float>(sqrt(bc2d)), step_dev, lr_dev);
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -30,8 +30,10 @@ int argmax_finalize(const float* part_max, const float* part_idx, int M, int n_t
                     int64_t* out_ids, float* out_max, cudaStream_t s);
 // dlogits (fp32 [M,V]) -> bf16 copy (autograd compatibility path)
 int grad_sumsq(const float* g, long long n, float* sumsq, cudaStream_t s);
+// step_dev / lr_dev (optional): device-resident step counter (incremented here) and learning rate,
+// so that a captured CUDA graph of the train step stays valid across replays
 int adamw_step(float* p, bf16* p16, const float* g, float* m, float* v, long long n,
                const float* sumsq, float max_norm, float lr, float b1, float b2, float eps,
-               float wd, int step, cudaStream_t s);
+               float wd, int step, cudaStream_t s, int* step_dev = nullptr, const float* lr_dev = nullptr);
 
 }  // namespace b200

@@ -91,6 +91,21 @@ class DataParallel:
         dist.all_reduce(s, op=dist.ReduceOp.SUM, group=self.group)
         return torch.cat([s * inv, self._cnt])
 
+    def backward_and_allreduce(self, inv_count: torch.Tensor) -> None:
+        """Backward one gradient bucket at a time; each bucket's all-reduce is launched on the comm
+        stream behind a (torch) event recorded right after the bucket's last gradient write, so it
+        overlaps the rest of backward.  Fork/join through torch events only: the whole sequence can
+        be captured in a CUDA graph (train.GraphedTrainStep)."""
+        g = self.engine.grads
+        cur = torch.cuda.current_stream()
+        for i, ((off, cnt), ev) in enumerate(zip(self.buckets, self.events)):
+            self.engine.backward_parts(i, i, inv_count)
+            ev.record(cur)
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(ev)
+                dist.all_reduce(g[off:off + cnt], op=dist.ReduceOp.SUM, group=self.group)
+        cur.wait_stream(self.comm_stream)
+
     def allreduce_buckets(self) -> None:
         """Launch one all-reduce per bucket on the comm stream as soon as backward has finished
         it, then make the compute stream wait for all of them (before clip + AdamW)."""

@@ -64,6 +64,9 @@ class DecoderEngine:
             self.grads = torch.zeros(self.total, device=self.device, dtype=torch.float32)
             self.pe = sinusoid_table(max_seq_len, embed_dim).to(self.device).contiguous()
             self._scal = torch.zeros(8, device=self.device, dtype=torch.float32)
+            self._step_dev = torch.zeros(1, device=self.device, dtype=torch.int32)
+            self._lr_dev = torch.zeros(1, device=self.device, dtype=torch.float32)
+        self._lr_host = None
         self.exp_avg = None
         self.exp_avg_sq = None
         self.opt_step = 0
@@ -197,6 +200,11 @@ class DecoderEngine:
                                               L.cur_stream()), "backward")
         return dmem
 
+    def backward_parts(self, first: int, last: int, inv_count: Optional[torch.Tensor] = None) -> None:
+        """Parts [first, last] of backward (0 = LM head, k = layer L-k, L+1 = embedding/projection)."""
+        L.check(self.lib.b200_engine_backward_parts(self.handle, L.ptr(inv_count), None, first, last, L.cur_stream()),
+                "backward_parts")
+
     def backward_from_dlogits(self, dlogits: torch.Tensor, want_dmemory: bool = False) -> Optional[torch.Tensor]:
         dlogits = dlogits.to(torch.float32).contiguous()
         dmem = None
@@ -220,16 +228,19 @@ class DecoderEngine:
         if self.exp_avg is None:
             self.exp_avg = torch.zeros_like(self.params)
             self.exp_avg_sq = torch.zeros_like(self.params)
-        self.opt_step += 1
+        self.opt_step += 1           # host mirror of the device-side counter (state_dict / resume)
+        if self._lr_host != lr and not torch.cuda.is_current_stream_capturing():
+            self._lr_dev.fill_(lr)   # lr lives on the device so that a captured step can be replayed
+            self._lr_host = lr
         sumsq = self._scal[0:1]
         sumsq.zero_()
         st = L.cur_stream()
         L.check(self.lib.b200_grad_sumsq(L.ptr(self.grads), C.c_int64(self.total), L.ptr(sumsq), st), "grad_sumsq")
-        L.check(self.lib.b200_adamw_step(L.ptr(self.params), L.ptr(self.params_bf16), L.ptr(self.grads),
-                                         L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq), C.c_int64(self.total),
-                                         L.ptr(sumsq), C.c_float(max_norm), C.c_float(lr), C.c_float(betas[0]),
-                                         C.c_float(betas[1]), C.c_float(eps), C.c_float(weight_decay),
-                                         self.opt_step, st), "adamw_step")
+        L.check(self.lib.b200_adamw_step_dev(L.ptr(self.params), L.ptr(self.params_bf16), L.ptr(self.grads),
+                                             L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq), C.c_int64(self.total),
+                                             L.ptr(sumsq), C.c_float(max_norm), L.ptr(self._lr_dev),
+                                             C.c_float(betas[0]), C.c_float(betas[1]), C.c_float(eps),
+                                             C.c_float(weight_decay), L.ptr(self._step_dev), st), "adamw_step")
         # the kernel wrote both the fp32 master and the bf16 shadow: nothing to re-sync
         return sumsq
 

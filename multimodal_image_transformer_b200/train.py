@@ -43,6 +43,7 @@ class B200AdamW:
     def load_state_dict(self, sd) -> None:
         e = self.engine
         e.opt_step = int(sd["step"])
+        e._step_dev.fill_(e.opt_step)
         if sd["exp_avg"] is not None:
             e.exp_avg = sd["exp_avg"].to(e.device).clone()
             e.exp_avg_sq = sd["exp_avg_sq"].to(e.device).clone()
@@ -65,13 +66,61 @@ def fused_train_step(model, images, decoder_input_tokens, target_tokens, optimiz
         out = decoder.loss(decoder_input_tokens, target_tokens, images, None, ignore_index, training=True)
     if dp is not None and dp.world_size > 1:
         inv = dp.global_inv_count(out)                 # 1 / (non-PAD targets over all ranks)
-        decoder.backward(inv_count=inv, events=dp.events)
-        dp.allreduce_buckets()
+        dp.backward_and_allreduce(inv)                 # bucketed all-reduce overlapped with backward
         out = dp.global_loss(out, inv)
     else:
         decoder.backward()
     optimizer.step(max_grad_norm=grad_clip_value)
     return out
+
+
+class GraphedTrainStep:
+    """Fused train step replayed from a CUDA graph (removes the ~2-4 us launch gap after
+    each of the ~210 kernels of a step).  The first `warmup` calls run eagerly (they are real steps);
+    the next call captures the step over static input buffers and replays it from then on.  The
+    AdamW step counter and learning rate live on the device, so replays stay exact."""
+
+    def __init__(self, model, optimizer: B200AdamW, ignore_index: int, grad_clip_value: float, warmup: int = 2,
+                 dp: Optional[DataParallel] = None):
+        self.model, self.optimizer = model, optimizer
+        self.ignore_index, self.clip = ignore_index, grad_clip_value
+        self.warmup, self.calls = warmup, 0
+        self.dp = dp          # data-parallel: the bucketed NCCL all-reduces are captured as graph nodes too
+        self.graph, self.static_in, self.static_out = None, None, None
+
+    def _eager(self, images, tokens, targets):
+        return fused_train_step(self.model, images, tokens, targets, self.optimizer, self.ignore_index, self.clip, self.dp)
+
+    def __call__(self, images, tokens, targets) -> torch.Tensor:
+        self.calls += 1
+        if self.graph is None:
+            if self.calls <= self.warmup:
+                return self._eager(images, tokens, targets)
+            # the tensors of the capturing call become the static inputs: later calls that pass the same
+            # tensors (e.g. a staging slot refilled by an H2D copy) replay without any extra copy
+            self.static_in = (images, tokens, targets)
+            eng = (self.model.decoder if hasattr(self.model, "decoder") else self.model).engine
+            lr = self.optimizer.param_groups[0]["lr"]
+            if eng._lr_host != lr:
+                eng._lr_dev.fill_(lr)
+                eng._lr_host = lr
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.static_out = self._eager(*self.static_in)
+            self.graph.replay()
+            return self.static_out
+        for d, s in zip(self.static_in, (images, tokens, targets)):
+            if d.data_ptr() != s.data_ptr():
+                d.copy_(s, non_blocking=True)
+        eng = (self.model.decoder if hasattr(self.model, "decoder") else self.model).engine
+        lr = self.optimizer.param_groups[0]["lr"]
+        if eng._lr_host != lr:
+            eng._lr_dev.fill_(lr)
+            eng._lr_host = lr
+        eng.opt_step += 1
+        self.graph.replay()
+        return self.static_out
 
 
 def train_one_epoch(model, dataloader, optimizer, criterion, device, grad_clip_value, scheduler, epoch,

@@ -145,6 +145,24 @@ def test_train_trajectory_vs_reference_golden(cuda_dev):
             assert d.mean() < 0.35 * g["train_lr"], k
 
 
+def test_graphed_train_step_matches_reference_golden(cuda_dev):
+    """train.GraphedTrainStep (eager warm-up step, capture, replay) follows the same trajectory."""
+    from multimodal_image_transformer_b200.decoder import TransformerDecoder
+    from multimodal_image_transformer_b200.train import B200AdamW, GraphedTrainStep
+    g = load_golden("nano")
+    c = g["config"]
+    torch.manual_seed(g["seed"])
+    dec = TransformerDecoder(c["V"], c["E"], c["H"], c["L"], c["F"], c["ML"], dropout=0.0, pad_idx=0).train()
+    opt = B200AdamW(dec, lr=g["train_lr"], betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-5)
+    step = GraphedTrainStep(dec, opt, 0, 5.0, warmup=1)
+    tok, tgt, mem = (g[k].to(cuda_dev) for k in ("tokens", "targets", "memory"))
+    losses = [step(mem, tok, tgt)[0].item() for _ in range(3)]
+    assert step.graph is not None
+    for a, b in zip(losses, g["train_losses"]):
+        assert abs(a - b) < 2e-3 * b, (losses, g["train_losses"])
+    assert dec.engine.opt_step == 3 and int(dec.engine._step_dev.item()) == 3
+
+
 def test_dropin_module_state_dict_and_autograd(cuda_dev):
     """decoder.TransformerDecoder: reference constructor signature, bit-identical seeded init,
     reference state_dict keys/shapes, and the logits -> criterion -> backward() loop of train.py."""
