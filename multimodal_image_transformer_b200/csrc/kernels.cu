@@ -444,24 +444,37 @@ int ce_mean(const float* loss_sum, const float* valid_count, float* out, cudaStr
   return 0;
 }
 
-__global__ void argmax_finalize_kernel(const float* __restrict__ part_max, const float* __restrict__ part_idx,
-                                       int M, int n_tiles, int64_t* __restrict__ out_ids,
-                                       float* __restrict__ out_max) {
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per row: lanes scan the per-tile partials, then a shuffle reduction keeps the maximum
+// with the LOWEST column index on ties (torch.argmax returns the first maximal index)
+__global__ void __launch_bounds__(256)
+argmax_finalize_kernel(const float* __restrict__ part_max, const float* __restrict__ part_idx,
+                       int M, int n_tiles, int64_t* __restrict__ out_ids, float* __restrict__ out_max) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (row >= M) return;
   const float* pm = part_max + static_cast<long long>(row) * n_tiles;
   const float* pi = part_idx + static_cast<long long>(row) * n_tiles;
   float best = -INFINITY;
-  int idx = 0;
-  for (int i = 0; i < n_tiles; ++i) {   // increasing column order + strict '>' = first index on ties
-    if (pm[i] > best) { best = pm[i]; idx = __float_as_int(pi[i]); }
+  int idx = 0x7fffffff;
+  for (int i = lane; i < n_tiles; i += 32) {
+    const float v = pm[i];
+    const int id = __float_as_int(pi[i]);
+    if (v > best || (v == best && id < idx)) { best = v; idx = id; }
   }
-  out_ids[row] = idx;
-  if (out_max) out_max[row] = best;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ov > best || (ov == best && oi < idx)) { best = ov; idx = oi; }
+  }
+  if (lane == 0) {
+    out_ids[row] = idx == 0x7fffffff ? 0 : idx;
+    if (out_max) out_max[row] = best;
+  }
 }
 int argmax_finalize(const float* part_max, const float* part_idx, int M, int n_tiles, int64_t* out_ids,
                     float* out_max, cudaStream_t s) {
-  argmax_finalize_kernel<<<cdiv(M, 128), 128, 0, s>>>(part_max, part_idx, M, n_tiles, out_ids, out_max);
+  argmax_finalize_kernel<<<cdiv(M, 8), 256, 0, s>>>(part_max, part_idx, M, n_tiles, out_ids, out_max);
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;

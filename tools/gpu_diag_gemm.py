@@ -128,6 +128,26 @@ def main():
                 e1.record(); torch.cuda.synchronize()
                 ms = e0.elapsed_time(e1) / 10
                 print(f"   cuBLAS same shape: {ms*1e3:.1f} us  {2*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
+    if "small" in which:
+        for (M, N, K) in [(512, 768, 768), (512, 2304, 768), (512, 3072, 768), (512, 768, 3072), (512, 10000, 768)]:
+            A = torch.randn(M, K, device=dev).bfloat16(); B = torch.randn(N, K, device=dev).bfloat16()
+            bias = torch.randn(N, device=dev); res = torch.randn(M, N, device=dev).bfloat16()
+            D = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+            D32 = torch.zeros(M, N, device=dev, dtype=torch.float32)
+            cases = [("bn128", dict(block_n=128, D=D, bias=bias)), ("bn256", dict(block_n=256, D=D, bias=bias)),
+                     ("bn128+res", dict(block_n=128, D=D, bias=bias, residual=res))]
+            for sk in (2, 3, 6):
+                cases.append((f"f32 splitk{sk} bn128", dict(block_n=128, D=D32, d_fp32=True, accumulate=True, split_k=sk)))
+                cases.append((f"f32 splitk{sk} bn256", dict(block_n=256, D=D32, d_fp32=True, accumulate=True, split_k=sk)))
+            for tag, kw in cases:
+                for _ in range(5): run_gemm(A, B, M, N, K, 0, 0, **kw)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(50): run_gemm(A, B, M, N, K, 0, 0, **kw)
+                e1.record(); torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 50
+                print(f"M{M} N{N} K{K} {tag:20s}: {ms*1e3:.1f} us {2*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
     if "noepi" in which:
         for (M, N, K) in [(12032, 3072, 768), (12032, 768, 768), (12032, 768, 3072), (12032, 2304, 768)]:
             A = torch.randn(M, K, device=dev).bfloat16(); B = torch.randn(N, K, device=dev).bfloat16()
