@@ -155,6 +155,8 @@ __device__ __forceinline__ void fill_key_bias(float* sBias, const AttnDev& p, in
 template <int HD, int NT>
 __global__ void __launch_bounds__(128)
 attn_fwd_kernel(const AttnDev p) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int LD = HD + 8;
   extern __shared__ __align__(16) uint8_t smem_attn[];
   bf16* sQ = reinterpret_cast<bf16*>(smem_attn);
@@ -249,6 +251,8 @@ attn_fwd_kernel(const AttnDev p) {
 template <int HD, int NT>
 __global__ void __launch_bounds__(128)
 attn_bwd_kernel(const AttnDev p) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int LD = HD + 8;
   extern __shared__ __align__(16) uint8_t smem_attn[];
   bf16* sQ = reinterpret_cast<bf16*>(smem_attn);
@@ -410,6 +414,8 @@ attn_bwd_kernel(const AttnDev p) {
 template <int HD, int NT, int MAXI>
 __global__ void __launch_bounds__(256, 2)
 attn_bwd2_kernel(const AttnDev p) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int LD = HD + 8;
   constexpr int KB = NT * 8;
   extern __shared__ __align__(16) uint8_t smem_attn[];
@@ -658,7 +664,7 @@ static int launch_fwd(const AttnDev& d, cudaStream_t s) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<HD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = smem;
   }
-  attn_fwd_kernel<HD, NT><<<dim3(d.H, d.B), 128, smem, s>>>(d);
+  B200_CHECK_CUDA(launch_kernel(attn_fwd_kernel<HD, NT>, dim3(d.H, d.B), dim3(128), smem, s, true, 1, d));
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -672,7 +678,7 @@ static int launch_bwd(const AttnDev& d, cudaStream_t s) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<HD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = smem;
   }
-  attn_bwd_kernel<HD, NT><<<dim3(d.H, d.B), 128, smem, s>>>(d);
+  B200_CHECK_CUDA(launch_kernel(attn_bwd_kernel<HD, NT>, dim3(d.H, d.B), dim3(128), smem, s, true, 1, d));
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -690,7 +696,7 @@ static int launch_bwd2(const AttnDev& d, cudaStream_t s) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd2_kernel<HD, NT, MAXI>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = smem;
   }
-  attn_bwd2_kernel<HD, NT, MAXI><<<dim3(d.H, d.B), 256, smem, s>>>(d);
+  B200_CHECK_CUDA(launch_kernel(attn_bwd2_kernel<HD, NT, MAXI>, dim3(d.H, d.B), dim3(256), smem, s, true, 1, d));
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;

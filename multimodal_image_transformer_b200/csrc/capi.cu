@@ -5,6 +5,7 @@
 #include "kernels.cuh"
 #include "attention.cuh"
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <atomic>
 #include <vector>
@@ -16,6 +17,11 @@ void set_last_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static const bool on = getenv("B200_NO_PDL") == nullptr;
+  return on;
 }
 
 static std::atomic<long long> g_launches{0};

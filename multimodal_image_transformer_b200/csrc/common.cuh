@@ -38,6 +38,45 @@ void note_launch(int n = 1);
 bool gemm_profile_enabled();
 void gemm_profile_record(cudaStream_t s, bool begin, double flops);
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// Every kernel of the engine executes pdl_wait() before it touches global memory written by an
+// earlier kernel (and before it overwrites anything an earlier kernel may still read), then
+// pdl_trigger().  Launched through launch_kernel(..., pdl = true) the grid may therefore be
+// scheduled while its predecessor drains: block scheduling, barrier initialisation, TMEM
+// allocation and tensor-map prefetch overlap the predecessor's tail instead of following it.
+// Without the launch attribute both instructions are no-ops.  B200_NO_PDL=1 disables the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+int device_sm_count();
+
+template <class... KP, class... AP>
+inline cudaError_t launch_kernel(void (*kern)(KP...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                 bool pdl, int cluster, AP&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (cluster > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cluster;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl && pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KP>(args)...);
+}
+
 // ------------------------------------------------------------------ small utils
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -134,6 +173,14 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+
+// 1-D bulk copy global -> shared (bytes and both addresses multiples of 16), completion on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
 // CTA-pair variant (cta_group::2): data lands in THIS CTA's shared memory, completion bytes are

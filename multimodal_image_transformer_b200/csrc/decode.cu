@@ -5,6 +5,7 @@
 // loads from a head-major layout; all beams of an image share that stream.
 #include "decode.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace b200 {
 
@@ -13,6 +14,8 @@ static inline int cdiv(long long a, long long b) { return static_cast<int>((a + 
 // ------------------------------------------------------------------------------------------
 __global__ void kv_to_head_major_kernel(const bf16* __restrict__ kv, bf16* __restrict__ k_hm,
                                         bf16* __restrict__ v_hm, int B, int S, int H, int hd) {
+  pdl_wait();
+  pdl_trigger();
   const int vpr = hd >> 3;  // 16-byte vectors per head row
   const long long total = static_cast<long long>(B) * S * H * vpr;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -30,174 +33,259 @@ __global__ void kv_to_head_major_kernel(const bf16* __restrict__ kv, bf16* __res
 
 int kv_to_head_major(const bf16* kv, bf16* k_hm, bf16* v_hm, int B, int S, int H, int hd, cudaStream_t s) {
   const long long total = static_cast<long long>(B) * S * H * (hd / 8);
-  kv_to_head_major_kernel<<<cdiv(total, 256), 256, 0, s>>>(kv, k_hm, v_hm, B, S, H, hd);
-  note_launch();
-  B200_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
-
-__global__ void kv_append_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ kcache,
-                                 bf16* __restrict__ vcache, int R, int H, int hd, int max_len, int pos) {
-  const int vpr = hd >> 3;
-  const long long total = static_cast<long long>(R) * H * vpr;
-  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (idx >= total) return;
-  const int c = static_cast<int>(idx % vpr);
-  const int h = static_cast<int>((idx / vpr) % H);
-  const int r = static_cast<int>(idx / (static_cast<long long>(vpr) * H));
-  const int E = H * hd;
-  const bf16* src = qkv + static_cast<long long>(r) * 3 * E + E + h * hd + c * 8;
-  const long long dst = ((static_cast<long long>(r) * H + h) * max_len + pos) * hd + c * 8;
-  *reinterpret_cast<uint4*>(kcache + dst) = *reinterpret_cast<const uint4*>(src);
-  *reinterpret_cast<uint4*>(vcache + dst) = *reinterpret_cast<const uint4*>(src + E);
-}
-
-int kv_append(const bf16* qkv, bf16* kcache, bf16* vcache, int R, int H, int hd, int max_len, int pos, cudaStream_t s) {
-  const long long total = static_cast<long long>(R) * H * (hd / 8);
-  kv_append_kernel<<<cdiv(total, 256), 256, 0, s>>>(qkv, kcache, vcache, R, H, hd, max_len, pos);
+  B200_CHECK_CUDA(launch_kernel(kv_to_head_major_kernel, dim3(cdiv(total, 256)), dim3(256), 0, s, true, 1, kv, k_hm, v_hm, B, S, H, hd));
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 // ------------------------------------------------------------------------------------------
-// single-query attention over a resident-in-HBM K/V stream
+// Single-position cross attention over a K/V stream that lives in HBM (flash-decoding, one query
+// per hypothesis).  Work item = one (group, head): a contiguous [nkeys, HD] K plane and V plane.
+// Persistent CTAs; a producer warp streams 64-key chunks of K and V with 1-D bulk copies
+// (cp.async.bulk + mbarrier) through a shared-memory ring that runs ahead ACROSS work items, so the
+// HBM pipe never drains between heads; four consumer warps keep an online-softmax state per lane
+// group (GL lanes share one key row, 16 bytes each).  A lane group takes its keys of a chunk four
+// at a time: four independent score chains, ONE running-max update, four accumulations -- the
+// loop-carried dependency is per batch, not per key.  The 4*KPW partial states are merged once per
+// item; the next item's queries are fetched before the merge.  All NQ queries of a group (the
+// beams of one image) share the stream.
 // ------------------------------------------------------------------------------------------
+struct DecAttnArgs {
+  const bf16* q; long long q_rs;
+  const bf16* k; const bf16* v;     // [groups][H][kv_len][HD]
+  int kv_len, nkeys;                // row capacity / valid keys
+  bf16* o; long long o_rs;
+  int groups, nq, H;
+  const unsigned char* key_pad;     // [groups][nkeys] or null
+  float scale;
+};
+
+static constexpr int DEC_CK = 64;       // keys per chunk
+static constexpr int DEC_STAGES = 3;
+static constexpr int DEC_THREADS = 160; // 4 consumer warps + 1 producer warp
+
+__device__ __forceinline__ float exp_diff(float a, float m) {   // exp(a - m) with exp(-inf - -inf) = 0
+  return (a == -INFINITY) ? 0.f : __expf(a - m);
+}
+__device__ __forceinline__ void unpack8f(const uint4& u, float (&f)[8]) {
+  const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
 template <int HD, int NQ>
-__global__ void __launch_bounds__(128)
-attn_decode_kernel(const bf16* __restrict__ q, long long q_rs, const bf16* __restrict__ k,
-                   const bf16* __restrict__ v, int kv_len, int nkeys, bf16* __restrict__ o, long long o_rs,
-                   int nq, int H, const unsigned char* __restrict__ key_pad, float scale) {
+__global__ void __launch_bounds__(DEC_THREADS)
+attn_decode_stream_kernel(const DecAttnArgs a) {
   constexpr int GL = (HD <= 32) ? 4 : (HD <= 64 ? 8 : 16);   // lanes cooperating on one key row
   constexpr int KPW = 32 / GL;                               // keys per warp per iteration
   constexpr int KPI = 4 * KPW;                               // keys per CTA per iteration
-  extern __shared__ float sm_dec[];
-  float* sc = sm_dec;                      // [NQ][nkeys]
-  float* red = sm_dec + NQ * nkeys;        // [4][NQ][HD]
-  __shared__ float s_inv[NQ];
+  constexpr int NIT = DEC_CK / KPI;                          // iterations per chunk (multiple of 4)
+  constexpr int PLANE = DEC_CK * HD * 2;                     // bytes of one K (or V) chunk
+  constexpr int STAGE = 2 * PLANE;
+  constexpr int RED_STRIDE = HD + 2;
+  extern __shared__ __align__(128) uint8_t sm_dec[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm_dec + DEC_STAGES * STAGE);
+  uint64_t* empty = full + DEC_STAGES;
+  float* red = reinterpret_cast<float*>(empty + DEC_STAGES + 2);   // [2][4][NQ][RED_STRIDE]
 
-  const int h = blockIdx.x, g = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < DEC_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 4); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  pdl_wait();
+  pdl_trigger();
+
+  const int n_items = a.groups * a.H;
+  const int nch = (a.nkeys + DEC_CK - 1) / DEC_CK;
+  const long long plane_elems = static_cast<long long>(a.kv_len) * HD;
+
+  if (warp == 4) {
+    // ============================ producer ============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const bf16* kp = a.k + item * plane_elems;
+        const bf16* vp = a.v + item * plane_elems;
+        for (int c = 0; c < nch; ++c) {
+          const int nk = min(DEC_CK, a.nkeys - c * DEC_CK);
+          const uint32_t bytes = static_cast<uint32_t>(nk) * HD * 2;
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* dst = sm_dec + stage * STAGE;
+          mbar_arrive_expect_tx(&full[stage], 2 * bytes);
+          bulk_load_1d(dst, kp + static_cast<long long>(c) * DEC_CK * HD, bytes, &full[stage]);
+          bulk_load_1d(dst + PLANE, vp + static_cast<long long>(c) * DEC_CK * HD, bytes, &full[stage]);
+          if (++stage == DEC_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    return;
+  }
+
+  // ============================== consumers ==============================
   const int gl = lane % GL, kg = lane / GL;
   const int d0 = gl * 8;
   const bool active = d0 < HD;
-  const long long kv_base = (static_cast<long long>(g) * H + h) * kv_len * HD;
-  const bf16* kp = k + kv_base;
-  const bf16* vp = v + kv_base;
+  int stage = 0, par = 0;
+  uint32_t phase = 0;
 
-  float qr[NQ][8];
-#pragma unroll
-  for (int i = 0; i < NQ; ++i) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) qr[i][j] = 0.f;
-    if (active && i < nq) {
-      const uint4 u = *reinterpret_cast<const uint4*>(q + (static_cast<long long>(g) * nq + i) * q_rs + h * HD + d0);
-      const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
-      qr[i][0] = a.x; qr[i][1] = a.y; qr[i][2] = b.x; qr[i][3] = b.y;
-      qr[i][4] = c.x; qr[i][5] = c.y; qr[i][6] = d.x; qr[i][7] = d.y;
-    }
-  }
-
-  // ---- phase 1: scores
-#pragma unroll 4
-  for (int j0 = 0; j0 < nkeys; j0 += KPI) {
-    const int j = j0 + warp * KPW + kg;
-    float part[NQ];
-#pragma unroll
-    for (int i = 0; i < NQ; ++i) part[i] = 0.f;
-    if (active && j < nkeys) {
-      const uint4 u = ldg_nc_v4(kp + static_cast<long long>(j) * HD + d0);
-      const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
-      const float kf[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
-#pragma unroll
-      for (int i = 0; i < NQ; ++i) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) part[i] = fmaf(qr[i][e], kf[e], part[i]);
-      }
-    }
+  uint4 qraw[NQ];
+  auto fetch_q = [&](int item) {
+    const int g = item / a.H, h = item % a.H;
 #pragma unroll
     for (int i = 0; i < NQ; ++i) {
-#pragma unroll
-      for (int off = GL / 2; off > 0; off >>= 1) part[i] += __shfl_xor_sync(0xffffffffu, part[i], off);
+      qraw[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (active && i < a.nq && item < n_items)
+        qraw[i] = *reinterpret_cast<const uint4*>(a.q + (static_cast<long long>(g) * a.nq + i) * a.q_rs + h * HD + d0);
     }
-    if (gl == 0 && j < nkeys) {
-      const bool masked = key_pad != nullptr && key_pad[static_cast<long long>(g) * nkeys + j] != 0;
-#pragma unroll
-      for (int i = 0; i < NQ; ++i) sc[i * nkeys + j] = masked ? -INFINITY : part[i] * scale;
-    }
-  }
-  __syncthreads();
+  };
+  fetch_q(blockIdx.x);
 
-  // ---- softmax: warp i normalises query i
-  if (warp < NQ) {
-    float* row = sc + warp * nkeys;
-    float m = -INFINITY;
-    for (int j = lane; j < nkeys; j += 32) m = fmaxf(m, row[j]);
-    m = warp_max(m);
-    float sum = 0.f;
-    for (int j = lane; j < nkeys; j += 32) {
-      const float p = (m == -INFINITY) ? 0.f : __expf(row[j] - m);
-      row[j] = p;
-      sum += p;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x, par ^= 1) {
+    const int g = item / a.H, h = item % a.H;
+    float qr[NQ][8], m[NQ], l[NQ], acc[NQ][8];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+      m[i] = -INFINITY;
+      l[i] = 0.f;
+      unpack8f(qraw[i], qr[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { qr[i][e] *= a.scale; acc[i][e] = 0.f; }
     }
-    sum = warp_sum(sum);
-    if (lane == 0) s_inv[warp] = sum > 0.f ? 1.f / sum : 0.f;
-  }
-  __syncthreads();
 
-  // ---- phase 2: o = P V
-  float acc[NQ][8];
+    for (int c = 0; c < nch; ++c) {
+      mbar_wait(&full[stage], phase);
+      const uint8_t* sk = sm_dec + stage * STAGE;
+      const uint8_t* sv = sk + PLANE;
+      const int nk = min(DEC_CK, a.nkeys - c * DEC_CK);
+      const unsigned char* padp = a.key_pad ? a.key_pad + static_cast<long long>(g) * a.nkeys + c * DEC_CK : nullptr;
 #pragma unroll
-  for (int i = 0; i < NQ; ++i)
+      for (int it0 = 0; it0 < NIT; it0 += 4) {
+        if (it0 * KPI + warp * KPW >= nk) break;            // warp-uniform: nothing left for this warp
+        float sc[4][NQ];
+        uint4 vu[4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[i][e] = 0.f;
-#pragma unroll 4
-  for (int j0 = 0; j0 < nkeys; j0 += KPI) {
-    const int j = j0 + warp * KPW + kg;
-    if (active && j < nkeys) {
-      const uint4 u = ldg_nc_v4(vp + static_cast<long long>(j) * HD + d0);
-      const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
-      const float vf[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+        for (int u = 0; u < 4; ++u) {
+          const int j = (it0 + u) * KPI + warp * KPW + kg;
+          bool valid = j < nk;
+          uint4 ku = make_uint4(0u, 0u, 0u, 0u);
+          vu[u] = make_uint4(0u, 0u, 0u, 0u);
+          if (valid && active) {
+            ku = *reinterpret_cast<const uint4*>(sk + j * (HD * 2) + d0 * 2);
+            vu[u] = *reinterpret_cast<const uint4*>(sv + j * (HD * 2) + d0 * 2);
+          }
+          if (valid && padp != nullptr && padp[j] != 0) valid = false;
+          float kf[8];
+          unpack8f(ku, kf);
+#pragma unroll
+          for (int i = 0; i < NQ; ++i) {
+            float part = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) part = fmaf(qr[i][e], kf[e], part);
+#pragma unroll
+            for (int off = GL / 2; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+            sc[u][i] = valid ? part : -INFINITY;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+          const float cm = fmaxf(fmaxf(sc[0][i], sc[1][i]), fmaxf(sc[2][i], sc[3][i]));
+          if (cm > m[i]) {                       // uniform within the lane group
+            const float corr = exp_diff(m[i], cm);
+            l[i] *= corr;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[i][e] *= corr;
+            m[i] = cm;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float vf[8];
+          unpack8f(vu[u], vf);
+#pragma unroll
+          for (int i = 0; i < NQ; ++i) {
+            const float p = exp_diff(sc[u][i], m[i]);
+            l[i] += p;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[i][e] = fmaf(p, vf[e], acc[i][e]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stage]);
+      if (++stage == DEC_STAGES) { stage = 0; phase ^= 1; }
+    }
+    fetch_q(item + gridDim.x);   // next item's queries travel while this item is merged
+
+    // merge the KPW lane groups of this warp
+#pragma unroll
+    for (int off = GL; off < 32; off <<= 1) {
 #pragma unroll
       for (int i = 0; i < NQ; ++i) {
-        const float p = sc[i * nkeys + j];
+        const float mo = __shfl_xor_sync(0xffffffffu, m[i], off);
+        const float lo = __shfl_xor_sync(0xffffffffu, l[i], off);
+        const float mm = fmaxf(m[i], mo);
+        const float cs = exp_diff(m[i], mm), co = exp_diff(mo, mm);
+        l[i] = l[i] * cs + lo * co;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[i][e] = fmaf(p, vf[e], acc[i][e]);
+        for (int e = 0; e < 8; ++e) {
+          const float ao = __shfl_xor_sync(0xffffffffu, acc[i][e], off);
+          acc[i][e] = acc[i][e] * cs + ao * co;
+        }
+        m[i] = mm;
       }
     }
-  }
-  // combine the KPW key groups of a warp, then the 4 warps
+    float* rp = red + (par * 4 + warp) * NQ * RED_STRIDE;
+    if (kg == 0 && active) {
 #pragma unroll
-  for (int i = 0; i < NQ; ++i)
+      for (int i = 0; i < NQ; ++i) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e)
+        for (int e = 0; e < 8; ++e) rp[i * RED_STRIDE + d0 + e] = acc[i][e];
+        if (gl == 0) { rp[i * RED_STRIDE + HD] = m[i]; rp[i * RED_STRIDE + HD + 1] = l[i]; }
+      }
+    }
+    named_barrier_sync(1, 128);
+    const float* rb = red + par * 4 * NQ * RED_STRIDE;
+    for (int idx = threadIdx.x; idx < NQ * HD; idx += 128) {
+      const int i = idx / HD, d = idx % HD;
+      if (i < a.nq) {
+        float mm = -INFINITY;
 #pragma unroll
-      for (int off = GL; off < 32; off <<= 1) acc[i][e] += __shfl_xor_sync(0xffffffffu, acc[i][e], off);
-  if (kg == 0 && active) {
+        for (int w = 0; w < 4; ++w) mm = fmaxf(mm, rb[(w * NQ + i) * RED_STRIDE + HD]);
+        float ls = 0.f, val = 0.f;
 #pragma unroll
-    for (int i = 0; i < NQ; ++i)
-#pragma unroll
-      for (int e = 0; e < 8; ++e) red[(warp * NQ + i) * HD + d0 + e] = acc[i][e];
-  }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < NQ * HD; idx += blockDim.x) {
-    const int i = idx / HD, d = idx % HD;
-    if (i < nq) {
-      const float val = (red[(0 * NQ + i) * HD + d] + red[(1 * NQ + i) * HD + d] + red[(2 * NQ + i) * HD + d] +
-                         red[(3 * NQ + i) * HD + d]) * s_inv[i];
-      o[(static_cast<long long>(g) * nq + i) * o_rs + h * HD + d] = __float2bfloat16(val);
+        for (int w = 0; w < 4; ++w) {
+          const float cw = exp_diff(rb[(w * NQ + i) * RED_STRIDE + HD], mm);
+          ls = fmaf(rb[(w * NQ + i) * RED_STRIDE + HD + 1], cw, ls);
+          val = fmaf(rb[(w * NQ + i) * RED_STRIDE + d], cw, val);
+        }
+        a.o[(static_cast<long long>(g) * a.nq + i) * a.o_rs + h * HD + d] = __float2bfloat16(ls > 0.f ? val / ls : 0.f);
+      }
     }
   }
 }
 
 template <int HD, int NQ>
-static int launch_attn_decode(const bf16* q, long long q_rs, const bf16* k, const bf16* v, int kv_len, int nkeys,
-                              bf16* o, long long o_rs, int groups, int nq, int H, const unsigned char* key_pad,
-                              float scale, cudaStream_t s) {
-  const size_t smem = (static_cast<size_t>(NQ) * nkeys + 4 * NQ * HD) * sizeof(float);
-  attn_decode_kernel<HD, NQ><<<dim3(H, groups), 128, smem, s>>>(q, q_rs, k, v, kv_len, nkeys, o, o_rs, nq, H, key_pad, scale);
+static int launch_attn_decode(const DecAttnArgs& a, cudaStream_t s) {
+  auto kern = attn_decode_stream_kernel<HD, NQ>;
+  const size_t smem = static_cast<size_t>(DEC_STAGES) * 2 * DEC_CK * HD * 2 + (2 * DEC_STAGES + 2) * sizeof(uint64_t) +
+                      static_cast<size_t>(2) * 4 * NQ * (HD + 2) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = true;
+  }
+  int per_sm = static_cast<int>((220 * 1024) / (smem + 1024));
+  const int reg_cap = NQ > 1 ? 3 : 4;       // 160 threads x ~100 (NQ = 1) / 128 (NQ = 4) registers
+  per_sm = per_sm < 1 ? 1 : (per_sm > reg_cap ? reg_cap : per_sm);
+  static const int per_sm_env = getenv("B200_DEC_ATTN_PER_SM") ? atoi(getenv("B200_DEC_ATTN_PER_SM")) : 0;
+  if (per_sm_env > 0 && per_sm_env < per_sm) per_sm = per_sm_env;
+  const int items = a.groups * a.H;
+  const int cap = device_sm_count() * per_sm;
+  B200_CHECK_CUDA(launch_kernel(kern, dim3(items < cap ? items : cap), dim3(DEC_THREADS), smem, s, true, 1, a));
   note_launch();
-  B200_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -205,11 +293,14 @@ int attn_decode(const bf16* q, long long q_rs, const bf16* k, const bf16* v, int
                 long long o_rs, int groups, int nq, int H, int hd, const unsigned char* key_pad, float scale,
                 cudaStream_t s) {
   B200_REQUIRE(nq >= 1 && nq <= 4, "attn_decode: %d queries per group (supported: 1..4)", nq);
-  B200_REQUIRE(nkeys >= 1 && nkeys <= 1024, "attn_decode: nkeys %d out of range", nkeys);
-#define B200_AD(HDV)                                                                                         \
-  do {                                                                                                       \
-    if (nq == 1) return launch_attn_decode<HDV, 1>(q, q_rs, k, v, kv_len, nkeys, o, o_rs, groups, nq, H, key_pad, scale, s); \
-    return launch_attn_decode<HDV, 4>(q, q_rs, k, v, kv_len, nkeys, o, o_rs, groups, nq, H, key_pad, scale, s); \
+  B200_REQUIRE(nkeys >= 1 && nkeys <= kv_len, "attn_decode: nkeys %d outside [1, %d]", nkeys, kv_len);
+  DecAttnArgs a = {};
+  a.q = q; a.q_rs = q_rs; a.k = k; a.v = v; a.kv_len = kv_len; a.nkeys = nkeys; a.o = o; a.o_rs = o_rs;
+  a.groups = groups; a.nq = nq; a.H = H; a.key_pad = key_pad; a.scale = scale;
+#define B200_AD(HDV)                                              \
+  do {                                                            \
+    if (nq == 1) return launch_attn_decode<HDV, 1>(a, s);         \
+    return launch_attn_decode<HDV, 4>(a, s);                      \
   } while (0)
   switch (hd) {
     case 32: B200_AD(32);
@@ -222,10 +313,147 @@ int attn_decode(const bf16* q, long long q_rs, const bf16* k, const bf16* v, int
 }
 
 // ------------------------------------------------------------------------------------------
+// Self attention of one decode position with the cache append fused in.  One WARP per (row, head):
+// the current position's q / k / v come straight from the packed QKV projection, k and v are
+// written to cache row `pos` and attended together with the cached rows [0, pos).  GL lanes share a
+// key row (16 bytes each), eight rows per lane group are in flight at a time; scores go through a
+// per-warp shared-memory strip, so there is no block-level synchronisation at all.
+// ------------------------------------------------------------------------------------------
+template <int HD>
+__global__ void __launch_bounds__(128)
+attn_decode_self_kernel(const bf16* __restrict__ qkv, long long rs, bf16* __restrict__ kcache,
+                        bf16* __restrict__ vcache, int max_len, int pos, bf16* __restrict__ o, long long o_rs,
+                        int n_items, int H, float scale) {
+  constexpr int GL = (HD <= 32) ? 4 : (HD <= 64 ? 8 : 16);
+  constexpr int KPW = 32 / GL;
+  constexpr int UNR = 8;
+  extern __shared__ float sm_self[];    // [4][pos + 1]
+  pdl_wait();
+  pdl_trigger();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * 4 + warp;
+  if (item >= n_items) return;
+  const int nkeys = pos + 1;
+  float* sc = sm_self + warp * nkeys;
+  const int r = item / H, h = item % H;
+  const int E = H * HD;
+  const int gl = lane % GL, kg = lane / GL;
+  const int d0 = gl * 8;
+  const bool active = d0 < HD;
+  const bf16* qp = qkv + static_cast<long long>(r) * rs + h * HD + d0;
+  bf16* kb = kcache + static_cast<long long>(item) * max_len * HD + d0;
+  bf16* vb = vcache + static_cast<long long>(item) * max_len * HD + d0;
+  uint4 qu = make_uint4(0u, 0u, 0u, 0u), kn = qu, vn = qu;
+  if (active) {
+    qu = *reinterpret_cast<const uint4*>(qp);
+    kn = *reinterpret_cast<const uint4*>(qp + E);
+    vn = *reinterpret_cast<const uint4*>(qp + 2 * E);
+    if (kg == 0) {
+      *reinterpret_cast<uint4*>(kb + static_cast<long long>(pos) * HD) = kn;
+      *reinterpret_cast<uint4*>(vb + static_cast<long long>(pos) * HD) = vn;
+    }
+  }
+  float qf[8];
+  unpack8f(qu, qf);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) qf[e] *= scale;
+
+  // ---- scores
+  for (int j0 = 0; j0 < nkeys; j0 += KPW * UNR) {
+    uint4 ku[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int j = j0 + u * KPW + kg;
+      ku[u] = (j == pos) ? kn : make_uint4(0u, 0u, 0u, 0u);
+      if (active && j < pos) ku[u] = ldg_nc_v4(kb + static_cast<long long>(j) * HD);
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int j = j0 + u * KPW + kg;
+      float kf[8];
+      unpack8f(ku[u], kf);
+      float part = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) part = fmaf(qf[e], kf[e], part);
+#pragma unroll
+      for (int off = GL / 2; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+      if (gl == 0 && j < nkeys) sc[j] = part;
+    }
+  }
+  __syncwarp();
+  float mx = -INFINITY;
+  for (int j = lane; j < nkeys; j += 32) mx = fmaxf(mx, sc[j]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j < nkeys; j += 32) {
+    const float p = __expf(sc[j] - mx);
+    sc[j] = p;
+    sum += p;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+
+  // ---- o = P V
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int j0 = 0; j0 < nkeys; j0 += KPW * UNR) {
+    uint4 vu[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int j = j0 + u * KPW + kg;
+      vu[u] = (j == pos) ? vn : make_uint4(0u, 0u, 0u, 0u);
+      if (active && j < pos) vu[u] = ldg_nc_v4(vb + static_cast<long long>(j) * HD);
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int j = j0 + u * KPW + kg;
+      const float p = j < nkeys ? sc[j] : 0.f;
+      float vf[8];
+      unpack8f(vu[u], vf);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = fmaf(p, vf[e], acc[e]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+#pragma unroll
+    for (int off = GL; off < 32; off <<= 1) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], off);
+  if (kg == 0 && active) {
+    const float inv = 1.f / sum;
+    uint4 out;
+    out.x = pack_bf16(acc[0] * inv, acc[1] * inv); out.y = pack_bf16(acc[2] * inv, acc[3] * inv);
+    out.z = pack_bf16(acc[4] * inv, acc[5] * inv); out.w = pack_bf16(acc[6] * inv, acc[7] * inv);
+    *reinterpret_cast<uint4*>(o + static_cast<long long>(r) * o_rs + h * HD + d0) = out;
+  }
+}
+
+int attn_decode_append(const bf16* qkv, long long qkv_rs, bf16* kcache, bf16* vcache, int max_len, int pos, bf16* o,
+                       long long o_rs, int R, int H, int hd, float scale, cudaStream_t s) {
+  B200_REQUIRE(pos >= 0 && pos < max_len, "attn_decode_append: position %d outside the cache (%d rows)", pos, max_len);
+  B200_REQUIRE(max_len <= 4096, "attn_decode_append: cache rows %d > 4096", max_len);
+  const int items = R * H;
+  const size_t smem = static_cast<size_t>(4) * (pos + 1) * sizeof(float);
+#define B200_AS(HDV)                                                                                              \
+  B200_CHECK_CUDA(launch_kernel(attn_decode_self_kernel<HDV>, dim3(cdiv(items, 4)), dim3(128), smem, s, true, 1, \
+                                qkv, qkv_rs, kcache, vcache, max_len, pos, o, o_rs, items, H, scale))
+  switch (hd) {
+    case 32: B200_AS(32); break;
+    case 64: B200_AS(64); break;
+    case 96: B200_AS(96); break;
+    case 128: B200_AS(128); break;
+    default: B200_REQUIRE(false, "attn_decode_append: head dim %d not in {32,64,96,128}", hd);
+  }
+#undef B200_AS
+  note_launch();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 __global__ void greedy_update_kernel(const int64_t* __restrict__ next_ids, int64_t* __restrict__ cur,
                                      int64_t* __restrict__ out_tokens, int* __restrict__ out_len,
                                      unsigned char* __restrict__ finished, int* __restrict__ n_finished, int R,
                                      int max_len, int pos, long long end_id, long long pad_id) {
+  pdl_wait();
+  pdl_trigger();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R) return;
   long long tok = next_ids[r];
@@ -245,8 +473,8 @@ __global__ void greedy_update_kernel(const int64_t* __restrict__ next_ids, int64
 int greedy_update(const int64_t* next_ids, int64_t* cur_tokens, int64_t* out_tokens, int* out_len,
                   unsigned char* finished, int* n_finished, int R, int max_len, int pos, long long end_id,
                   long long pad_id, cudaStream_t s) {
-  greedy_update_kernel<<<cdiv(R, 128), 128, 0, s>>>(next_ids, cur_tokens, out_tokens, out_len, finished, n_finished,
-                                                    R, max_len, pos, end_id, pad_id);
+  B200_CHECK_CUDA(launch_kernel(greedy_update_kernel, dim3(cdiv(R, 128)), dim3(128), 0, s, true, 1, next_ids, cur_tokens, out_tokens, out_len, finished, n_finished,
+                                                    R, max_len, pos, end_id, pad_id));
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -278,6 +506,8 @@ __global__ void __launch_bounds__(256)
 beam_topk_kernel(const float* __restrict__ logits, const float* __restrict__ beam_scores,
                  const unsigned char* __restrict__ finished, int beam, int V, long long end_id, int first_step,
                  int64_t* __restrict__ out_tokens, int* __restrict__ out_parent, float* __restrict__ out_scores) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float s_lse[TOPK_MAX];
   __shared__ float s_red[8];
   __shared__ Cand s_top[8][TOPK_MAX];
@@ -356,8 +586,8 @@ int beam_topk(const float* logits, const float* beam_scores, const unsigned char
               int V, long long end_id, int first_step, int64_t* out_tokens, int* out_parent, float* out_scores,
               cudaStream_t s) {
   B200_REQUIRE(beam >= 1 && beam <= TOPK_MAX, "beam_topk: beam %d out of range (1..%d)", beam, TOPK_MAX);
-  beam_topk_kernel<<<B, 256, 0, s>>>(logits, beam_scores, finished, beam, V, end_id, first_step, out_tokens,
-                                     out_parent, out_scores);
+  B200_CHECK_CUDA(launch_kernel(beam_topk_kernel, dim3(B), dim3(256), 0, s, true, 1, logits, beam_scores, finished, beam, V, end_id, first_step, out_tokens,
+                                     out_parent, out_scores));
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -368,6 +598,8 @@ __global__ void beam_advance_kernel(const int64_t* __restrict__ seq_in, int64_t*
                                     const unsigned char* __restrict__ fin_in, unsigned char* __restrict__ fin_out,
                                     const int64_t* __restrict__ tokens, const int* __restrict__ parent, int R,
                                     int beam, int max_len, int pos, long long end_id) {
+  pdl_wait();
+  pdl_trigger();
   const int r = blockIdx.x;
   if (r >= R) return;
   const int src = (r / beam) * beam + parent[r];
@@ -383,7 +615,7 @@ __global__ void beam_advance_kernel(const int64_t* __restrict__ seq_in, int64_t*
 int beam_advance(const int64_t* seq_in, int64_t* seq_out, const unsigned char* fin_in, unsigned char* fin_out,
                  const int64_t* tokens, const int* parent, int R, int beam, int max_len, int pos, long long end_id,
                  cudaStream_t s) {
-  beam_advance_kernel<<<R, 64, 0, s>>>(seq_in, seq_out, fin_in, fin_out, tokens, parent, R, beam, max_len, pos, end_id);
+  B200_CHECK_CUDA(launch_kernel(beam_advance_kernel, dim3(R), dim3(64), 0, s, true, 1, seq_in, seq_out, fin_in, fin_out, tokens, parent, R, beam, max_len, pos, end_id));
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -394,6 +626,8 @@ __global__ void beam_finalize_kernel(const int64_t* __restrict__ seqs, const flo
                                      int max_len, int n_tok, long long end_id, long long pad_id,
                                      int64_t* __restrict__ out_tokens, int* __restrict__ out_len,
                                      float* __restrict__ out_score) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.x;
   if (threadIdx.x != 0) return;
   int best = 0;
@@ -411,29 +645,33 @@ __global__ void beam_finalize_kernel(const int64_t* __restrict__ seqs, const flo
 int beam_finalize(const int64_t* seqs, const float* scores, int B, int beam, int max_len, int n_tok,
                   long long end_id, long long pad_id, int64_t* out_tokens, int* out_len, float* out_score,
                   cudaStream_t s) {
-  beam_finalize_kernel<<<B, 32, 0, s>>>(seqs, scores, beam, max_len, n_tok, end_id, pad_id, out_tokens, out_len, out_score);
+  B200_CHECK_CUDA(launch_kernel(beam_finalize_kernel, dim3(B), dim3(32), 0, s, true, 1, seqs, scores, beam, max_len, n_tok, end_id, pad_id, out_tokens, out_len, out_score));
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 __global__ void fill_i64_kernel(int64_t* p, long long n, long long v) {
+  pdl_wait();
+  pdl_trigger();
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i < n) p[i] = v;
 }
 int fill_i64(int64_t* p, long long n, long long v, cudaStream_t s) {
-  fill_i64_kernel<<<cdiv(n, 256), 256, 0, s>>>(p, n, v);
+  B200_CHECK_CUDA(launch_kernel(fill_i64_kernel, dim3(cdiv(n, 256)), dim3(256), 0, s, true, 1, p, n, v));
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 // out[r*stride] = v for r < n   (column fill: START token of every sequence)
 __global__ void fill_col_i64_kernel(int64_t* p, long long n, long long stride, long long v) {
+  pdl_wait();
+  pdl_trigger();
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i < n) p[i * stride] = v;
 }
 int fill_col_i64(int64_t* p, long long n, long long stride, long long v, cudaStream_t s) {
-  fill_col_i64_kernel<<<cdiv(n, 256), 256, 0, s>>>(p, n, stride, v);
+  B200_CHECK_CUDA(launch_kernel(fill_col_i64_kernel, dim3(cdiv(n, 256)), dim3(256), 0, s, true, 1, p, n, stride, v));
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -442,6 +680,8 @@ int fill_col_i64(int64_t* p, long long n, long long stride, long long v, cudaStr
 __global__ void cache_reorder_kernel(const bf16* __restrict__ src_k, const bf16* __restrict__ src_v,
                                      bf16* __restrict__ dst_k, bf16* __restrict__ dst_v,
                                      const int* __restrict__ parent, int beam, int H, int hd, int max_len, int npos) {
+  pdl_wait();
+  pdl_trigger();
   const int vpr = hd >> 3;
   const int r = blockIdx.y;                      // destination row
   const int b = r / beam;
@@ -464,7 +704,7 @@ int cache_reorder(const bf16* src_k, const bf16* src_v, bf16* dst_k, bf16* dst_v
   const int npos = pos + 1;
   const long long per_row = static_cast<long long>(H) * npos * (hd / 8);
   dim3 grid(cdiv(per_row, 256) > 8 ? 8 : cdiv(per_row, 256), B * beam);
-  cache_reorder_kernel<<<grid, 256, 0, s>>>(src_k, src_v, dst_k, dst_v, parent, beam, H, hd, max_len, npos);
+  B200_CHECK_CUDA(launch_kernel(cache_reorder_kernel, grid, dim3(256), 0, s, true, 1, src_k, src_v, dst_k, dst_v, parent, beam, H, hd, max_len, npos));
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -7,15 +7,17 @@ namespace b200 {
 // cross K/V from the projection GEMM's [B*S, 2E] layout into head-major [B][H][S][hd] K and V
 // planes (contiguous per (image, head): what the decode kernel streams).
 int kv_to_head_major(const bf16* kv, bf16* k_hm, bf16* v_hm, int B, int S, int H, int hd, cudaStream_t s);
-// append this step's K/V (columns [E,2E) and [2E,3E) of qkv [R,3E]) to the self cache at `pos`
-// cache layout [R][H][max_len][hd]
-int kv_append(const bf16* qkv, bf16* kcache, bf16* vcache, int R, int H, int hd, int max_len, int pos, cudaStream_t s);
 // single-query attention: for every group g (image) and head h, NQ query rows (beams) attend
 // over the same nkeys keys.  q/o: [groups*nq, H*hd] rows; K/V: [groups][H][kv_len][hd], reading
 // the first nkeys rows.  key_pad: optional [groups, nkeys] uint8.
 int attn_decode(const bf16* q, long long q_rs, const bf16* k, const bf16* v, int kv_len, int nkeys,
                 bf16* o, long long o_rs, int groups, int nq, int H, int hd, const unsigned char* key_pad,
                 float scale, cudaStream_t s);
+// self attention of one decode position with the cache append fused in: q/k/v of the current position
+// are the three E-wide column blocks of qkv [R, 3E]; k/v are written to cache row `pos` of
+// [R][H][max_len][hd] and attended together with rows [0,pos).
+int attn_decode_append(const bf16* qkv, long long qkv_rs, bf16* kcache, bf16* vcache, int max_len, int pos, bf16* o,
+                       long long o_rs, int R, int H, int hd, float scale, cudaStream_t s);
 // greedy bookkeeping after a step: finished rows emit pad_id, END marks a row finished
 int greedy_update(const int64_t* next_ids, int64_t* cur_tokens, int64_t* out_tokens, int* out_len,
                   unsigned char* finished, int* n_finished, int R, int max_len, int pos, long long end_id,

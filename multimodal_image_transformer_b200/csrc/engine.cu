@@ -95,10 +95,21 @@ struct b200_engine {
     float *scratch = nullptr, *logits = nullptr, *scores[2] = {nullptr, nullptr}, *best = nullptr;
     int64_t *ids = nullptr, *cur_tok = nullptr, *seq[2] = {nullptr, nullptr};
     int *parent = nullptr, *out_len = nullptr, *n_finished = nullptr;
+    int64_t* out_tok = nullptr;    // [B, max_len] staging of the best hypotheses (stable address for the graph)
+    float* out_score = nullptr;    // [B]
     unsigned char* fin[2] = {nullptr, nullptr};
     const uint8_t* mem_pad = nullptr;
     int64_t bytes = 0;
     bool ready = false;
+    // Independent image ranges ("partitions"): every decode op is row-local, so each partition runs
+    // its own launch chain on its own stream.  A chain is latency-bound (~70 dependent small
+    // kernels per position) while the cross-attention K/V stream is HBM-bound; concurrent chains
+    // fill the SMs the skinny GEMMs leave idle and keep the HBM pipe busy.
+    struct Part { int b0 = 0, nb = 0; float* parts = nullptr; };
+    std::vector<Part> part;
+    int ksplit_e = 1, ksplit_f = 1;     // split-K of the E-deep / F-deep skinny GEMMs feeding a LayerNorm
+    std::vector<cudaStream_t> side;     // streams of partitions 1.. (partition 0 runs on the caller's)
+    std::vector<cudaEvent_t> ev;        // [0] fork, [p] join of partition p
     // CUDA-graph cache of the whole generation loop (one per (workspace, shape, ids) key)
     cudaGraphExec_t graph = nullptr;
     cudaStream_t cap_stream = nullptr;
@@ -176,9 +187,14 @@ void build_plan(const b200_engine* e, Plan* pl, uint8_t* base, int B, int T, int
 }
 
 // y = x W^T + b  with optional activation / residual; W rows [row0,row0+N) of a [*,K] matrix
+static int dec_gemm_stages() {
+  static const int v = getenv("B200_DEC_GEMM_STAGES") ? atoi(getenv("B200_DEC_GEMM_STAGES")) : 0;
+  return v;
+}
 int linear_fwd(const bf16* x, int64_t ldx, const bf16* W, const float* bias, bf16* y, int64_t ldy, int M,
-               int N, int K, int act, const bf16* residual, int64_t ldr, cudaStream_t s) {
+               int N, int K, int act, const bf16* residual, int64_t ldr, cudaStream_t s, int max_stages = 0) {
   GemmProblem g;
+  g.max_stages = max_stages;
   g.M = M; g.N = N; g.K = K;
   g.A = x; g.lda = ldx; g.B = W; g.ldb = K;
   g.D = y; g.ldd = ldy; g.bias = bias; g.act = act; g.residual = residual; g.ldr = ldr;
@@ -409,43 +425,136 @@ void build_decode_plan(const b200_engine* e, b200_engine::Decode* d, uint8_t* ba
   d->best = b.take<float>(R);
   d->ids = b.take<int64_t>(R); d->cur_tok = b.take<int64_t>(R);
   d->parent = b.take<int>(R); d->out_len = b.take<int>(R); d->n_finished = b.take<int>(4);
+  d->out_tok = b.take<int64_t>(static_cast<int64_t>(B) * max_len); d->out_score = b.take<float>(B);
+  // partitions: whole 128-row GEMM tiles where possible
+  const char* forced_env = getenv("B200_DECODE_PARTS");   // read per plan: tests compare partitionings
+  const int forced = forced_env ? atoi(forced_env) : 0;
+  int P = forced > 0 ? forced : (R >= 512 ? 4 : (R >= 256 ? 2 : 1));
+  if (P > B) P = B;
+  if (P > 8) P = 8;
+  int per = (B + P - 1) / P;
+  const int gran = beam <= 128 ? (128 / beam > 0 ? 128 / beam : 1) : 1;   // images per 128 rows
+  if (per > gran) per = (per + gran - 1) / gran * gran;
+  d->part.clear();
+  for (int b0 = 0; b0 < B; b0 += per) {
+    b200_engine::Decode::Part pt;
+    pt.b0 = b0;
+    pt.nb = (B - b0 < per) ? (B - b0) : per;
+    d->part.push_back(pt);
+  }
+  // split-K of the LayerNorm-fed GEMMs: enough CTAs to cover the SMs, at least 2 k-blocks per split
+  const int rows_p = per * beam;
+  const int tiles = ((rows_p + 127) / 128) * static_cast<int>((E + 127) / 128);
+  auto pick = [&](int64_t K) {
+    const int kb = static_cast<int>((K + 63) / 64);
+    int sk = 148 / (tiles > 0 ? tiles : 1);
+    if (sk > kb / 2) sk = kb / 2;
+    if (sk > 8) sk = 8;
+    if (sk < 1) sk = 1;
+    return gemm_effective_splits(static_cast<int>(K), sk);
+  };
+  d->ksplit_e = pick(E);
+  d->ksplit_f = pick(F);
+  if (getenv("B200_DEC_KSPLIT_E")) d->ksplit_e = gemm_effective_splits(static_cast<int>(E), atoi(getenv("B200_DEC_KSPLIT_E")));
+  if (getenv("B200_DEC_KSPLIT_F")) d->ksplit_f = gemm_effective_splits(static_cast<int>(F), atoi(getenv("B200_DEC_KSPLIT_F")));
+  const int ks_max = d->ksplit_e > d->ksplit_f ? d->ksplit_e : d->ksplit_f;
+  for (auto& pt : d->part) {
+    const int64_t mpad = (static_cast<int64_t>(pt.nb) * beam + 127) / 128 * 128;
+    pt.parts = b.take<float>(ks_max * mpad * E);
+  }
   d->bytes = (b.off + 255) & ~static_cast<int64_t>(255);
 }
 
-// one decode position for every row: tokens [R] at position pos -> final hidden in *x_out
-int decode_hidden(b200_engine* e, const int64_t* tokens, int pos, bf16** x_out, cudaStream_t s) {
+// y = LayerNorm(x W^T + b + residual) for the skinny decode GEMMs: split-K fp32 partial slabs,
+// summed together with bias and residual inside the LayerNorm kernel
+int linear_ln_fwd(const bf16* x, int64_t ldx, const bf16* W, const float* bias, const bf16* residual,
+                  const float* gamma, const float* beta, float* parts, int split, bf16* y, int M, int N, int K,
+                  float eps, cudaStream_t s) {
+  GemmProblem g;
+  g.M = M; g.N = N; g.K = K;
+  g.A = x; g.lda = ldx; g.B = W; g.ldb = K;
+  g.D = parts; g.ldd = N; g.d_fp32 = true; g.partials = true; g.split_k = split; g.block_n = 128;
+  g.max_stages = dec_gemm_stages();
+  RC(gemm_launch(g, s));
+  const long long mpad = (static_cast<long long>(M) + 127) / 128 * 128;
+  return layernorm_reduce_fwd(parts, gemm_effective_splits(K, split), mpad * N, N, bias, residual, N, gamma, beta, y, M, N, eps, s);
+}
+
+// one decode position for the rows of one partition: tokens[r] at position pos -> final hidden in *x_out
+// (`cur` = live copy of the self-attention cache)
+int decode_hidden(b200_engine* e, const b200_engine::Decode::Part& pt, int cur, const int64_t* tokens, int pos,
+                  bf16** x_out, cudaStream_t s) {
   const auto& c = e->cfg;
   auto& d = e->dec;
   const int E = c.embed_dim, F = c.ff_dim, H = c.num_heads, L = c.num_layers, hd = E / H;
-  const int R = d.R, B = d.B, S = d.S;
+  const int S = d.S;
+  const int64_t r0 = static_cast<int64_t>(pt.b0) * d.beam;
+  const int R = pt.nb * d.beam, B = pt.nb;
   const float scale = 1.0f / sqrtf(static_cast<float>(hd));
   B200_REQUIRE(pos >= 0 && pos < d.max_len && pos < c.max_seq_len, "decode: position %d out of range", pos);
-  bf16* x = d.xa;
-  bf16* xn = d.xb;
-  RC(embed_pe_fwd(tokens, e->pf + e->emb, e->pe, x, R, 1, E, c.vocab_size, sqrtf(static_cast<float>(E)), s, pos));
-  const int64_t self_stride = static_cast<int64_t>(R) * d.max_len * E;
-  const int64_t cross_stride = static_cast<int64_t>(B) * S * E;
+  bf16* x = d.xa + r0 * E;
+  bf16* xn = d.xb + r0 * E;
+  bf16* qkv = d.qkv + r0 * 3 * E;
+  bf16* attn = d.attn + r0 * E;
+  bf16* x1 = d.x1 + r0 * E;
+  bf16* qc = d.qc + r0 * E;
+  bf16* x2 = d.x2 + r0 * E;
+  bf16* h = d.h + r0 * F;
+  const uint8_t* mem_pad = d.mem_pad ? d.mem_pad + static_cast<int64_t>(pt.b0) * S : nullptr;
+  RC(embed_pe_fwd(tokens + r0, e->pf + e->emb, e->pe, x, R, 1, E, c.vocab_size, sqrtf(static_cast<float>(E)), s, pos));
+  const int64_t self_stride = static_cast<int64_t>(d.R) * d.max_len * E;
+  const int64_t cross_stride = static_cast<int64_t>(d.B) * S * E;
+  const int64_t self_off = r0 * d.max_len * E;
+  const int64_t cross_off = static_cast<int64_t>(pt.b0) * S * E;
   for (int l = 0; l < L; ++l) {
     const LayerOff& o = e->lo[l];
-    bf16* kc_l = d.kcache[d.cur] + l * self_stride;
-    bf16* vc_l = d.vcache[d.cur] + l * self_stride;
-    RC(linear_fwd(x, E, e->ph + o.sa_w, e->pf + o.sa_b, d.qkv, 3 * E, R, 3 * E, E, 0, nullptr, 0, s));
-    RC(kv_append(d.qkv, kc_l, vc_l, R, H, hd, d.max_len, pos, s));
-    RC(attn_decode(d.qkv, 3 * E, kc_l, vc_l, d.max_len, pos + 1, d.attn, E, R, 1, H, hd, nullptr, scale, s));
-    RC(linear_fwd(d.attn, E, e->ph + o.sa_ow, e->pf + o.sa_ob, d.y, E, R, E, E, 0, x, E, s));
-    RC(layernorm_fwd(d.y, e->pf + o.n1_w, e->pf + o.n1_b, d.x1, nullptr, nullptr, R, E, c.ln_eps, s));
-    RC(linear_fwd(d.x1, E, e->ph + o.ca_w, e->pf + o.ca_b, d.qc, E, R, E, E, 0, nullptr, 0, s));
-    RC(attn_decode(d.qc, E, d.kc + l * cross_stride, d.vc + l * cross_stride, S, S, d.attn, E, B, d.beam, H, hd,
-                   d.mem_pad, scale, s));
-    RC(linear_fwd(d.attn, E, e->ph + o.ca_ow, e->pf + o.ca_ob, d.y, E, R, E, E, 0, d.x1, E, s));
-    RC(layernorm_fwd(d.y, e->pf + o.n2_w, e->pf + o.n2_b, d.x2, nullptr, nullptr, R, E, c.ln_eps, s));
-    RC(linear_fwd(d.x2, E, e->ph + o.l1_w, e->pf + o.l1_b, d.h, F, R, F, E, c.act, nullptr, 0, s));
-    RC(linear_fwd(d.h, F, e->ph + o.l2_w, e->pf + o.l2_b, d.y, E, R, E, F, 0, d.x2, E, s));
-    RC(layernorm_fwd(d.y, e->pf + o.n3_w, e->pf + o.n3_b, xn, nullptr, nullptr, R, E, c.ln_eps, s));
+    bf16* kc_l = d.kcache[cur] + l * self_stride + self_off;
+    bf16* vc_l = d.vcache[cur] + l * self_stride + self_off;
+    RC(linear_fwd(x, E, e->ph + o.sa_w, e->pf + o.sa_b, qkv, 3 * E, R, 3 * E, E, 0, nullptr, 0, s, dec_gemm_stages()));
+    RC(attn_decode_append(qkv, 3 * E, kc_l, vc_l, d.max_len, pos, attn, E, R, H, hd, scale, s));
+    RC(linear_ln_fwd(attn, E, e->ph + o.sa_ow, e->pf + o.sa_ob, x, e->pf + o.n1_w, e->pf + o.n1_b, pt.parts, d.ksplit_e,
+                     x1, R, E, E, c.ln_eps, s));
+    RC(linear_fwd(x1, E, e->ph + o.ca_w, e->pf + o.ca_b, qc, E, R, E, E, 0, nullptr, 0, s, dec_gemm_stages()));
+    RC(attn_decode(qc, E, d.kc + l * cross_stride + cross_off, d.vc + l * cross_stride + cross_off, S, S, attn, E, B,
+                   d.beam, H, hd, mem_pad, scale, s));
+    RC(linear_ln_fwd(attn, E, e->ph + o.ca_ow, e->pf + o.ca_ob, x1, e->pf + o.n2_w, e->pf + o.n2_b, pt.parts, d.ksplit_e,
+                     x2, R, E, E, c.ln_eps, s));
+    RC(linear_fwd(x2, E, e->ph + o.l1_w, e->pf + o.l1_b, h, F, R, F, E, c.act, nullptr, 0, s, dec_gemm_stages()));
+    RC(linear_ln_fwd(h, F, e->ph + o.l2_w, e->pf + o.l2_b, x2, e->pf + o.n3_w, e->pf + o.n3_b, pt.parts, d.ksplit_f,
+                     xn, R, E, F, c.ln_eps, s));
     bf16* t = x; x = xn; xn = t;
   }
   *x_out = x;
   return 0;
+}
+
+// Runs body(partition, stream) for every partition: partition 0 on `s`, the others on side streams
+// forked from / joined back into `s` with events (valid eagerly and under stream capture).
+template <class Body>
+int for_each_part(b200_engine* e, cudaStream_t s, Body body) {
+  auto& d = e->dec;
+  const int P = static_cast<int>(d.part.size());
+  while (static_cast<int>(d.side.size()) < P - 1) {
+    cudaStream_t st;
+    B200_CHECK_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    d.side.push_back(st);
+  }
+  while (static_cast<int>(d.ev.size()) < P) {
+    cudaEvent_t ev;
+    B200_CHECK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    d.ev.push_back(ev);
+  }
+  if (P > 1) {
+    B200_CHECK_CUDA(cudaEventRecord(d.ev[0], s));
+    for (int p = 1; p < P; ++p) B200_CHECK_CUDA(cudaStreamWaitEvent(d.side[p - 1], d.ev[0], 0));
+  }
+  int rc = 0;
+  for (int p = 0; p < P && rc == 0; ++p) rc = body(d.part[p], p == 0 ? s : d.side[p - 1]);
+  for (int p = 1; p < P; ++p) {   // always join, also on error, so a capture is never left forked
+    cudaEventRecord(d.ev[p], d.side[p - 1]);
+    cudaStreamWaitEvent(s, d.ev[p], 0);
+  }
+  return rc;
 }
 
 uint64_t mix_key(std::initializer_list<uint64_t> v) {
@@ -549,6 +658,10 @@ int b200_engine_create(const b200_engine_config* cfg, b200_engine** out) {
 void b200_engine_destroy(b200_engine* e) {
   if (e && e->dec.graph) cudaGraphExecDestroy(e->dec.graph);
   if (e && e->dec.cap_stream) cudaStreamDestroy(e->dec.cap_stream);
+  if (e) {
+    for (auto st : e->dec.side) cudaStreamDestroy(st);
+    for (auto ev : e->dec.ev) cudaEventDestroy(ev);
+  }
   delete e;
 }
 
@@ -771,15 +884,27 @@ int b200_engine_decode_begin(b200_engine* e, const float* memory, const uint8_t*
   return 0;
 }
 
+// LM head of one partition: greedy ids (argmax fused into the GEMM epilogue)
+static int decode_argmax_part(b200_engine* e, const b200_engine::Decode::Part& pt, int cur, const int64_t* tokens_in,
+                              int pos, int64_t* next_ids, cudaStream_t s) {
+  auto& d = e->dec;
+  const int E = e->cfg.embed_dim, V = e->cfg.vocab_size;
+  const int64_t r0 = static_cast<int64_t>(pt.b0) * d.beam;
+  const int R = pt.nb * d.beam;
+  bf16* x = nullptr;
+  RC(decode_hidden(e, pt, cur, tokens_in, pos, &x, s));
+  const int64_t n_tiles = gemm_num_n_tiles(V, 128);
+  return b200_lmhead_argmax(x, E, e->ph + e->fc_w, E, e->pf + e->fc_b, R, V, E, next_ids + r0, d.best + r0,
+                            d.scratch + 2 * r0 * n_tiles, s);
+}
+
 int b200_engine_decode_step(b200_engine* e, const int64_t* tokens_in, int32_t pos, int64_t* next_ids, void* stream) {
   B200_REQUIRE(e && tokens_in && next_ids, "decode_step: null argument");
   B200_REQUIRE(e->dec.ready, "decode_step: call decode_begin first");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  bf16* x = nullptr;
-  RC(decode_hidden(e, tokens_in, pos, &x, s));
-  const int E = e->cfg.embed_dim, V = e->cfg.vocab_size;
-  return b200_lmhead_argmax(x, E, e->ph + e->fc_w, E, e->pf + e->fc_b, e->dec.R, V, E, next_ids, e->dec.best,
-                            e->dec.scratch, stream);
+  return for_each_part(e, s, [&](const b200_engine::Decode::Part& pt, cudaStream_t ps) -> int {
+    return decode_argmax_part(e, pt, e->dec.cur, tokens_in, pos, next_ids, ps);
+  });
 }
 
 int b200_engine_generate_greedy(b200_engine* e, int64_t start_id, int64_t end_id, int32_t max_len,
@@ -802,20 +927,25 @@ int b200_engine_generate_greedy(b200_engine* e, int64_t start_id, int64_t end_id
     B200_CHECK_CUDA(cudaMemsetAsync(d.out_len, 0, sizeof(int) * R, ws));
     return 0;
   };
-  auto one_step = [&](int pos, cudaStream_t ws) -> int {
-    RC(b200_engine_decode_step(e, d.cur_tok, pos, d.ids, ws));
-    return greedy_update(d.ids, d.cur_tok, toks, d.out_len, d.fin[0], d.n_finished, R, ld, pos, end_id, pad, ws);
+  // positions [p0, p1) of one partition, back to back on its stream (rows are independent)
+  auto steps = [&](const b200_engine::Decode::Part& pt, int p0, int p1, cudaStream_t ps) -> int {
+    const int64_t r0 = pt.b0;
+    for (int pos = p0; pos < p1; ++pos) {
+      RC(decode_argmax_part(e, pt, 0, d.cur_tok, pos, d.ids, ps));
+      RC(greedy_update(d.ids + r0, d.cur_tok + r0, toks + r0 * ld, d.out_len + r0, d.fin[0] + r0, d.n_finished, pt.nb, ld,
+                       pos, end_id, pad, ps));
+    }
+    return 0;
   };
   if (stop_check_interval > 0) {
     RC(prologue(s));
-    for (int pos = 0; pos + 1 < max_len; ++pos) {
-      RC(one_step(pos, s));
-      if ((pos + 1) % stop_check_interval == 0) {   // the reference's early exit (model.py:239-240), batched
-        int nf = 0;
-        B200_CHECK_CUDA(cudaMemcpyAsync(&nf, d.n_finished, sizeof(int), cudaMemcpyDeviceToHost, s));
-        B200_CHECK_CUDA(cudaStreamSynchronize(s));
-        if (nf >= R) break;
-      }
+    for (int p0 = 0; p0 + 1 < max_len; p0 += stop_check_interval) {
+      const int p1 = (p0 + stop_check_interval < max_len - 1) ? p0 + stop_check_interval : max_len - 1;
+      RC(for_each_part(e, s, [&](const b200_engine::Decode::Part& pt, cudaStream_t ps) -> int { return steps(pt, p0, p1, ps); }));
+      int nf = 0;   // the reference's early exit (model.py:239-240), batched
+      B200_CHECK_CUDA(cudaMemcpyAsync(&nf, d.n_finished, sizeof(int), cudaMemcpyDeviceToHost, s));
+      B200_CHECK_CUDA(cudaStreamSynchronize(s));
+      if (nf >= R) break;
     }
   } else {
     const uint64_t key = mix_key({reinterpret_cast<uint64_t>(d.kc), static_cast<uint64_t>(R), static_cast<uint64_t>(d.S),
@@ -823,8 +953,9 @@ int b200_engine_generate_greedy(b200_engine* e, int64_t start_id, int64_t end_id
                                   static_cast<uint64_t>(end_id), reinterpret_cast<uint64_t>(d.mem_pad), 1ull});
     RC(run_maybe_graphed(e, key, s, [&](cudaStream_t ws) -> int {
       RC(prologue(ws));
-      for (int pos = 0; pos + 1 < max_len; ++pos) RC(one_step(pos, ws));
-      return 0;
+      return for_each_part(e, ws, [&](const b200_engine::Decode::Part& pt, cudaStream_t ps) -> int {
+        return steps(pt, 0, max_len - 1, ps);
+      });
     }));
   }
   B200_CHECK_CUDA(cudaMemcpy2DAsync(out_tokens, static_cast<size_t>(max_len) * sizeof(int64_t), toks,
@@ -844,37 +975,57 @@ int b200_engine_generate_beam(b200_engine* e, int64_t start_id, int64_t end_id, 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const auto& c = e->cfg;
   const int E = c.embed_dim, V = c.vocab_size, H = c.num_heads, L = c.num_layers, hd = E / H;
-  const int R = d.R, B = d.B, beam = d.beam;
-  float* logits = d.logits;
-  B200_REQUIRE(logits != nullptr, "generate_beam: decode_begin was called with beam=1; use generate_greedy");
-  int cs = 0;   // live copy of seq / scores / finished flags
-  RC(fill_i64(d.seq[0], static_cast<long long>(R) * d.max_len, c.pad_idx, s));
-  RC(fill_col_i64(d.seq[0], R, d.max_len, start_id, s));
-  RC(fill_i64(d.cur_tok, R, start_id, s));
-  B200_CHECK_CUDA(cudaMemsetAsync(d.fin[0], 0, R, s));
-  B200_CHECK_CUDA(cudaMemsetAsync(d.scores[0], 0, sizeof(float) * R, s));
-  int n_tok = 1;
-  for (int pos = 0; pos + 1 < max_len; ++pos) {
-    bf16* x = nullptr;
-    RC(decode_hidden(e, d.cur_tok, pos, &x, s));
-    GemmProblem g;
-    g.M = R; g.N = V; g.K = E;
-    g.A = x; g.lda = E; g.B = e->ph + e->fc_w; g.ldb = E;
-    g.D = logits; g.ldd = V; g.d_fp32 = true; g.bias = e->pf + e->fc_b; g.split_k = 1;
-    RC(gemm_launch(g, s));
-    RC(beam_topk(logits, d.scores[cs], d.fin[cs], B, beam, V, end_id, pos == 0, d.cur_tok, d.parent, d.scores[cs ^ 1], s));
-    RC(beam_advance(d.seq[cs], d.seq[cs ^ 1], d.fin[cs], d.fin[cs ^ 1], d.cur_tok, d.parent, R, beam, d.max_len, pos, end_id, s));
-    // the self-attention cache follows the surviving hypotheses
-    for (int l = 0; l < L; ++l) {
-      const int64_t off = static_cast<int64_t>(l) * R * d.max_len * E;
-      RC(cache_reorder(d.kcache[d.cur] + off, d.vcache[d.cur] + off, d.kcache[d.cur ^ 1] + off, d.vcache[d.cur ^ 1] + off,
-                       d.parent, B, beam, H, hd, d.max_len, pos, s));
-    }
-    d.cur ^= 1;
-    cs ^= 1;
-    ++n_tok;
-  }
-  return beam_finalize(d.seq[cs], d.scores[cs], B, beam, d.max_len, n_tok, end_id, c.pad_idx, out_tokens, out_len, out_score, s);
+  const int R = d.R, beam = d.beam;
+  B200_REQUIRE(d.logits != nullptr, "generate_beam: decode_begin was called with beam=1; use generate_greedy");
+  const uint64_t key = mix_key({reinterpret_cast<uint64_t>(d.kc), static_cast<uint64_t>(R), static_cast<uint64_t>(d.S),
+                                static_cast<uint64_t>(d.max_len), static_cast<uint64_t>(max_len), static_cast<uint64_t>(start_id),
+                                static_cast<uint64_t>(end_id), reinterpret_cast<uint64_t>(d.mem_pad), static_cast<uint64_t>(beam),
+                                reinterpret_cast<uint64_t>(out_tokens), reinterpret_cast<uint64_t>(out_len),
+                                reinterpret_cast<uint64_t>(out_score), 2ull});
+  // every partition (a range of images with all their hypotheses) runs the whole search on its stream;
+  // the live copies of the cache / sequences / scores alternate identically in every partition
+  RC(run_maybe_graphed(e, key, s, [&](cudaStream_t ws) -> int {
+    RC(fill_i64(d.seq[0], static_cast<long long>(R) * d.max_len, c.pad_idx, ws));
+    RC(fill_col_i64(d.seq[0], R, d.max_len, start_id, ws));
+    RC(fill_i64(d.cur_tok, R, start_id, ws));
+    B200_CHECK_CUDA(cudaMemsetAsync(d.fin[0], 0, R, ws));
+    B200_CHECK_CUDA(cudaMemsetAsync(d.scores[0], 0, sizeof(float) * R, ws));
+    return for_each_part(e, ws, [&](const b200_engine::Decode::Part& pt, cudaStream_t ps) -> int {
+      const int64_t r0 = static_cast<int64_t>(pt.b0) * beam;
+      const int Rp = pt.nb * beam;
+      float* logits = d.logits + r0 * V;
+      int cur = 0, cs = 0, n_tok = 1;
+      for (int pos = 0; pos + 1 < max_len; ++pos) {
+        bf16* x = nullptr;
+        RC(decode_hidden(e, pt, cur, d.cur_tok, pos, &x, ps));
+        GemmProblem g;
+        g.M = Rp; g.N = V; g.K = E;
+        g.A = x; g.lda = E; g.B = e->ph + e->fc_w; g.ldb = E;
+        g.D = logits; g.ldd = V; g.d_fp32 = true; g.bias = e->pf + e->fc_b; g.split_k = 1;
+        RC(gemm_launch(g, ps));
+        RC(beam_topk(logits, d.scores[cs] + r0, d.fin[cs] + r0, pt.nb, beam, V, end_id, pos == 0, d.cur_tok + r0, d.parent + r0,
+                     d.scores[cs ^ 1] + r0, ps));
+        RC(beam_advance(d.seq[cs] + r0 * d.max_len, d.seq[cs ^ 1] + r0 * d.max_len, d.fin[cs] + r0, d.fin[cs ^ 1] + r0,
+                        d.cur_tok + r0, d.parent + r0, Rp, beam, d.max_len, pos, end_id, ps));
+        // the self-attention cache follows the surviving hypotheses
+        for (int l = 0; l < L; ++l) {
+          const int64_t off = (static_cast<int64_t>(l) * R + r0) * d.max_len * E;
+          RC(cache_reorder(d.kcache[cur] + off, d.vcache[cur] + off, d.kcache[cur ^ 1] + off, d.vcache[cur ^ 1] + off,
+                           d.parent + r0, pt.nb, beam, H, hd, d.max_len, pos, ps));
+        }
+        cur ^= 1;
+        cs ^= 1;
+        ++n_tok;
+      }
+      return beam_finalize(d.seq[cs] + r0 * d.max_len, d.scores[cs] + r0, pt.nb, beam, d.max_len, n_tok, end_id, c.pad_idx,
+                           d.out_tok + static_cast<int64_t>(pt.b0) * d.max_len, d.out_len + pt.b0, d.out_score + pt.b0, ps);
+    });
+  }));
+  const int B = d.B;
+  B200_CHECK_CUDA(cudaMemcpyAsync(out_tokens, d.out_tok, sizeof(int64_t) * B * d.max_len, cudaMemcpyDeviceToDevice, s));
+  B200_CHECK_CUDA(cudaMemcpyAsync(out_len, d.out_len, sizeof(int) * B, cudaMemcpyDeviceToDevice, s));
+  if (out_score) B200_CHECK_CUDA(cudaMemcpyAsync(out_score, d.out_score, sizeof(float) * B, cudaMemcpyDeviceToDevice, s));
+  return 0;
 }
 
 }  // extern "C"

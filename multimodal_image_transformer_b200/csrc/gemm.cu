@@ -33,6 +33,8 @@ struct GemmDev {
   int M, N, K;
   int num_m_tiles, num_n_tiles, split_k, kb_per_split, num_k_blocks;
   void* D; long long ldd; int d_fp32; int accumulate;
+  int max_stages;  // > 0: cap of the operand ring depth (skinny launches leave shared memory to co-resident kernels)
+  int part_rows;   // > 0: split-K partial slabs of this many rows each (plain stores at row split*part_rows + m)
   const float* bias;
   const bf16* residual; long long ldr;
   const bf16* relu_mask; long long ldm;
@@ -85,7 +87,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   constexpr uint32_t TMEM_COLS = ACC_STAGES * BLOCK_N;
   constexpr int NSH = BLOCK_N / CL;            // B rows (N) staged by this CTA
   const bool has_aux_smem = p.aux_mode != 0;
-  const int STAGES = L::stages(has_aux_smem);
+  const int STAGES = (p.max_stages > 0 && p.max_stages < L::stages(has_aux_smem)) ? p.max_stages : L::stages(has_aux_smem);
 
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();   // 128-byte swizzle atoms need a 1024-byte aligned base
@@ -129,6 +131,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
+  pdl_wait();
+  pdl_trigger();
 
   // work items are enumerated per cluster; both CTAs of a pair walk the same sequence
   const int num_m_groups = (p.num_m_tiles + CL - 1) / CL;
@@ -426,7 +431,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (elected) {
             if (slab_live) {
               if (EPI == EPI_STD && p.accumulate) tma_reduce_add_2d(&tmap_d, sCb, scol0, m0);
-              else tma_store_2d(&tmap_d, sCb, scol0, m0);
+              else tma_store_2d(&tmap_d, sCb, scol0, m0 + split * p.part_rows);
             }
             bulk_commit();
             bulk_wait_read<1>();                   // the store issued from the OTHER buffer has finished reading it
@@ -455,7 +460,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       tile_par ^= 1;
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
-    if (STORES && elected) bulk_wait_all();        // shared memory must outlive the asynchronous stores
+    if (STORES && elected) bulk_wait_read<0>();    // shared memory must outlive the stores' reads (the writes complete with the grid)
   }
 
   tc_fence_before();
@@ -528,36 +533,29 @@ int device_sm_count() {
 }
 
 int gemm_num_n_tiles(int N, int block_n) { return (N + block_n - 1) / block_n; }
+int gemm_effective_splits(int K, int split_k) {
+  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  if (split_k < 1) split_k = 1;
+  const int per = (num_kb + split_k - 1) / split_k;
+  return (num_kb + per - 1) / per;
+}
 
 template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, int CL>
 static int launch_instance(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td,
                            const CUtensorMap& tx, const GemmDev& d, int grid, cudaStream_t stream) {
   auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, EPI, CL>;
   static bool configured = false;
-  const int smem = SmemLayout<BLOCK_N, CL>::total(d.aux_mode != 0);
+  using SL = SmemLayout<BLOCK_N, CL>;
+  const bool aux = d.aux_mode != 0;
+  const int st = (d.max_stages > 0 && d.max_stages < SL::stages(aux)) ? d.max_stages : SL::stages(aux);
+  const int smem = st * SL::STAGE_BYTES + SL::epi_bytes(aux) + BAR_BYTES;
   if (!configured) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
     configured = true;
   }
   const bool prof = gemm_profile_enabled();
   if (prof) gemm_profile_record(stream, true, 2.0 * d.M * static_cast<double>(d.N) * d.K);
-  if constexpr (CL == 1) {
-    kern<<<grid, NUM_THREADS, smem, stream>>>(ta, tb, td, tx, d);
-  } else {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    B200_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, td, tx, d));
-  }
+  B200_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(NUM_THREADS), smem, stream, !prof, CL, ta, tb, td, tx, d));
   if (prof) gemm_profile_record(stream, false, 0.0);
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
@@ -590,8 +588,10 @@ int gemm_launch(const GemmProblem& q, cudaStream_t stream, int* n_tiles_out) {
 
   int block_n = q.block_n;
   int split_k = q.split_k;
-  const bool may_split = (q.epi == EPI_STD) && q.d_fp32 && q.accumulate;
-  if (split_k > 1) B200_REQUIRE(may_split, "gemm: split_k > 1 needs d_fp32 && accumulate");
+  const bool may_split = (q.epi == EPI_STD) && q.d_fp32 && (q.accumulate || q.partials);
+  if (split_k > 1) B200_REQUIRE(may_split, "gemm: split_k > 1 needs d_fp32 && (accumulate || partials)");
+  B200_REQUIRE(!q.partials || (q.epi == EPI_STD && q.d_fp32 && !q.accumulate && !q.bias && !q.residual && !q.relu_mask && q.act == 0 && q.split_k >= 1),
+               "gemm: partials mode is a bare fp32 product with an explicit split_k");
   if (block_n == 0 || split_k == 0) {
     // pick (block_n, split_k) maximising full-wave efficiency; prefer the wider tile and fewer
     // splits on ties (wider tiles halve shared-memory operand traffic per flop).
@@ -629,6 +629,8 @@ int gemm_launch(const GemmProblem& q, cudaStream_t stream, int* n_tiles_out) {
   d.kb_per_split = (num_kb + split_k - 1) / split_k;
   d.split_k = (num_kb + d.kb_per_split - 1) / d.kb_per_split;  // no empty splits
   d.D = q.D; d.ldd = q.ldd; d.d_fp32 = q.d_fp32; d.accumulate = q.accumulate;
+  d.part_rows = q.partials ? m_tiles * BLOCK_M : 0;
+  d.max_stages = q.max_stages;
   d.bias = q.bias; d.residual = q.residual; d.ldr = q.ldr; d.relu_mask = q.relu_mask; d.ldm = q.ldm;
   d.act = q.act;
   d.targets = reinterpret_cast<const long long*>(q.targets); d.ignore_index = q.ignore_index;
@@ -651,7 +653,8 @@ int gemm_launch(const GemmProblem& q, cudaStream_t stream, int* n_tiles_out) {
   // output and residual / mask tiles travel through 128-row x 128-byte TMA boxes
   CUtensorMap td = ta, tx = ta;
   if (q.epi == EPI_STD || q.epi == EPI_CE_BWD) {
-    if (q.d_fp32) rc = make_tmap_2d_f32(&td, q.D, q.N, q.M, q.ldd * 4, 32, BLOCK_M);
+    if (q.partials) rc = make_tmap_2d_f32(&td, q.D, q.N, static_cast<uint64_t>(d.split_k) * d.part_rows, q.ldd * 4, 32, BLOCK_M);
+    else if (q.d_fp32) rc = make_tmap_2d_f32(&td, q.D, q.N, q.M, q.ldd * 4, 32, BLOCK_M);
     else          rc = make_tmap_2d_bf16(&td, q.D, q.N, q.M, q.ldd * 2, 64, BLOCK_M);
     if (rc) return rc;
   }
@@ -723,6 +726,7 @@ __global__ void gemm_check_kernel(GemmDev p, const bf16* A, long long lda, int a
 
 int gemm_check_launch(const GemmProblem& q, cudaStream_t stream) {
   B200_REQUIRE(q.epi == EPI_STD, "gemm_check: standard epilogue only");
+  B200_REQUIRE(!q.partials, "gemm_check: partials mode not modelled");
   GemmDev d = {};
   d.M = q.M; d.N = q.N; d.K = q.K;
   d.D = q.D; d.ldd = q.ldd; d.d_fp32 = q.d_fp32; d.accumulate = q.accumulate;
@@ -731,7 +735,7 @@ int gemm_check_launch(const GemmProblem& q, cudaStream_t stream) {
   const long long total = static_cast<long long>(q.M) * q.N;
   const int threads = 256;
   const long long blocks = (total + threads - 1) / threads;
-  gemm_check_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(d, q.A, q.lda, q.a_mn, q.B, q.ldb, q.b_mn);
+  gemm_check_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(d, q.A, q.lda, q.a_mn, q.B, q.ldb, q.b_mn);  // test instrument: plain launch
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -15,6 +15,11 @@ struct GemmProblem {
   const bf16* residual = nullptr; int64_t ldr = 0;
   const bf16* relu_mask = nullptr; int64_t ldm = 0;
   int act = 0;
+  // partials: split-K without atomics.  D is an fp32 [split_k][Mpad][ldd] stack (Mpad = M rounded up
+  // to 128); split i stores its partial product into slab i and the consumer (layernorm_reduce_fwd)
+  // sums the slabs.  Used by the skinny decode GEMMs, whose latency is the per-CTA K loop.
+  bool partials = false;
+  int max_stages = 0;   // > 0: cap of the shared-memory operand ring depth
   int split_k = 1;   // 0 = auto
   int block_n = 0;   // 0 = auto
   // --- fused softmax-CE / argmax epilogues (LM head) ---
@@ -31,6 +36,8 @@ struct GemmProblem {
 int gemm_launch(const GemmProblem& p, cudaStream_t stream, int* n_tiles_out = nullptr);
 int gemm_check_launch(const GemmProblem& p, cudaStream_t stream);
 int gemm_num_n_tiles(int N, int block_n);
+// number of non-empty K splits a launch with this (K, split_k) uses (= slabs written in partials mode)
+int gemm_effective_splits(int K, int split_k);
 int device_sm_count();
 
 }  // namespace b200

@@ -13,6 +13,8 @@ static inline int cdiv(long long a, long long b) { return static_cast<int>((a + 
 __global__ void embed_pe_fwd_kernel(const int64_t* __restrict__ tokens, const float* __restrict__ emb,
                                     const float* __restrict__ pe, bf16* __restrict__ x, int rows,
                                     int T, int E, int V, float scale, int t0) {
+  pdl_wait();
+  pdl_trigger();
   const int vec_per_row = E >> 3;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (idx >= static_cast<long long>(rows) * vec_per_row) return;
@@ -36,7 +38,7 @@ int embed_pe_fwd(const int64_t* tokens, const float* emb, const float* pe, bf16*
                  int E, int V, float scale, cudaStream_t s, int t0) {
   B200_REQUIRE(E % 8 == 0, "embed: E (%d) must be a multiple of 8", E);
   const long long n = static_cast<long long>(B) * T * (E / 8);
-  embed_pe_fwd_kernel<<<cdiv(n, 256), 256, 0, s>>>(tokens, emb, pe, x, B * T, T, E, V, scale, t0);
+  B200_CHECK_CUDA(launch_kernel(embed_pe_fwd_kernel, dim3(cdiv(n, 256)), dim3(256), 0, s, true, 1, tokens, emb, pe, x, B * T, T, E, V, scale, t0));
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -46,6 +48,8 @@ int embed_pe_fwd(const int64_t* tokens, const float* emb, const float* pe, bf16*
 __global__ void embed_bwd_kernel(const int64_t* __restrict__ tokens, const bf16* __restrict__ dx,
                                  float* __restrict__ demb, int rows, int E, int V, long long pad_idx,
                                  float scale) {
+  pdl_wait();
+  pdl_trigger();
   const int vec_per_row = E >> 3;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (idx >= static_cast<long long>(rows) * vec_per_row) return;
@@ -64,7 +68,7 @@ int embed_bwd(const int64_t* tokens, const bf16* dx, float* demb, int B, int T, 
               long long pad_idx, float scale, cudaStream_t s) {
   B200_REQUIRE(E % 8 == 0, "embed_bwd: E (%d) must be a multiple of 8", E);
   const long long n = static_cast<long long>(B) * T * (E / 8);
-  embed_bwd_kernel<<<cdiv(n, 256), 256, 0, s>>>(tokens, dx, demb, B * T, E, V, pad_idx, scale);
+  B200_CHECK_CUDA(launch_kernel(embed_bwd_kernel, dim3(cdiv(n, 256)), dim3(256), 0, s, true, 1, tokens, dx, demb, B * T, E, V, pad_idx, scale));
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -91,6 +95,8 @@ __global__ void __launch_bounds__(128)
 layernorm_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ beta, bf16* __restrict__ y, float* __restrict__ mean,
                      float* __restrict__ rstd, int rows, int E, float eps) {
+  pdl_wait();
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 4 + warp;
   if (row >= rows) return;
@@ -145,12 +151,111 @@ int layernorm_fwd(const bf16* x, const float* gamma, const float* beta, bf16* y,
   B200_REQUIRE(E % 8 == 0 && E <= LN_MAXV * 256, "layernorm: E (%d) must be a multiple of 8 and <= %d", E, LN_MAXV * 256);
   if (rows == 0) return 0;
   const int nv = cdiv(E / 8, 32);
-#define B200_LN_FWD(NV) layernorm_fwd_kernel<NV><<<cdiv(rows, 4), 128, 0, s>>>(x, gamma, beta, y, mean, rstd, rows, E, eps)
+#define B200_LN_FWD(NV) B200_CHECK_CUDA(launch_kernel(layernorm_fwd_kernel<NV>, dim3(cdiv(rows, 4)), dim3(128), 0, s, true, 1, x, gamma, beta, y, mean, rstd, rows, E, eps))
   if (nv <= 1) B200_LN_FWD(1); else if (nv == 2) B200_LN_FWD(2); else if (nv == 3) B200_LN_FWD(3);
   else if (nv == 4) B200_LN_FWD(4); else B200_LN_FWD(8);
 #undef B200_LN_FWD
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// LayerNorm over y = sum_s parts[s] + bias + residual: the consumer of a split-K "partials" GEMM
+// (gemm.cuh).  The pre-norm sum never exists in bf16, the bias / residual epilogue of the GEMM
+// and the separate LayerNorm pass over its output collapse into this one kernel.
+template <int NV>
+__global__ void __launch_bounds__(128)
+layernorm_reduce_fwd_kernel(const float* __restrict__ parts, int nsplit, long long slab_stride, long long ldp,
+                            const float* __restrict__ bias, const bf16* __restrict__ residual, long long ldr,
+                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                            bf16* __restrict__ y, int rows, int E, float eps) {
+  pdl_wait();
+  pdl_trigger();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 4 + warp;
+  if (row >= rows) return;
+  const int nvec = E >> 3;
+  float v[NV][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      if (residual) unpack8(ldg_nc_v4(residual + static_cast<long long>(row) * ldr + vi * 8), v[i]);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+      }
+      if (bias) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + vi * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + vi * 8) + 1);
+        v[i][0] += b0.x; v[i][1] += b0.y; v[i][2] += b0.z; v[i][3] += b0.w;
+        v[i][4] += b1.x; v[i][5] += b1.y; v[i][6] += b1.z; v[i][7] += b1.w;
+      }
+      const float* pr = parts + static_cast<long long>(row) * ldp + vi * 8;
+      for (int s0 = 0; s0 < nsplit; s0 += 4) {     // four slabs (eight 16-byte loads) in flight at a time
+        float4 a0[4], a1[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          a0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          a1[u] = a0[u];
+          if (s0 + u < nsplit) {
+            a0[u] = *reinterpret_cast<const float4*>(pr + (s0 + u) * slab_stride);
+            a1[u] = *(reinterpret_cast<const float4*>(pr + (s0 + u) * slab_stride) + 1);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          v[i][0] += a0[u].x; v[i][1] += a0[u].y; v[i][2] += a0[u].z; v[i][3] += a0[u].w;
+          v[i][4] += a1[u].x; v[i][5] += a1[u].y; v[i][6] += a1[u].z; v[i][7] += a1[u].w;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += v[i][j];
+    }
+  }
+  const float mu = warp_sum(sum) / E;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (lane + i * 32 < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mu; sq += d * d; }
+    }
+  }
+  const float rs = rsqrtf(warp_sum(sq) / E + eps);
+  bf16* yr = y + static_cast<long long>(row) * E;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8) + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8) + 1);
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mu) * rs * g[j] + b[j];
+      *reinterpret_cast<uint4*>(yr + vi * 8) = pack8(o);
+    }
+  }
+}
+
+int layernorm_reduce_fwd(const float* parts, int nsplit, long long slab_stride, long long ldp, const float* bias,
+                         const bf16* residual, long long ldr, const float* gamma, const float* beta, bf16* y,
+                         int rows, int E, float eps, cudaStream_t s) {
+  B200_REQUIRE(E % 8 == 0 && E <= LN_MAXV * 256, "layernorm_reduce: E (%d) must be a multiple of 8 and <= %d", E, LN_MAXV * 256);
+  B200_REQUIRE(nsplit >= 1 && ldp % 4 == 0 && slab_stride % 4 == 0, "layernorm_reduce: bad partial layout");
+  if (rows == 0) return 0;
+  const int nv = cdiv(E / 8, 32);
+#define B200_LNR(NV) B200_CHECK_CUDA(launch_kernel(layernorm_reduce_fwd_kernel<NV>, dim3(cdiv(rows, 4)), dim3(128), 0, s, true, 1, \
+                                                   parts, nsplit, slab_stride, ldp, bias, residual, ldr, gamma, beta, y, rows, E, eps))
+  if (nv <= 1) B200_LNR(1); else if (nv == 2) B200_LNR(2); else if (nv == 3) B200_LNR(3);
+  else if (nv == 4) B200_LNR(4); else B200_LNR(8);
+#undef B200_LNR
+  note_launch();
   return 0;
 }
 
@@ -167,6 +272,8 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                      const float* __restrict__ rstd, bf16* __restrict__ dx,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum,
                      int rows, int E) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sm_red[];  // [3][4][E]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = E >> 3;
@@ -284,7 +391,7 @@ int layernorm_bwd(const bf16* dy, const bf16* x, const float* gamma, const float
       B200_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * NV * 256 * 4)); \
       configured = true;                                                                             \
     }                                                                                                \
-    layernorm_bwd_kernel<NV><<<blocks, 128, smem, s>>>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, dxsum, rows, E); \
+    B200_CHECK_CUDA(launch_kernel(layernorm_bwd_kernel<NV>, dim3(blocks), dim3(128), smem, s, true, 1, dy, x, gamma, mean, rstd, dx, dgamma, dbeta, dxsum, rows, E)); \
   } while (0)
   if (nv <= 1) B200_LN_BWD(1); else if (nv == 2) B200_LN_BWD(2); else if (nv == 3) B200_LN_BWD(3);
   else if (nv == 4) B200_LN_BWD(4); else B200_LN_BWD(8);
@@ -299,6 +406,8 @@ int layernorm_bwd(const bf16* dy, const bf16* x, const float* gamma, const float
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 colsum_kernel(const bf16* __restrict__ x, long long ldx, float* __restrict__ out, int M, int N) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float red[8][256];
   const int cv = threadIdx.x & 31;   // column vector within the block's 256-column strip
   const int rl = threadIdx.x >> 5;   // row lane 0..7
@@ -330,7 +439,7 @@ int colsum(const bf16* x, long long ldx, float* out, int M, int N, cudaStream_t 
   B200_REQUIRE(N % 8 == 0 && ldx % 8 == 0, "colsum: N (%d) and ldx (%lld) must be multiples of 8", N, ldx);
   if (M == 0) return 0;
   dim3 grid(cdiv(N, 256), cdiv(M, 128));
-  colsum_kernel<<<grid, 256, 0, s>>>(x, ldx, out, M, N);
+  B200_CHECK_CUDA(launch_kernel(colsum_kernel, grid, dim3(256), 0, s, true, 1, x, ldx, out, M, N));
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -340,6 +449,8 @@ int colsum(const bf16* x, long long ldx, float* out, int M, int N, cudaStream_t 
 // casts
 // ------------------------------------------------------------------------------------------
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
+  pdl_wait();
+  pdl_trigger();
   const long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 8;
   if (i + 8 <= n) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(src + i));
@@ -353,6 +464,8 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __rest
   }
 }
 __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, long long n) {
+  pdl_wait();
+  pdl_trigger();
   const long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 8;
   if (i + 8 <= n) {
     float f[8];
@@ -366,7 +479,7 @@ __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, float* __rest
 int cast_f32_to_bf16(const float* src, bf16* dst, long long n, cudaStream_t s) {
   if (n == 0) return 0;
   B200_REQUIRE(((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0), "cast: pointers must be 16-byte aligned");
-  cast_f32_bf16_kernel<<<cdiv(cdiv(n, 8), 256), 256, 0, s>>>(src, dst, n);
+  B200_CHECK_CUDA(launch_kernel(cast_f32_bf16_kernel, dim3(cdiv(cdiv(n, 8), 256)), dim3(256), 0, s, true, 1, src, dst, n));
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -374,7 +487,7 @@ int cast_f32_to_bf16(const float* src, bf16* dst, long long n, cudaStream_t s) {
 int cast_bf16_to_f32(const bf16* src, float* dst, long long n, cudaStream_t s) {
   if (n == 0) return 0;
   B200_REQUIRE(((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0), "cast: pointers must be 16-byte aligned");
-  cast_bf16_f32_kernel<<<cdiv(cdiv(n, 8), 256), 256, 0, s>>>(src, dst, n);
+  B200_CHECK_CUDA(launch_kernel(cast_bf16_f32_kernel, dim3(cdiv(cdiv(n, 8), 256)), dim3(256), 0, s, true, 1, src, dst, n));
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -389,6 +502,8 @@ ce_finalize_kernel(const float* __restrict__ part_max, const float* __restrict__
                    int n_tiles, long long ignore_index, float* __restrict__ row_lse,
                    float* __restrict__ row_loss, float* __restrict__ loss_sum,
                    float* __restrict__ valid_count) {
+  pdl_wait();
+  pdl_trigger();
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   float loss = 0.f, cnt = 0.f;
   if (row < M) {
@@ -424,21 +539,23 @@ ce_finalize_kernel(const float* __restrict__ part_max, const float* __restrict__
 int ce_finalize(const float* part_max, const float* part_sum, const float* tgt_logit,
                 const int64_t* targets, int M, int n_tiles, long long ignore_index, float* row_lse,
                 float* row_loss, float* loss_sum, float* valid_count, cudaStream_t s) {
-  ce_finalize_kernel<<<cdiv(M, 256), 256, 0, s>>>(part_max, part_sum, tgt_logit, targets, M, n_tiles,
-                                                 ignore_index, row_lse, row_loss, loss_sum, valid_count);
+  B200_CHECK_CUDA(launch_kernel(ce_finalize_kernel, dim3(cdiv(M, 256)), dim3(256), 0, s, true, 1, part_max, part_sum, tgt_logit, targets, M, n_tiles,
+                                                 ignore_index, row_lse, row_loss, loss_sum, valid_count));
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 __global__ void ce_mean_kernel(const float* loss_sum, const float* valid_count, float* out) {
+  pdl_wait();
+  pdl_trigger();
   const float c = *valid_count;
   out[0] = *loss_sum / c;   // 0/0 -> NaN, as nn.CrossEntropyLoss does when every target is ignored
   out[1] = c;
   out[2] = 1.f / c;
 }
 int ce_mean(const float* loss_sum, const float* valid_count, float* out, cudaStream_t s) {
-  ce_mean_kernel<<<1, 1, 0, s>>>(loss_sum, valid_count, out);
+  B200_CHECK_CUDA(launch_kernel(ce_mean_kernel, dim3(1), dim3(1), 0, s, true, 1, loss_sum, valid_count, out));
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -449,6 +566,8 @@ int ce_mean(const float* loss_sum, const float* valid_count, float* out, cudaStr
 __global__ void __launch_bounds__(256)
 argmax_finalize_kernel(const float* __restrict__ part_max, const float* __restrict__ part_idx,
                        int M, int n_tiles, int64_t* __restrict__ out_ids, float* __restrict__ out_max) {
+  pdl_wait();
+  pdl_trigger();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -474,7 +593,7 @@ argmax_finalize_kernel(const float* __restrict__ part_max, const float* __restri
 }
 int argmax_finalize(const float* part_max, const float* part_idx, int M, int n_tiles, int64_t* out_ids,
                     float* out_max, cudaStream_t s) {
-  argmax_finalize_kernel<<<cdiv(M, 8), 256, 0, s>>>(part_max, part_idx, M, n_tiles, out_ids, out_max);
+  B200_CHECK_CUDA(launch_kernel(argmax_finalize_kernel, dim3(cdiv(M, 8)), dim3(256), 0, s, true, 1, part_max, part_idx, M, n_tiles, out_ids, out_max));
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -485,6 +604,8 @@ int argmax_finalize(const float* part_max, const float* part_idx, int M, int n_t
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 grad_sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ sumsq) {
+  pdl_wait();
+  pdl_trigger();
   float acc = 0.f;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 4;
   for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4; i < n; i += stride) {
@@ -509,7 +630,7 @@ int grad_sumsq(const float* g, long long n, float* sumsq, cudaStream_t s) {
   if (n == 0) return 0;
   int blocks = cdiv(n, 256 * 4 * 8);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  grad_sumsq_kernel<<<blocks, 256, 0, s>>>(g, n, sumsq);
+  B200_CHECK_CUDA(launch_kernel(grad_sumsq_kernel, dim3(blocks), dim3(256), 0, s, true, 1, g, n, sumsq));
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -520,6 +641,8 @@ adamw_kernel(float* __restrict__ p, bf16* __restrict__ p16, const float* __restr
              float* __restrict__ m, float* __restrict__ v, long long n, const float* __restrict__ sumsq,
              float max_norm, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
              const int* __restrict__ step_dev, const float* __restrict__ lr_dev) {
+  pdl_wait();
+  pdl_trigger();
   if (step_dev != nullptr) {   // graph-replay mode: the step count (and lr) live on the device
     const float t = static_cast<float>(*step_dev);
     bc1 = 1.f - powf(b1, t);
@@ -578,7 +701,9 @@ adamw_kernel(float* __restrict__ p, bf16* __restrict__ p16, const float* __restr
   }
 }
 
-__global__ void inc_step_kernel(int* step) { *step += 1; }
+__global__ void inc_step_kernel(int* step) {
+  pdl_wait();
+  pdl_trigger(); *step += 1; }
 
 int adamw_step(float* p, bf16* p16, const float* g, float* m, float* v, long long n,
                const float* sumsq, float max_norm, float lr, float b1, float b2, float eps, float wd,
@@ -586,7 +711,7 @@ int adamw_step(float* p, bf16* p16, const float* g, float* m, float* v, long lon
   if (n == 0) return 0;
   B200_REQUIRE(step >= 1 || step_dev != nullptr, "adamw: step must be >= 1");
   if (step_dev != nullptr) {
-    inc_step_kernel<<<1, 1, 0, s>>>(step_dev);
+    B200_CHECK_CUDA(launch_kernel(inc_step_kernel, dim3(1), dim3(1), 0, s, true, 1, step_dev));
     note_launch();
     if (step < 1) step = 1;
   }
@@ -595,9 +720,9 @@ int adamw_step(float* p, bf16* p16, const float* g, float* m, float* v, long lon
   const double bc1d = 1.0 - pow(static_cast<double>(b1), step);
   const double bc2d = 1.0 - pow(static_cast<double>(b2), step);
   (void)bc1; (void)bc2;
-  adamw_kernel<<<cdiv(cdiv(n, 4), 256), 256, 0, s>>>(p, p16, g, m, v, n, sumsq, max_norm, lr, b1, b2, eps,
+  B200_CHECK_CUDA(launch_kernel(adamw_kernel, dim3(cdiv(cdiv(n, 4), 256)), dim3(256), 0, s, true, 1, p, p16, g, m, v, n, sumsq, max_norm, lr, b1, b2, eps,
                                                       wd, static_cast<float>(bc1d),
-                                                      static_cast<float>(sqrt(bc2d)), step_dev, lr_dev);
+                                                      static_cast<float>(sqrt(bc2d)), step_dev, lr_dev));
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;

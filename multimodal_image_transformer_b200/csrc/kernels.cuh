@@ -12,6 +12,11 @@ int embed_bwd(const int64_t* tokens, const bf16* dx, float* demb, int B, int T, 
               long long pad_idx, float scale, cudaStream_t s);
 int layernorm_fwd(const bf16* x, const float* gamma, const float* beta, bf16* y, float* mean,
                   float* rstd, int rows, int E, float eps, cudaStream_t s);
+// y = LayerNorm(sum_s parts[s] + bias + residual): parts = fp32 split-K slabs of a "partials" GEMM
+// (slab s at parts + s*slab_stride, row pitch ldp)
+int layernorm_reduce_fwd(const float* parts, int nsplit, long long slab_stride, long long ldp, const float* bias,
+                         const bf16* residual, long long ldr, const float* gamma, const float* beta, bf16* y,
+                         int rows, int E, float eps, cudaStream_t s);
 // dxsum (optional): += column sums of dx, i.e. the bias gradient of the Linear feeding this LayerNorm
 int layernorm_bwd(const bf16* dy, const bf16* x, const float* gamma, const float* mean,
                   const float* rstd, bf16* dx, float* dgamma, float* dbeta, float* dxsum, int rows, int E,

@@ -272,6 +272,35 @@ def test_beam_search_vs_oracle_spec(cuda_dev):
     assert sum(a == b for a, b in zip(out, greedy)) >= c["B"] - 1
 
 
+@pytest.mark.parametrize("name,beam", [("tiny", 1), ("hd96", 1), ("tiny", 3)])
+def test_decode_partitions_are_equivalent(cuda_dev, name, beam, monkeypatch):
+    """Generation over independent image partitions on parallel streams (graph replay included) gives
+    exactly the tokens of the single-partition run: every decode op is row-local."""
+    c = dict(CFGS[name], B=11)
+    p = O.init_params(c["V"], c["E"], c["H"], c["L"], c["F"], c["ML"], seed=8)
+    p["fc_out.bias"][2] += 1.0
+    g = torch.Generator().manual_seed(9)
+    mem = torch.randn(c["B"], c["S"], c["E"], generator=g)
+    mpm = torch.zeros(c["B"], c["S"], dtype=torch.bool)
+    mpm[2, c["S"] // 3:] = True
+    eng = make_engine(c, p, cuda_dev)
+    outs = []
+    for parts in ("1", "3", "4"):
+        monkeypatch.setenv("B200_DECODE_PARTS", parts)
+        runs = []
+        for rep in range(3):      # eager, capture, replay
+            eng.decode_begin(mem.to(cuda_dev), mpm.to(cuda_dev), beam=beam, max_len=12)
+            if beam == 1:
+                toks, lens = eng.generate_greedy(1, 2, 12, stop_check_interval=0)
+            else:
+                toks, lens, _ = eng.generate_beam(1, 2, 12)
+            runs.append((toks.cpu().clone(), lens.cpu().clone()))
+        for t, l in runs[1:]:
+            assert torch.equal(t, runs[0][0]) and torch.equal(l, runs[0][1])
+        outs.append(runs[0])
+    for t, l in outs[1:]:
+        assert torch.equal(t, outs[0][0]) and torch.equal(l, outs[0][1])
+
 def test_full_size_properties_cfg2(cuda_dev):
     """BASELINE cfg2 (B=256, T=47, S=197, E=768, H=12, F=3072, L=6, V=10000): too big for the CPU
     oracle, so check size-independent properties: loss at init ~ ln V, gradient norms finite, padding
