@@ -185,6 +185,13 @@ int32_t b200_engine_num_params(const b200_engine* e);
 /* params_f32/grads_f32/params_bf16: arenas of b200_engine_param_count() elements. */
 int b200_engine_bind(b200_engine* e, float* params_f32, void* params_bf16, float* grads_f32,
                      const float* pe_f32);
+/* Dropout of the training forward (reference config.py:69 DROPOUT = 0.1; modules: decoder.py:72,
+ * torch/nn/modules/transformer.py:1175,1195,1199, attention-probability dropout functional.py:6682).
+ * p = 0 disables it.  state_dev: caller-owned device buffer of two uint32 [seed, counter]; every
+ * forward with training = 1 advances the counter once and derives all 1 + 6 L masks from
+ * (seed, counter, site, element index) without storing them; backward regenerates the same masks.
+ * Forwards with training = 0 and generation never drop. */
+int b200_engine_set_dropout(b200_engine* e, float p, uint32_t* state_dev);
 /* `mem_dim` is the width of the memory rows handed to the forward calls: embed_dim (already
  * projected, the decoder.TransformerDecoder.forward contract) or enc_dim (the engine applies
  * model.py:145's projection itself).  training = 1 keeps every activation backward needs. */

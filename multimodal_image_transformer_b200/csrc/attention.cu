@@ -55,7 +55,16 @@ struct AttnDev {
   const long long* key_tokens; long long pad_idx;
   const unsigned char* key_pad_mask;
   float scale;
+  DropCfg drop;
 };
+
+// keep-decision of probability (row i, key j) of head bh; see common.cuh for the element order
+__device__ __forceinline__ uint32_t attn_drop_pair(const AttnDev& p, int bh, int row, int key) {
+  return (static_cast<uint32_t>(bh) * p.Tq + row) * static_cast<uint32_t>((p.Tk + 1) >> 1) + (static_cast<uint32_t>(key) >> 1);
+}
+__device__ __forceinline__ bool attn_drop_keep(uint32_t r, int key, uint32_t thr) {
+  return ((key & 1) ? (r >> 16) : (r & 0xFFFFu)) >= thr;
+}
 
 // cooperative asynchronous copy (cp.async, 16 B per request, all requests in flight at once) of
 // `rows` x HD bf16 (row stride ts elements) into padded smem; rows [rows, rows_padded) are
@@ -176,6 +185,8 @@ attn_fwd_kernel(const AttnDev p) {
   __syncthreads();
 
   const float sl2 = p.scale * LOG2E;
+  const uint32_t dkey = p.drop.thr ? drop_key(p.drop) : 0u;
+  const int bh = b * p.H + h;
   for (int mt = warp; mt * 16 < p.TQP; mt += 4) {
     const int row0 = mt * 16;
     float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
@@ -218,6 +229,13 @@ attn_fwd_kernel(const AttnDev p) {
           const float pv = (mm == -INFINITY) ? 0.f : exp2f(s[j][e] - mm);
           s[j][e] = pv;
           ps[e >> 1] += pv;
+        }
+        if (p.drop.thr) {      // the row sum keeps the undropped probabilities; P V sees dropout(P)
+#pragma unroll
+          for (int rh = 0; rh < 2; ++rh) {
+            const uint32_t r = drop_rand(dkey, attn_drop_pair(p, bh, row0 + g + rh * 8, kb0 + j * 8 + 2 * t));
+            drop_apply2(s[j][2 * rh], s[j][2 * rh + 1], r, p.drop.thr, p.drop.scale);
+          }
         }
       }
 #pragma unroll
@@ -298,6 +316,8 @@ attn_bwd_kernel(const AttnDev p) {
   __syncthreads();
 
   const float sl2 = p.scale * LOG2E;
+  const uint32_t dkey = p.drop.thr ? drop_key(p.drop) : 0u;
+  const int bh = b * p.H + h;
 
   // ---- phase 1: dQ, one 16-query tile per warp iteration
   for (int mt = warp; mt * 16 < p.TQP; mt += 4) {
@@ -327,7 +347,10 @@ attn_bwd_kernel(const AttnDev p) {
           float ds = 0.f;
           if (j * 8 < avail && key < p.TKP && !(p.causal && key > row)) {
             const float pv = exp2f(s[j][e] * sl2 + sBias[key] - ((e >> 1) ? lse1 : lse0));
-            ds = pv * (dp[j][e] - ((e >> 1) ? d1 : d0)) * p.scale;
+            float dpe = dp[j][e];
+            if (p.drop.thr)
+              dpe = attn_drop_keep(drop_rand(dkey, attn_drop_pair(p, bh, row, key)), key, p.drop.thr) ? dpe * p.drop.scale : 0.f;
+            ds = pv * (dpe - ((e >> 1) ? d1 : d0)) * p.scale;
           }
           s[j][e] = ds;
         }
@@ -377,7 +400,14 @@ attn_bwd_kernel(const AttnDev p) {
           float pv = 0.f, ds = 0.f;
           if (j * 8 < avail && qi < p.TQP && !(p.causal && key > qi)) {
             pv = exp2f(st[j][e] * sl2 + ((e >> 1) ? kb_1 : kb_0) - sLse[qi]);
-            ds = pv * (dpt[j][e] - sD[qi]) * p.scale;
+            float dpe = dpt[j][e];
+            bool keep = true;
+            if (p.drop.thr) {
+              keep = attn_drop_keep(drop_rand(dkey, attn_drop_pair(p, bh, qi, key)), key, p.drop.thr);
+              dpe = keep ? dpe * p.drop.scale : 0.f;
+            }
+            ds = pv * (dpe - sD[qi]) * p.scale;
+            if (p.drop.thr) pv = keep ? pv * p.drop.scale : 0.f;     // dV = dropout(P)^T dO
           }
           st[j][e] = pv;
           dpt[j][e] = ds;
@@ -464,6 +494,8 @@ attn_bwd2_kernel(const AttnDev p) {
   __syncthreads();   // O is dead from here on; sPS is free
 
   const float sl2 = p.scale * LOG2E;
+  const uint32_t dkey = p.drop.thr ? drop_key(p.drop) : 0u;
+  const int bh = b * p.H + h;
   const int n_qt = p.TQP / 16;
   const int NB = (p.TKP + KB - 1) / KB;
   const int items = n_qt * NB;
@@ -493,6 +525,11 @@ attn_bwd2_kernel(const AttnDev p) {
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
           float pv[4], ds[4];
+          uint32_t rr[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+          if (p.drop.thr) {
+            rr[0] = drop_rand(dkey, attn_drop_pair(p, bh, row0 + g, key0 + j * 8 + 2 * t));
+            rr[1] = drop_rand(dkey, attn_drop_pair(p, bh, row0 + g + 8, key0 + j * 8 + 2 * t));
+          }
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int key = key0 + j * 8 + 2 * t + (e & 1);
@@ -500,7 +537,15 @@ attn_bwd2_kernel(const AttnDev p) {
             pv[e] = 0.f; ds[e] = 0.f;
             if (j * 8 < avail && !(p.causal && key > row)) {
               pv[e] = exp2f(sacc[j][e] * sl2 + sBias[key] - ((e >> 1) ? lse1 : lse0));
-              ds[e] = pv[e] * (dp[j][e] - ((e >> 1) ? d1 : d0)) * p.scale;
+              float dpe = dp[j][e];
+              if (p.drop.thr) {
+                const bool keep = attn_drop_keep(rr[e >> 1], e & 1, p.drop.thr);
+                dpe = keep ? dpe * p.drop.scale : 0.f;
+                ds[e] = pv[e] * (dpe - ((e >> 1) ? d1 : d0)) * p.scale;
+                pv[e] = keep ? pv[e] * p.drop.scale : 0.f;      // dV = dropout(P)^T dO
+              } else {
+                ds[e] = pv[e] * (dpe - ((e >> 1) ? d1 : d0)) * p.scale;
+              }
             }
           }
           pP[ii][j][0] = pack_bf16(pv[0], pv[1]); pP[ii][j][1] = pack_bf16(pv[2], pv[3]);
@@ -653,6 +698,7 @@ static void fill_dev(const AttnArgs& a, AttnDev* d) {
   d->key_tokens = reinterpret_cast<const long long*>(a.key_tokens); d->pad_idx = a.pad_idx;
   d->key_pad_mask = a.key_pad_mask;
   d->scale = a.scale;
+  d->drop = a.drop;
 }
 
 template <int HD, int NT>

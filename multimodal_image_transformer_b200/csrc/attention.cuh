@@ -16,6 +16,7 @@ struct AttnArgs {
   const int64_t* key_tokens = nullptr; long long pad_idx = 0;
   const unsigned char* key_pad_mask = nullptr;
   float scale = 1.f;
+  DropCfg drop = DropCfg{nullptr, 0u, 0u, 1.f};           // dropout on the probabilities (functional.py:6682)
 };
 struct AttnGrads {
   const bf16* d_o = nullptr; long long do_bs = 0, do_ts = 0;

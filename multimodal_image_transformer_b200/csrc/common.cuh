@@ -113,6 +113,40 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t v) {
   return __bfloat1622float2(t);
 }
 
+// ------------------------------------------------------------------ dropout
+// Counter-based masks (no mask is ever stored): forward and backward regenerate the same bits from
+// (seed, step counter, site, element index).  One 32-bit draw decides a PAIR of adjacent elements
+// (16-bit thresholds: P(drop) = thr / 65536).  state = device [seed, counter]; the counter is
+// advanced once per training forward, so a replayed CUDA graph draws fresh masks every step.
+// Sites of a decoder with L layers (the reference's dropout modules: decoder.py:72,
+// torch/nn/modules/transformer.py:1175,1195,1199 and the attention-probability dropout of
+// torch/nn/functional.py:6682): 0 = embedding + PE; 1 + 6l + {0 self-attn probabilities,
+// 1 dropout1, 2 cross-attn probabilities, 3 dropout2, 4 FFN activation, 5 dropout3}.
+// Element order: row-major [rows, N] tensors -> pair = (row * N + col) / 2; attention
+// probabilities -> pair = ((b * H + h) * Tq + i) * ceil(Tk / 2) + j / 2.
+struct DropCfg {
+  const uint32_t* state;   // null / thr == 0: no dropout
+  uint32_t site;
+  uint32_t thr;            // round(p * 65536)
+  float scale;             // 1 / (1 - p)
+};
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ uint32_t drop_key(const DropCfg& d) {
+  const uint32_t seed = d.state[0], ctr = d.state[1];
+  return mix32(seed ^ mix32(ctr * 0x9E3779B9u + 0x7F4A7C15u) ^ ((d.site + 1u) * 0x85EBCA77u));
+}
+// low half decides element 2*pair, high half element 2*pair + 1; keep iff half >= thr
+__device__ __forceinline__ uint32_t drop_rand(uint32_t key, uint32_t pair) {
+  return mix32(pair * 0x9E3779B1u + key);
+}
+__device__ __forceinline__ void drop_apply2(float& a, float& b, uint32_t r, uint32_t thr, float scale) {
+  a = ((r & 0xFFFFu) >= thr) ? a * scale : 0.f;
+  b = ((r >> 16) >= thr) ? b * scale : 0.f;
+}
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -45,6 +45,7 @@ struct Plan {
   bf16* x_final = nullptr;    // [M, E]
   float *row_lse = nullptr, *row_loss = nullptr, *ce_scratch = nullptr, *scalars = nullptr;
   // backward temporaries
+  bf16* dxd = nullptr;        // [M, E] dropout-masked copy of a LayerNorm input gradient (dropout > 0 only)
   bf16 *dlogits = nullptr, *dxa = nullptr, *dxb = nullptr, *dxc = nullptr, *dh = nullptr,
        *dqkv = nullptr, *dkv = nullptr, *dattn = nullptr, *dqc = nullptr, *dmemp16 = nullptr;
   float* dmemp = nullptr;     // [B*S, E] fp32 accumulator of d(projected memory)
@@ -75,6 +76,10 @@ struct b200_engine {
   bf16* ph = nullptr;
   float* gf = nullptr;
   const float* pe = nullptr;
+  // dropout (reference config.py:69 DROPOUT = 0.1): probability + caller-owned device state [seed, counter]
+  float drop_p = 0.f;
+  uint32_t* drop_state = nullptr;
+  bool plan_dropout = false;     // the last training forward applied dropout (backward must regenerate the masks)
   uint8_t* ws = nullptr;
   int64_t ws_bytes = 0;
   Plan plan;   // of the last forward
@@ -175,6 +180,7 @@ void build_plan(const b200_engine* e, Plan* pl, uint8_t* base, int B, int T, int
     pl->dxa = b.take<bf16>(M * E);
     pl->dxb = b.take<bf16>(M * E);
     pl->dxc = b.take<bf16>(M * E);
+    pl->dxd = b.take<bf16>(M * E);
     pl->dh = b.take<bf16>(M * F);
     pl->dqkv = b.take<bf16>(M * 3 * E);
     pl->dkv = b.take<bf16>(Ms * 2 * E);
@@ -191,10 +197,13 @@ static int dec_gemm_stages() {
   static const int v = getenv("B200_DEC_GEMM_STAGES") ? atoi(getenv("B200_DEC_GEMM_STAGES")) : 0;
   return v;
 }
+const DropCfg NO_DROP = DropCfg{nullptr, 0u, 0u, 1.f};
 int linear_fwd(const bf16* x, int64_t ldx, const bf16* W, const float* bias, bf16* y, int64_t ldy, int M,
-               int N, int K, int act, const bf16* residual, int64_t ldr, cudaStream_t s, int max_stages = 0) {
+               int N, int K, int act, const bf16* residual, int64_t ldr, cudaStream_t s, int max_stages = 0,
+               DropCfg drop = NO_DROP) {
   GemmProblem g;
   g.max_stages = max_stages;
+  g.drop = drop;
   g.M = M; g.N = N; g.K = K;
   g.A = x; g.lda = ldx; g.B = W; g.ldb = K;
   g.D = y; g.ldd = ldy; g.bias = bias; g.act = act; g.residual = residual; g.ldr = ldr;
@@ -203,8 +212,10 @@ int linear_fwd(const bf16* x, int64_t ldx, const bf16* W, const float* bias, bf1
 }
 // dx = dy W (+ residual) (* relu mask);  W is [N_out, K_in] as stored
 int linear_dgrad(const bf16* dy, int64_t lddy, const bf16* W, int N_out, int K_in, bf16* dx, int64_t lddx,
-                 int M, const bf16* residual, int64_t ldr, const bf16* relu_mask, int64_t ldm, cudaStream_t s) {
+                 int M, const bf16* residual, int64_t ldr, const bf16* relu_mask, int64_t ldm, cudaStream_t s,
+                 float mask_scale = 1.f) {
   GemmProblem g;
+  g.mask_scale = mask_scale;
   g.M = M; g.N = K_in; g.K = N_out;
   g.A = dy; g.lda = lddy; g.B = W; g.ldb = K_in; g.b_mn = true;
   g.D = dx; g.ldd = lddx; g.residual = residual; g.ldr = ldr; g.relu_mask = relu_mask; g.ldm = ldm;
@@ -225,6 +236,15 @@ int linear_wgrad(const bf16* dy, int64_t lddy, const bf16* x, int64_t ldx, float
 
 #define RC(expr) do { if (int _rc = (expr)) return _rc; } while (0)
 
+DropCfg drop_site(const b200_engine* e, int id) {
+  DropCfg d;
+  d.state = e->drop_state;
+  d.site = static_cast<uint32_t>(id);
+  d.thr = static_cast<uint32_t>(e->drop_p * 65536.0f + 0.5f);
+  d.scale = 1.0f / (1.0f - e->drop_p);
+  return d;
+}
+
 int run_forward(b200_engine* e, const int64_t* tokens, const float* memory, const uint8_t* mem_pad, int B,
                 int T, int S, int mem_dim, int training, cudaStream_t s) {
   const auto& c = e->cfg;
@@ -241,11 +261,18 @@ int run_forward(b200_engine* e, const int64_t* tokens, const float* memory, cons
   const int M = B * T, Ms = B * S;
   const float scale = 1.0f / sqrtf(static_cast<float>(hd));
 
+  // dropout only in training mode (model.train(), train.py:64); eval / generation never drop
+  const bool dropping = training && e->drop_p > 0.f;
+  B200_REQUIRE(!dropping || e->drop_state, "engine: dropout enabled without a device state buffer");
+  e->plan_dropout = dropping;
+  if (dropping) RC(drop_advance(e->drop_state, s));
+  auto site = [&](int id) { return dropping ? drop_site(e, id) : NO_DROP; };
+
   RC(cast_f32_to_bf16(memory, pl.mem16, static_cast<long long>(Ms) * mem_dim, s));
   if (mem_dim != E)
     RC(linear_fwd(pl.mem16, mem_dim, e->ph + e->proj_w, e->pf + e->proj_b, pl.memp, E, Ms, E, mem_dim, 0, nullptr, 0, s));
 
-  RC(embed_pe_fwd(tokens, e->pf + e->emb, e->pe, pl.xs[0], B, T, E, c.vocab_size, sqrtf(static_cast<float>(E)), s));
+  RC(embed_pe_fwd(tokens, e->pf + e->emb, e->pe, pl.xs[0], B, T, E, c.vocab_size, sqrtf(static_cast<float>(E)), s, 0, site(0)));
 
   for (int l = 0; l < L; ++l) {
     const LayerOff& o = e->lo[l];
@@ -259,9 +286,9 @@ int run_forward(b200_engine* e, const int64_t* tokens, const float* memory, cons
     sa.q_bs = sa.k_bs = sa.v_bs = static_cast<long long>(T) * 3 * E; sa.q_ts = sa.k_ts = sa.v_ts = 3 * E;
     sa.o = a.attn_o; sa.o_bs = static_cast<long long>(T) * E; sa.o_ts = E;
     sa.lse = a.lse_s; sa.B = B; sa.H = H; sa.Tq = T; sa.Tk = T; sa.hd = hd; sa.causal = 1;
-    sa.key_tokens = tokens; sa.pad_idx = c.pad_idx; sa.scale = scale;
+    sa.key_tokens = tokens; sa.pad_idx = c.pad_idx; sa.scale = scale; sa.drop = site(1 + 6 * l + 0);
     RC(attn_fwd(sa, s));
-    RC(linear_fwd(a.attn_o, E, e->ph + o.sa_ow, e->pf + o.sa_ob, a.y1, E, M, E, E, 0, x, E, s));
+    RC(linear_fwd(a.attn_o, E, e->ph + o.sa_ow, e->pf + o.sa_ob, a.y1, E, M, E, E, 0, x, E, s, 0, site(1 + 6 * l + 1)));
     RC(layernorm_fwd(a.y1, e->pf + o.n1_w, e->pf + o.n1_b, a.x1, a.mean1, a.rstd1, M, E, c.ln_eps, s));
     // --- cross-attention block
     RC(linear_fwd(a.x1, E, e->ph + o.ca_w, e->pf + o.ca_b, a.qc, E, M, E, E, 0, nullptr, 0, s));
@@ -271,13 +298,13 @@ int run_forward(b200_engine* e, const int64_t* tokens, const float* memory, cons
     ca.k = a.kvc; ca.v = a.kvc + E; ca.k_bs = ca.v_bs = static_cast<long long>(S) * 2 * E; ca.k_ts = ca.v_ts = 2 * E;
     ca.o = a.attn_c; ca.o_bs = static_cast<long long>(T) * E; ca.o_ts = E;
     ca.lse = a.lse_c; ca.B = B; ca.H = H; ca.Tq = T; ca.Tk = S; ca.hd = hd; ca.causal = 0;
-    ca.key_pad_mask = mem_pad; ca.scale = scale;
+    ca.key_pad_mask = mem_pad; ca.scale = scale; ca.drop = site(1 + 6 * l + 2);
     RC(attn_fwd(ca, s));
-    RC(linear_fwd(a.attn_c, E, e->ph + o.ca_ow, e->pf + o.ca_ob, a.y2, E, M, E, E, 0, a.x1, E, s));
+    RC(linear_fwd(a.attn_c, E, e->ph + o.ca_ow, e->pf + o.ca_ob, a.y2, E, M, E, E, 0, a.x1, E, s, 0, site(1 + 6 * l + 3)));
     RC(layernorm_fwd(a.y2, e->pf + o.n2_w, e->pf + o.n2_b, a.x2, a.mean2, a.rstd2, M, E, c.ln_eps, s));
     // --- feed-forward block
-    RC(linear_fwd(a.x2, E, e->ph + o.l1_w, e->pf + o.l1_b, a.h, F, M, F, E, c.act, nullptr, 0, s));
-    RC(linear_fwd(a.h, F, e->ph + o.l2_w, e->pf + o.l2_b, a.y3, E, M, E, F, 0, a.x2, E, s));
+    RC(linear_fwd(a.x2, E, e->ph + o.l1_w, e->pf + o.l1_b, a.h, F, M, F, E, c.act, nullptr, 0, s, 0, site(1 + 6 * l + 4)));
+    RC(linear_fwd(a.h, F, e->ph + o.l2_w, e->pf + o.l2_b, a.y3, E, M, E, F, 0, a.x2, E, s, 0, site(1 + 6 * l + 5)));
     RC(layernorm_fwd(a.y3, e->pf + o.n3_w, e->pf + o.n3_b, x_out, a.mean3, a.rstd3, M, E, c.ln_eps, s));
   }
   return 0;
@@ -300,6 +327,9 @@ int run_backward(b200_engine* e, bool have_dlogits, float* dmemory, void* const*
   const bool need_dmemp = (pl.mem_dim != E) || dmemory != nullptr;
   B200_REQUIRE(!(dmemory && pl.mem_dim != E), "engine: dmemory is only available when memory is already embed_dim wide");
   (void)have_dlogits;
+  const bool dropping = e->plan_dropout;
+  auto site = [&](int id) { return dropping ? drop_site(e, id) : NO_DROP; };
+  const float keep_scale = dropping ? 1.0f / (1.0f - e->drop_p) : 1.0f;
   int ev = 0;
   auto mark = [&](void) {
     if (events && ev < n_events && events[ev]) cudaEventRecord(static_cast<cudaEvent_t>(events[ev]), s);
@@ -324,26 +354,34 @@ int run_backward(b200_engine* e, bool have_dlogits, float* dmemory, void* const*
     LayerAct& a = pl.act[l];
     float* g = e->gf;
     // LN3
+    // With dropout, y = x + dropout(z): the LayerNorm backward emits the gradient of y (residual
+    // branch) and, masked and rescaled, the gradient of z (operand of the Linear's dgrad / wgrad and
+    // of its bias sum).  Without dropout the two coincide and dz* alias dy*.
     bf16* dy3 = spare1;
-    RC(layernorm_bwd(dx, a.y3, e->pf + o.n3_w, a.mean3, a.rstd3, dy3, g + o.n3_w, g + o.n3_b, g + o.l2_b, M, E, s));
-    // FFN (linear2's bias gradient = column sums of dy3, produced by the LayerNorm backward above)
-    RC(linear_wgrad(dy3, E, a.h, F, g + o.l2_w, nullptr, M, E, F, s));
-    RC(linear_dgrad(dy3, E, e->ph + o.l2_w, E, F, pl.dh, F, M, nullptr, 0, a.h, F, s));
+    bf16* dz3 = dropping ? pl.dxd : dy3;
+    RC(layernorm_bwd(dx, a.y3, e->pf + o.n3_w, a.mean3, a.rstd3, dy3, g + o.n3_w, g + o.n3_b, g + o.l2_b, M, E, s,
+                     dropping ? dz3 : nullptr, site(1 + 6 * l + 5)));
+    // FFN (linear2's bias gradient = column sums of dz3, produced by the LayerNorm backward above)
+    RC(linear_wgrad(dz3, E, a.h, F, g + o.l2_w, nullptr, M, E, F, s));
+    // h = dropout(relu(.)) is positive exactly where the unit is active AND kept
+    RC(linear_dgrad(dz3, E, e->ph + o.l2_w, E, F, pl.dh, F, M, nullptr, 0, a.h, F, s, keep_scale));
     RC(linear_wgrad(pl.dh, F, a.x2, E, g + o.l1_w, g + o.l1_b, M, F, E, s));
     bf16* dx2 = spare2;
     RC(linear_dgrad(pl.dh, F, e->ph + o.l1_w, F, E, dx2, E, M, dy3, E, nullptr, 0, s));
     // LN2
     bf16* dy2 = dx;   // dx (grad of layer output) is dead now
-    RC(layernorm_bwd(dx2, a.y2, e->pf + o.n2_w, a.mean2, a.rstd2, dy2, g + o.n2_w, g + o.n2_b, g + o.ca_ob, M, E, s));
+    bf16* dz2 = dropping ? pl.dxd : dy2;      // dz3 is dead (its last reader, the FFN dgrad above, is ordered before)
+    RC(layernorm_bwd(dx2, a.y2, e->pf + o.n2_w, a.mean2, a.rstd2, dy2, g + o.n2_w, g + o.n2_b, g + o.ca_ob, M, E, s,
+                     dropping ? dz2 : nullptr, site(1 + 6 * l + 3)));
     // cross-attention
-    RC(linear_wgrad(dy2, E, a.attn_c, E, g + o.ca_ow, nullptr, M, E, E, s));
-    RC(linear_dgrad(dy2, E, e->ph + o.ca_ow, E, E, pl.dattn, E, M, nullptr, 0, nullptr, 0, s));
+    RC(linear_wgrad(dz2, E, a.attn_c, E, g + o.ca_ow, nullptr, M, E, E, s));
+    RC(linear_dgrad(dz2, E, e->ph + o.ca_ow, E, E, pl.dattn, E, M, nullptr, 0, nullptr, 0, s));
     AttnArgs ca;
     ca.q = a.qc; ca.q_bs = static_cast<long long>(T) * E; ca.q_ts = E;
     ca.k = a.kvc; ca.v = a.kvc + E; ca.k_bs = ca.v_bs = static_cast<long long>(S) * 2 * E; ca.k_ts = ca.v_ts = 2 * E;
     ca.o = a.attn_c; ca.o_bs = static_cast<long long>(T) * E; ca.o_ts = E;
     ca.lse = a.lse_c; ca.B = B; ca.H = H; ca.Tq = T; ca.Tk = S; ca.hd = hd; ca.causal = 0;
-    ca.key_pad_mask = e->last_mem_pad; ca.scale = scale;
+    ca.key_pad_mask = e->last_mem_pad; ca.scale = scale; ca.drop = site(1 + 6 * l + 2);
     AttnGrads cg;
     cg.d_o = pl.dattn; cg.do_bs = static_cast<long long>(T) * E; cg.do_ts = E;
     cg.dq = pl.dqc; cg.dq_bs = static_cast<long long>(T) * E; cg.dq_ts = E;
@@ -362,16 +400,18 @@ int run_backward(b200_engine* e, bool have_dlogits, float* dmemory, void* const*
     RC(linear_dgrad(pl.dqc, E, e->ph + o.ca_w, E, E, dx1, E, M, dy2, E, nullptr, 0, s));
     // LN1
     bf16* dy1 = spare2;   // dx2 is dead
-    RC(layernorm_bwd(dx1, a.y1, e->pf + o.n1_w, a.mean1, a.rstd1, dy1, g + o.n1_w, g + o.n1_b, g + o.sa_ob, M, E, s));
+    bf16* dz1 = dropping ? pl.dxd : dy1;      // dz2 is dead
+    RC(layernorm_bwd(dx1, a.y1, e->pf + o.n1_w, a.mean1, a.rstd1, dy1, g + o.n1_w, g + o.n1_b, g + o.sa_ob, M, E, s,
+                     dropping ? dz1 : nullptr, site(1 + 6 * l + 1)));
     // self-attention
-    RC(linear_wgrad(dy1, E, a.attn_o, E, g + o.sa_ow, nullptr, M, E, E, s));
-    RC(linear_dgrad(dy1, E, e->ph + o.sa_ow, E, E, pl.dattn, E, M, nullptr, 0, nullptr, 0, s));
+    RC(linear_wgrad(dz1, E, a.attn_o, E, g + o.sa_ow, nullptr, M, E, E, s));
+    RC(linear_dgrad(dz1, E, e->ph + o.sa_ow, E, E, pl.dattn, E, M, nullptr, 0, nullptr, 0, s));
     AttnArgs sa;
     sa.q = a.qkv; sa.k = a.qkv + E; sa.v = a.qkv + 2 * E;
     sa.q_bs = sa.k_bs = sa.v_bs = static_cast<long long>(T) * 3 * E; sa.q_ts = sa.k_ts = sa.v_ts = 3 * E;
     sa.o = a.attn_o; sa.o_bs = static_cast<long long>(T) * E; sa.o_ts = E;
     sa.lse = a.lse_s; sa.B = B; sa.H = H; sa.Tq = T; sa.Tk = T; sa.hd = hd; sa.causal = 1;
-    sa.key_tokens = e->last_tokens; sa.pad_idx = c.pad_idx; sa.scale = scale;
+    sa.key_tokens = e->last_tokens; sa.pad_idx = c.pad_idx; sa.scale = scale; sa.drop = site(1 + 6 * l + 0);
     AttnGrads sg;
     sg.d_o = pl.dattn; sg.do_bs = static_cast<long long>(T) * E; sg.do_ts = E;
     sg.dq = pl.dqkv; sg.dk = pl.dqkv + E; sg.dv = pl.dqkv + 2 * E;
@@ -384,7 +424,7 @@ int run_backward(b200_engine* e, bool have_dlogits, float* dmemory, void* const*
     mark();
   }
   if (last_part < L + 1) return 0;
-  RC(embed_bwd(e->last_tokens, dx, e->gf + e->emb, B, T, E, V, c.pad_idx, sqrtf(static_cast<float>(E)), s));
+  RC(embed_bwd(e->last_tokens, dx, e->gf + e->emb, B, T, E, V, c.pad_idx, sqrtf(static_cast<float>(E)), s, site(0)));
   if (pl.mem_dim != E) {
     RC(cast_f32_to_bf16(pl.dmemp, pl.dmemp16, static_cast<long long>(Ms) * E, s));
     RC(linear_wgrad(pl.dmemp16, E, pl.mem16, pl.mem_dim, e->gf + e->proj_w, e->gf + e->proj_b, Ms, E, pl.mem_dim, s));
@@ -429,7 +469,9 @@ void build_decode_plan(const b200_engine* e, b200_engine::Decode* d, uint8_t* ba
   // partitions: whole 128-row GEMM tiles where possible
   const char* forced_env = getenv("B200_DECODE_PARTS");   // read per plan: tests compare partitionings
   const int forced = forced_env ? atoi(forced_env) : 0;
-  int P = forced > 0 ? forced : (R >= 512 ? 4 : (R >= 256 ? 2 : 1));
+  // Measured on B200 (cfg2, 512 rows): generation is bound by the ~75 dependent launches per position
+  // (launch rate, not SM occupancy), so concurrent partitions buy < 3 %; one partition by default.
+  int P = forced > 0 ? forced : 1;
   if (P > B) P = B;
   if (P > 8) P = 8;
   int per = (B + P - 1) / P;
@@ -442,13 +484,13 @@ void build_decode_plan(const b200_engine* e, b200_engine::Decode* d, uint8_t* ba
     pt.nb = (B - b0 < per) ? (B - b0) : per;
     d->part.push_back(pt);
   }
-  // split-K of the LayerNorm-fed GEMMs: enough CTAs to cover the SMs, at least 2 k-blocks per split
+  // split-K of the LayerNorm-fed GEMMs: enough CTAs to cover the SMs
   const int rows_p = per * beam;
   const int tiles = ((rows_p + 127) / 128) * static_cast<int>((E + 127) / 128);
   auto pick = [&](int64_t K) {
     const int kb = static_cast<int>((K + 63) / 64);
     int sk = 148 / (tiles > 0 ? tiles : 1);
-    if (sk > kb / 2) sk = kb / 2;
+    if (sk > kb / 4) sk = kb / 4;        // >= 4 k-blocks per split: beyond that the LayerNorm-side reduction costs more than the K loop saves
     if (sk > 8) sk = 8;
     if (sk < 1) sk = 1;
     return gemm_effective_splits(static_cast<int>(K), sk);
@@ -689,6 +731,16 @@ int b200_engine_bind(b200_engine* e, float* params_f32, void* params_bf16, float
   B200_REQUIRE((reinterpret_cast<uintptr_t>(params_f32) & 255) == 0 && (reinterpret_cast<uintptr_t>(params_bf16) & 255) == 0 &&
                (reinterpret_cast<uintptr_t>(grads_f32) & 255) == 0, "engine_bind: arenas must be 256-byte aligned");
   e->pf = params_f32; e->ph = static_cast<bf16*>(params_bf16); e->gf = grads_f32; e->pe = pe_f32;
+  return 0;
+}
+
+int b200_engine_set_dropout(b200_engine* e, float p, uint32_t* state_dev) {
+  B200_REQUIRE(e, "set_dropout: null engine");
+  B200_REQUIRE(p >= 0.f && p < 1.f, "set_dropout: probability %f outside [0, 1)", p);
+  B200_REQUIRE(p == 0.f || (state_dev != nullptr && (reinterpret_cast<uintptr_t>(state_dev) & 7) == 0),
+               "set_dropout: p > 0 needs an 8-byte aligned device buffer of two uint32 [seed, counter]");
+  e->drop_p = p;
+  e->drop_state = state_dev;
   return 0;
 }
 

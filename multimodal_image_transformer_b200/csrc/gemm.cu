@@ -33,6 +33,8 @@ struct GemmDev {
   int M, N, K;
   int num_m_tiles, num_n_tiles, split_k, kb_per_split, num_k_blocks;
   void* D; long long ldd; int d_fp32; int accumulate;
+  DropCfg drop;    // thr != 0: dropout of the (bias + activation) result, before the residual add
+  float mask_scale;  // factor applied where the ReLU mask passes (1 / (1 - p) of the FFN-activation dropout)
   int max_stages;  // > 0: cap of the operand ring depth (skinny launches leave shared memory to co-resident kernels)
   int part_rows;   // > 0: split-K partial slabs of this many rows each (plain stores at row split*part_rows + m)
   const float* bias;
@@ -280,6 +282,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint32_t t_row = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(ew * 32) << 16);
 
       // per-row state of the fused LM-head epilogues
+      uint32_t dkey = 0u;
+      if constexpr (EPI == EPI_STD) {
+        if (p.drop.thr) dkey = drop_key(p.drop);
+      }
       float run_max = -INFINITY, run_sum = 0.f, tgt_val = 0.f;
       int best_idx = 0x7fffffff;
       long long tgt = -1;
@@ -337,6 +343,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
             }
+            if (p.drop.thr) {
+              const uint32_t pair0 = (static_cast<uint32_t>(row) * static_cast<uint32_t>(p.N) + static_cast<uint32_t>(col0)) >> 1;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) drop_apply2(v[2 * i], v[2 * i + 1], drop_rand(dkey, pair0 + i), p.drop.thr, p.drop.scale);
+            }
             if (has_aux) {
               if (half == 0) {                    // slab b of the aux tile has landed
                 mbar_wait(&aux_full[b], aux_phase[b]);
@@ -354,8 +365,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     v[g * 8 + q * 2] += f.x;
                     v[g * 8 + q * 2 + 1] += f.y;
                   } else {
-                    if (!(f.x > 0.f)) v[g * 8 + q * 2] = 0.f;
-                    if (!(f.y > 0.f)) v[g * 8 + q * 2 + 1] = 0.f;
+                    v[g * 8 + q * 2] = (f.x > 0.f) ? v[g * 8 + q * 2] * p.mask_scale : 0.f;
+                    v[g * 8 + q * 2 + 1] = (f.y > 0.f) ? v[g * 8 + q * 2 + 1] * p.mask_scale : 0.f;
                   }
                 }
               }
@@ -631,6 +642,10 @@ int gemm_launch(const GemmProblem& q, cudaStream_t stream, int* n_tiles_out) {
   d.D = q.D; d.ldd = q.ldd; d.d_fp32 = q.d_fp32; d.accumulate = q.accumulate;
   d.part_rows = q.partials ? m_tiles * BLOCK_M : 0;
   d.max_stages = q.max_stages;
+  d.drop = q.drop;
+  d.mask_scale = q.mask_scale;
+  B200_REQUIRE(q.drop.thr == 0 || (q.epi == EPI_STD && !q.d_fp32 && static_cast<long long>(q.M) * q.N < (1ll << 32)),
+               "gemm: dropout needs the standard bf16 epilogue and M*N < 2^32");
   d.bias = q.bias; d.residual = q.residual; d.ldr = q.ldr; d.relu_mask = q.relu_mask; d.ldm = q.ldm;
   d.act = q.act;
   d.targets = reinterpret_cast<const long long*>(q.targets); d.ignore_index = q.ignore_index;
@@ -714,7 +729,7 @@ __global__ void gemm_check_kernel(GemmDev p, const bf16* A, long long lda, int a
   if (p.bias) acc += p.bias[n];
   if (p.act == 1) acc = fmaxf(acc, 0.f);
   else if (p.act == 2) acc = gelu_erf(acc);
-  if (p.relu_mask && !(__bfloat162float(p.relu_mask[static_cast<long long>(m) * p.ldm + n]) > 0.f)) acc = 0.f;
+  if (p.relu_mask) acc = (__bfloat162float(p.relu_mask[static_cast<long long>(m) * p.ldm + n]) > 0.f) ? acc * p.mask_scale : 0.f;
   if (p.residual) acc += __bfloat162float(p.residual[static_cast<long long>(m) * p.ldr + n]);
   if (p.d_fp32) {
     float* d = reinterpret_cast<float*>(p.D) + static_cast<long long>(m) * p.ldd + n;
@@ -732,6 +747,8 @@ int gemm_check_launch(const GemmProblem& q, cudaStream_t stream) {
   d.D = q.D; d.ldd = q.ldd; d.d_fp32 = q.d_fp32; d.accumulate = q.accumulate;
   d.bias = q.bias; d.residual = q.residual; d.ldr = q.ldr; d.relu_mask = q.relu_mask; d.ldm = q.ldm;
   d.act = q.act;
+  d.mask_scale = q.mask_scale;
+  B200_REQUIRE(q.drop.thr == 0, "gemm_check: dropout not modelled");
   const long long total = static_cast<long long>(q.M) * q.N;
   const int threads = 256;
   const long long blocks = (total + threads - 1) / threads;

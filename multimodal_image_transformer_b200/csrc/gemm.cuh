@@ -15,6 +15,8 @@ struct GemmProblem {
   const bf16* residual = nullptr; int64_t ldr = 0;
   const bf16* relu_mask = nullptr; int64_t ldm = 0;
   int act = 0;
+  DropCfg drop = DropCfg{nullptr, 0u, 0u, 1.f};   // dropout of act(A B^T + bias), applied before the residual add
+  float mask_scale = 1.f;                          // factor where relu_mask passes
   // partials: split-K without atomics.  D is an fp32 [split_k][Mpad][ldd] stack (Mpad = M rounded up
   // to 128); split i stores its partial product into slab i and the consumer (layernorm_reduce_fwd)
   // sums the slabs.  Used by the skinny decode GEMMs, whose latency is the per-CTA K loop.

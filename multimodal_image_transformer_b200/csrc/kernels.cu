@@ -7,12 +7,24 @@ namespace b200 {
 
 static inline int cdiv(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 o;
+  o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
+  o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+  return o;
+}
+
+
 // ------------------------------------------------------------------------------------------
 // token embedding * sqrt(E) + sinusoidal PE   (decoder.py:168-170, 71-72)
 // ------------------------------------------------------------------------------------------
 __global__ void embed_pe_fwd_kernel(const int64_t* __restrict__ tokens, const float* __restrict__ emb,
                                     const float* __restrict__ pe, bf16* __restrict__ x, int rows,
-                                    int T, int E, int V, float scale, int t0) {
+                                    int T, int E, int V, float scale, int t0, const DropCfg dc) {
   pdl_wait();
   pdl_trigger();
   const int vec_per_row = E >> 3;
@@ -26,19 +38,22 @@ __global__ void embed_pe_fwd_kernel(const int64_t* __restrict__ tokens, const fl
   const float4* e4 = reinterpret_cast<const float4*>(emb + tok * E + c);
   const float4* p4 = reinterpret_cast<const float4*>(pe + static_cast<long long>(t) * E + c);
   const float4 e0 = __ldg(e4), e1 = __ldg(e4 + 1), p0 = __ldg(p4), p1 = __ldg(p4 + 1);
-  uint4 o;
-  o.x = pack_bf16(fmaf(e0.x, scale, p0.x), fmaf(e0.y, scale, p0.y));
-  o.y = pack_bf16(fmaf(e0.z, scale, p0.z), fmaf(e0.w, scale, p0.w));
-  o.z = pack_bf16(fmaf(e1.x, scale, p1.x), fmaf(e1.y, scale, p1.y));
-  o.w = pack_bf16(fmaf(e1.z, scale, p1.z), fmaf(e1.w, scale, p1.w));
-  *reinterpret_cast<uint4*>(x + static_cast<long long>(row) * E + c) = o;
+  float f[8] = {fmaf(e0.x, scale, p0.x), fmaf(e0.y, scale, p0.y), fmaf(e0.z, scale, p0.z), fmaf(e0.w, scale, p0.w),
+                fmaf(e1.x, scale, p1.x), fmaf(e1.y, scale, p1.y), fmaf(e1.z, scale, p1.z), fmaf(e1.w, scale, p1.w)};
+  if (dc.thr) {                                    // decoder.py:72
+    const uint32_t key = drop_key(dc);
+    const uint32_t pair0 = (static_cast<uint32_t>(row) * E + c) >> 1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) drop_apply2(f[2 * j], f[2 * j + 1], drop_rand(key, pair0 + j), dc.thr, dc.scale);
+  }
+  *reinterpret_cast<uint4*>(x + static_cast<long long>(row) * E + c) = pack8(f);
 }
 
 int embed_pe_fwd(const int64_t* tokens, const float* emb, const float* pe, bf16* x, int B, int T,
-                 int E, int V, float scale, cudaStream_t s, int t0) {
+                 int E, int V, float scale, cudaStream_t s, int t0, DropCfg dc) {
   B200_REQUIRE(E % 8 == 0, "embed: E (%d) must be a multiple of 8", E);
   const long long n = static_cast<long long>(B) * T * (E / 8);
-  B200_CHECK_CUDA(launch_kernel(embed_pe_fwd_kernel, dim3(cdiv(n, 256)), dim3(256), 0, s, true, 1, tokens, emb, pe, x, B * T, T, E, V, scale, t0));
+  B200_CHECK_CUDA(launch_kernel(embed_pe_fwd_kernel, dim3(cdiv(n, 256)), dim3(256), 0, s, true, 1, tokens, emb, pe, x, B * T, T, E, V, scale, t0, dc));
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -47,7 +62,7 @@ int embed_pe_fwd(const int64_t* tokens, const float* emb, const float* pe, bf16*
 // scatter-add into the embedding gradient; the padding row receives nothing (decoder.py:105)
 __global__ void embed_bwd_kernel(const int64_t* __restrict__ tokens, const bf16* __restrict__ dx,
                                  float* __restrict__ demb, int rows, int E, int V, long long pad_idx,
-                                 float scale) {
+                                 float scale, const DropCfg dc) {
   pdl_wait();
   pdl_trigger();
   const int vec_per_row = E >> 3;
@@ -58,19 +73,38 @@ __global__ void embed_bwd_kernel(const int64_t* __restrict__ tokens, const bf16*
   const long long tok = tokens[row];
   if (tok == pad_idx || tok < 0 || tok >= V) return;
   const uint4 g = ldg_nc_v4(dx + static_cast<long long>(row) * E + c);
-  const float2 a = unpack_bf16(g.x), b = unpack_bf16(g.y), cc = unpack_bf16(g.z), d = unpack_bf16(g.w);
+  float f[8];
+  unpack8(g, f);
+  if (dc.thr) {
+    const uint32_t key = drop_key(dc);
+    const uint32_t pair0 = (static_cast<uint32_t>(row) * E + c) >> 1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) drop_apply2(f[2 * j], f[2 * j + 1], drop_rand(key, pair0 + j), dc.thr, dc.scale);
+  }
   float* dst = demb + tok * E + c;
-  red_add_v4_f32(dst, a.x * scale, a.y * scale, b.x * scale, b.y * scale);
-  red_add_v4_f32(dst + 4, cc.x * scale, cc.y * scale, d.x * scale, d.y * scale);
+  red_add_v4_f32(dst, f[0] * scale, f[1] * scale, f[2] * scale, f[3] * scale);
+  red_add_v4_f32(dst + 4, f[4] * scale, f[5] * scale, f[6] * scale, f[7] * scale);
 }
 
 int embed_bwd(const int64_t* tokens, const bf16* dx, float* demb, int B, int T, int E, int V,
-              long long pad_idx, float scale, cudaStream_t s) {
+              long long pad_idx, float scale, cudaStream_t s, DropCfg dc) {
   B200_REQUIRE(E % 8 == 0, "embed_bwd: E (%d) must be a multiple of 8", E);
   const long long n = static_cast<long long>(B) * T * (E / 8);
-  B200_CHECK_CUDA(launch_kernel(embed_bwd_kernel, dim3(cdiv(n, 256)), dim3(256), 0, s, true, 1, tokens, dx, demb, B * T, E, V, pad_idx, scale));
+  B200_CHECK_CUDA(launch_kernel(embed_bwd_kernel, dim3(cdiv(n, 256)), dim3(256), 0, s, true, 1, tokens, dx, demb, B * T, E, V, pad_idx, scale, dc));
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// one draw of fresh dropout masks per training forward (state = [seed, counter], see common.cuh)
+__global__ void drop_advance_kernel(uint32_t* state) {
+  pdl_wait();
+  pdl_trigger();
+  state[1] += 1u;
+}
+int drop_advance(uint32_t* state, cudaStream_t s) {
+  B200_CHECK_CUDA(launch_kernel(drop_advance_kernel, dim3(1), dim3(1), 0, s, true, 1, state));
+  note_launch();
   return 0;
 }
 
@@ -78,17 +112,6 @@ int embed_bwd(const int64_t* tokens, const bf16* dx, float* demb, int B, int T, 
 // LayerNorm (torch.nn.LayerNorm: biased variance, eps inside the sqrt), one warp per row
 // ------------------------------------------------------------------------------------------
 static constexpr int LN_MAXV = 8;  // 8 x (8 bf16) x 32 lanes = E up to 2048
-
-__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
-  const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
-  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
-}
-__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
-  uint4 o;
-  o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
-  o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
-  return o;
-}
 
 template <int NV>
 __global__ void __launch_bounds__(128)
@@ -271,7 +294,7 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                      const float* __restrict__ gamma, const float* __restrict__ mean,
                      const float* __restrict__ rstd, bf16* __restrict__ dx,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum,
-                     int rows, int E) {
+                     int rows, int E, bf16* __restrict__ dx_drop, const DropCfg dc) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ float sm_red[];  // [3][4][E]
@@ -290,6 +313,7 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
       gam[i][4] = g1.x; gam[i][5] = g1.y; gam[i][6] = g1.z; gam[i][7] = g1.w;
     }
   }
+  const uint32_t dkey = dc.thr ? drop_key(dc) : 0u;
   const int stride = gridDim.x * 4;
   for (int row0 = blockIdx.x * 4 + warp; row0 < rows; row0 += 2 * stride) {
     uint4 xr[2][NV], dr[2][NV];
@@ -342,11 +366,18 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
         if (vi < nvec) {
           float o[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            o[j] = rs[q] * (g[i][j] - c1 - xh[i][j] * c2);
-            dsx[i][j] += o[j];
-          }
+          for (int j = 0; j < 8; ++j) o[j] = rs[q] * (g[i][j] - c1 - xh[i][j] * c2);
           *reinterpret_cast<uint4*>(dxr + vi * 8) = pack8(o);
+          if (dc.thr) {
+            // the Linear that fed this LayerNorm went through dropout (x + dropout(z)): its operand
+            // gradient dz = dx * mask / (1 - p) goes to dx_drop, the residual branch keeps dx
+            const uint32_t pair0 = (static_cast<uint32_t>(row) * E + vi * 8) >> 1;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) drop_apply2(o[2 * j], o[2 * j + 1], drop_rand(dkey, pair0 + j), dc.thr, dc.scale);
+            *reinterpret_cast<uint4*>(dx_drop + static_cast<long long>(row) * E + vi * 8) = pack8(o);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dsx[i][j] += o[j];
         }
       }
     }
@@ -376,7 +407,8 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
 
 int layernorm_bwd(const bf16* dy, const bf16* x, const float* gamma, const float* mean,
                   const float* rstd, bf16* dx, float* dgamma, float* dbeta, float* dxsum, int rows, int E,
-                  cudaStream_t s) {
+                  cudaStream_t s, bf16* dx_drop, DropCfg dc) {
+  B200_REQUIRE(dc.thr == 0 || dx_drop != nullptr, "layernorm_bwd: dropout needs the second output");
   B200_REQUIRE(E % 8 == 0 && E <= LN_MAXV * 256, "layernorm_bwd: E (%d) must be a multiple of 8 and <= %d", E, LN_MAXV * 256);
   if (rows == 0) return 0;
   int blocks = cdiv(rows, 8);          // two rows per warp iteration
@@ -391,7 +423,7 @@ int layernorm_bwd(const bf16* dy, const bf16* x, const float* gamma, const float
       B200_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * NV * 256 * 4)); \
       configured = true;                                                                             \
     }                                                                                                \
-    B200_CHECK_CUDA(launch_kernel(layernorm_bwd_kernel<NV>, dim3(blocks), dim3(128), smem, s, true, 1, dy, x, gamma, mean, rstd, dx, dgamma, dbeta, dxsum, rows, E)); \
+    B200_CHECK_CUDA(launch_kernel(layernorm_bwd_kernel<NV>, dim3(blocks), dim3(128), smem, s, true, 1, dy, x, gamma, mean, rstd, dx, dgamma, dbeta, dxsum, rows, E, dx_drop, dc)); \
   } while (0)
   if (nv <= 1) B200_LN_BWD(1); else if (nv == 2) B200_LN_BWD(2); else if (nv == 3) B200_LN_BWD(3);
   else if (nv == 4) B200_LN_BWD(4); else B200_LN_BWD(8);

@@ -7,9 +7,11 @@ namespace b200 {
 
 // position of row r is (r % T) + t0  (t0 > 0: single-position decode steps)
 int embed_pe_fwd(const int64_t* tokens, const float* emb, const float* pe, bf16* x, int B, int T,
-                 int E, int V, float scale, cudaStream_t s, int t0 = 0);
+                 int E, int V, float scale, cudaStream_t s, int t0 = 0, DropCfg dc = DropCfg{nullptr, 0u, 0u, 1.f});
 int embed_bwd(const int64_t* tokens, const bf16* dx, float* demb, int B, int T, int E, int V,
-              long long pad_idx, float scale, cudaStream_t s);
+              long long pad_idx, float scale, cudaStream_t s, DropCfg dc = DropCfg{nullptr, 0u, 0u, 1.f});
+// advances the dropout step counter (state[1]) on the stream
+int drop_advance(uint32_t* state, cudaStream_t s);
 int layernorm_fwd(const bf16* x, const float* gamma, const float* beta, bf16* y, float* mean,
                   float* rstd, int rows, int E, float eps, cudaStream_t s);
 // y = LayerNorm(sum_s parts[s] + bias + residual): parts = fp32 split-K slabs of a "partials" GEMM
@@ -17,10 +19,11 @@ int layernorm_fwd(const bf16* x, const float* gamma, const float* beta, bf16* y,
 int layernorm_reduce_fwd(const float* parts, int nsplit, long long slab_stride, long long ldp, const float* bias,
                          const bf16* residual, long long ldr, const float* gamma, const float* beta, bf16* y,
                          int rows, int E, float eps, cudaStream_t s);
+// dx_drop / dc (optional): second output dx * dropout-mask / (1 - p) of site dc (and dxsum sums THAT);
 // dxsum (optional): += column sums of dx, i.e. the bias gradient of the Linear feeding this LayerNorm
 int layernorm_bwd(const bf16* dy, const bf16* x, const float* gamma, const float* mean,
                   const float* rstd, bf16* dx, float* dgamma, float* dbeta, float* dxsum, int rows, int E,
-                  cudaStream_t s);
+                  cudaStream_t s, bf16* dx_drop = nullptr, DropCfg dc = DropCfg{nullptr, 0u, 0u, 1.f});
 int colsum(const bf16* x, long long ldx, float* out, int M, int N, cudaStream_t s);
 int cast_f32_to_bf16(const float* src, bf16* dst, long long n, cudaStream_t s);
 int cast_bf16_to_f32(const bf16* src, float* dst, long long n, cudaStream_t s);

@@ -144,6 +144,9 @@ class TransformerDecoder(nn.Module):
         self.fc_out.weight = P("fc_out.weight")
         self.fc_out.bias = P("fc_out.bias")
         eng.load(init)
+        # dropout at the reference's sites (decoder.py:72,112-118) in train mode; the mask generator is
+        # counter-based, seeded from torch's CPU generator so torch.manual_seed() controls it
+        eng.set_dropout(self.dropout_p, torch.initial_seed() & 0x7FFFFFFF)
 
     # ------------------------------------------------------------------ nn.Module plumbing
     def _apply(self, fn, recurse=True):
@@ -164,16 +167,14 @@ class TransformerDecoder(nn.Module):
     def _mask(self, memory_padding_mask):
         return None if memory_padding_mask is None else memory_padding_mask.to(self.engine.device)
 
-    def _warn_dropout(self):
-        if self.training and self.dropout_p > 0 and not getattr(self, "_dropout_warned", False):
-            warnings.warn("b200 TransformerDecoder: dropout>0 is not applied by the CUDA path yet "
-                          "(parity and benchmarks run with dropout=0); training proceeds without dropout")
-            self._dropout_warned = True
+    def set_dropout_seed(self, seed: int) -> None:
+        """Re-seed the dropout masks (data-parallel replicas use seed + rank)."""
+        self.engine.set_dropout(self.dropout_p, seed)
 
     # ------------------------------------------------------------------ reference API
     def forward(self, tgt_tokens: torch.Tensor, memory: torch.Tensor,
                 memory_padding_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
-        self._warn_dropout()
+        self.engine.dropout_active(self.training)
         dev = self.engine.device
         tgt_tokens = tgt_tokens.to(dev)
         memory = memory.to(dev)
@@ -189,8 +190,8 @@ class TransformerDecoder(nn.Module):
              training: Optional[bool] = None) -> torch.Tensor:
         """mean CE over targets != ignore_index with the LM head fused into the loss (logits are
         never materialised).  Returns a device tensor [loss, n_valid]; no host sync."""
-        self._warn_dropout()
         training = self.training if training is None else training
+        self.engine.dropout_active(self.training and training)
         return self.engine.forward_loss(tgt_tokens, target_tokens, memory, self._mask(memory_padding_mask),
                                         ignore_index, training=training)
 

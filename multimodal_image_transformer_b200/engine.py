@@ -84,6 +84,36 @@ class DecoderEngine:
         except Exception:
             pass
 
+    # ------------------------------------------------------------------ dropout
+    def set_dropout(self, p: float, seed: int = 0) -> None:
+        """Enable dropout (probability p at the reference's 1 + 6 L sites) for forwards with
+        training=True; p = 0 disables.  Masks are a pure function of (seed, step counter, site,
+        element), so the device state [seed, counter] is all that is kept."""
+        p = float(p)
+        if p > 0:
+            self._drop_state = torch.tensor([seed & 0x7FFFFFFF, 0], device=self.device, dtype=torch.int32)
+        else:
+            self._drop_state = None
+        self.dropout_p = p
+        self._drop_active = None
+        self.dropout_active(True)
+
+    def dropout_active(self, active: bool) -> None:
+        """Train-mode switch (nn.Module.train()/eval()): dropout applies only while active."""
+        active = bool(active) and getattr(self, "dropout_p", 0.0) > 0
+        if getattr(self, "_drop_active", None) is active:
+            return
+        self._drop_active = active
+        L.check(self.lib.b200_engine_set_dropout(self.handle, self.dropout_p if active else 0.0,
+                                                 L.ptr(self._drop_state) if active else None), "set_dropout")
+
+    def dropout_state(self):
+        """(seed, counter) as host ints; the counter is the value the LAST training forward used."""
+        if getattr(self, "_drop_state", None) is None:
+            return None
+        s = self._drop_state.cpu()
+        return int(s[0]), int(s[1])
+
     # ------------------------------------------------------------------ arenas
     def shapes(self) -> Dict[str, Tuple[int, ...]]:
         E, F, V = self.embed_dim, self.ff_dim, self.vocab_size

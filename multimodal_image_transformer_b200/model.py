@@ -166,7 +166,7 @@ class _ProjectedDecoderFunction(torch.autograd.Function):
 
 def _forward_with_projection(model: ImageToTextModel, tgt_tokens, memory):
     dec = model.decoder
-    dec._warn_dropout()
+    dec.engine.dropout_active(dec.training)
     tgt_tokens = tgt_tokens.to(dec.engine.device)
     params = [model.projection.weight, model.projection.bias] + dec._flat_params()
     if torch.is_grad_enabled() and any(p.requires_grad for p in params):

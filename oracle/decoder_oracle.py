@@ -63,6 +63,64 @@ def sinusoid_table(max_len: int, d_model: int) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------
+# dropout masks
+# ------------------------------------------------------------------------------------------------
+# torch's dropout (decoder.py:72; transformer.py:1175,1195,1199; the attention-probability dropout
+# inside F.scaled_dot_product_attention, functional.py:6682) is x * Bernoulli(1-p) / (1-p) with
+# masks from torch's global generator, which no other implementation can reproduce.  The CUDA
+# path draws its masks from a counter-based generator instead (csrc/common.cuh: DropCfg); the
+# oracle restates THAT generator here so that a dropout-on forward/backward can be compared
+# element for element: same semantics as torch (mask, then scale by 1/(1-p), same 1 + 6 L sites),
+# different random stream.
+_M32 = 0xFFFFFFFF
+
+
+def _mix32(x: torch.Tensor) -> torch.Tensor:
+    x = x & _M32
+    x = x ^ (x >> 16)
+    x = (x * 0x85EBCA6B) & _M32
+    x = x ^ (x >> 13)
+    x = (x * 0xC2B2AE35) & _M32
+    x = x ^ (x >> 16)
+    return x
+
+
+class DropSpec:
+    """(p, seed, counter) of one training forward; site numbering as in csrc/common.cuh."""
+
+    def __init__(self, p: float, seed: int, counter: int):
+        self.p, self.seed, self.counter = float(p), int(seed), int(counter)
+        self.thr = int(self.p * 65536.0 + 0.5)
+        self.scale = 1.0 / (1.0 - self.p)
+
+    def key(self, site: int) -> int:
+        c = _mix32(torch.tensor((self.counter * 0x9E3779B9 + 0x7F4A7C15) & _M32, dtype=torch.int64))
+        k = torch.tensor(self.seed & _M32, dtype=torch.int64) ^ c ^ (((site + 1) * 0x85EBCA77) & _M32)
+        return int(_mix32(k))
+
+    def keep(self, site: int, elem_index: torch.Tensor) -> torch.Tensor:
+        """elem_index: int64 tensor of flat element indices (pair = index >> 1, half = index & 1)."""
+        pair = elem_index >> 1
+        r = _mix32(((pair * 0x9E3779B1) & _M32) + self.key(site))
+        half = torch.where((elem_index & 1) == 1, r >> 16, r & 0xFFFF)
+        return half >= self.thr
+
+    def rows(self, site: int, x: torch.Tensor) -> torch.Tensor:
+        """dropout of a (..., N) tensor viewed as row-major [rows, N]."""
+        n = x.numel()
+        keep = self.keep(site, torch.arange(n, dtype=torch.int64)).view(x.shape)
+        return x * keep * self.scale
+
+    def probs(self, site: int, a: torch.Tensor) -> torch.Tensor:
+        """dropout of attention probabilities (B,H,Tq,Tk): index ((b*H+h)*Tq+i) * 2*ceil(Tk/2) + j."""
+        B, H, Tq, Tk = a.shape
+        tk2 = 2 * ((Tk + 1) // 2)
+        row = torch.arange(B * H * Tq, dtype=torch.int64).view(B, H, Tq, 1)
+        idx = row * tk2 + torch.arange(Tk, dtype=torch.int64).view(1, 1, 1, Tk)
+        return a * self.keep(site, idx) * self.scale
+
+
+# ------------------------------------------------------------------------------------------------
 # forward
 # ------------------------------------------------------------------------------------------------
 def _layer_norm(x, w, b, eps=1e-5):
@@ -80,7 +138,7 @@ def _ident(t):
     return t
 
 
-def _attention(q, k, v, num_heads, add_mask, r=_ident):
+def _attention(q, k, v, num_heads, add_mask, r=_ident, drop=None, site=0):
     """q (B,Tq,E), k/v (B,Tk,E), add_mask broadcastable to (B,H,Tq,Tk) or None.
     functional.py:6682 — softmax(q k^T / sqrt(hd) + mask) v, heads = column blocks of width hd."""
     B, Tq, E = q.shape
@@ -92,14 +150,21 @@ def _attention(q, k, v, num_heads, add_mask, r=_ident):
     s = qh @ kh.transpose(-1, -2) / math.sqrt(hd)
     if add_mask is not None:
         s = s + add_mask
-    a = r(torch.softmax(s, dim=-1))
+    a = torch.softmax(s, dim=-1)
+    if drop is not None:
+        a = drop.probs(site, a)
+    a = r(a)
     return (a @ vh).transpose(1, 2).reshape(B, Tq, E)
 
 
 def decoder_hidden(p: Params, tokens: torch.Tensor, memory: torch.Tensor,
                    memory_padding_mask: Optional[torch.Tensor], num_heads: int,
-                   pad_idx: int = 0, act: str = "relu", emulate_bf16: bool = False) -> torch.Tensor:
+                   pad_idx: int = 0, act: str = "relu", emulate_bf16: bool = False,
+                   drop: Optional["DropSpec"] = None) -> torch.Tensor:
     """Everything of decoder.py:134-186 up to (not including) fc_out; returns (B,T,E).
+
+    drop: None = eval / p = 0 (what the golden fixtures pin); a DropSpec applies dropout at the
+    reference's 1 + 6 L sites with the CUDA path's counter-based masks (see DropSpec).
 
     emulate_bf16=True rounds GEMM weights and every tensor the CUDA path stores to bf16 at the
     same points (fp32 accumulation, fp32 biases / LayerNorm parameters / embedding table).  It is
@@ -116,7 +181,8 @@ def decoder_hidden(p: Params, tokens: torch.Tensor, memory: torch.Tensor,
     while f"transformer_decoder.layers.{L}.norm1.weight" in p:
         L += 1
     # decoder.py:168-170 (dropout is identity in eval / p=0, which is what parity runs use)
-    x = r(p["token_embedding.weight"][tokens] * math.sqrt(E) + p["positional_encoding.pe"][:, :T])
+    dr = (lambda site, t: drop.rows(site, t)) if drop is not None else (lambda site, t: t)
+    x = r(dr(0, p["token_embedding.weight"][tokens] * math.sqrt(E) + p["positional_encoding.pe"][:, :T]))
     # decoder.py:158,162 -> functional.py:6608-6621: float causal + bool key padding, merged
     self_mask = causal_mask(T).view(1, 1, T, T) + torch.zeros(B, 1, 1, T).masked_fill(
         padding_mask(tokens, pad_idx).view(B, 1, 1, T), float("-inf"))
@@ -131,28 +197,29 @@ def decoder_hidden(p: Params, tokens: torch.Tensor, memory: torch.Tensor,
         # self-attention block, transformer.py:1158-1175
         qkv = r(x @ p[pre + "self_attn.in_proj_weight"].t() + p[pre + "self_attn.in_proj_bias"])
         q, k, v = qkv.split(E, dim=-1)
-        sa = r(_attention(q, k, v, num_heads, self_mask, r))
-        sa = sa @ p[pre + "self_attn.out_proj.weight"].t() + p[pre + "self_attn.out_proj.bias"]
+        sa = r(_attention(q, k, v, num_heads, self_mask, r, drop, 1 + 6 * l + 0))
+        sa = dr(1 + 6 * l + 1, sa @ p[pre + "self_attn.out_proj.weight"].t() + p[pre + "self_attn.out_proj.bias"])
         x = r(_layer_norm(r(x + sa), p[pre + "norm1.weight"], p[pre + "norm1.bias"]))
         # cross-attention block, transformer.py:1177-1195 ; functional.py:5847-5864
         w, b = p[pre + "multihead_attn.in_proj_weight"], p[pre + "multihead_attn.in_proj_bias"]
         q = r(x @ w[:E].t() + b[:E])
         kv = r(memory @ w[E:].t() + b[E:])
         k, v = kv.split(E, dim=-1)
-        ca = r(_attention(q, k, v, num_heads, cross_mask, r))
-        ca = ca @ p[pre + "multihead_attn.out_proj.weight"].t() + p[pre + "multihead_attn.out_proj.bias"]
+        ca = r(_attention(q, k, v, num_heads, cross_mask, r, drop, 1 + 6 * l + 2))
+        ca = dr(1 + 6 * l + 3, ca @ p[pre + "multihead_attn.out_proj.weight"].t() + p[pre + "multihead_attn.out_proj.bias"])
         x = r(_layer_norm(r(x + ca), p[pre + "norm2.weight"], p[pre + "norm2.bias"]))
         # feed-forward block, transformer.py:1197-1199
-        h = r(fact(x @ p[pre + "linear1.weight"].t() + p[pre + "linear1.bias"]))
-        ff = h @ p[pre + "linear2.weight"].t() + p[pre + "linear2.bias"]
+        h = r(dr(1 + 6 * l + 4, fact(x @ p[pre + "linear1.weight"].t() + p[pre + "linear1.bias"])))
+        ff = dr(1 + 6 * l + 5, h @ p[pre + "linear2.weight"].t() + p[pre + "linear2.bias"])
         x = r(_layer_norm(r(x + ff), p[pre + "norm3.weight"], p[pre + "norm3.bias"]))
     return x
 
 
 def decoder_forward(p: Params, tokens, memory, memory_padding_mask=None, num_heads: int = 8,
-                    pad_idx: int = 0, act: str = "relu", emulate_bf16: bool = False) -> torch.Tensor:
+                    pad_idx: int = 0, act: str = "relu", emulate_bf16: bool = False,
+                    drop: Optional["DropSpec"] = None) -> torch.Tensor:
     """decoder.TransformerDecoder.forward (decoder.py:134-193): logits (B,T,V), fp32."""
-    x = decoder_hidden(p, tokens, memory, memory_padding_mask, num_heads, pad_idx, act, emulate_bf16)
+    x = decoder_hidden(p, tokens, memory, memory_padding_mask, num_heads, pad_idx, act, emulate_bf16, drop)
     w = _ste_bf16(p["fc_out.weight"]) if emulate_bf16 else p["fc_out.weight"]
     return x @ w.t() + p["fc_out.bias"]
 
@@ -178,7 +245,7 @@ def cross_entropy(logits: torch.Tensor, targets: torch.Tensor, ignore_index: int
 
 def loss_and_grads(p: Params, tokens, targets, memory, memory_padding_mask=None, num_heads=8,
                    pad_idx=0, ignore_index=0, proj: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
-                   emulate_bf16: bool = False) -> Tuple[torch.Tensor, Params]:
+                   emulate_bf16: bool = False, drop: Optional["DropSpec"] = None) -> Tuple[torch.Tensor, Params]:
     """train.py:83-93 for the decoder (+ optional projection): loss and d loss / d every
     floating-point parameter, by autograd over the restatement.  The embedding's padding row gets
     a zero gradient (nn.Embedding padding_idx, decoder.py:105)."""
@@ -195,7 +262,7 @@ def loss_and_grads(p: Params, tokens, targets, memory, memory_padding_mask=None,
         else:
             mem = project_memory(memory, *proj_leaves)
     loss = cross_entropy(decoder_forward(q, tokens, mem, memory_padding_mask, num_heads, pad_idx,
-                                         emulate_bf16=emulate_bf16), targets, ignore_index)
+                                         emulate_bf16=emulate_bf16, drop=drop), targets, ignore_index)
     loss.backward()
     grads = {k: v.grad for k, v in leaves.items()}
     grads["token_embedding.weight"][pad_idx].zero_()

@@ -101,6 +101,93 @@ def test_gradients_vs_oracle(cuda_dev, name):
     assert rel_l2(eng.grads, 2 * first) < 1e-3
 
 
+_LONG = dict(V=264, E=128, H=2, L=2, F=256, ML=100, B=2, T=99, S=197)   # reference MAX_SEQ_LEN: two-phase attention backward
+
+
+@pytest.mark.parametrize("name", ["tiny", "hd96", "cfg1", "long"])
+def test_dropout_matches_oracle_with_same_masks(cuda_dev, name):
+    """Dropout p=0.1 at the reference's 1 + 6 L sites (decoder.py:72; transformer.py:1175,1195,1199;
+    attention probabilities, functional.py:6682).  torch's random stream cannot be reproduced, so
+    the oracle applies torch's dropout SEMANTICS with the CUDA path's counter-based masks
+    (oracle.DropSpec) and loss / logits / every gradient are compared as in the p=0 tests."""
+    c = _LONG if name == "long" else CFGS[name]
+    p = O.init_params(c["V"], c["E"], c["H"], c["L"], c["F"], c["ML"], seed=42)
+    tok, tgt, mem, mpm = synth(c, 43)
+    eng = make_engine(c, p, cuda_dev)
+    eng.set_dropout(0.1, seed=77)
+    tokd, tgtd, memd = tok.to(cuda_dev), tgt.to(cuda_dev), mem.to(cuda_dev)
+    # eval-mode forwards ignore dropout entirely
+    with torch.no_grad():
+        ref0 = O.decoder_forward(p, tok, mem, None, c["H"])
+    assert row_max_rel(eng.forward_logits(tokd, memd, None, training=False), ref0) < 2e-2
+    assert eng.dropout_state() == (77, 0)
+    # training forward: logits under mask set #1
+    got = eng.forward_logits(tokd, memd, mpm.to(cuda_dev), training=True)
+    assert eng.dropout_state() == (77, 1)
+    with torch.no_grad():
+        ref = O.decoder_forward(p, tok, mem, mpm, c["H"], drop=O.DropSpec(0.1, 77, 1))
+    assert row_max_rel(got, ref) < 2e-2
+    assert row_max_rel(got, ref0) > 5e-2            # and the masks really did something
+    # loss + gradients under mask set #2
+    eng.zero_grad()
+    out = eng.forward_loss(tokd, tgtd, memd, None, 0, training=True)
+    eng.backward()
+    torch.cuda.synchronize()
+    spec = O.DropSpec(0.1, *eng.dropout_state())
+    assert spec.counter == 2
+    lref, g32 = O.loss_and_grads(p, tok, tgt, mem, None, c["H"], drop=spec)
+    _, g16 = O.loss_and_grads(p, tok, tgt, mem, None, c["H"], emulate_bf16=True, drop=spec)
+    assert abs(out[0].item() - lref.item()) < 1e-3 * lref.item()
+    for k in g32:
+        got_g = eng.view(k, eng.grads)
+        assert _grad_close(got_g, g16[k]), (k, rel_l2(got_g, g16[k]))
+        assert _grad_close(got_g, g32[k]), (k, rel_l2(got_g, g32[k]))
+    assert float(eng.view("token_embedding.weight", eng.grads)[0].abs().max()) == 0.0
+    # fresh masks every training forward; the same (seed, counter) reproduces bit for bit
+    l3 = eng.forward_loss(tokd, tgtd, memd, None, 0, training=True)[0].item()
+    assert l3 != out[0].item()
+    eng.set_dropout(0.1, seed=77)
+    eng.forward_logits(tokd, memd, mpm.to(cuda_dev), training=True)
+    again = eng.forward_loss(tokd, tgtd, memd, None, 0, training=True)[0].item()
+    assert again == out[0].item()
+
+
+def test_dropout_module_train_eval_and_graph(cuda_dev):
+    """nn.Module contract: dropout only in train() mode; a CUDA-graph replay of the fused step draws
+    new masks each replay (the counter lives on the device); drop fraction ~ p."""
+    from multimodal_image_transformer_b200.decoder import TransformerDecoder
+    from multimodal_image_transformer_b200.train import B200AdamW, GraphedTrainStep
+    c = CFGS["tiny"]
+    torch.manual_seed(5)
+    dec = TransformerDecoder(c["V"], c["E"], c["H"], c["L"], c["F"], c["ML"], dropout=0.1, pad_idx=0, device=cuda_dev)
+    tok, tgt, mem, _ = synth(c, 43)
+    tokd, tgtd, memd = tok.to(cuda_dev), tgt.to(cuda_dev), mem.to(cuda_dev)
+    dec.eval()
+    with torch.no_grad():
+        a = dec(tokd, memd)
+        b = dec(tokd, memd)
+    assert torch.equal(a, b)
+    dec.train()
+    with torch.no_grad():
+        l1 = dec.loss(tokd, tgtd, memd)[0].item()
+        l2 = dec.loss(tokd, tgtd, memd)[0].item()
+    assert l1 != l2
+    dec.eval()
+    with torch.no_grad():
+        assert torch.equal(dec(tokd, memd), a)
+    dec.train()
+    opt = B200AdamW(dec, lr=1e-4)
+    step = GraphedTrainStep(dec, opt, 0, 5.0, warmup=1)
+    before = dec.engine.dropout_state()[1]
+    losses = [step(memd, tokd, tgtd)[0].item() for _ in range(5)]
+    assert dec.engine.dropout_state()[1] == before + 5
+    assert len(set(losses)) == 5 and all(torch.isfinite(torch.tensor(losses)))
+    # drop fraction of the embedding site, measured through the oracle's restatement of the generator
+    spec = O.DropSpec(0.1, 1234, 3)
+    frac = 1.0 - spec.keep(0, torch.arange(1 << 20, dtype=torch.int64)).float().mean().item()
+    assert abs(frac - 0.1) < 2e-3
+
+
 def test_projection_path_cfg1(cuda_dev):
     """BASELINE cfg1: 768-wide CLIP features projected to the 512-wide decoder inside the engine."""
     c = CFGS["cfg1"]
