@@ -263,6 +263,176 @@ attn_fwd_kernel(const AttnDev p) {
   }
 }
 
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// ------------------------------------------------------------------------------------------
+// forward, split-key variant (the default when it fits): the keys of one (image, head) are cut into
+// KS ranges of whole 16-key tiles and every (query tile, key range) pair gets its OWN warp, so a
+// 47 x 197 problem keeps 12 warps busy instead of 3.  Each warp does one S = Q K^T block (<= NT*8
+// keys), a local softmax and one P V product; the KS partial (max, sum, O) triples of a query tile are
+// merged through shared memory (aliased onto the K/V tiles once every warp is done with them).
+// The elementwise part is written for issue slots: key bias (padding) in registers, causal
+// compare only where the block touches the diagonal, ex2.approx.ftz, no per-element branches.
+// ------------------------------------------------------------------------------------------
+template <int HD, int NT>
+__global__ void __launch_bounds__(512)
+attn_fwd_split_kernel(const AttnDev p, int KS) {
+  pdl_wait();
+  pdl_trigger();
+  constexpr int LD = HD + 8;
+  constexpr int LDO = HD + 4;                       // fp32 partial-O row pitch
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  bf16* sQ = reinterpret_cast<bf16*>(smem_attn);
+  bf16* sK = sQ + p.TQP * LD;
+  bf16* sV = sK + p.TKP * LD;
+  float* sBias = reinterpret_cast<float*>(sV + p.TKP * LD);
+  float* sML = sBias + p.TKP;                       // [items][16][2] local (max, sum)
+  float* sO = reinterpret_cast<float*>(sK);         // [items][16][LDO] partial O, aliases K/V
+
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int n_kt = p.TKP / 16;
+
+  load_rows<HD>(sQ, p.q + b * p.q_bs + h * HD, p.q_ts, p.Tq, p.TQP);
+  load_rows<HD>(sK, p.k + b * p.k_bs + h * HD, p.k_ts, p.Tk, p.TKP);
+  load_rows<HD>(sV, p.v + b * p.v_bs + h * HD, p.v_ts, p.Tk, p.TKP);
+  fill_key_bias(sBias, p, b);
+  cp_async_wait_all();
+  __syncthreads();
+
+  const int mt = warp / KS, ks = warp % KS;
+  const int row0 = mt * 16;
+  int kt0 = (n_kt * ks) / KS, kt1 = (n_kt * (ks + 1)) / KS;
+  if (p.causal) kt1 = min(kt1, mt + 1);             // key tiles right of the diagonal are fully masked
+  const int key0 = kt0 * 16;
+  const int avail = max(kt1 - kt0, 0) * 16;         // keys of this item (multiple of 16, <= NT * 8)
+
+  float s[NT][4], o[HD / 8][4];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+  float m_loc[2] = {-INFINITY, -INFINITY}, l_loc[2] = {0.f, 0.f};
+  if (avail > 0) {
+    mma_abt<HD, NT>(s, sQ, row0, sK, key0, avail);
+    const float sl2 = p.scale * LOG2E;
+    const bool diag = p.causal && (key0 + avail > row0);     // warp-uniform: block reaches the diagonal
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      if (j * 8 < avail) {                                    // warp-uniform
+        const float2 kb = *reinterpret_cast<const float2*>(sBias + key0 + j * 8 + 2 * t);
+        s[j][0] = fmaf(s[j][0], sl2, kb.x); s[j][1] = fmaf(s[j][1], sl2, kb.y);
+        s[j][2] = fmaf(s[j][2], sl2, kb.x); s[j][3] = fmaf(s[j][3], sl2, kb.y);
+        if (diag) {
+          const int key = key0 + j * 8 + 2 * t, r0 = row0 + g;
+          if (key > r0) s[j][0] = -INFINITY;
+          if (key + 1 > r0) s[j][1] = -INFINITY;
+          if (key > r0 + 8) s[j][2] = -INFINITY;
+          if (key + 1 > r0 + 8) s[j][3] = -INFINITY;
+        }
+        mx[0] = fmaxf(mx[0], fmaxf(s[j][0], s[j][1]));
+        mx[1] = fmaxf(mx[1], fmaxf(s[j][2], s[j][3]));
+      } else {
+        s[j][0] = s[j][1] = s[j][2] = s[j][3] = -INFINITY;
+      }
+    }
+    m_loc[0] = quad_max(mx[0]);
+    m_loc[1] = quad_max(mx[1]);
+    const float ms0 = (m_loc[0] == -INFINITY) ? 0.f : m_loc[0];   // fully masked row: every p becomes 0
+    const float ms1 = (m_loc[1] == -INFINITY) ? 0.f : m_loc[1];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      s[j][0] = ex2_ftz(s[j][0] - ms0); s[j][1] = ex2_ftz(s[j][1] - ms0);
+      s[j][2] = ex2_ftz(s[j][2] - ms1); s[j][3] = ex2_ftz(s[j][3] - ms1);
+      l_loc[0] += s[j][0] + s[j][1];
+      l_loc[1] += s[j][2] + s[j][3];
+    }
+    l_loc[0] = quad_sum(l_loc[0]);
+    l_loc[1] = quad_sum(l_loc[1]);
+    if (p.drop.thr) {      // the row sums keep the undropped probabilities; P V sees dropout(P)
+      const uint32_t dkey = drop_key(p.drop);
+      const int bh = b * p.H + h;
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        if (j * 8 < avail) {
+#pragma unroll
+          for (int rh = 0; rh < 2; ++rh) {
+            const uint32_t r = drop_rand(dkey, attn_drop_pair(p, bh, row0 + g + rh * 8, key0 + j * 8 + 2 * t));
+            drop_apply2(s[j][2 * rh], s[j][2 * rh + 1], r, p.drop.thr, p.drop.scale);
+          }
+        }
+      }
+    }
+    mma_pb<HD, NT>(o, s, sV, key0, avail);
+  }
+
+  if (KS == 1) {           // no merge needed: normalise and store straight from registers
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int row = row0 + g + r * 8;
+      const float inv = l_loc[r] > 0.f ? 1.f / l_loc[r] : 0.f;
+      if (row < p.Tq) {
+        bf16* orow = p.o + b * p.o_bs + row * p.o_ts + h * HD;
+#pragma unroll
+        for (int i = 0; i < HD / 8; ++i)
+          *reinterpret_cast<uint32_t*>(orow + i * 8 + 2 * t) = pack_bf16(o[i][2 * r] * inv, o[i][2 * r + 1] * inv);
+        if (p.lse && t == 0)
+          p.lse[(static_cast<long long>(b) * p.H + h) * p.Tq + row] = (l_loc[r] > 0.f) ? m_loc[r] * LN2 + logf(l_loc[r]) : -INFINITY;
+      }
+    }
+    return;
+  }
+
+  __syncthreads();         // every warp is done with K and V: their space now holds the partial O tiles
+  {
+    float* po = sO + static_cast<size_t>(warp) * 16 * LDO;
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) {
+      *reinterpret_cast<float2*>(po + g * LDO + i * 8 + 2 * t) = make_float2(o[i][0], o[i][1]);
+      *reinterpret_cast<float2*>(po + (g + 8) * LDO + i * 8 + 2 * t) = make_float2(o[i][2], o[i][3]);
+    }
+    if (t == 0) {
+      sML[(warp * 16 + g) * 2] = m_loc[0]; sML[(warp * 16 + g) * 2 + 1] = l_loc[0];
+      sML[(warp * 16 + g + 8) * 2] = m_loc[1]; sML[(warp * 16 + g + 8) * 2 + 1] = l_loc[1];
+    }
+  }
+  __syncthreads();
+  // merge: the KS warps of a query tile share its 16 rows; each lane owns one 8-wide column strip of a row
+  constexpr int CPR = HD / 8;                      // 8-column strips per row
+  const int first = mt * KS;                       // first item of this query tile
+  for (int idx = ks * 32 + lane; idx < 16 * CPR; idx += KS * 32) {
+    const int rr = idx / CPR, cs = (idx % CPR) * 8;
+    float M = -INFINITY;
+    for (int q = 0; q < KS; ++q) M = fmaxf(M, sML[((first + q) * 16 + rr) * 2]);
+    float L = 0.f, acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int q = 0; q < KS; ++q) {
+      const float mq = sML[((first + q) * 16 + rr) * 2];
+      const float w = (mq == -INFINITY) ? 0.f : ex2_ftz(mq - M);
+      L = fmaf(sML[((first + q) * 16 + rr) * 2 + 1], w, L);
+      const float* src = sO + (static_cast<size_t>(first + q) * 16 + rr) * LDO + cs;
+      const float4 a0 = *reinterpret_cast<const float4*>(src), a1 = *reinterpret_cast<const float4*>(src + 4);
+      acc[0] = fmaf(a0.x, w, acc[0]); acc[1] = fmaf(a0.y, w, acc[1]); acc[2] = fmaf(a0.z, w, acc[2]); acc[3] = fmaf(a0.w, w, acc[3]);
+      acc[4] = fmaf(a1.x, w, acc[4]); acc[5] = fmaf(a1.y, w, acc[5]); acc[6] = fmaf(a1.z, w, acc[6]); acc[7] = fmaf(a1.w, w, acc[7]);
+    }
+    const int row = row0 + rr;
+    if (row < p.Tq) {
+      const float inv = L > 0.f ? 1.f / L : 0.f;
+      uint4 out;
+      out.x = pack_bf16(acc[0] * inv, acc[1] * inv); out.y = pack_bf16(acc[2] * inv, acc[3] * inv);
+      out.z = pack_bf16(acc[4] * inv, acc[5] * inv); out.w = pack_bf16(acc[6] * inv, acc[7] * inv);
+      *reinterpret_cast<uint4*>(p.o + b * p.o_bs + row * p.o_ts + h * HD + cs) = out;
+      if (p.lse && cs == 0)
+        p.lse[(static_cast<long long>(b) * p.H + h) * p.Tq + row] = (L > 0.f) ? M * LN2 + logf(L) : -INFINITY;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------
@@ -522,30 +692,37 @@ attn_bwd2_kernel(const AttnDev p) {
         mma_abt<HD, NT>(dp, sdO, row0, sV, key0, avail);
         const float lse0 = sLse[row0 + g], lse1 = sLse[row0 + g + 8];
         const float d0 = sD[row0 + g], d1 = sD[row0 + g + 8];
+        const bool diag = p.causal && (key0 + avail > row0);      // warp-uniform: block reaches the diagonal
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
-          float pv[4], ds[4];
-          uint32_t rr[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
-          if (p.drop.thr) {
-            rr[0] = drop_rand(dkey, attn_drop_pair(p, bh, row0 + g, key0 + j * 8 + 2 * t));
-            rr[1] = drop_rand(dkey, attn_drop_pair(p, bh, row0 + g + 8, key0 + j * 8 + 2 * t));
-          }
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int key = key0 + j * 8 + 2 * t + (e & 1);
-            const int row = row0 + g + (e >> 1) * 8;
-            pv[e] = 0.f; ds[e] = 0.f;
-            if (j * 8 < avail && !(p.causal && key > row)) {
-              pv[e] = exp2f(sacc[j][e] * sl2 + sBias[key] - ((e >> 1) ? lse1 : lse0));
-              float dpe = dp[j][e];
-              if (p.drop.thr) {
-                const bool keep = attn_drop_keep(rr[e >> 1], e & 1, p.drop.thr);
-                dpe = keep ? dpe * p.drop.scale : 0.f;
-                ds[e] = pv[e] * (dpe - ((e >> 1) ? d1 : d0)) * p.scale;
-                pv[e] = keep ? pv[e] * p.drop.scale : 0.f;      // dV = dropout(P)^T dO
-              } else {
-                ds[e] = pv[e] * (dpe - ((e >> 1) ? d1 : d0)) * p.scale;
-              }
+          float pv[4] = {0.f, 0.f, 0.f, 0.f}, ds[4] = {0.f, 0.f, 0.f, 0.f};
+          if (j * 8 < avail) {                                   // warp-uniform
+            // masked keys carry a -inf bias, padded query rows a +inf lse: both give P = 0 without a branch
+            const float2 kb = *reinterpret_cast<const float2*>(sBias + key0 + j * 8 + 2 * t);
+            pv[0] = ex2_ftz(fmaf(sacc[j][0], sl2, kb.x) - lse0);
+            pv[1] = ex2_ftz(fmaf(sacc[j][1], sl2, kb.y) - lse0);
+            pv[2] = ex2_ftz(fmaf(sacc[j][2], sl2, kb.x) - lse1);
+            pv[3] = ex2_ftz(fmaf(sacc[j][3], sl2, kb.y) - lse1);
+            if (diag) {
+              const int key = key0 + j * 8 + 2 * t, r0 = row0 + g;
+              if (key > r0) pv[0] = 0.f;
+              if (key + 1 > r0) pv[1] = 0.f;
+              if (key > r0 + 8) pv[2] = 0.f;
+              if (key + 1 > r0 + 8) pv[3] = 0.f;
+            }
+            float dpe[4] = {dp[j][0], dp[j][1], dp[j][2], dp[j][3]};
+            if (p.drop.thr) {
+              const uint32_t ra = drop_rand(dkey, attn_drop_pair(p, bh, row0 + g, key0 + j * 8 + 2 * t));
+              const uint32_t rb = drop_rand(dkey, attn_drop_pair(p, bh, row0 + g + 8, key0 + j * 8 + 2 * t));
+              drop_apply2(dpe[0], dpe[1], ra, p.drop.thr, p.drop.scale);
+              drop_apply2(dpe[2], dpe[3], rb, p.drop.thr, p.drop.scale);
+              ds[0] = pv[0] * (dpe[0] - d0) * p.scale; ds[1] = pv[1] * (dpe[1] - d0) * p.scale;
+              ds[2] = pv[2] * (dpe[2] - d1) * p.scale; ds[3] = pv[3] * (dpe[3] - d1) * p.scale;
+              drop_apply2(pv[0], pv[1], ra, p.drop.thr, p.drop.scale);      // dV = dropout(P)^T dO
+              drop_apply2(pv[2], pv[3], rb, p.drop.thr, p.drop.scale);
+            } else {
+              ds[0] = pv[0] * (dpe[0] - d0) * p.scale; ds[1] = pv[1] * (dpe[1] - d0) * p.scale;
+              ds[2] = pv[2] * (dpe[2] - d1) * p.scale; ds[3] = pv[3] * (dpe[3] - d1) * p.scale;
             }
           }
           pP[ii][j][0] = pack_bf16(pv[0], pv[1]); pP[ii][j][1] = pack_bf16(pv[2], pv[3]);
@@ -770,10 +947,53 @@ static int dispatch_bwd(const AttnDev& d, cudaStream_t s, int nt_fallback) {
   return nt_fallback == 8 ? launch_bwd<HD, 8>(d, s) : launch_bwd<HD, 4>(d, s);
 }
 
+// split-key forward: KS key ranges per query tile, one warp per (query tile, range).  Returns 1 when
+// the shape does not fit (too many warps, ranges longer than NT*8 keys, partial tiles larger than the
+// K/V space they alias) and the caller falls back to the query-tile-per-warp kernel.
+template <int HD>
+static int try_launch_fwd_split(const AttnDev& d, cudaStream_t s) {
+  static const bool off = getenv("B200_ATTN_FWD_V1") != nullptr;
+  if (off) return 1;
+  constexpr int LD = HD + 8, LDO = HD + 4;
+  const int n_qt = d.TQP / 16, n_kt = d.TKP / 16;
+  if (n_qt > 16) return 1;
+  int KS = 16 / n_qt;
+  if (KS > n_kt) KS = n_kt;
+  // partial O tiles alias the K/V tiles
+  while (KS > 1 && static_cast<size_t>(n_qt) * KS * 16 * LDO * 4 > static_cast<size_t>(2) * d.TKP * LD * 2) --KS;
+  const int tiles_per = (n_kt + KS - 1) / KS;            // longest range, in 16-key tiles
+  if (tiles_per > 4) return 1;
+  const int items = n_qt * KS;
+  const size_t smem = static_cast<size_t>(d.TQP + 2 * d.TKP) * LD * 2 + (d.TKP + items * 32) * sizeof(float) + 16;
+  if (smem > 227 * 1024) return 1;
+  auto launch = [&](auto kern) -> int {
+    static size_t configured = 0;
+    if (smem > configured) {
+      B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      configured = smem;
+    }
+    B200_CHECK_CUDA(launch_kernel(kern, dim3(d.H, d.B), dim3(items * 32), smem, s, true, 1, d, KS));
+    note_launch();
+    return 0;
+  };
+  if (tiles_per <= 2) return launch(attn_fwd_split_kernel<HD, 4>);
+  return launch(attn_fwd_split_kernel<HD, 8>);
+}
+
 int attn_fwd(const AttnArgs& a, cudaStream_t s) {
   if (int rc = check_common(a)) return rc;
   AttnDev d;
   fill_dev(a, &d);
+  {
+    int rc = 1;
+    switch (a.hd) {
+      case 32: rc = try_launch_fwd_split<32>(d, s); break;
+      case 64: rc = try_launch_fwd_split<64>(d, s); break;
+      case 96: rc = try_launch_fwd_split<96>(d, s); break;
+      default: rc = try_launch_fwd_split<128>(d, s); break;
+    }
+    if (rc <= 0) return rc;
+  }
   switch (a.hd) {
     case 32: return launch_fwd<32, 8>(d, s);
     case 64: return launch_fwd<64, 8>(d, s);
