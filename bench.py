@@ -56,20 +56,61 @@ def synth_batch(c, seed, full_length=True):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md).  NVML is polled
+    every ~5 ms from a thread (the timed region of a default run is only a few hundred ms, too
+    short for `nvidia-smi -lms`); nvidia-smi is the fallback when pynvml is unavailable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index=0):
-        self.proc, self.lines, self.idx = None, [], str(gpu_index)
+        self.idx = int(gpu_index)
+        self.samples, self.power, self.reasons, self.max_mhz = [], [], set(), None
+        self._stop = threading.Event()
+        self.thread, self.proc, self.lines = None, None, []
+
+    def _nvml_loop(self, nv, h):
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for n, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:
+                break
+            time.sleep(0.005)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.idx, "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES remapping when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = self.idx
+            if vis:
+                ids = [x for x in vis.split(",") if x.strip() != ""]
+                if self.idx < len(ids) and ids[self.idx].strip().isdigit():
+                    phys = int(ids[self.idx])
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
         except Exception:
             self.proc = None
 
@@ -78,30 +119,37 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
+        self._stop.set()
+        if self.proc is not None:
+            self.proc.terminate()
             try:
-                sm.append(float(f[1]))
-                mx = float(f[2])
-            except ValueError:
-                continue
-            for n, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm),
-                "reasons": sorted(reasons)}
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for ln in self.lines:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    self.samples.append(float(f[1]))
+                    self.max_mhz = float(f[2])
+                    self.power.append(float(f[3]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, f[5:9]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+        elif self.thread is not None:
+            self.thread.join(timeout=1)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "samples": 0, "reasons": ["clock sampling unavailable"]}
+        sm = sorted(self.samples)
+        out = {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.max_mhz, "samples": len(sm),
+               "reasons": sorted(self.reasons)}
+        if self.power:
+            out["power_w_max"] = max(self.power)
+        return out
 
 
 def measured_peaks():
@@ -170,6 +218,9 @@ def workload_config(c, n_gpus, dropout):
 # B200 arm
 # ------------------------------------------------------------------------------------------------
 def run_b200(args):
+    # stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     import torch.distributed as dist
     from multimodal_image_transformer_b200 import _lib as L
     from multimodal_image_transformer_b200.decoder import TransformerDecoder
@@ -231,7 +282,6 @@ def run_b200(args):
             for i in range(per):
                 ms_i = sum(pl_ms[k * per + i] for k in range(args.steps)) / args.steps
                 f.write(f"{i},{pl_fl[i] / 1e9:.2f},{ms_i * 1e3:.1f},{pl_fl[i] / 1e9 / max(ms_i, 1e-9):.1f}\n")
-    clocks = sampler.stop() if rank == 0 else None
     ms_eager = e0.elapsed_time(e1) / args.steps
     use_graph = not args.no_graph
     graphed = []
@@ -255,6 +305,7 @@ def run_b200(args):
         ms = e0.elapsed_time(e1) / args.steps
     else:
         ms = ms_eager
+    clocks = sampler.stop() if rank == 0 else None     # sampled over the eager AND the graph-replay timed regions
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -280,8 +280,6 @@ static int launch_attn_decode(const DecAttnArgs& a, cudaStream_t s) {
   int per_sm = static_cast<int>((220 * 1024) / (smem + 1024));
   const int reg_cap = NQ > 1 ? 3 : 4;       // 160 threads x ~100 (NQ = 1) / 128 (NQ = 4) registers
   per_sm = per_sm < 1 ? 1 : (per_sm > reg_cap ? reg_cap : per_sm);
-  static const int per_sm_env = getenv("B200_DEC_ATTN_PER_SM") ? atoi(getenv("B200_DEC_ATTN_PER_SM")) : 0;
-  if (per_sm_env > 0 && per_sm_env < per_sm) per_sm = per_sm_env;
   const int items = a.groups * a.H;
   const int cap = device_sm_count() * per_sm;
   B200_CHECK_CUDA(launch_kernel(kern, dim3(items < cap ? items : cap), dim3(DEC_THREADS), smem, s, true, 1, a));

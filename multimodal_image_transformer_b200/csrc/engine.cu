@@ -193,16 +193,19 @@ void build_plan(const b200_engine* e, Plan* pl, uint8_t* base, int B, int T, int
 }
 
 // y = x W^T + b  with optional activation / residual; W rows [row0,row0+N) of a [*,K] matrix
-static int dec_gemm_stages() {
-  static const int v = getenv("B200_DEC_GEMM_STAGES") ? atoi(getenv("B200_DEC_GEMM_STAGES")) : 0;
-  return v;
+// y = act(x W^T + b) for a decode position (rows = hypotheses being decoded)
+int linear_dec(const bf16* x, int64_t ldx, const bf16* W, const float* bias, bf16* y, int64_t ldy, int M, int N, int K,
+               int act, cudaStream_t s) {
+  GemmProblem g;
+  g.M = M; g.N = N; g.K = K;
+  g.A = x; g.lda = ldx; g.B = W; g.ldb = K;
+  g.D = y; g.ldd = ldy; g.bias = bias; g.act = act; g.split_k = 1; g.block_n = 128;
+  return gemm_launch(g, s);
 }
 const DropCfg NO_DROP = DropCfg{nullptr, 0u, 0u, 1.f};
 int linear_fwd(const bf16* x, int64_t ldx, const bf16* W, const float* bias, bf16* y, int64_t ldy, int M,
-               int N, int K, int act, const bf16* residual, int64_t ldr, cudaStream_t s, int max_stages = 0,
-               DropCfg drop = NO_DROP) {
+               int N, int K, int act, const bf16* residual, int64_t ldr, cudaStream_t s, DropCfg drop = NO_DROP) {
   GemmProblem g;
-  g.max_stages = max_stages;
   g.drop = drop;
   g.M = M; g.N = N; g.K = K;
   g.A = x; g.lda = ldx; g.B = W; g.ldb = K;
@@ -288,7 +291,7 @@ int run_forward(b200_engine* e, const int64_t* tokens, const float* memory, cons
     sa.lse = a.lse_s; sa.B = B; sa.H = H; sa.Tq = T; sa.Tk = T; sa.hd = hd; sa.causal = 1;
     sa.key_tokens = tokens; sa.pad_idx = c.pad_idx; sa.scale = scale; sa.drop = site(1 + 6 * l + 0);
     RC(attn_fwd(sa, s));
-    RC(linear_fwd(a.attn_o, E, e->ph + o.sa_ow, e->pf + o.sa_ob, a.y1, E, M, E, E, 0, x, E, s, 0, site(1 + 6 * l + 1)));
+    RC(linear_fwd(a.attn_o, E, e->ph + o.sa_ow, e->pf + o.sa_ob, a.y1, E, M, E, E, 0, x, E, s, site(1 + 6 * l + 1)));
     RC(layernorm_fwd(a.y1, e->pf + o.n1_w, e->pf + o.n1_b, a.x1, a.mean1, a.rstd1, M, E, c.ln_eps, s));
     // --- cross-attention block
     RC(linear_fwd(a.x1, E, e->ph + o.ca_w, e->pf + o.ca_b, a.qc, E, M, E, E, 0, nullptr, 0, s));
@@ -300,11 +303,11 @@ int run_forward(b200_engine* e, const int64_t* tokens, const float* memory, cons
     ca.lse = a.lse_c; ca.B = B; ca.H = H; ca.Tq = T; ca.Tk = S; ca.hd = hd; ca.causal = 0;
     ca.key_pad_mask = mem_pad; ca.scale = scale; ca.drop = site(1 + 6 * l + 2);
     RC(attn_fwd(ca, s));
-    RC(linear_fwd(a.attn_c, E, e->ph + o.ca_ow, e->pf + o.ca_ob, a.y2, E, M, E, E, 0, a.x1, E, s, 0, site(1 + 6 * l + 3)));
+    RC(linear_fwd(a.attn_c, E, e->ph + o.ca_ow, e->pf + o.ca_ob, a.y2, E, M, E, E, 0, a.x1, E, s, site(1 + 6 * l + 3)));
     RC(layernorm_fwd(a.y2, e->pf + o.n2_w, e->pf + o.n2_b, a.x2, a.mean2, a.rstd2, M, E, c.ln_eps, s));
     // --- feed-forward block
-    RC(linear_fwd(a.x2, E, e->ph + o.l1_w, e->pf + o.l1_b, a.h, F, M, F, E, c.act, nullptr, 0, s, 0, site(1 + 6 * l + 4)));
-    RC(linear_fwd(a.h, F, e->ph + o.l2_w, e->pf + o.l2_b, a.y3, E, M, E, F, 0, a.x2, E, s, 0, site(1 + 6 * l + 5)));
+    RC(linear_fwd(a.x2, E, e->ph + o.l1_w, e->pf + o.l1_b, a.h, F, M, F, E, c.act, nullptr, 0, s, site(1 + 6 * l + 4)));
+    RC(linear_fwd(a.h, F, e->ph + o.l2_w, e->pf + o.l2_b, a.y3, E, M, E, F, 0, a.x2, E, s, site(1 + 6 * l + 5)));
     RC(layernorm_fwd(a.y3, e->pf + o.n3_w, e->pf + o.n3_b, x_out, a.mean3, a.rstd3, M, E, c.ln_eps, s));
   }
   return 0;
@@ -497,8 +500,6 @@ void build_decode_plan(const b200_engine* e, b200_engine::Decode* d, uint8_t* ba
   };
   d->ksplit_e = pick(E);
   d->ksplit_f = pick(F);
-  if (getenv("B200_DEC_KSPLIT_E")) d->ksplit_e = gemm_effective_splits(static_cast<int>(E), atoi(getenv("B200_DEC_KSPLIT_E")));
-  if (getenv("B200_DEC_KSPLIT_F")) d->ksplit_f = gemm_effective_splits(static_cast<int>(F), atoi(getenv("B200_DEC_KSPLIT_F")));
   const int ks_max = d->ksplit_e > d->ksplit_f ? d->ksplit_e : d->ksplit_f;
   for (auto& pt : d->part) {
     const int64_t mpad = (static_cast<int64_t>(pt.nb) * beam + 127) / 128 * 128;
@@ -516,7 +517,6 @@ int linear_ln_fwd(const bf16* x, int64_t ldx, const bf16* W, const float* bias, 
   g.M = M; g.N = N; g.K = K;
   g.A = x; g.lda = ldx; g.B = W; g.ldb = K;
   g.D = parts; g.ldd = N; g.d_fp32 = true; g.partials = true; g.split_k = split; g.block_n = 128;
-  g.max_stages = dec_gemm_stages();
   RC(gemm_launch(g, s));
   const long long mpad = (static_cast<long long>(M) + 127) / 128 * 128;
   return layernorm_reduce_fwd(parts, gemm_effective_splits(K, split), mpad * N, N, bias, residual, N, gamma, beta, y, M, N, eps, s);
@@ -552,16 +552,16 @@ int decode_hidden(b200_engine* e, const b200_engine::Decode::Part& pt, int cur, 
     const LayerOff& o = e->lo[l];
     bf16* kc_l = d.kcache[cur] + l * self_stride + self_off;
     bf16* vc_l = d.vcache[cur] + l * self_stride + self_off;
-    RC(linear_fwd(x, E, e->ph + o.sa_w, e->pf + o.sa_b, qkv, 3 * E, R, 3 * E, E, 0, nullptr, 0, s, dec_gemm_stages()));
+    RC(linear_dec(x, E, e->ph + o.sa_w, e->pf + o.sa_b, qkv, 3 * E, R, 3 * E, E, 0, s));
     RC(attn_decode_append(qkv, 3 * E, kc_l, vc_l, d.max_len, pos, attn, E, R, H, hd, scale, s));
     RC(linear_ln_fwd(attn, E, e->ph + o.sa_ow, e->pf + o.sa_ob, x, e->pf + o.n1_w, e->pf + o.n1_b, pt.parts, d.ksplit_e,
                      x1, R, E, E, c.ln_eps, s));
-    RC(linear_fwd(x1, E, e->ph + o.ca_w, e->pf + o.ca_b, qc, E, R, E, E, 0, nullptr, 0, s, dec_gemm_stages()));
+    RC(linear_dec(x1, E, e->ph + o.ca_w, e->pf + o.ca_b, qc, E, R, E, E, 0, s));
     RC(attn_decode(qc, E, d.kc + l * cross_stride + cross_off, d.vc + l * cross_stride + cross_off, S, S, attn, E, B,
                    d.beam, H, hd, mem_pad, scale, s));
     RC(linear_ln_fwd(attn, E, e->ph + o.ca_ow, e->pf + o.ca_ob, x1, e->pf + o.n2_w, e->pf + o.n2_b, pt.parts, d.ksplit_e,
                      x2, R, E, E, c.ln_eps, s));
-    RC(linear_fwd(x2, E, e->ph + o.l1_w, e->pf + o.l1_b, h, F, R, F, E, c.act, nullptr, 0, s, dec_gemm_stages()));
+    RC(linear_dec(x2, E, e->ph + o.l1_w, e->pf + o.l1_b, h, F, R, F, E, c.act, s));
     RC(linear_ln_fwd(h, F, e->ph + o.l2_w, e->pf + o.l2_b, x2, e->pf + o.n3_w, e->pf + o.n3_b, pt.parts, d.ksplit_f,
                      xn, R, E, F, c.ln_eps, s));
     bf16* t = x; x = xn; xn = t;

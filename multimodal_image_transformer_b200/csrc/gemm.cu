@@ -35,7 +35,6 @@ struct GemmDev {
   void* D; long long ldd; int d_fp32; int accumulate;
   DropCfg drop;    // thr != 0: dropout of the (bias + activation) result, before the residual add
   float mask_scale;  // factor applied where the ReLU mask passes (1 / (1 - p) of the FFN-activation dropout)
-  int max_stages;  // > 0: cap of the operand ring depth (skinny launches leave shared memory to co-resident kernels)
   int part_rows;   // > 0: split-K partial slabs of this many rows each (plain stores at row split*part_rows + m)
   const float* bias;
   const bf16* residual; long long ldr;
@@ -89,7 +88,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   constexpr uint32_t TMEM_COLS = ACC_STAGES * BLOCK_N;
   constexpr int NSH = BLOCK_N / CL;            // B rows (N) staged by this CTA
   const bool has_aux_smem = p.aux_mode != 0;
-  const int STAGES = (p.max_stages > 0 && p.max_stages < L::stages(has_aux_smem)) ? p.max_stages : L::stages(has_aux_smem);
+  const int STAGES = L::stages(has_aux_smem);
 
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();   // 128-byte swizzle atoms need a 1024-byte aligned base
@@ -556,10 +555,7 @@ static int launch_instance(const CUtensorMap& ta, const CUtensorMap& tb, const C
                            const CUtensorMap& tx, const GemmDev& d, int grid, cudaStream_t stream) {
   auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, EPI, CL>;
   static bool configured = false;
-  using SL = SmemLayout<BLOCK_N, CL>;
-  const bool aux = d.aux_mode != 0;
-  const int st = (d.max_stages > 0 && d.max_stages < SL::stages(aux)) ? d.max_stages : SL::stages(aux);
-  const int smem = st * SL::STAGE_BYTES + SL::epi_bytes(aux) + BAR_BYTES;
+  const int smem = SmemLayout<BLOCK_N, CL>::total(d.aux_mode != 0);
   if (!configured) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
     configured = true;
@@ -641,7 +637,6 @@ int gemm_launch(const GemmProblem& q, cudaStream_t stream, int* n_tiles_out) {
   d.split_k = (num_kb + d.kb_per_split - 1) / d.kb_per_split;  // no empty splits
   d.D = q.D; d.ldd = q.ldd; d.d_fp32 = q.d_fp32; d.accumulate = q.accumulate;
   d.part_rows = q.partials ? m_tiles * BLOCK_M : 0;
-  d.max_stages = q.max_stages;
   d.drop = q.drop;
   d.mask_scale = q.mask_scale;
   B200_REQUIRE(q.drop.thr == 0 || (q.epi == EPI_STD && !q.d_fp32 && static_cast<long long>(q.M) * q.N < (1ll << 32)),

@@ -21,7 +21,6 @@ struct GemmProblem {
   // to 128); split i stores its partial product into slab i and the consumer (layernorm_reduce_fwd)
   // sums the slabs.  Used by the skinny decode GEMMs, whose latency is the per-CTA K loop.
   bool partials = false;
-  int max_stages = 0;   // > 0: cap of the shared-memory operand ring depth
   int split_k = 1;   // 0 = auto
   int block_n = 0;   // 0 = auto
   // --- fused softmax-CE / argmax epilogues (LM head) ---
