@@ -18,6 +18,7 @@ class B200AdamW:
 
     def __init__(self, model, lr=config.LEARNING_RATE, betas=(config.ADAM_BETA1, config.ADAM_BETA2),
                  eps=config.ADAM_EPS, weight_decay=config.WEIGHT_DECAY, max_grad_norm: float = 0.0):
+        self.model_ref = model
         self.decoder = model.decoder if hasattr(model, "decoder") else model
         self.engine = self.decoder.engine
         self.param_groups = [dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
@@ -34,14 +35,63 @@ class B200AdamW:
         self.last_grad_sumsq = self.engine.adamw_step(lr=g["lr"], betas=g["betas"], eps=g["eps"],
                                                       weight_decay=g["weight_decay"], max_norm=mn)
 
-    def state_dict(self):
+    # ---- checkpoint compatibility (reference train.py:351-357, 424): torch.optim.AdamW layout
+    def _named_trainable(self):
+        """(index in the reference optimizer's parameter list, engine tensor name) of every trainable
+        parameter.  The reference builds AdamW over model.parameters() (train.py:319), which lists the
+        frozen encoder's parameters first: they keep their slots but never get state."""
+        model = self.model_ref
+        names, offset = [], 0
+        if hasattr(model, "encoder") and hasattr(model, "decoder"):
+            offset = sum(1 for _ in model.encoder.parameters())
+            if any(n.startswith("projection.") for n in self.engine.layout):
+                names += ["projection.weight", "projection.bias"]
+        names += [n for n in self.engine.layout if not n.startswith("projection.")]
+        return [(offset + i, n) for i, n in enumerate(names)], offset
+
+    def state_dict(self, torch_format: bool = True):
+        """torch.optim.AdamW-shaped state ({'state': {idx: {step, exp_avg, exp_avg_sq}}, 'param_groups'}) so a
+        checkpoint written here resumes in the reference and vice versa; torch_format=False returns
+        the flat-arena form."""
         e = self.engine
-        return {"step": e.opt_step, "exp_avg": None if e.exp_avg is None else e.exp_avg.clone(),
-                "exp_avg_sq": None if e.exp_avg_sq is None else e.exp_avg_sq.clone(),
-                "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]}
+        groups = [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]
+        if not torch_format:
+            return {"step": e.opt_step, "exp_avg": None if e.exp_avg is None else e.exp_avg.clone(),
+                    "exp_avg_sq": None if e.exp_avg_sq is None else e.exp_avg_sq.clone(), "param_groups": groups}
+        named, offset = self._named_trainable()
+        state = {}
+        if e.exp_avg is not None:
+            for idx, name in named:
+                state[idx] = {"step": torch.tensor(float(e.opt_step)),
+                              "exp_avg": e.view(name, e.exp_avg).clone(), "exp_avg_sq": e.view(name, e.exp_avg_sq).clone()}
+        g0 = dict(groups[0])
+        g0.setdefault("amsgrad", False)
+        g0["params"] = list(range(offset + len(named)))
+        return {"state": state, "param_groups": [g0]}
 
     def load_state_dict(self, sd) -> None:
         e = self.engine
+        if "state" in sd:                       # torch.optim.AdamW layout (ours or the reference's)
+            named, _ = self._named_trainable()
+            if sd["state"]:
+                if e.exp_avg is None:
+                    e.exp_avg = torch.zeros_like(e.params)
+                    e.exp_avg_sq = torch.zeros_like(e.params)
+                steps = set()
+                for idx, name in named:
+                    st = sd["state"].get(idx, sd["state"].get(str(idx)))
+                    if st is None:
+                        continue
+                    e.view(name, e.exp_avg).copy_(st["exp_avg"].to(e.device))
+                    e.view(name, e.exp_avg_sq).copy_(st["exp_avg_sq"].to(e.device))
+                    steps.add(int(float(st["step"])))
+                if len(steps) > 1:
+                    raise ValueError("B200AdamW keeps one step counter; the checkpoint has per-parameter steps %s" % sorted(steps))
+                e.opt_step = steps.pop() if steps else 0
+                e._step_dev.fill_(e.opt_step)
+            for g, s_ in zip(self.param_groups, sd["param_groups"]):
+                g.update({k: v for k, v in s_.items() if k in ("lr", "betas", "eps", "weight_decay")})
+            return
         e.opt_step = int(sd["step"])
         e._step_dev.fill_(e.opt_step)
         if sd["exp_avg"] is not None:
@@ -49,6 +99,20 @@ class B200AdamW:
             e.exp_avg_sq = sd["exp_avg_sq"].to(e.device).clone()
         for g, s in zip(self.param_groups, sd["param_groups"]):
             g.update(s)
+
+
+def trim_batch(decoder_input_tokens: torch.Tensor, target_tokens: torch.Tensor, pad_idx: int, multiple: int = 8):
+    """Drop the all-PAD tail columns of a collated batch.  The reference pads every caption to
+    MAX_SEQ_LEN (tokenizer.py:306, dataset.py:195-197), so most columns of a real batch are PAD for
+    every sample; they contribute nothing to the loss (CrossEntropyLoss(ignore_index=PAD),
+    train.py:327), are masked as attention keys (decoder.py:162) and their embedding-row gradient
+    is zero (decoder.py:105), so cutting them changes neither loss nor gradients -- only the work.
+    The kept length is rounded up to `multiple` to bound the number of distinct shapes."""
+    T = decoder_input_tokens.shape[1]
+    live = ((decoder_input_tokens != pad_idx) | (target_tokens != pad_idx)).any(dim=0)
+    n = int(live.nonzero().max().item()) + 1 if bool(live.any()) else 1
+    n = min(T, (n + multiple - 1) // multiple * multiple)
+    return decoder_input_tokens[:, :n], target_tokens[:, :n]
 
 
 def _ignore_index(criterion) -> int:
@@ -129,10 +193,14 @@ def train_one_epoch(model, dataloader, optimizer, criterion, device, grad_clip_v
     model.train()
     total_loss, num_batches = 0.0, len(dataloader)
     fused = isinstance(optimizer, B200AdamW)
+    pad = int(getattr(model, "decoder_pad_idx", getattr(model, "pad_idx", config.PAD_TOKEN_ID)))
     for i, batch in enumerate(dataloader):
         images = batch["images"].to(device, non_blocking=True)
-        tokens = batch["decoder_input_tokens"].to(device, non_blocking=True)
-        targets = batch["target_tokens"].to(device, non_blocking=True)
+        tokens, targets = batch["decoder_input_tokens"], batch["target_tokens"]
+        if fused and _ignore_index(criterion) == pad:
+            tokens, targets = trim_batch(tokens, targets, pad)      # on the host tensors: no device sync
+        tokens = tokens.to(device, non_blocking=True)
+        targets = targets.to(device, non_blocking=True)
         if fused:
             out = fused_train_step(model, images, tokens, targets, optimizer, _ignore_index(criterion),
                                    grad_clip_value, dp)
@@ -163,10 +231,14 @@ def evaluate(model, dataloader, criterion, device):
     model.eval()
     total_loss, num_batches = 0.0, len(dataloader)
     ii = _ignore_index(criterion)
+    pad = int(getattr(model, "decoder_pad_idx", getattr(model, "pad_idx", config.PAD_TOKEN_ID)))
     with torch.no_grad():
         for batch in dataloader:
             images = batch["images"].to(device, non_blocking=True)
-            tokens = batch["decoder_input_tokens"].to(device, non_blocking=True)
-            targets = batch["target_tokens"].to(device, non_blocking=True)
+            tokens, targets = batch["decoder_input_tokens"], batch["target_tokens"]
+            if ii == pad:
+                tokens, targets = trim_batch(tokens, targets, pad)
+            tokens = tokens.to(device, non_blocking=True)
+            targets = targets.to(device, non_blocking=True)
             total_loss += float(model.loss(images, tokens, targets, ii, training=False)[0].item())
     return total_loss / max(num_batches, 1)

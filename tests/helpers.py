@@ -14,6 +14,8 @@ CFGS = {
     "cfg1": dict(V=10000, E=512, H=8, L=4, F=2048, ML=100, B=8, T=31, S=50),
     # BASELINE cfg2 decoder at reduced batch (oracle finishes in seconds); full batch in bench.py
     "cfg2s": dict(V=10000, E=768, H=12, L=6, F=3072, ML=100, B=4, T=47, S=197),
+    # BASELINE cfg5 decoder (CLIP ViT-L/14 features 257x1024, 12 layers, d=1024, 16 heads) at batch 2
+    "cfg5s": dict(V=10000, E=1024, H=16, L=12, F=4096, ML=100, B=2, T=47, S=257),
 }
 
 

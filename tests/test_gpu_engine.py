@@ -37,7 +37,7 @@ def _case(name, seed=42):
     return c, p, synth(c, seed + 1)
 
 
-@pytest.mark.parametrize("name", ["nano", "tiny", "hd96", "cfg1", "cfg2s"])
+@pytest.mark.parametrize("name", ["nano", "tiny", "hd96", "cfg1", "cfg2s", "cfg5s"])
 def test_forward_logits_and_loss_vs_oracle(cuda_dev, name):
     c, p, (tok, tgt, mem, mpm) = _case(name)
     eng = make_engine(c, p, cuda_dev)
@@ -387,6 +387,69 @@ def test_decode_partitions_are_equivalent(cuda_dev, name, beam, monkeypatch):
         outs.append(runs[0])
     for t, l in outs[1:]:
         assert torch.equal(t, outs[0][0]) and torch.equal(l, outs[0][1])
+
+def test_trim_batch_keeps_loss_and_gradients(cuda_dev):
+    """train.trim_batch drops the all-PAD tail columns of a collated batch (the reference pads every
+    caption to MAX_SEQ_LEN): same loss, same gradients, less work."""
+    from multimodal_image_transformer_b200.train import trim_batch
+    c = dict(CFGS["tiny"], T=40)
+    p = O.init_params(c["V"], c["E"], c["H"], c["L"], c["F"], c["ML"], seed=11)
+    tok, tgt, mem, _ = synth(c, 12)
+    tok[:, 19:] = 0
+    tgt[:, 18:] = 0                         # longest caption: 19 tokens -> 24 kept columns
+    tok2, tgt2 = trim_batch(tok, tgt, 0)
+    assert tok2.shape[1] == 24 and torch.equal(tok2, tok[:, :24])
+    eng = make_engine(c, p, cuda_dev)
+    res = []
+    for a, b in ((tok, tgt), (tok2, tgt2)):
+        eng.zero_grad()
+        out = eng.forward_loss(a.to(cuda_dev), b.to(cuda_dev), mem.to(cuda_dev), None, 0, training=True)
+        eng.backward()
+        res.append((out.cpu().clone(), eng.grads.clone()))
+    assert res[0][0][1].item() == res[1][0][1].item()
+    assert abs(res[0][0][0].item() - res[1][0][0].item()) < 1e-6 * res[0][0][0].item()
+    assert rel_l2(res[1][1], res[0][1]) < 2e-3          # fp32 atomics / split-K order only
+
+
+def test_optimizer_state_dict_is_torch_adamw_shaped(cuda_dev):
+    """B200AdamW.state_dict() has the layout of torch.optim.AdamW over model.parameters() (reference
+    train.py:319-325, saved at :424, restored at :351-357): one fused step here equals one torch
+    AdamW step on the same gradients, entry by entry, and the dict round-trips."""
+    from multimodal_image_transformer_b200.decoder import TransformerDecoder
+    from multimodal_image_transformer_b200.train import B200AdamW
+    c = CFGS["nano"]
+    torch.manual_seed(3)
+    dec = TransformerDecoder(c["V"], c["E"], c["H"], c["L"], c["F"], c["ML"], dropout=0.0, pad_idx=0, device=cuda_dev)
+    dec.train()
+    opt = B200AdamW(dec, lr=1e-3, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-5)
+    names = list(dec.engine.layout)
+    before = {n: dec.engine.view(n).detach().cpu().clone() for n in names}
+    tok, tgt, mem, _ = synth(c, 5)
+    opt.zero_grad()
+    dec.loss(tok.to(cuda_dev), tgt.to(cuda_dev), mem.to(cuda_dev))
+    dec.backward()
+    grads = {n: dec.engine.view(n, dec.engine.grads).detach().cpu().clone() for n in names}
+    opt.step(max_grad_norm=0.0)
+    sd = opt.state_dict()
+    assert set(sd) == {"state", "param_groups"} and sd["param_groups"][0]["params"] == list(range(len(names)))
+    ref_params = [torch.nn.Parameter(before[n].clone()) for n in names]
+    ref = torch.optim.AdamW(ref_params, lr=1e-3, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-5)
+    for p_, n in zip(ref_params, names):
+        p_.grad = grads[n].clone()
+    ref.step()
+    rsd = ref.state_dict()
+    for i, n in enumerate(names):
+        assert float(sd["state"][i]["step"]) == float(rsd["state"][i]["step"]) == 1.0
+        assert rel_l2(sd["state"][i]["exp_avg"], rsd["state"][i]["exp_avg"]) < 1e-5, n
+        assert rel_l2(sd["state"][i]["exp_avg_sq"], rsd["state"][i]["exp_avg_sq"]) < 1e-5, n
+        assert (dec.engine.view(n).cpu() - ref_params[i].detach()).abs().max() < 1e-6, n
+    # a reference-written optimizer checkpoint restores into the fused optimizer (and ours into torch)
+    opt2 = B200AdamW(dec, lr=5e-4)
+    opt2.load_state_dict(rsd)
+    assert dec.engine.opt_step == 1 and opt2.param_groups[0]["lr"] == 1e-3
+    assert rel_l2(dec.engine.exp_avg, opt.engine.exp_avg) < 1e-6
+    ref.load_state_dict(sd)
+
 
 def test_full_size_properties_cfg2(cuda_dev):
     """BASELINE cfg2 (B=256, T=47, S=197, E=768, H=12, F=3072, L=6, V=10000): too big for the CPU
