@@ -65,6 +65,14 @@ static constexpr int DEC_CK = 64;       // keys per chunk
 static constexpr int DEC_STAGES = 3;
 static constexpr int DEC_THREADS = 160; // 4 consumer warps + 1 producer warp
 
+__device__ __forceinline__ float quad_max_dec(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum_dec(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
 __device__ __forceinline__ float exp_diff(float a, float m) {   // exp(a - m) with exp(-inf - -inf) = 0
   return (a == -INFINITY) ? 0.f : __expf(a - m);
 }
@@ -287,6 +295,246 @@ static int launch_attn_decode(const DecAttnArgs& a, cudaStream_t s) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// Tensor-core variant of the stream kernel (HD = 64 / 128, nq <= 8): the scalar kernel above is
+// issue-bound (64 % issue-active at 55 % of DRAM peak: ~36 warp-instructions per key), so here the
+// 64-key chunks arrive as 128-byte-swizzled TMA tiles and each consumer warp runs S = Q K^T and
+// P V for its 16 keys of the chunk on mma.sync.m16n8k16 (Q = a 16-row tile whose first nq rows are
+// the hypotheses of the image, the rest zero): ~3.5 warp-instructions per key, all beams for free.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dec_ldsm_x4(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+__device__ __forceinline__ void dec_ldsm_x4_t(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+__device__ __forceinline__ void dec_mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float dec_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+static constexpr int DECM_NQ = 4;       // rows of the partial-state exchange (nq <= 4)
+
+template <int HD, int DECM_STAGES, int MINB>
+__global__ void __launch_bounds__(DEC_THREADS, MINB)
+attn_decode_mma_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
+                       const DecAttnArgs a) {
+  constexpr int NBOX = HD / 64;                       // 64-column TMA boxes per K (or V) chunk
+  constexpr int BOX = DEC_CK * 128;                   // 8 KB: 64 rows x 128 B, 128-byte swizzled
+  constexpr int STAGE = 2 * NBOX * BOX;
+  constexpr int RED_STRIDE = HD + 2;
+  extern __shared__ __align__(1024) uint8_t sm_decm[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm_decm + DECM_STAGES * STAGE);
+  uint64_t* empty = full + DECM_STAGES;
+  float* red = reinterpret_cast<float*>(empty + DECM_STAGES + 2);   // [2][4][DECM_NQ][RED_STRIDE]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    if ((smem_u32(sm_decm) & 1023u) != 0u) __trap();
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    for (int i = 0; i < DECM_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 4); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  pdl_wait();
+  pdl_trigger();
+
+  const int n_items = a.groups * a.H;
+  const int nch = (a.nkeys + DEC_CK - 1) / DEC_CK;
+
+  if (warp == 4) {
+    // ============================ producer ============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int row0 = item * a.kv_len;
+        for (int c = 0; c < nch; ++c) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* dst = sm_decm + stage * STAGE;
+          mbar_arrive_expect_tx(&full[stage], STAGE);
+#pragma unroll
+          for (int bx = 0; bx < NBOX; ++bx) {
+            tma_load_2d(dst + bx * BOX, &tmap_k, &full[stage], bx * 64, row0 + c * DEC_CK);
+            tma_load_2d(dst + (NBOX + bx) * BOX, &tmap_v, &full[stage], bx * 64, row0 + c * DEC_CK);
+          }
+          if (++stage == DECM_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    return;
+  }
+
+  // ============================== consumers ==============================
+  const int g = lane >> 2, t = lane & 3;
+  const int mi = lane >> 3, r8 = lane & 7;
+  const float sl2 = a.scale * 1.4426950408889634f;
+  int stage = 0, par = 0;
+  uint32_t phase = 0;
+  uint32_t qn[HD / 16][2];
+  auto fetch_q = [&](int item) {
+    const int grp = item / a.H, h = item % a.H;
+#pragma unroll
+    for (int ks = 0; ks < HD / 16; ++ks) {
+      qn[ks][0] = qn[ks][1] = 0u;
+      if (g < a.nq && item < n_items) {
+        const bf16* qp = a.q + (static_cast<long long>(grp) * a.nq + g) * a.q_rs + h * HD + ks * 16 + 2 * t;
+        qn[ks][0] = *reinterpret_cast<const uint32_t*>(qp);
+        qn[ks][1] = *reinterpret_cast<const uint32_t*>(qp + 8);
+      }
+    }
+  };
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x, par ^= 1) {
+    const int grp = item / a.H, h = item % a.H;
+    fetch_q(item);
+    // Q as mma A fragments: row g (< nq) = hypothesis g of this image, rows >= nq are zero
+    uint32_t qa[HD / 16][4];
+#pragma unroll
+    for (int ks = 0; ks < HD / 16; ++ks) {
+      qa[ks][0] = qn[ks][0]; qa[ks][2] = qn[ks][1];
+      qa[ks][1] = qa[ks][3] = 0u;
+    }
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+    float o[HD / 8][4];
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+
+    for (int c = 0; c < nch; ++c) {
+      mbar_wait(&full[stage], phase);
+      const int nk = min(DEC_CK, a.nkeys - c * DEC_CK);
+      const int kw0 = warp * 16;                       // this warp's keys of the chunk
+      if (kw0 < nk) {                                  // warp-uniform
+        const uint32_t sk = smem_u32(sm_decm + stage * STAGE);
+        const uint32_t sv = sk + NBOX * BOX;
+        float sc[2][4];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) { sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f; }
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks) {
+          uint32_t b[4];
+          const int row = kw0 + (mi >> 1) * 8 + r8;
+          const int unit = (ks & 3) * 2 + (mi & 1);
+          dec_ldsm_x4(b, sk + (ks >> 2) * BOX + row * 128 + ((unit ^ r8) << 4));
+          dec_mma16816(sc[0], qa[ks], b[0], b[1]);
+          dec_mma16816(sc[1], qa[ks], b[2], b[3]);
+        }
+        const unsigned char* padp = a.key_pad ? a.key_pad + static_cast<long long>(grp) * a.nkeys + c * DEC_CK : nullptr;
+        float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int key = kw0 + j * 8 + 2 * t + (e & 1);
+            bool valid = key < nk;
+            if (valid && padp != nullptr && padp[key] != 0) valid = false;
+            const float v = valid ? sc[j][e] * sl2 : -INFINITY;
+            sc[j][e] = v;
+            mx[e >> 1] = fmaxf(mx[e >> 1], v);
+          }
+        }
+        float alpha[2], ms[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const float mn = fmaxf(m_run[r], quad_max_dec(mx[r]));
+          alpha[r] = (m_run[r] == -INFINITY) ? 0.f : dec_ex2(m_run[r] - mn);
+          m_run[r] = mn;
+          ms[r] = (mn == -INFINITY) ? 0.f : mn;
+        }
+        float ps[2] = {0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float pv = dec_ex2(sc[j][e] - ms[e >> 1]);
+            sc[j][e] = pv;
+            ps[e >> 1] += pv;
+          }
+        }
+        l_run[0] = l_run[0] * alpha[0] + ps[0];
+        l_run[1] = l_run[1] * alpha[1] + ps[1];
+#pragma unroll
+        for (int i = 0; i < HD / 8; ++i) {
+          o[i][0] *= alpha[0]; o[i][1] *= alpha[0]; o[i][2] *= alpha[1]; o[i][3] *= alpha[1];
+        }
+        uint32_t pa[4];
+        pa[0] = pack_bf16(sc[0][0], sc[0][1]); pa[1] = pack_bf16(sc[0][2], sc[0][3]);
+        pa[2] = pack_bf16(sc[1][0], sc[1][1]); pa[3] = pack_bf16(sc[1][2], sc[1][3]);
+#pragma unroll
+        for (int dn = 0; dn < HD / 8; dn += 2) {
+          uint32_t b[4];
+          const int row = kw0 + (mi & 1) * 8 + r8;
+          const int unit = (dn & 7) + (mi >> 1);
+          dec_ldsm_x4_t(b, sv + (dn >> 3) * BOX + row * 128 + ((unit ^ r8) << 4));
+          dec_mma16816(o[dn], pa, b[0], b[1]);
+          dec_mma16816(o[dn + 1], pa, b[2], b[3]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stage]);
+      if (++stage == DECM_STAGES) { stage = 0; phase ^= 1; }
+    }
+
+    // ---- merge the four warps' states of rows < nq (row g of the tile lives in lanes 4g .. 4g+3)
+    const float lsum = quad_sum_dec(l_run[0]);
+    float* rp = red + (par * 4 + warp) * DECM_NQ * RED_STRIDE;
+    if (g < a.nq) {
+#pragma unroll
+      for (int i = 0; i < HD / 8; ++i)
+        *reinterpret_cast<float2*>(rp + g * RED_STRIDE + i * 8 + 2 * t) = make_float2(o[i][0], o[i][1]);
+      if (t == 0) { rp[g * RED_STRIDE + HD] = m_run[0]; rp[g * RED_STRIDE + HD + 1] = lsum; }
+    }
+    named_barrier_sync(1, 128);
+    const float* rb = red + par * 4 * DECM_NQ * RED_STRIDE;
+    for (int idx = threadIdx.x; idx < a.nq * HD; idx += 128) {
+      const int i = idx / HD, d = idx % HD;
+      float mm = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) mm = fmaxf(mm, rb[(w * DECM_NQ + i) * RED_STRIDE + HD]);
+      float ls = 0.f, val = 0.f;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const float mw = rb[(w * DECM_NQ + i) * RED_STRIDE + HD];
+        const float cw = (mw == -INFINITY) ? 0.f : dec_ex2(mw - mm);
+        ls = fmaf(rb[(w * DECM_NQ + i) * RED_STRIDE + HD + 1], cw, ls);
+        val = fmaf(rb[(w * DECM_NQ + i) * RED_STRIDE + d], cw, val);
+      }
+      a.o[(static_cast<long long>(grp) * a.nq + i) * a.o_rs + h * HD + d] = __float2bfloat16(ls > 0.f ? val / ls : 0.f);
+    }
+  }
+}
+
+template <int HD, int DECM_STAGES, int MINB>
+static int launch_attn_decode_mma(const DecAttnArgs& a, cudaStream_t s) {
+  auto kern = attn_decode_mma_kernel<HD, DECM_STAGES, MINB>;
+  const size_t smem = static_cast<size_t>(DECM_STAGES) * 2 * (HD / 64) * DEC_CK * 128 + (2 * DECM_STAGES + 2) * sizeof(uint64_t) +
+                      static_cast<size_t>(2) * 4 * DECM_NQ * (HD + 2) * sizeof(float) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = true;
+  }
+  const long long rows = static_cast<long long>(a.groups) * a.H * a.kv_len;
+  CUtensorMap tk, tv;
+  if (int rc = make_tmap_2d_bf16(&tk, a.k, HD, static_cast<uint64_t>(rows), static_cast<uint64_t>(HD) * 2, 64, DEC_CK)) return rc;
+  if (int rc = make_tmap_2d_bf16(&tv, a.v, HD, static_cast<uint64_t>(rows), static_cast<uint64_t>(HD) * 2, 64, DEC_CK)) return rc;
+  int per_sm = static_cast<int>((220 * 1024) / (smem + 1024));
+  per_sm = per_sm < 1 ? 1 : (per_sm > MINB ? MINB : per_sm);
+  const int items = a.groups * a.H;
+  const int cap = device_sm_count() * per_sm;
+  B200_CHECK_CUDA(launch_kernel(kern, dim3(items < cap ? items : cap), dim3(DEC_THREADS), smem, s, true, 1, tk, tv, a));
+  note_launch();
+  return 0;
+}
+
 int attn_decode(const bf16* q, long long q_rs, const bf16* k, const bf16* v, int kv_len, int nkeys, bf16* o,
                 long long o_rs, int groups, int nq, int H, int hd, const unsigned char* key_pad, float scale,
                 cudaStream_t s) {
@@ -295,6 +543,13 @@ int attn_decode(const bf16* q, long long q_rs, const bf16* k, const bf16* v, int
   DecAttnArgs a = {};
   a.q = q; a.q_rs = q_rs; a.k = k; a.v = v; a.kv_len = kv_len; a.nkeys = nkeys; a.o = o; a.o_rs = o_rs;
   a.groups = groups; a.nq = nq; a.H = H; a.key_pad = key_pad; a.scale = scale;
+  static const bool scalar_only = getenv("B200_DEC_ATTN_SCALAR") != nullptr;     // A/B switch
+  if (!scalar_only && nq <= DECM_NQ && (reinterpret_cast<uintptr_t>(k) & 15) == 0 && (reinterpret_cast<uintptr_t>(v) & 15) == 0) {
+    // measured on B200 (512 images x 12 heads, S = 197): ring depth 2 with 4 CTAs per SM 0.82 ms per position,
+    // depth 3 0.84, depth 4 (3 CTAs) 0.95, depth 1 0.92; 5-6 CTAs per SM (register cap 72 / 64, spills) 0.95-1.05
+    if (hd == 64) return launch_attn_decode_mma<64, 2, 4>(a, s);
+    if (hd == 128) return launch_attn_decode_mma<128, 2, 2>(a, s);
+  }
 #define B200_AD(HDV)                                              \
   do {                                                            \
     if (nq == 1) return launch_attn_decode<HDV, 1>(a, s);         \
