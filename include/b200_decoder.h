@@ -185,6 +185,11 @@ int32_t b200_engine_num_params(const b200_engine* e);
 /* params_f32/grads_f32/params_bf16: arenas of b200_engine_param_count() elements. */
 int b200_engine_bind(b200_engine* e, float* params_f32, void* params_bf16, float* grads_f32,
                      const float* pe_f32);
+/* Element type of the `memory` argument of every later call: 0 = fp32 (what the reference's encoder
+ * hands over, model.py:133-151; cast to bf16 by the engine), 1 = bf16 (pre-cast / cached frozen-encoder
+ * features: consumed in place, so the buffer must stay valid and unchanged until the backward of the
+ * same step has run; half the host->device bytes).  dmemory stays fp32. */
+int b200_engine_set_memory_dtype(b200_engine* e, int32_t is_bf16);
 /* Dropout of the training forward (reference config.py:69 DROPOUT = 0.1; modules: decoder.py:72,
  * torch/nn/modules/transformer.py:1175,1195,1199, attention-probability dropout functional.py:6682).
  * p = 0 disables it.  state_dev: caller-owned device buffer of two uint32 [seed, counter]; every

@@ -93,6 +93,7 @@ SIGNATURES = {
     "b200_engine_param_name": (C.c_int, [_P, _I32, C.c_char_p, _I32]),
     "b200_engine_num_params": (_I32, [_P]),
     "b200_engine_bind": (C.c_int, [_P, _P, _P, _P, _P]),
+    "b200_engine_set_memory_dtype": (C.c_int, [_P, _I32]),
     "b200_engine_set_dropout": (C.c_int, [_P, _F, _P]),
     "b200_engine_workspace_bytes": (_I64, [_P, _I32, _I32, _I32, _I32, _I32]),
     "b200_engine_set_workspace": (C.c_int, [_P, _P, _I64]),

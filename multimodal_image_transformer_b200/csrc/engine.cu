@@ -79,6 +79,7 @@ struct b200_engine {
   // dropout (reference config.py:69 DROPOUT = 0.1): probability + caller-owned device state [seed, counter]
   float drop_p = 0.f;
   uint32_t* drop_state = nullptr;
+  bool mem_bf16 = false;         // `memory` arguments are bf16 (cached frozen-encoder features) instead of fp32
   bool plan_dropout = false;     // the last training forward applied dropout (backward must regenerate the masks)
   uint8_t* ws = nullptr;
   int64_t ws_bytes = 0;
@@ -271,7 +272,15 @@ int run_forward(b200_engine* e, const int64_t* tokens, const float* memory, cons
   if (dropping) RC(drop_advance(e->drop_state, s));
   auto site = [&](int id) { return dropping ? drop_site(e, id) : NO_DROP; };
 
-  RC(cast_f32_to_bf16(memory, pl.mem16, static_cast<long long>(Ms) * mem_dim, s));
+  if (e->mem_bf16) {
+    // bf16 features are consumed in place (no cast pass); the caller keeps them alive and unchanged until backward is done
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(memory) & 15) == 0, "engine: bf16 memory must be 16-byte aligned");
+    const bool same = pl.memp == pl.mem16;
+    pl.mem16 = reinterpret_cast<bf16*>(const_cast<float*>(memory));
+    if (same) pl.memp = pl.mem16;
+  } else {
+    RC(cast_f32_to_bf16(memory, pl.mem16, static_cast<long long>(Ms) * mem_dim, s));
+  }
   if (mem_dim != E)
     RC(linear_fwd(pl.mem16, mem_dim, e->ph + e->proj_w, e->pf + e->proj_b, pl.memp, E, Ms, E, mem_dim, 0, nullptr, 0, s));
 
@@ -734,6 +743,12 @@ int b200_engine_bind(b200_engine* e, float* params_f32, void* params_bf16, float
   return 0;
 }
 
+int b200_engine_set_memory_dtype(b200_engine* e, int32_t is_bf16) {
+  B200_REQUIRE(e, "set_memory_dtype: null engine");
+  e->mem_bf16 = is_bf16 != 0;
+  return 0;
+}
+
 int b200_engine_set_dropout(b200_engine* e, float p, uint32_t* state_dev) {
   B200_REQUIRE(e, "set_dropout: null engine");
   B200_REQUIRE(p >= 0.f && p < 1.f, "set_dropout: probability %f outside [0, 1)", p);
@@ -923,7 +938,14 @@ int b200_engine_decode_begin(b200_engine* e, const float* memory, const uint8_t*
   d.mem_pad = mem_pad;
   d.cur = 0;
   const int Ms = B * S;
-  RC(cast_f32_to_bf16(memory, d.mem16, static_cast<long long>(Ms) * mem_dim, s));
+  if (e->mem_bf16) {
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(memory) & 15) == 0, "decode_begin: bf16 memory must be 16-byte aligned");
+    const bool same = d.memp == d.mem16;
+    d.mem16 = reinterpret_cast<bf16*>(const_cast<float*>(memory));     // only read inside this call
+    if (same) d.memp = d.mem16;
+  } else {
+    RC(cast_f32_to_bf16(memory, d.mem16, static_cast<long long>(Ms) * mem_dim, s));
+  }
   if (mem_dim != E)
     RC(linear_fwd(d.mem16, mem_dim, e->ph + e->proj_w, e->pf + e->proj_b, d.memp, E, Ms, E, mem_dim, 0, nullptr, 0, s));
   // image-side K/V: projected ONCE per image and layer (the reference redoes this every token)

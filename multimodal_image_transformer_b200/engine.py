@@ -176,11 +176,19 @@ class DecoderEngine:
             L.check(self.lib.b200_engine_set_workspace(self.handle, L.ptr(self._ws), C.c_int64(self._ws.numel())),
                     "set_workspace")
 
-    @staticmethod
-    def _prep(tokens, memory, mem_pad):
+    def _mem(self, memory: torch.Tensor) -> torch.Tensor:
+        """fp32 features are cast by the engine; bf16 features (e.g. model.FeatureCache) are consumed in place."""
+        is_bf16 = memory.dtype == torch.bfloat16
+        memory = memory.contiguous() if is_bf16 else memory.to(torch.float32).contiguous()
+        if getattr(self, "_mem_bf16", None) is not is_bf16:
+            L.check(self.lib.b200_engine_set_memory_dtype(self.handle, int(is_bf16)), "set_memory_dtype")
+            self._mem_bf16 = is_bf16
+        return memory
+
+    def _prep(self, tokens, memory, mem_pad):
         assert tokens.dtype == torch.int64 and tokens.is_cuda and tokens.dim() == 2
         tokens = tokens.contiguous()
-        memory = memory.to(torch.float32).contiguous()
+        memory = self._mem(memory)
         assert memory.dim() == 3 and memory.shape[0] == tokens.shape[0]
         if mem_pad is not None:
             mem_pad = mem_pad.to(torch.uint8).contiguous()
@@ -220,8 +228,7 @@ class DecoderEngine:
                  events: Optional[List[torch.cuda.Event]] = None) -> Optional[torch.Tensor]:
         dmem = None
         if want_dmemory:
-            _, memory = self._keep[0], self._keep[1]
-            dmem = torch.empty_like(memory)
+            dmem = torch.empty_like(self._keep[1], dtype=torch.float32)
         ev_arr, n_ev = None, 0
         if events:
             n_ev = len(events)
@@ -239,7 +246,7 @@ class DecoderEngine:
         dlogits = dlogits.to(torch.float32).contiguous()
         dmem = None
         if want_dmemory:
-            dmem = torch.empty_like(self._keep[1])
+            dmem = torch.empty_like(self._keep[1], dtype=torch.float32)
         L.check(self.lib.b200_engine_backward_from_dlogits(self.handle, L.ptr(dlogits), L.ptr(dmem),
                                                            L.cur_stream()), "backward_from_dlogits")
         return dmem
@@ -278,7 +285,7 @@ class DecoderEngine:
     def decode_begin(self, memory: torch.Tensor, mem_pad: Optional[torch.Tensor] = None, beam: int = 1,
                      max_len: int = 100) -> None:
         """Project the image memory once per image into per-layer cross K/V and reset the caches."""
-        memory = memory.to(self.device, torch.float32).contiguous()
+        memory = self._mem(memory.to(self.device))
         if mem_pad is not None:
             mem_pad = mem_pad.to(self.device, torch.uint8).contiguous()
         B, S, mem_dim = memory.shape

@@ -43,6 +43,37 @@ class _Projection(_Holder):
         return ops.linear(x, self.weight, self.bias)
 
 
+class FeatureCache:
+    """Frozen-encoder features computed ONCE per image and kept in pinned host memory as bf16
+    (SURVEY section 8f.2).  The reference runs the frozen tower on every image in every epoch
+    (model.py:133-141) although its weights never change (model.py:87-89); with the decoder on the
+    fast path that encoder pass is what bounds an epoch.  `get(keys, pixel_values)` encodes only
+    the images whose key (e.g. the dataset's image path) is new, and returns the batch's features
+    as one bf16 device tensor that the engine consumes in place (half the host->device bytes of fp32)."""
+
+    def __init__(self, model: "ImageToTextModel"):
+        self.model = model
+        self.store = {}
+        self.hits = 0
+        self.misses = 0
+
+    @torch.no_grad()
+    def get(self, keys, pixel_values: torch.Tensor) -> torch.Tensor:
+        dev = self.model.decoder.engine.device
+        missing = [i for i, k in enumerate(keys) if k not in self.store]
+        if missing:
+            feats = self.model.encode(pixel_values[missing].to(dev)).to(torch.bfloat16).cpu()
+            for j, i in enumerate(missing):
+                self.store[keys[i]] = feats[j].clone().pin_memory()
+        self.misses += len(missing)
+        self.hits += len(keys) - len(missing)
+        first = self.store[keys[0]]
+        stage = torch.empty((len(keys),) + tuple(first.shape), dtype=torch.bfloat16).pin_memory()
+        for i, k in enumerate(keys):
+            stage[i].copy_(self.store[k])
+        return stage.to(dev, non_blocking=True)
+
+
 class ImageToTextModel(nn.Module):
     def __init__(self, decoder_vocab_size: int, decoder_embed_dim: int, decoder_heads: int,
                  decoder_layers: int, decoder_ff_dim: int, decoder_max_seq_len: int,
@@ -98,9 +129,12 @@ class ImageToTextModel(nn.Module):
             return self.decoder(tgt_tokens, memory, None)
         return _forward_with_projection(self, tgt_tokens, memory)
 
-    def loss(self, image_tensors, tgt_tokens, target_tokens, ignore_index: int = 0, training=None) -> torch.Tensor:
-        """Fused path: encoder -> (projection + decoder + LM head + CE) without logits."""
-        memory = self.encode(image_tensors)
+    def loss(self, image_tensors, tgt_tokens, target_tokens, ignore_index: int = 0, training=None,
+             memory: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Fused path: encoder -> (projection + decoder + LM head + CE) without logits.  `memory`
+        (e.g. from a FeatureCache) skips the frozen encoder."""
+        if memory is None:
+            memory = self.encode(image_tensors)
         return self.decoder.loss(tgt_tokens.to(memory.device), target_tokens.to(memory.device), memory, None,
                                  ignore_index, training)
 

@@ -75,3 +75,47 @@ def test_model_generate_vs_reference(cuda_dev):
         img = Image.fromarray(rs.randint(0, 256, (224, 224, 3), dtype=np.uint8), "RGB")
         got = m.generate(img, 1, 2, max_len=g["generate_max_len"], method="greedy")
         assert got == ref, (got, ref)
+
+
+def test_bf16_memory_and_feature_cache(cuda_dev):
+    """bf16 features are consumed in place (loss / gradients equal the fp32-input path on bf16-rounded
+    features) and FeatureCache runs the frozen tower once per image key."""
+    from multimodal_image_transformer_b200.model import FeatureCache
+    g = torch.load(GOLDEN, weights_only=True)
+    m = _build(cuda_dev, g)
+    eng = m.decoder.engine
+    images, tok, tgt = _images(g).to(cuda_dev), g["tokens"].to(cuda_dev), g["targets"].to(cuda_dev)
+    with torch.no_grad():
+        feat32 = m.encode(images)
+    feat16 = feat32.to(torch.bfloat16)
+    res = []
+    for mem in (feat16.float(), feat16):
+        eng.zero_grad()
+        out = eng.forward_loss(tok, tgt, mem, None, 0, training=True)
+        eng.backward()
+        res.append((out.cpu().clone(), eng.grads.clone()))
+    assert res[0][0][0].item() == res[1][0][0].item()
+    assert torch.equal(res[0][1], res[1][1]) or (res[0][1] - res[1][1]).abs().max() < 1e-6 * res[0][1].abs().max() + 1e-9
+    # generation accepts bf16 memory too
+    eng.decode_begin(feat16, None, beam=1, max_len=8)
+    t16, _ = eng.generate_greedy(1, 2, 8)
+    eng.decode_begin(feat16.float(), None, beam=1, max_len=8)
+    t32, _ = eng.generate_greedy(1, 2, 8)
+    assert torch.equal(t16, t32)
+    # cache: second epoch never touches the encoder
+    calls = {"n": 0}
+    orig = m.encoder.forward
+
+    def counted(*a, **k):
+        calls["n"] += 1
+        return orig(*a, **k)
+    m.encoder.forward = counted
+    cache = FeatureCache(m)
+    keys = [f"img{i}" for i in range(images.shape[0])]
+    a = cache.get(keys, images)
+    b = cache.get(keys[::-1], images.flip(0))
+    assert calls["n"] == 1 and cache.misses == len(keys) and cache.hits == len(keys)
+    assert a.dtype == torch.bfloat16 and torch.equal(a, b.flip(0)) and torch.equal(a, feat16)
+    l_cached = m.loss(None, tok, tgt, memory=a, training=False)[0].item()
+    l_direct = m.loss(images, tok, tgt, training=False)[0].item()
+    assert abs(l_cached - l_direct) < 2e-3 * l_direct
