@@ -374,9 +374,11 @@ def init_params(vocab_size, embed_dim, num_heads, num_layers, ff_dim, max_seq_le
                 pad_idx=0) -> Params:
     """Builds the same torch.nn modules, in the same order, that decoder.py:105-124 builds, then
     applies the Xavier pass of decoder.py:128-132, so that for one seed the values are bit-identical
-    to the reference's (checked in tests/test_oracle.py when /root/reference is present)."""
+    to the reference's (checked in tests/test_oracle.py when /root/reference is present).
+    seed=None continues the current torch RNG stream (model.py builds encoder and projection first)."""
     import torch.nn as nn
-    torch.manual_seed(seed)
+    if seed is not None:
+        torch.manual_seed(seed)
     emb = nn.Embedding(vocab_size, embed_dim, padding_idx=pad_idx)
     nn.Dropout(p=0.0)
     layer = nn.TransformerDecoderLayer(d_model=embed_dim, nhead=num_heads, dim_feedforward=ff_dim,

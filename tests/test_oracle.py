@@ -136,3 +136,28 @@ def test_oracle_matches_live_reference():
         sys.path.remove(REF)
         for m in ("config", "decoder", "utils"):
             sys.modules.pop(m, None)
+
+
+def test_model_level_oracle_matches_reference_model_golden():
+    """tests/golden/model_cfg1.pt comes from the unmodified reference model.ImageToTextModel (BASELINE
+    configs[0]); the oracle (CLS token of the frozen tower -> projection -> decoder restatement -> CE)
+    must reproduce its logits and loss from the same seed and construction order (model.py:30-114)."""
+    from transformers import CLIPConfig, CLIPModel
+    g = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "model_cfg1.pt"), weights_only=True)
+    c = g["config"]
+    torch.manual_seed(g["seed"])
+    tower = CLIPModel(CLIPConfig()).vision_model.eval()           # the reference's (offline) AutoModel.from_pretrained draw
+    lin = torch.nn.Linear(768, c["E"])                            # model.py:99
+    p = O.init_params(c["V"], c["E"], c["H"], c["L"], c["F"], c["ML"], seed=None)
+    assert abs(float(lin.weight.double().sum()) - g["weight_checksum"]["projection.weight"]) < 1e-6
+    assert abs(float(p["fc_out.weight"].double().sum()) - g["weight_checksum"]["decoder.fc_out.weight"]) < 1e-5
+    gen = torch.Generator().manual_seed(g["seed"])
+    images = torch.randn(c["B"], 3, 224, 224, generator=gen)
+    with torch.no_grad():
+        cls = tower(pixel_values=images).last_hidden_state[:, 0, :]                      # model.py:141
+        mem = O.project_memory(cls.unsqueeze(1), lin.weight, lin.bias)                   # model.py:145-151
+        logits = O.decoder_forward(p, g["tokens"], mem, None, c["H"])
+    assert abs(float(cls.double().sum()) - g["cls_checksum"]) < 1e-3
+    assert (logits[:, :, ::97] - g["logits_sub"]).abs().max() < 5e-5
+    loss = O.cross_entropy(logits, g["targets"], 0)
+    assert abs(loss.item() - g["loss"]) < 1e-5 * g["loss"]
