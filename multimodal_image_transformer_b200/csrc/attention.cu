@@ -882,7 +882,7 @@ template <int HD, int NT>
 static int launch_fwd(const AttnDev& d, cudaStream_t s) {
   const size_t smem = AttnSmem<HD>::fwd_bytes(d.TQP, d.TKP);
   B200_REQUIRE(smem <= 227 * 1024, "attention fwd: %zu B of shared memory needed (> 227 KB)", smem);
-  static size_t configured = 0;
+  static size_t configured = 48 * 1024;      // the default limit: never lower it
   if (smem > configured) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<HD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = smem;
@@ -896,7 +896,7 @@ template <int HD, int NT>
 static int launch_bwd(const AttnDev& d, cudaStream_t s) {
   const size_t smem = AttnSmem<HD>::bwd_bytes(d.TQP, d.TKP);
   B200_REQUIRE(smem <= 227 * 1024, "attention bwd: %zu B of shared memory needed (> 227 KB)", smem);
-  static size_t configured = 0;
+  static size_t configured = 48 * 1024;      // the default limit: never lower it
   if (smem > configured) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<HD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = smem;
@@ -914,7 +914,7 @@ static int launch_bwd2(const AttnDev& d, cudaStream_t s) {
   const size_t smem = static_cast<size_t>(2 * d.TQP + 2 * d.TKP) * LD * 2 + static_cast<size_t>(d.TQP) * (LDP > LD ? LDP : LD) * 2 +
                       (d.TKP + 2 * d.TQP) * sizeof(float) + 16;
   B200_REQUIRE(smem <= 227 * 1024, "attention bwd: %zu B of shared memory needed (> 227 KB)", smem);
-  static size_t configured = 0;
+  static size_t configured = 48 * 1024;      // the default limit: never lower it
   if (smem > configured) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd2_kernel<HD, NT, MAXI>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = smem;
@@ -947,6 +947,21 @@ static int dispatch_bwd(const AttnDev& d, cudaStream_t s, int nt_fallback) {
   return nt_fallback == 8 ? launch_bwd<HD, 8>(d, s) : launch_bwd<HD, 4>(d, s);
 }
 
+// one function (and one `configured` high-water mark) per kernel instantiation: the dynamic shared-memory
+// limit of a kernel must never be lowered below what a later, larger launch of the SAME kernel needs
+template <int HD, int NT>
+static int launch_fwd_split(const AttnDev& d, int KS, int items, size_t smem, cudaStream_t s) {
+  auto kern = attn_fwd_split_kernel<HD, NT>;
+  static size_t configured = 48 * 1024;      // the default limit
+  if (smem > configured) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = smem;
+  }
+  B200_CHECK_CUDA(launch_kernel(kern, dim3(d.H, d.B), dim3(items * 32), smem, s, true, 1, d, KS));
+  note_launch();
+  return 0;
+}
+
 // split-key forward: KS key ranges per query tile, one warp per (query tile, range).  Returns 1 when
 // the shape does not fit (too many warps, ranges longer than NT*8 keys, partial tiles larger than the
 // K/V space they alias) and the caller falls back to the query-tile-per-warp kernel.
@@ -966,18 +981,8 @@ static int try_launch_fwd_split(const AttnDev& d, cudaStream_t s) {
   const int items = n_qt * KS;
   const size_t smem = static_cast<size_t>(d.TQP + 2 * d.TKP) * LD * 2 + (d.TKP + items * 32) * sizeof(float) + 16;
   if (smem > 227 * 1024) return 1;
-  auto launch = [&](auto kern) -> int {
-    static size_t configured = 0;
-    if (smem > configured) {
-      B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-      configured = smem;
-    }
-    B200_CHECK_CUDA(launch_kernel(kern, dim3(d.H, d.B), dim3(items * 32), smem, s, true, 1, d, KS));
-    note_launch();
-    return 0;
-  };
-  if (tiles_per <= 2) return launch(attn_fwd_split_kernel<HD, 4>);
-  return launch(attn_fwd_split_kernel<HD, 8>);
+  if (tiles_per <= 2) return launch_fwd_split<HD, 4>(d, KS, items, smem, s);
+  return launch_fwd_split<HD, 8>(d, KS, items, smem, s);
 }
 
 int attn_fwd(const AttnArgs& a, cudaStream_t s) {

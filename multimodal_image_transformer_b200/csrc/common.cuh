@@ -19,6 +19,7 @@ void set_last_error(const char* fmt, ...);
     cudaError_t _e = (expr);                                                              \
     if (_e != cudaSuccess) {                                                              \
       b200::set_last_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      (void)cudaGetLastError(); /* reported once: do not poison the next, unrelated call */ \
       return -2;                                                                          \
     }                                                                                     \
   } while (0)

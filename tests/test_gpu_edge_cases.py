@@ -1,0 +1,124 @@
+"""Edge cases of the decoder path on the B200: degenerate shapes, maximum lengths, masks that
+remove everything, shapes the reference crashes on (section 7.3)."""
+import pytest
+import torch
+
+from oracle import decoder_oracle as O
+from tests.helpers import CFGS, make_engine, row_max_rel, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _params(c, seed=21):
+    return O.init_params(c["V"], c["E"], c["H"], c["L"], c["F"], c["ML"], seed=seed)
+
+
+@pytest.mark.parametrize("B,T,S", [(1, 1, 1), (1, 5, 1), (3, 1, 7), (2, 40, 1)])
+def test_degenerate_shapes_match_oracle(cuda_dev, B, T, S):
+    """One sample, one position, one memory token (the reference's CLS-only memory, model.py:151),
+    T = max_seq_len."""
+    c = dict(CFGS["tiny"], B=B, T=T, S=S)
+    p = _params(c)
+    g = torch.Generator().manual_seed(3)
+    tok = torch.randint(4, c["V"], (B, T), generator=g)
+    tok[:, 0] = 1
+    tgt = torch.randint(4, c["V"], (B, T), generator=g)
+    if T > 8:
+        tok[0, T - 3:] = 0
+        tgt[0, T - 4:] = 0
+    mem = torch.randn(B, S, c["E"], generator=g)
+    eng = make_engine(c, p, cuda_dev)
+    with torch.no_grad():
+        ref = O.decoder_forward(p, tok, mem, None, c["H"])
+    got = eng.forward_logits(tok.to(cuda_dev), mem.to(cuda_dev), None)
+    assert row_max_rel(got, ref) < 2e-2
+    lref, gref = O.loss_and_grads(p, tok, tgt, mem, None, c["H"], emulate_bf16=True)
+    eng.zero_grad()
+    out = eng.forward_loss(tok.to(cuda_dev), tgt.to(cuda_dev), mem.to(cuda_dev), None, 0, training=True)
+    eng.backward()
+    assert abs(out[0].item() - lref.item()) < 2e-3 * abs(lref.item())
+    k = "fc_out.weight"
+    got_g = eng.view(k, eng.grads).float().cpu()
+    assert torch.nn.functional.cosine_similarity(got_g.flatten(), gref[k].flatten(), dim=0).item() > 0.995
+
+
+def test_sequence_longer_than_positional_table_is_rejected(cuda_dev):
+    """The reference crashes inside the positional-encoding add when T > max_seq_len (decoder.py:71);
+    here it is an argument error before anything is launched."""
+    c = dict(CFGS["tiny"], T=CFGS["tiny"]["ML"] + 1)
+    eng = make_engine(c, _params(c), cuda_dev)
+    tok = torch.ones(2, c["T"], dtype=torch.long, device=cuda_dev)
+    mem = torch.zeros(2, 3, c["E"], device=cuda_dev)
+    with pytest.raises(RuntimeError, match="max_seq_len"):
+        eng.forward_logits(tok, mem, None)
+    with pytest.raises(RuntimeError, match="max_len"):
+        eng.decode_begin(mem, None, beam=1, max_len=c["ML"] + 1)
+
+
+def test_all_targets_ignored_and_fully_masked_rows(cuda_dev):
+    """Every target == ignore_index -> NaN loss like nn.CrossEntropyLoss (0/0) and zero gradients' worth of
+    dlogits; a caption whose first token is PAD (fully masked attention row: NaN in PyTorch, documented as
+    zeros here) stays finite and does not disturb the other rows."""
+    c = dict(CFGS["tiny"], B=3)
+    p = _params(c)
+    tok, tgt, mem, _ = synth(c, 5)
+    eng = make_engine(c, p, cuda_dev)
+    out = eng.forward_loss(tok.to(cuda_dev), torch.zeros_like(tgt).to(cuda_dev), mem.to(cuda_dev), None, 0, training=False)
+    assert torch.isnan(out[0]) and out[1].item() == 0
+    with torch.no_grad():
+        ref = O.decoder_forward(p, tok, mem, None, c["H"])
+    tok2 = tok.clone()
+    tok2[1, :] = 0                                    # row 1: PAD everywhere, incl. position 0
+    got = eng.forward_logits(tok2.to(cuda_dev), mem.to(cuda_dev), None).cpu()
+    assert torch.isfinite(got).all()
+    assert row_max_rel(got[0], ref[0]) < 2e-2 and row_max_rel(got[2], ref[2]) < 2e-2
+    mpm = torch.ones(c["B"], c["S"], dtype=torch.bool)     # every image token masked: cross attention contributes zeros
+    assert torch.isfinite(eng.forward_logits(tok.to(cuda_dev), mem.to(cuda_dev), mpm.to(cuda_dev))).all()
+
+
+def test_generation_stops_and_pads_like_the_reference_loop(cuda_dev):
+    """END at the first step, END never, max_len = 2 (one generated token): lengths and PAD fill
+    follow model.py:216-242 (ids = START .. END)."""
+    c = dict(CFGS["tiny"], B=4)
+    p = _params(c)
+    p["fc_out.bias"][2] += 50.0                           # END always wins
+    mem = torch.randn(c["B"], c["S"], c["E"], generator=torch.Generator().manual_seed(1))
+    eng = make_engine(c, p, cuda_dev)
+    eng.decode_begin(mem.to(cuda_dev), None, beam=1, max_len=9)
+    for interval in (0, 2):
+        toks, lens = eng.generate_greedy(1, 2, 9, stop_check_interval=interval)
+        assert lens.tolist() == [2] * c["B"] and toks[:, :2].tolist() == [[1, 2]] * c["B"] and toks[:, 2:].eq(0).all()
+        eng.decode_begin(mem.to(cuda_dev), None, beam=1, max_len=9)
+    eng.decode_begin(mem.to(cuda_dev), None, beam=2, max_len=9)
+    bt, bl, bs = eng.generate_beam(1, 2, 9)
+    assert bl.tolist() == [2] * c["B"] and bt[:, :2].tolist() == [[1, 2]] * c["B"]
+    p["fc_out.bias"][2] -= 100.0                          # END never wins: all rows run to max_len
+    eng2 = make_engine(c, p, cuda_dev)
+    eng2.decode_begin(mem.to(cuda_dev), None, beam=1, max_len=2)
+    toks, lens = eng2.generate_greedy(1, 2, 2)
+    assert toks.shape == (c["B"], 2) and lens.tolist() == [2] * c["B"] and (toks[:, 1] != 2).all()
+
+
+def test_head_dim_128_forward_backward_and_generation(cuda_dev):
+    """hd = 128 (BASELINE cfg5's secondary head layout, E=1024 / H=8): attention and both decode-attention
+    kernels have their own instantiations for it."""
+    c = dict(V=520, E=256, H=2, L=2, F=512, ML=40, B=3, T=19, S=37)
+    p = _params(c, seed=4)
+    tok, tgt, mem, mpm = synth(c, 6)
+    eng = make_engine(c, p, cuda_dev)
+    with torch.no_grad():
+        ref = O.decoder_forward(p, tok, mem, mpm, c["H"])
+        greedy = O.greedy_generate(p, mem, 1, 2, 10, c["H"])
+    assert row_max_rel(eng.forward_logits(tok.to(cuda_dev), mem.to(cuda_dev), mpm.to(cuda_dev)), ref) < 2e-2
+    lref, g16 = O.loss_and_grads(p, tok, tgt, mem, None, c["H"], emulate_bf16=True)
+    eng.zero_grad()
+    out = eng.forward_loss(tok.to(cuda_dev), tgt.to(cuda_dev), mem.to(cuda_dev), None, 0, training=True)
+    eng.backward()
+    assert abs(out[0].item() - lref.item()) < 1e-3 * lref.item()
+    for k in ("transformer_decoder.layers.0.self_attn.in_proj_weight", "transformer_decoder.layers.1.multihead_attn.in_proj_weight", "fc_out.weight"):
+        got = eng.view(k, eng.grads).float().cpu().flatten()
+        assert torch.nn.functional.cosine_similarity(got, g16[k].flatten(), dim=0).item() > 0.995, k
+    eng.decode_begin(mem.to(cuda_dev), None, beam=1, max_len=10)
+    toks, lens = eng.generate_greedy(1, 2, 10)
+    got = [toks[b, :int(lens[b])].tolist() for b in range(c["B"])]
+    assert sum(a == b for a, b in zip(got, greedy)) >= c["B"] - 1
