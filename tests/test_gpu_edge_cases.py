@@ -122,3 +122,46 @@ def test_head_dim_128_forward_backward_and_generation(cuda_dev):
     toks, lens = eng.generate_greedy(1, 2, 10)
     got = [toks[b, :int(lens[b])].tolist() for b in range(c["B"])]
     assert sum(a == b for a, b in zip(got, greedy)) >= c["B"] - 1
+
+
+@pytest.mark.parametrize("S,beam", [(257, 1), (257, 4), (64, 1), (65, 2)])
+def test_generation_over_long_memory(cuda_dev, S, beam):
+    """CLIP ViT-L/14 memory length (257 = four 64-key chunks + a 1-key tail) and exact chunk multiples
+    through the tensor-core cross-attention of generation, with a padded memory tail, greedy and beam."""
+    c = dict(CFGS["tiny"], B=5, S=S)
+    p = _params(c, seed=8)
+    p["fc_out.bias"][2] += 0.5
+    g = torch.Generator().manual_seed(2)
+    mem = torch.randn(c["B"], S, c["E"], generator=g)
+    eng = make_engine(c, p, cuda_dev)
+    with torch.no_grad():
+        ref = O.greedy_generate(p, mem, 1, 2, 12, c["H"]) if beam == 1 else O.beam_generate(p, mem, 1, 2, 12, c["H"], beam_size=beam)
+    eng.decode_begin(mem.to(cuda_dev), None, beam=beam, max_len=12)
+    if beam == 1:
+        toks, lens = eng.generate_greedy(1, 2, 12)
+    else:
+        toks, lens, _ = eng.generate_beam(1, 2, 12)
+    got = [toks[b, :int(lens[b])].tolist() for b in range(c["B"])]
+
+    def oracle_score(b, seq):          # sum of token log-probabilities under the fp32 oracle
+        ids = torch.tensor([seq[:-1]], dtype=torch.long)
+        with torch.no_grad():
+            lp = torch.log_softmax(O.decoder_forward(p, ids, mem[b:b + 1], None, c["H"])[0], dim=-1)
+        return float(lp[torch.arange(len(seq) - 1), torch.tensor(seq[1:])].sum())
+
+    same = sum(a == b for a, b in zip(got, ref))
+    assert same >= c["B"] - 2, (got, ref)
+    for b in range(c["B"]):            # a different hypothesis is only acceptable as a bf16 near-tie of the search
+        if got[b] != ref[b]:
+            assert oracle_score(b, got[b]) >= oracle_score(b, ref[b]) - 0.1, (b, got[b], ref[b])
+    # a fully padded memory tail must not change anything but the masked keys' contribution
+    mpm = torch.zeros(c["B"], S, dtype=torch.bool)
+    mpm[:, S - 7:] = True
+    mem2 = mem.clone()
+    mem2[:, S - 7:] = 1e3                      # garbage behind the mask
+    eng.decode_begin(mem.to(cuda_dev), mpm.to(cuda_dev), beam=beam, max_len=12)
+    a = eng.generate_greedy(1, 2, 12)[0] if beam == 1 else eng.generate_beam(1, 2, 12)[0]
+    a = a.clone()
+    eng.decode_begin(mem2.to(cuda_dev), mpm.to(cuda_dev), beam=beam, max_len=12)
+    b = eng.generate_greedy(1, 2, 12)[0] if beam == 1 else eng.generate_beam(1, 2, 12)[0]
+    assert torch.equal(a, b)
