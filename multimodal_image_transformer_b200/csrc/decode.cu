@@ -59,6 +59,17 @@ struct DecAttnArgs {
   int groups, nq, H;
   const unsigned char* key_pad;     // [groups][nkeys] or null
   float scale;
+  // optional L2 warm-up for the NEXT cross-attention launch (the following layer's K / V planes): the
+  // producer warp, once its own stream is issued, requests the first pf_bytes of each plane into L2.
+  // Between two cross-attention launches HBM is nearly idle (a chain of ~10 small launches), so the
+  // head of the next stream is fetched in that shadow.  Hint only: results do not depend on it.
+  const bf16* pf_k; const bf16* pf_v; long long pf_bytes;
+  int stream_evict_first;           // 1: the K/V stream is loaded with the L2 evict-first priority (read once)
+  int tail16;                       // 1: a last chunk of < 64 keys is fetched as 16-row boxes
+  // optional dynamic work distribution: sched[0] = next (image, head) item, sched[1] = units that ran dry; both
+  // zero before the launch and zero again after it (the last unit resets them).  A unit that starts late
+  // (its SM was busy with another stream's kernel) then simply takes fewer items.
+  int* sched;
 };
 
 static constexpr int DEC_CK = 64;       // keys per chunk
@@ -323,24 +334,45 @@ __device__ __forceinline__ float dec_ex2(float x) {
 
 static constexpr int DECM_NQ = 4;       // rows of the partial-state exchange (nq <= 4)
 
-template <int HD, int DECM_STAGES, int MINB>
-__global__ void __launch_bounds__(DEC_THREADS, MINB)
+// bytes of one producer/consumer unit: ring + barriers + merge buffer, rounded to the swizzle alignment
+template <int HD, int DECM_STAGES>
+__host__ __device__ constexpr size_t decm_unit_bytes() {
+  return ((static_cast<size_t>(DECM_STAGES) * 2 * (HD / 64) * DEC_CK * 128 + (2 * DECM_STAGES + 2) * sizeof(uint64_t) +
+           static_cast<size_t>(2) * 4 * DECM_NQ * (HD + 2) * sizeof(float) + (DECM_STAGES + 4) * sizeof(int)) + 1023) / 1024 * 1024;
+}
+
+// SUB = 1: the CTA is one unit (1 producer + 4 consumer warps), MINB CTAs per SM.
+// SUB > 1: a "fat" CTA of SUB independent units with private rings / barriers (one CTA per SM): a grid
+//          smaller than the SM count then leaves whole SMs to concurrently running kernels -- the launch
+//          chains of the other image partitions -- which a grid of small CTAs (spread over every SM by
+//          the block scheduler) cannot do.
+template <int HD, int DECM_STAGES, int MINB, int SUB>
+__global__ void __launch_bounds__(DEC_THREADS * SUB, SUB == 1 ? MINB : 1)
 attn_decode_mma_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
+                       const __grid_constant__ CUtensorMap tmap_k16, const __grid_constant__ CUtensorMap tmap_v16,
                        const DecAttnArgs a) {
   constexpr int NBOX = HD / 64;                       // 64-column TMA boxes per K (or V) chunk
   constexpr int BOX = DEC_CK * 128;                   // 8 KB: 64 rows x 128 B, 128-byte swizzled
   constexpr int STAGE = 2 * NBOX * BOX;
   constexpr int RED_STRIDE = HD + 2;
-  extern __shared__ __align__(1024) uint8_t sm_decm[];
+  extern __shared__ __align__(1024) uint8_t sm_decm_all[];
+  const int sub = (SUB == 1) ? 0 : static_cast<int>(threadIdx.x) / DEC_THREADS;       // warp-uniform
+  const int ltid = (SUB == 1) ? static_cast<int>(threadIdx.x) : static_cast<int>(threadIdx.x) % DEC_THREADS;
+  const int vcta = static_cast<int>(blockIdx.x) * SUB + sub;                           // unit index / count
+  const int vgrid = static_cast<int>(gridDim.x) * SUB;
+  uint8_t* sm_decm = sm_decm_all + static_cast<size_t>(sub) * decm_unit_bytes<HD, DECM_STAGES>();
   uint64_t* full = reinterpret_cast<uint64_t*>(sm_decm + DECM_STAGES * STAGE);
   uint64_t* empty = full + DECM_STAGES;
   float* red = reinterpret_cast<float*>(empty + DECM_STAGES + 2);   // [2][4][DECM_NQ][RED_STRIDE]
+  volatile int* item_ring = reinterpret_cast<volatile int*>(red + 2 * 4 * DECM_NQ * RED_STRIDE);   // [DECM_STAGES]: item whose first chunk is in the stage
+  const bool dyn = a.sched != nullptr;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
+  const int warp = ltid >> 5, lane = ltid & 31;
+  if (ltid == 0) {
     if ((smem_u32(sm_decm) & 1023u) != 0u) __trap();
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
+    if (a.tail16) { tma_prefetch_desc(&tmap_k16); tma_prefetch_desc(&tmap_v16); }
     for (int i = 0; i < DECM_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 4); }
     fence_barrier_init();
   }
@@ -356,19 +388,67 @@ attn_decode_mma_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const uint64_t pol = l2_policy_evict_first();
+      const bool hint = a.stream_evict_first != 0;
+      auto ld = [&](void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+        if (hint) tma_load_2d_hint(dst, map, bar, c0, c1, pol);
+        else tma_load_2d(dst, map, bar, c0, c1);
+      };
+      // a short last chunk travels as 16-row boxes (same swizzled placement as the 64-row box: 2 KB per
+      // 16 rows) instead of dragging up to 48 rows of the next item through L2 -> SM
+      const int tail_tiles = (a.nkeys - (nch - 1) * DEC_CK + 15) / 16;
+      const bool tail16 = a.tail16 != 0 && tail_tiles < DEC_CK / 16;
+      for (int item = dyn ? atomicAdd(a.sched, 1) : vcta; item < n_items; item = dyn ? atomicAdd(a.sched, 1) : item + vgrid) {
         const int row0 = item * a.kv_len;
         for (int c = 0; c < nch; ++c) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* dst = sm_decm + stage * STAGE;
-          mbar_arrive_expect_tx(&full[stage], STAGE);
+          if (dyn && c == 0) item_ring[stage] = item;      // published by the barrier arrive below (release)
+          if (tail16 && c == nch - 1) {
+            mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>(tail_tiles) * 2u * NBOX * 2048u);
 #pragma unroll
-          for (int bx = 0; bx < NBOX; ++bx) {
-            tma_load_2d(dst + bx * BOX, &tmap_k, &full[stage], bx * 64, row0 + c * DEC_CK);
-            tma_load_2d(dst + (NBOX + bx) * BOX, &tmap_v, &full[stage], bx * 64, row0 + c * DEC_CK);
+            for (int bx = 0; bx < NBOX; ++bx) {
+              for (int tt = 0; tt < tail_tiles; ++tt) {
+                ld(dst + bx * BOX + tt * 2048, &tmap_k16, &full[stage], bx * 64, row0 + c * DEC_CK + tt * 16);
+                ld(dst + (NBOX + bx) * BOX + tt * 2048, &tmap_v16, &full[stage], bx * 64, row0 + c * DEC_CK + tt * 16);
+              }
+            }
+          } else {
+            mbar_arrive_expect_tx(&full[stage], STAGE);
+#pragma unroll
+            for (int bx = 0; bx < NBOX; ++bx) {
+              ld(dst + bx * BOX, &tmap_k, &full[stage], bx * 64, row0 + c * DEC_CK);
+              ld(dst + (NBOX + bx) * BOX, &tmap_v, &full[stage], bx * 64, row0 + c * DEC_CK);
+            }
           }
           if (++stage == DECM_STAGES) { stage = 0; phase ^= 1; }
         }
+      }
+      if (dyn) {
+        // no more items: tell the consumers (an empty stage carrying item -1), then account for this unit;
+        // the last unit to get here re-arms the counters for the next launch
+        mbar_wait(&empty[stage], phase ^ 1);
+        item_ring[stage] = -1;
+        mbar_arrive(&full[stage]);
+        __threadfence();
+        if (atomicAdd(a.sched + 1, 1) == vgrid - 1) {
+          a.sched[0] = 0;
+          a.sched[1] = 0;
+          __threadfence();
+        }
+      }
+    }
+    __syncwarp();
+    if (a.pf_bytes > 0) {
+      // 4 KB requests, spread over the producer lanes of all CTAs
+      constexpr long long CH = 4096;
+      const long long nch_pf = (a.pf_bytes + CH - 1) / CH;
+      for (long long c = static_cast<long long>(vcta) * 32 + lane; c < nch_pf; c += static_cast<long long>(vgrid) * 32) {
+        const long long off = c * CH;
+        const uint32_t n = static_cast<uint32_t>((a.pf_bytes - off < CH ? a.pf_bytes - off : CH) & ~15ll);
+        if (n == 0) continue;
+        l2_prefetch_bulk(reinterpret_cast<const uint8_t*>(a.pf_k) + off, n);
+        l2_prefetch_bulk(reinterpret_cast<const uint8_t*>(a.pf_v) + off, n);
       }
     }
     return;
@@ -393,7 +473,14 @@ attn_decode_mma_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
       }
     }
   };
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x, par ^= 1) {
+  for (int item = vcta;; item += vgrid, par ^= 1) {
+    if (dyn) {
+      mbar_wait(&full[stage], phase);      // the item's first chunk (waited for again below: already complete)
+      item = item_ring[stage];
+      if (item < 0) break;
+    } else if (item >= n_items) {
+      break;
+    }
     const int grp = item / a.H, h = item % a.H;
     fetch_q(item);
     // Q as mma A fragments: row g (< nq) = hypothesis g of this image, rows >= nq are zero
@@ -492,9 +579,9 @@ attn_decode_mma_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
         *reinterpret_cast<float2*>(rp + g * RED_STRIDE + i * 8 + 2 * t) = make_float2(o[i][0], o[i][1]);
       if (t == 0) { rp[g * RED_STRIDE + HD] = m_run[0]; rp[g * RED_STRIDE + HD + 1] = lsum; }
     }
-    named_barrier_sync(1, 128);
+    named_barrier_sync(1 + sub, 128);
     const float* rb = red + par * 4 * DECM_NQ * RED_STRIDE;
-    for (int idx = threadIdx.x; idx < a.nq * HD; idx += 128) {
+    for (int idx = ltid; idx < a.nq * HD; idx += 128) {
       const int i = idx / HD, d = idx % HD;
       float mm = -INFINITY;
 #pragma unroll
@@ -512,11 +599,12 @@ attn_decode_mma_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
   }
 }
 
-template <int HD, int DECM_STAGES, int MINB>
-static int launch_attn_decode_mma(const DecAttnArgs& a, cudaStream_t s) {
-  auto kern = attn_decode_mma_kernel<HD, DECM_STAGES, MINB>;
-  const size_t smem = static_cast<size_t>(DECM_STAGES) * 2 * (HD / 64) * DEC_CK * 128 + (2 * DECM_STAGES + 2) * sizeof(uint64_t) +
-                      static_cast<size_t>(2) * 4 * DECM_NQ * (HD + 2) * sizeof(float) + 1024;
+template <int HD, int DECM_STAGES, int MINB, int SUB>
+static int launch_attn_decode_mma(const DecAttnArgs& a, int grid_cap, cudaStream_t s) {
+  auto kern = attn_decode_mma_kernel<HD, DECM_STAGES, MINB, SUB>;
+  const size_t unit = decm_unit_bytes<HD, DECM_STAGES>();
+  const size_t smem = unit * SUB + 1024;
+  B200_REQUIRE(smem <= 227 * 1024, "attn_decode: %zu B of shared memory for %d units per CTA", smem, SUB);
   static bool configured = false;
   if (!configured) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -526,29 +614,48 @@ static int launch_attn_decode_mma(const DecAttnArgs& a, cudaStream_t s) {
   CUtensorMap tk, tv;
   if (int rc = make_tmap_2d_bf16(&tk, a.k, HD, static_cast<uint64_t>(rows), static_cast<uint64_t>(HD) * 2, 64, DEC_CK)) return rc;
   if (int rc = make_tmap_2d_bf16(&tv, a.v, HD, static_cast<uint64_t>(rows), static_cast<uint64_t>(HD) * 2, 64, DEC_CK)) return rc;
-  int per_sm = static_cast<int>((220 * 1024) / (smem + 1024));
-  per_sm = per_sm < 1 ? 1 : (per_sm > MINB ? MINB : per_sm);
+  CUtensorMap tk16 = tk, tv16 = tv;
+  if (a.tail16) {
+    if (int rc = make_tmap_2d_bf16(&tk16, a.k, HD, static_cast<uint64_t>(rows), static_cast<uint64_t>(HD) * 2, 64, 16)) return rc;
+    if (int rc = make_tmap_2d_bf16(&tv16, a.v, HD, static_cast<uint64_t>(rows), static_cast<uint64_t>(HD) * 2, 64, 16)) return rc;
+  }
   const int items = a.groups * a.H;
-  const int cap = device_sm_count() * per_sm;
-  B200_CHECK_CUDA(launch_kernel(kern, dim3(items < cap ? items : cap), dim3(DEC_THREADS), smem, s, true, 1, tk, tv, a));
+  int cap;
+  if (SUB == 1) {
+    int per_sm = static_cast<int>((220 * 1024) / (smem + 1024));
+    per_sm = per_sm < 1 ? 1 : (per_sm > MINB ? MINB : per_sm);
+    cap = device_sm_count() * per_sm;
+  } else {
+    cap = device_sm_count();
+  }
+  if (grid_cap > 0 && grid_cap < cap) cap = grid_cap;
+  const int want = (items + SUB - 1) / SUB;
+  B200_CHECK_CUDA(launch_kernel(kern, dim3(want < cap ? want : cap), dim3(DEC_THREADS * SUB), smem, s, true, 1, tk, tv, tk16, tv16, a));
   note_launch();
   return 0;
 }
 
 int attn_decode(const bf16* q, long long q_rs, const bf16* k, const bf16* v, int kv_len, int nkeys, bf16* o,
                 long long o_rs, int groups, int nq, int H, int hd, const unsigned char* key_pad, float scale,
-                cudaStream_t s) {
+                cudaStream_t s, const bf16* pf_k, const bf16* pf_v, long long pf_bytes, int flags, int fat_grid, int* sched) {
   B200_REQUIRE(nq >= 1 && nq <= 4, "attn_decode: %d queries per group (supported: 1..4)", nq);
   B200_REQUIRE(nkeys >= 1 && nkeys <= kv_len, "attn_decode: nkeys %d outside [1, %d]", nkeys, kv_len);
   DecAttnArgs a = {};
   a.q = q; a.q_rs = q_rs; a.k = k; a.v = v; a.kv_len = kv_len; a.nkeys = nkeys; a.o = o; a.o_rs = o_rs;
   a.groups = groups; a.nq = nq; a.H = H; a.key_pad = key_pad; a.scale = scale;
+  if (pf_k && pf_v && pf_bytes > 0 && (reinterpret_cast<uintptr_t>(pf_k) & 15) == 0 && (reinterpret_cast<uintptr_t>(pf_v) & 15) == 0) {
+    a.pf_k = pf_k; a.pf_v = pf_v; a.pf_bytes = pf_bytes;
+  }
+  a.stream_evict_first = (flags & 1) ? 1 : 0;
+  a.tail16 = (flags & 2) ? 1 : 0;
+  a.sched = sched;
   static const bool scalar_only = getenv("B200_DEC_ATTN_SCALAR") != nullptr;     // A/B switch
   if (!scalar_only && nq <= DECM_NQ && (reinterpret_cast<uintptr_t>(k) & 15) == 0 && (reinterpret_cast<uintptr_t>(v) & 15) == 0) {
     // measured on B200 (512 images x 12 heads, S = 197): ring depth 2 with 4 CTAs per SM 0.82 ms per position,
     // depth 3 0.84, depth 4 (3 CTAs) 0.95, depth 1 0.92; 5-6 CTAs per SM (register cap 72 / 64, spills) 0.95-1.05
-    if (hd == 64) return launch_attn_decode_mma<64, 2, 4>(a, s);
-    if (hd == 128) return launch_attn_decode_mma<128, 2, 2>(a, s);
+    // fat_grid > 0: one fat CTA per SM on at most fat_grid SMs (the other SMs stay free for concurrent kernels)
+    if (hd == 64) return fat_grid > 0 ? launch_attn_decode_mma<64, 2, 4, 4>(a, fat_grid, s) : launch_attn_decode_mma<64, 2, 4, 1>(a, 0, s);
+    if (hd == 128) return fat_grid > 0 ? launch_attn_decode_mma<128, 2, 2, 2>(a, fat_grid, s) : launch_attn_decode_mma<128, 2, 2, 1>(a, 0, s);
   }
 #define B200_AD(HDV)                                              \
   do {                                                            \

@@ -9,10 +9,16 @@ namespace b200 {
 int kv_to_head_major(const bf16* kv, bf16* k_hm, bf16* v_hm, int B, int S, int H, int hd, cudaStream_t s);
 // single-query attention: for every group g (image) and head h, NQ query rows (beams) attend
 // over the same nkeys keys.  q/o: [groups*nq, H*hd] rows; K/V: [groups][H][kv_len][hd], reading
-// the first nkeys rows.  key_pad: optional [groups, nkeys] uint8.
+// the first nkeys rows.  key_pad: optional [groups, nkeys] uint8.  pf_k / pf_v / pf_bytes: optional L2
+// warm-up hint, the first pf_bytes of the K and V planes the NEXT call will stream; flags bit 0: load the
+// K/V stream with the L2 evict-first priority, bit 1: fetch a short last chunk as 16-row boxes
+// fat_grid > 0: run as at most fat_grid one-per-SM CTAs of several producer/consumer units each, leaving the
+// remaining SMs to concurrently running kernels; sched: optional two zeroed ints for dynamic (first come, first
+// served) item distribution, left zeroed again by the launch (all five: tensor-core kernel only).
 int attn_decode(const bf16* q, long long q_rs, const bf16* k, const bf16* v, int kv_len, int nkeys,
                 bf16* o, long long o_rs, int groups, int nq, int H, int hd, const unsigned char* key_pad,
-                float scale, cudaStream_t s);
+                float scale, cudaStream_t s, const bf16* pf_k = nullptr, const bf16* pf_v = nullptr,
+                long long pf_bytes = 0, int flags = 0, int fat_grid = 0, int* sched = nullptr);
 // self attention of one decode position with the cache append fused in: q/k/v of the current position
 // are the three E-wide column blocks of qkv [R, 3E]; k/v are written to cache row `pos` of
 // [R][H][max_len][hd] and attended together with rows [0,pos).

@@ -19,6 +19,15 @@ using namespace b200;
 
 namespace {
 
+// Default size (MB over K and V together) of the L2 warm-up of the next layer's cross K/V stream during
+// generation; B200_DEC_PREFETCH_MB overrides.  0 = off.
+constexpr double kDecPrefetchMB = 0.0;
+constexpr bool kDecSingleCta = true;    // skinny generation GEMMs as unpaired CTAs (no cluster start-up); B200_DEC_SINGLE_CTA overrides
+constexpr bool kDecAttnDyn = false;         // dynamically scheduled cross attention; B200_DEC_ATTN_DYN overrides
+constexpr bool kDecAttnStream = false;      // cross attention of all partitions on one stream; B200_DEC_ATTN_STREAM overrides
+constexpr int kDecFatGridPct = 70;          // % of the SMs given to the cross-attention stream when partitions run concurrently (104 of 148); B200_DEC_ATTN_GRID overrides
+constexpr int kDecKvFlags = 3;          // attn_decode flags (decode.cuh); B200_DEC_KV_FLAGS overrides
+
 struct ParamInfo {
   std::string name;
   int64_t offset, numel;
@@ -111,11 +120,24 @@ struct b200_engine {
     // its own launch chain on its own stream.  A chain is latency-bound (~70 dependent small
     // kernels per position) while the cross-attention K/V stream is HBM-bound; concurrent chains
     // fill the SMs the skinny GEMMs leave idle and keep the HBM pipe busy.
-    struct Part { int b0 = 0, nb = 0; float* parts = nullptr; };
+    struct Part { int b0 = 0, nb = 0; float* parts = nullptr; int* sched = nullptr; };
+    int* sched = nullptr;               // [8][2] work counters of the dynamically scheduled cross attention (zero between launches)
+    bool attn_dyn = false;
     std::vector<Part> part;
     int ksplit_e = 1, ksplit_f = 1;     // split-K of the E-deep / F-deep skinny GEMMs feeding a LayerNorm
+    int64_t pf_bytes = 0;               // per K / V plane: head of the next layer's cross K/V warmed into L2 (0 = off)
+    int kv_flags = 0;                   // 1 = K/V stream evict-first in L2, 2 = 16-row tail boxes (attn_decode flags), 4 = weights evict-last
+    bool single_cta = false;            // skinny GEMMs as unpaired CTAs
+    int attn_fat_grid = 0;              // > 0: cross attention as <= this many one-per-SM fat CTAs (decode.cuh)
+    int gemm_cap = 0;                   // > 0: persistent-grid cap of the generation GEMMs (the SMs left by the above)
     std::vector<cudaStream_t> side;     // streams of partitions 1.. (partition 0 runs on the caller's)
-    std::vector<cudaEvent_t> ev;        // [0] fork, [p] join of partition p
+    std::vector<cudaEvent_t> ev;        // [0] fork, [p] join of partition p, [P] join of the attention stream
+    // Optional dedicated stream for the cross-attention launches of ALL partitions (round robin): at most one
+    // K/V stream runs at a time, on its SM budget (attn_fat_grid), while the other partitions' chains run on
+    // the remaining SMs.  evq[p]: partition p's query is ready; eva[p]: its attention output is ready.
+    bool use_att_stream = false;
+    cudaStream_t att_stream = nullptr;
+    std::vector<cudaEvent_t> evq, eva;
     // CUDA-graph cache of the whole generation loop (one per (workspace, shape, ids) key)
     cudaGraphExec_t graph = nullptr;
     cudaStream_t cap_stream = nullptr;
@@ -196,8 +218,9 @@ void build_plan(const b200_engine* e, Plan* pl, uint8_t* base, int B, int T, int
 // y = x W^T + b  with optional activation / residual; W rows [row0,row0+N) of a [*,K] matrix
 // y = act(x W^T + b) for a decode position (rows = hypotheses being decoded)
 int linear_dec(const bf16* x, int64_t ldx, const bf16* W, const float* bias, bf16* y, int64_t ldy, int M, int N, int K,
-               int act, cudaStream_t s) {
+               int act, cudaStream_t s, bool single_cta = false) {
   GemmProblem g;
+  g.single_cta = single_cta;
   g.M = M; g.N = N; g.K = K;
   g.A = x; g.lda = ldx; g.B = W; g.ldb = K;
   g.D = y; g.ldd = ldy; g.bias = bias; g.act = act; g.split_k = 1; g.block_n = 128;
@@ -481,9 +504,14 @@ void build_decode_plan(const b200_engine* e, b200_engine::Decode* d, uint8_t* ba
   // partitions: whole 128-row GEMM tiles where possible
   const char* forced_env = getenv("B200_DECODE_PARTS");   // read per plan: tests compare partitionings
   const int forced = forced_env ? atoi(forced_env) : 0;
-  // Measured on B200 (cfg2, 512 rows): generation is bound by the ~75 dependent launches per position
-  // (launch rate, not SM occupancy), so concurrent partitions buy < 3 %; one partition by default.
-  int P = forced > 0 ? forced : 1;
+  // Measured on B200 (cfg2, 512 images, greedy; profiles/r01_decode_sweeps.txt): a position is a chain of ~75
+  // dependent launches (latency-bound, few SMs) around six HBM-bound cross-attention streams.  Four concurrent
+  // partitions of 128 rows overlap one partition's stream -- run as fat CTAs on 104 SMs -- with the other
+  // partitions' chains on the remaining SMs: 32.4 vs 39.1 ms per 512 captions.  Plain small-CTA attention grids
+  // fill every SM and serialise the partitions again (+3 % only).  Beam search (4x the rows per image, cache
+  // re-indexing) is not chain-bound and loses 5-7 % when partitioned, small K/V streams have nothing to overlap.
+  const bool stream_heavy = static_cast<double>(B) * S * E * 4.0 >= 128.0 * 1024 * 1024;   // K+V bytes of one layer
+  int P = forced > 0 ? forced : ((beam == 1 && B >= 256 && stream_heavy) ? 4 : 1);
   if (P > B) P = B;
   if (P > 8) P = 8;
   int per = (B + P - 1) / P;
@@ -496,23 +524,58 @@ void build_decode_plan(const b200_engine* e, b200_engine::Decode* d, uint8_t* ba
     pt.nb = (B - b0 < per) ? (B - b0) : per;
     d->part.push_back(pt);
   }
+  // L2 warm-up of the next layer's cross K/V stream (decode.cu: DecAttnArgs::pf_*): total MB over K and V,
+  // shared by the partitions.  Read per plan so that a sweep can compare settings in one process.
+  {
+    const char* pf_env = getenv("B200_DEC_PREFETCH_MB");
+    const double mb = pf_env ? atof(pf_env) : kDecPrefetchMB;
+    const int64_t plane = static_cast<int64_t>(per) * S * E * 2;          // bytes of one partition's K (or V) plane of a layer
+    int64_t want = static_cast<int64_t>(mb * 1024.0 * 1024.0 / 2.0 / static_cast<double>(d->part.size() ? d->part.size() : 1));
+    if (want > plane) want = plane;
+    d->pf_bytes = want > 0 ? (want & ~static_cast<int64_t>(4095)) : 0;
+    const char* fl_env = getenv("B200_DEC_KV_FLAGS");
+    d->kv_flags = fl_env ? (atoi(fl_env) & 7) : kDecKvFlags;
+  }
   // split-K of the LayerNorm-fed GEMMs: enough CTAs to cover the SMs
   const int rows_p = per * beam;
   const int tiles = ((rows_p + 127) / 128) * static_cast<int>((E + 127) / 128);
   auto pick = [&](int64_t K) {
     const int kb = static_cast<int>((K + 63) / 64);
     int sk = 148 / (tiles > 0 ? tiles : 1);
-    if (sk > kb / 4) sk = kb / 4;        // >= 4 k-blocks per split: beyond that the LayerNorm-side reduction costs more than the K loop saves
-    if (sk > 8) sk = 8;
+    // >= 6 k-blocks per split and at most 4 slabs: beyond that the LayerNorm-side reduction costs more than the
+    // K loop saves (sweep on B200: 2 / 4 splits for K = 768 / 3072 beat 3 / 6 by 3 %, 3 / 8 by 4 %)
+    if (sk > kb / 6) sk = kb / 6;
+    if (sk > 4) sk = 4;
     if (sk < 1) sk = 1;
     return gemm_effective_splits(static_cast<int>(K), sk);
   };
   d->ksplit_e = pick(E);
   d->ksplit_f = pick(F);
+  if (const char* v = getenv("B200_DEC_KSPLIT_E")) { if (atoi(v) > 0) d->ksplit_e = gemm_effective_splits(static_cast<int>(E), atoi(v)); }
+  if (const char* v = getenv("B200_DEC_KSPLIT_F")) { if (atoi(v) > 0) d->ksplit_f = gemm_effective_splits(static_cast<int>(F), atoi(v)); }
+  {
+    const char* v = getenv("B200_DEC_SINGLE_CTA");
+    d->single_cta = v ? (atoi(v) != 0) : kDecSingleCta;
+    const char* g = getenv("B200_DEC_ATTN_GRID");
+    d->attn_fat_grid = g ? atoi(g) : (d->part.size() > 1 ? (device_sm_count() * kDecFatGridPct + 50) / 100 : 0);
+    if (d->attn_fat_grid < 0) d->attn_fat_grid = 0;
+    if (d->attn_fat_grid >= device_sm_count()) d->attn_fat_grid = device_sm_count();
+    const char* as = getenv("B200_DEC_ATTN_STREAM");
+    d->use_att_stream = d->part.size() > 1 && (as ? atoi(as) != 0 : kDecAttnStream);
+    const char* gc = getenv("B200_DEC_GEMM_CTAS");
+    d->gemm_cap = gc ? atoi(gc) : (d->attn_fat_grid > 0 ? device_sm_count() - d->attn_fat_grid : 0);
+    if (d->gemm_cap < 0) d->gemm_cap = 0;
+  }
   const int ks_max = d->ksplit_e > d->ksplit_f ? d->ksplit_e : d->ksplit_f;
   for (auto& pt : d->part) {
     const int64_t mpad = (static_cast<int64_t>(pt.nb) * beam + 127) / 128 * 128;
     pt.parts = b.take<float>(ks_max * mpad * E);
+  }
+  d->sched = b.take<int>(16);
+  {
+    const char* dy = getenv("B200_DEC_ATTN_DYN");
+    d->attn_dyn = dy ? (atoi(dy) != 0) : kDecAttnDyn;
+    for (size_t p = 0; p < d->part.size(); ++p) d->part[p].sched = (d->attn_dyn && d->sched) ? d->sched + 2 * p : nullptr;
   }
   d->bytes = (b.off + 255) & ~static_cast<int64_t>(255);
 }
@@ -521,8 +584,9 @@ void build_decode_plan(const b200_engine* e, b200_engine::Decode* d, uint8_t* ba
 // summed together with bias and residual inside the LayerNorm kernel
 int linear_ln_fwd(const bf16* x, int64_t ldx, const bf16* W, const float* bias, const bf16* residual,
                   const float* gamma, const float* beta, float* parts, int split, bf16* y, int M, int N, int K,
-                  float eps, cudaStream_t s) {
+                  float eps, cudaStream_t s, bool single_cta = false) {
   GemmProblem g;
+  g.single_cta = single_cta;
   g.M = M; g.N = N; g.K = K;
   g.A = x; g.lda = ldx; g.B = W; g.ldb = K;
   g.D = parts; g.ldd = N; g.d_fp32 = true; g.partials = true; g.split_k = split; g.block_n = 128;
@@ -531,58 +595,93 @@ int linear_ln_fwd(const bf16* x, int64_t ldx, const bf16* W, const float* bias, 
   return layernorm_reduce_fwd(parts, gemm_effective_splits(K, split), mpad * N, N, bias, residual, N, gamma, beta, y, M, N, eps, s);
 }
 
-// one decode position for the rows of one partition: tokens[r] at position pos -> final hidden in *x_out
-// (`cur` = live copy of the self-attention cache)
-int decode_hidden(b200_engine* e, const b200_engine::Decode::Part& pt, int cur, const int64_t* tokens, int pos,
-                  bf16** x_out, cudaStream_t s) {
+// ---- one decode position, cut into the pieces between which partitions interleave ----
+struct DecPart {          // per-partition views of the decode workspace
+  const b200_engine::Decode::Part* pt;
+  int64_t r0; int R, B;
+  bf16 *xa, *xb, *qkv, *attn, *x1, *qc, *x2, *h;
+  const uint8_t* mem_pad;
+  int64_t self_off, cross_off, pf_bytes;
+};
+
+DecPart dec_part(const b200_engine* e, const b200_engine::Decode::Part& pt) {
+  const auto& d = e->dec;
+  const int64_t E = e->cfg.embed_dim, F = e->cfg.ff_dim;
+  DecPart v;
+  v.pt = &pt;
+  v.r0 = static_cast<int64_t>(pt.b0) * d.beam;
+  v.R = pt.nb * d.beam; v.B = pt.nb;
+  v.xa = d.xa + v.r0 * E; v.xb = d.xb + v.r0 * E;
+  v.qkv = d.qkv + v.r0 * 3 * E; v.attn = d.attn + v.r0 * E;
+  v.x1 = d.x1 + v.r0 * E; v.qc = d.qc + v.r0 * E; v.x2 = d.x2 + v.r0 * E;
+  v.h = d.h + v.r0 * F;
+  v.mem_pad = d.mem_pad ? d.mem_pad + static_cast<int64_t>(pt.b0) * d.S : nullptr;
+  v.self_off = v.r0 * d.max_len * E;
+  v.cross_off = static_cast<int64_t>(pt.b0) * d.S * E;
+  const int64_t plane_bytes = static_cast<int64_t>(pt.nb) * d.S * E * 2;
+  v.pf_bytes = d.pf_bytes < plane_bytes ? d.pf_bytes : (plane_bytes & ~static_cast<int64_t>(15));
+  return v;
+}
+// layer l reads its input from xa (even l) / xb (odd l) and leaves its output in the other one
+inline bf16* dec_x_in(const DecPart& v, int l) { return (l & 1) ? v.xb : v.xa; }
+inline bf16* dec_x_out(const DecPart& v, int l) { return (l & 1) ? v.xa : v.xb; }
+
+int dec_embed(b200_engine* e, const DecPart& v, const int64_t* tokens, int pos, cudaStream_t s) {
+  const auto& c = e->cfg;
+  B200_REQUIRE(pos >= 0 && pos < e->dec.max_len && pos < c.max_seq_len, "decode: position %d out of range", pos);
+  return embed_pe_fwd(tokens + v.r0, e->pf + e->emb, e->pe, v.xa, v.R, 1, c.embed_dim, c.vocab_size,
+                      sqrtf(static_cast<float>(c.embed_dim)), s, pos);
+}
+// self attention block + the cross-attention query:  QKV, attention over the cache (+ append), out-proj + LN1, Q
+int dec_pre(b200_engine* e, const DecPart& v, int l, int cur, int pos, cudaStream_t s) {
   const auto& c = e->cfg;
   auto& d = e->dec;
-  const int E = c.embed_dim, F = c.ff_dim, H = c.num_heads, L = c.num_layers, hd = E / H;
-  const int S = d.S;
-  const int64_t r0 = static_cast<int64_t>(pt.b0) * d.beam;
-  const int R = pt.nb * d.beam, B = pt.nb;
-  const float scale = 1.0f / sqrtf(static_cast<float>(hd));
-  B200_REQUIRE(pos >= 0 && pos < d.max_len && pos < c.max_seq_len, "decode: position %d out of range", pos);
-  bf16* x = d.xa + r0 * E;
-  bf16* xn = d.xb + r0 * E;
-  bf16* qkv = d.qkv + r0 * 3 * E;
-  bf16* attn = d.attn + r0 * E;
-  bf16* x1 = d.x1 + r0 * E;
-  bf16* qc = d.qc + r0 * E;
-  bf16* x2 = d.x2 + r0 * E;
-  bf16* h = d.h + r0 * F;
-  const uint8_t* mem_pad = d.mem_pad ? d.mem_pad + static_cast<int64_t>(pt.b0) * S : nullptr;
-  RC(embed_pe_fwd(tokens + r0, e->pf + e->emb, e->pe, x, R, 1, E, c.vocab_size, sqrtf(static_cast<float>(E)), s, pos));
+  const int E = c.embed_dim, H = c.num_heads, hd = E / H;
+  const LayerOff& o = e->lo[l];
   const int64_t self_stride = static_cast<int64_t>(d.R) * d.max_len * E;
-  const int64_t cross_stride = static_cast<int64_t>(d.B) * S * E;
-  const int64_t self_off = r0 * d.max_len * E;
-  const int64_t cross_off = static_cast<int64_t>(pt.b0) * S * E;
-  for (int l = 0; l < L; ++l) {
-    const LayerOff& o = e->lo[l];
-    bf16* kc_l = d.kcache[cur] + l * self_stride + self_off;
-    bf16* vc_l = d.vcache[cur] + l * self_stride + self_off;
-    RC(linear_dec(x, E, e->ph + o.sa_w, e->pf + o.sa_b, qkv, 3 * E, R, 3 * E, E, 0, s));
-    RC(attn_decode_append(qkv, 3 * E, kc_l, vc_l, d.max_len, pos, attn, E, R, H, hd, scale, s));
-    RC(linear_ln_fwd(attn, E, e->ph + o.sa_ow, e->pf + o.sa_ob, x, e->pf + o.n1_w, e->pf + o.n1_b, pt.parts, d.ksplit_e,
-                     x1, R, E, E, c.ln_eps, s));
-    RC(linear_dec(x1, E, e->ph + o.ca_w, e->pf + o.ca_b, qc, E, R, E, E, 0, s));
-    RC(attn_decode(qc, E, d.kc + l * cross_stride + cross_off, d.vc + l * cross_stride + cross_off, S, S, attn, E, B,
-                   d.beam, H, hd, mem_pad, scale, s));
-    RC(linear_ln_fwd(attn, E, e->ph + o.ca_ow, e->pf + o.ca_ob, x1, e->pf + o.n2_w, e->pf + o.n2_b, pt.parts, d.ksplit_e,
-                     x2, R, E, E, c.ln_eps, s));
-    RC(linear_dec(x2, E, e->ph + o.l1_w, e->pf + o.l1_b, h, F, R, F, E, c.act, s));
-    RC(linear_ln_fwd(h, F, e->ph + o.l2_w, e->pf + o.l2_b, x2, e->pf + o.n3_w, e->pf + o.n3_b, pt.parts, d.ksplit_f,
-                     xn, R, E, F, c.ln_eps, s));
-    bf16* t = x; x = xn; xn = t;
-  }
-  *x_out = x;
-  return 0;
+  bf16* kc_l = d.kcache[cur] + l * self_stride + v.self_off;
+  bf16* vc_l = d.vcache[cur] + l * self_stride + v.self_off;
+  bf16* x = dec_x_in(v, l);
+  RC(linear_dec(x, E, e->ph + o.sa_w, e->pf + o.sa_b, v.qkv, 3 * E, v.R, 3 * E, E, 0, s, d.single_cta));
+  RC(attn_decode_append(v.qkv, 3 * E, kc_l, vc_l, d.max_len, pos, v.attn, E, v.R, H, hd, 1.0f / sqrtf(static_cast<float>(hd)), s));
+  RC(linear_ln_fwd(v.attn, E, e->ph + o.sa_ow, e->pf + o.sa_ob, x, e->pf + o.n1_w, e->pf + o.n1_b, v.pt->parts, d.ksplit_e,
+                   v.x1, v.R, E, E, c.ln_eps, s, d.single_cta));
+  return linear_dec(v.x1, E, e->ph + o.ca_w, e->pf + o.ca_b, v.qc, E, v.R, E, E, 0, s, d.single_cta);
+}
+// cross attention over the image's K/V planes of layer l (the HBM-bound stream)
+int dec_cross(b200_engine* e, const DecPart& v, int l, cudaStream_t s) {
+  const auto& c = e->cfg;
+  auto& d = e->dec;
+  const int E = c.embed_dim, H = c.num_heads, L = c.num_layers, hd = E / H;
+  const int64_t cross_stride = static_cast<int64_t>(d.B) * d.S * E;
+  const int ln = (l + 1 < L) ? l + 1 : 0;   // the next launch streams layer l+1 (layer 0 of the next position after the last)
+  return attn_decode(v.qc, E, d.kc + l * cross_stride + v.cross_off, d.vc + l * cross_stride + v.cross_off, d.S, d.S, v.attn, E,
+                     v.B, d.beam, H, hd, v.mem_pad, 1.0f / sqrtf(static_cast<float>(hd)), s, d.kc + ln * cross_stride + v.cross_off,
+                     d.vc + ln * cross_stride + v.cross_off, v.pf_bytes, d.kv_flags, d.attn_fat_grid, v.pt->sched);
+}
+// cross out-proj + LN2, FFN1, FFN2 + LN3
+int dec_post(b200_engine* e, const DecPart& v, int l, cudaStream_t s) {
+  const auto& c = e->cfg;
+  auto& d = e->dec;
+  const int E = c.embed_dim, F = c.ff_dim;
+  const LayerOff& o = e->lo[l];
+  RC(linear_ln_fwd(v.attn, E, e->ph + o.ca_ow, e->pf + o.ca_ob, v.x1, e->pf + o.n2_w, e->pf + o.n2_b, v.pt->parts, d.ksplit_e,
+                   v.x2, v.R, E, E, c.ln_eps, s, d.single_cta));
+  RC(linear_dec(v.x2, E, e->ph + o.l1_w, e->pf + o.l1_b, v.h, F, v.R, F, E, c.act, s, d.single_cta));
+  return linear_ln_fwd(v.h, F, e->ph + o.l2_w, e->pf + o.l2_b, v.x2, e->pf + o.n3_w, e->pf + o.n3_b, v.pt->parts, d.ksplit_f,
+                       dec_x_out(v, l), v.R, E, F, c.ln_eps, s, d.single_cta);
 }
 
-// Runs body(partition, stream) for every partition: partition 0 on `s`, the others on side streams
-// forked from / joined back into `s` with events (valid eagerly and under stream capture).
-template <class Body>
-int for_each_part(b200_engine* e, cudaStream_t s, Body body) {
+// Streams of a (possibly partitioned) generation call: partition p's launch chain runs on S[p] (S[0] is the
+// caller's stream), the cross-attention launches of all partitions on SA when the plan asks for it.
+// parts_fork / parts_join bracket the work; both are valid eagerly and under stream capture.
+struct PartStreams {
+  std::vector<cudaStream_t> S;
+  cudaStream_t SA = nullptr;
+  std::vector<DecPart> view;
+};
+
+int parts_fork(b200_engine* e, cudaStream_t s, PartStreams* ps) {
   auto& d = e->dec;
   const int P = static_cast<int>(d.part.size());
   while (static_cast<int>(d.side.size()) < P - 1) {
@@ -590,22 +689,92 @@ int for_each_part(b200_engine* e, cudaStream_t s, Body body) {
     B200_CHECK_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     d.side.push_back(st);
   }
-  while (static_cast<int>(d.ev.size()) < P) {
-    cudaEvent_t ev;
-    B200_CHECK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    d.ev.push_back(ev);
-  }
+  auto grow = [](std::vector<cudaEvent_t>& v, int n) -> int {
+    while (static_cast<int>(v.size()) < n) {
+      cudaEvent_t ev;
+      B200_CHECK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      v.push_back(ev);
+    }
+    return 0;
+  };
+  RC(grow(d.ev, P + 1));
+  RC(grow(d.evq, P));
+  RC(grow(d.eva, P));
+  if (d.use_att_stream && !d.att_stream) B200_CHECK_CUDA(cudaStreamCreateWithFlags(&d.att_stream, cudaStreamNonBlocking));
+  ps->S.assign(1, s);
+  for (int p = 1; p < P; ++p) ps->S.push_back(d.side[p - 1]);
+  ps->SA = (d.use_att_stream && P > 1) ? d.att_stream : nullptr;
+  ps->view.clear();
+  for (int p = 0; p < P; ++p) ps->view.push_back(dec_part(e, d.part[p]));
   if (P > 1) {
     B200_CHECK_CUDA(cudaEventRecord(d.ev[0], s));
-    for (int p = 1; p < P; ++p) B200_CHECK_CUDA(cudaStreamWaitEvent(d.side[p - 1], d.ev[0], 0));
+    for (int p = 1; p < P; ++p) B200_CHECK_CUDA(cudaStreamWaitEvent(ps->S[p], d.ev[0], 0));
+    if (ps->SA) B200_CHECK_CUDA(cudaStreamWaitEvent(ps->SA, d.ev[0], 0));
   }
-  int rc = 0;
-  for (int p = 0; p < P && rc == 0; ++p) rc = body(d.part[p], p == 0 ? s : d.side[p - 1]);
-  for (int p = 1; p < P; ++p) {   // always join, also on error, so a capture is never left forked
-    cudaEventRecord(d.ev[p], d.side[p - 1]);
+  return 0;
+}
+// always called, also after an error, so that a capture is never left forked
+void parts_join(b200_engine* e, cudaStream_t s, const PartStreams& ps) {
+  auto& d = e->dec;
+  const int P = static_cast<int>(ps.S.size());
+  for (int p = 1; p < P; ++p) {
+    cudaEventRecord(d.ev[p], ps.S[p]);
     cudaStreamWaitEvent(s, d.ev[p], 0);
   }
+  if (ps.SA) {
+    cudaEventRecord(d.ev[P], ps.SA);
+    cudaStreamWaitEvent(s, d.ev[P], 0);
+  }
+}
+
+// one decode position for every partition: tokens[r] at position pos -> final hidden of partition p in x_out[p]
+// (`cur` = live copy of the self-attention cache).  Launch order: per layer, every partition's self-attention
+// block, then every partition's cross attention, then every partition's FFN block, so that the attention
+// stream (if any) sees the partitions round robin.
+int decode_hidden_all(b200_engine* e, const PartStreams& ps, int cur, const int64_t* tokens, int pos, bf16** x_out) {
+  auto& d = e->dec;
+  const int L = e->cfg.num_layers;
+  const int P = static_cast<int>(ps.S.size());
+  for (int p = 0; p < P; ++p) RC(dec_embed(e, ps.view[p], tokens, pos, ps.S[p]));
+  for (int l = 0; l < L; ++l) {
+    for (int p = 0; p < P; ++p) {
+      RC(dec_pre(e, ps.view[p], l, cur, pos, ps.S[p]));
+      if (ps.SA) B200_CHECK_CUDA(cudaEventRecord(d.evq[p], ps.S[p]));
+    }
+    for (int p = 0; p < P; ++p) {
+      if (ps.SA) {
+        B200_CHECK_CUDA(cudaStreamWaitEvent(ps.SA, d.evq[p], 0));
+        RC(dec_cross(e, ps.view[p], l, ps.SA));
+        B200_CHECK_CUDA(cudaEventRecord(d.eva[p], ps.SA));
+      } else {
+        RC(dec_cross(e, ps.view[p], l, ps.S[p]));
+      }
+    }
+    for (int p = 0; p < P; ++p) {
+      if (ps.SA) B200_CHECK_CUDA(cudaStreamWaitEvent(ps.S[p], d.eva[p], 0));
+      RC(dec_post(e, ps.view[p], l, ps.S[p]));
+    }
+  }
+  for (int p = 0; p < P; ++p) x_out[p] = dec_x_in(ps.view[p], L);
+  return 0;
+}
+
+// fork, run body(streams), join (the join also happens when body fails)
+template <class Body>
+int with_parts(b200_engine* e, cudaStream_t s, Body body) {
+  PartStreams ps;
+  RC(parts_fork(e, s, &ps));
+  const int rc = body(ps);
+  parts_join(e, s, ps);
   return rc;
+}
+
+// the plan's tuning knobs, folded into the CUDA-graph cache keys (a sweep re-plans with different settings)
+uint64_t dec_tuning_key(const b200_engine::Decode& d) {
+  return static_cast<uint64_t>(d.pf_bytes) * 8ull + static_cast<uint64_t>(d.kv_flags) + (static_cast<uint64_t>(d.ksplit_e) << 40) +
+         (static_cast<uint64_t>(d.ksplit_f) << 46) + (static_cast<uint64_t>(d.single_cta ? 1 : 0) << 52) +
+         (static_cast<uint64_t>(d.attn_fat_grid) << 53) + (static_cast<uint64_t>(d.use_att_stream ? 1 : 0) << 62) + (static_cast<uint64_t>(d.attn_dyn ? 1 : 0) << 61) ^
+         (static_cast<uint64_t>(d.gemm_cap) * 0x9E3779B97F4A7C15ull);
 }
 
 uint64_t mix_key(std::initializer_list<uint64_t> v) {
@@ -954,30 +1123,30 @@ int b200_engine_decode_begin(b200_engine* e, const float* memory, const uint8_t*
     RC(linear_fwd(d.memp, E, e->ph + o.ca_w + static_cast<int64_t>(E) * E, e->pf + o.ca_b + E, d.kv_tmp, 2 * E, Ms, 2 * E, E, 0, nullptr, 0, s));
     RC(kv_to_head_major(d.kv_tmp, d.kc + static_cast<int64_t>(l) * Ms * E, d.vc + static_cast<int64_t>(l) * Ms * E, B, S, H, hd, s));
   }
+  B200_CHECK_CUDA(cudaMemsetAsync(d.sched, 0, 16 * sizeof(int), s));
   d.ready = true;
   return 0;
 }
 
-// LM head of one partition: greedy ids (argmax fused into the GEMM epilogue)
-static int decode_argmax_part(b200_engine* e, const b200_engine::Decode::Part& pt, int cur, const int64_t* tokens_in,
-                              int pos, int64_t* next_ids, cudaStream_t s) {
+// LM head of one partition: greedy ids (argmax fused into the GEMM epilogue) from its final hidden state x
+static int decode_argmax_part(b200_engine* e, const DecPart& v, const bf16* x, int64_t* next_ids, cudaStream_t s) {
   auto& d = e->dec;
   const int E = e->cfg.embed_dim, V = e->cfg.vocab_size;
-  const int64_t r0 = static_cast<int64_t>(pt.b0) * d.beam;
-  const int R = pt.nb * d.beam;
-  bf16* x = nullptr;
-  RC(decode_hidden(e, pt, cur, tokens_in, pos, &x, s));
   const int64_t n_tiles = gemm_num_n_tiles(V, 128);
-  return b200_lmhead_argmax(x, E, e->ph + e->fc_w, E, e->pf + e->fc_b, R, V, E, next_ids + r0, d.best + r0,
-                            d.scratch + 2 * r0 * n_tiles, s);
+  return b200_lmhead_argmax(x, E, e->ph + e->fc_w, E, e->pf + e->fc_b, v.R, V, E, next_ids + v.r0, d.best + v.r0,
+                            d.scratch + 2 * v.r0 * n_tiles, s);
 }
 
 int b200_engine_decode_step(b200_engine* e, const int64_t* tokens_in, int32_t pos, int64_t* next_ids, void* stream) {
   B200_REQUIRE(e && tokens_in && next_ids, "decode_step: null argument");
   B200_REQUIRE(e->dec.ready, "decode_step: call decode_begin first");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  return for_each_part(e, s, [&](const b200_engine::Decode::Part& pt, cudaStream_t ps) -> int {
-    return decode_argmax_part(e, pt, e->dec.cur, tokens_in, pos, next_ids, ps);
+  GemmGridCap grid_cap(e->dec.gemm_cap, (e->dec.kv_flags & 4) != 0);
+  return with_parts(e, s, [&](const PartStreams& ps) -> int {
+    std::vector<bf16*> x(ps.S.size(), nullptr);
+    RC(decode_hidden_all(e, ps, e->dec.cur, tokens_in, pos, x.data()));
+    for (size_t p = 0; p < ps.S.size(); ++p) RC(decode_argmax_part(e, ps.view[p], x[p], next_ids, ps.S[p]));
+    return 0;
   });
 }
 
@@ -988,6 +1157,7 @@ int b200_engine_generate_greedy(b200_engine* e, int64_t start_id, int64_t end_id
   B200_REQUIRE(d.ready && d.beam == 1, "generate_greedy: call decode_begin(beam=1) first");
   B200_REQUIRE(max_len >= 2 && max_len <= d.max_len, "generate_greedy: max_len %d exceeds the decode plan's %d", max_len, d.max_len);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GemmGridCap grid_cap(d.gemm_cap, (d.kv_flags & 4) != 0);
   const int R = d.R;
   const long long pad = e->cfg.pad_idx;
   int64_t* toks = d.seq[0];          // [R, d.max_len] staging inside the workspace (stable address for the graph)
@@ -1001,13 +1171,17 @@ int b200_engine_generate_greedy(b200_engine* e, int64_t start_id, int64_t end_id
     B200_CHECK_CUDA(cudaMemsetAsync(d.out_len, 0, sizeof(int) * R, ws));
     return 0;
   };
-  // positions [p0, p1) of one partition, back to back on its stream (rows are independent)
-  auto steps = [&](const b200_engine::Decode::Part& pt, int p0, int p1, cudaStream_t ps) -> int {
-    const int64_t r0 = pt.b0;
+  // positions [p0, p1): every partition's chain on its own stream (rows are independent)
+  auto steps = [&](const PartStreams& ps, int p0, int p1) -> int {
+    std::vector<bf16*> x(ps.S.size(), nullptr);
     for (int pos = p0; pos < p1; ++pos) {
-      RC(decode_argmax_part(e, pt, 0, d.cur_tok, pos, d.ids, ps));
-      RC(greedy_update(d.ids + r0, d.cur_tok + r0, toks + r0 * ld, d.out_len + r0, d.fin[0] + r0, d.n_finished, pt.nb, ld,
-                       pos, end_id, pad, ps));
+      RC(decode_hidden_all(e, ps, 0, d.cur_tok, pos, x.data()));
+      for (size_t p = 0; p < ps.S.size(); ++p) {
+        const DecPart& v = ps.view[p];
+        RC(decode_argmax_part(e, v, x[p], d.ids, ps.S[p]));
+        RC(greedy_update(d.ids + v.r0, d.cur_tok + v.r0, toks + v.r0 * ld, d.out_len + v.r0, d.fin[0] + v.r0, d.n_finished,
+                         v.B, ld, pos, end_id, pad, ps.S[p]));
+      }
     }
     return 0;
   };
@@ -1015,7 +1189,7 @@ int b200_engine_generate_greedy(b200_engine* e, int64_t start_id, int64_t end_id
     RC(prologue(s));
     for (int p0 = 0; p0 + 1 < max_len; p0 += stop_check_interval) {
       const int p1 = (p0 + stop_check_interval < max_len - 1) ? p0 + stop_check_interval : max_len - 1;
-      RC(for_each_part(e, s, [&](const b200_engine::Decode::Part& pt, cudaStream_t ps) -> int { return steps(pt, p0, p1, ps); }));
+      RC(with_parts(e, s, [&](const PartStreams& ps) -> int { return steps(ps, p0, p1); }));
       int nf = 0;   // the reference's early exit (model.py:239-240), batched
       B200_CHECK_CUDA(cudaMemcpyAsync(&nf, d.n_finished, sizeof(int), cudaMemcpyDeviceToHost, s));
       B200_CHECK_CUDA(cudaStreamSynchronize(s));
@@ -1024,12 +1198,11 @@ int b200_engine_generate_greedy(b200_engine* e, int64_t start_id, int64_t end_id
   } else {
     const uint64_t key = mix_key({reinterpret_cast<uint64_t>(d.kc), static_cast<uint64_t>(R), static_cast<uint64_t>(d.S),
                                   static_cast<uint64_t>(d.max_len), static_cast<uint64_t>(max_len), static_cast<uint64_t>(start_id),
-                                  static_cast<uint64_t>(end_id), reinterpret_cast<uint64_t>(d.mem_pad), 1ull});
+                                  static_cast<uint64_t>(end_id), reinterpret_cast<uint64_t>(d.mem_pad),
+                                  dec_tuning_key(d), static_cast<uint64_t>(d.part.size()), 1ull});
     RC(run_maybe_graphed(e, key, s, [&](cudaStream_t ws) -> int {
       RC(prologue(ws));
-      return for_each_part(e, ws, [&](const b200_engine::Decode::Part& pt, cudaStream_t ps) -> int {
-        return steps(pt, 0, max_len - 1, ps);
-      });
+      return with_parts(e, ws, [&](const PartStreams& ps) -> int { return steps(ps, 0, max_len - 1); });
     }));
   }
   B200_CHECK_CUDA(cudaMemcpy2DAsync(out_tokens, static_cast<size_t>(max_len) * sizeof(int64_t), toks,
@@ -1047,6 +1220,7 @@ int b200_engine_generate_beam(b200_engine* e, int64_t start_id, int64_t end_id, 
   B200_REQUIRE(d.beam == 1 || d.logits != nullptr, "generate_beam: decode plan has no logits buffer");
   B200_REQUIRE(max_len >= 2 && max_len <= d.max_len, "generate_beam: max_len %d exceeds the decode plan's %d", max_len, d.max_len);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GemmGridCap grid_cap(d.gemm_cap, (d.kv_flags & 4) != 0);
   const auto& c = e->cfg;
   const int E = c.embed_dim, V = c.vocab_size, H = c.num_heads, L = c.num_layers, hd = E / H;
   const int R = d.R, beam = d.beam;
@@ -1055,7 +1229,8 @@ int b200_engine_generate_beam(b200_engine* e, int64_t start_id, int64_t end_id, 
                                 static_cast<uint64_t>(d.max_len), static_cast<uint64_t>(max_len), static_cast<uint64_t>(start_id),
                                 static_cast<uint64_t>(end_id), reinterpret_cast<uint64_t>(d.mem_pad), static_cast<uint64_t>(beam),
                                 reinterpret_cast<uint64_t>(out_tokens), reinterpret_cast<uint64_t>(out_len),
-                                reinterpret_cast<uint64_t>(out_score), 2ull});
+                                reinterpret_cast<uint64_t>(out_score), dec_tuning_key(d),
+                                static_cast<uint64_t>(d.part.size()), 2ull});
   // every partition (a range of images with all their hypotheses) runs the whole search on its stream;
   // the live copies of the cache / sequences / scores alternate identically in every partition
   RC(run_maybe_graphed(e, key, s, [&](cudaStream_t ws) -> int {
@@ -1064,35 +1239,44 @@ int b200_engine_generate_beam(b200_engine* e, int64_t start_id, int64_t end_id, 
     RC(fill_i64(d.cur_tok, R, start_id, ws));
     B200_CHECK_CUDA(cudaMemsetAsync(d.fin[0], 0, R, ws));
     B200_CHECK_CUDA(cudaMemsetAsync(d.scores[0], 0, sizeof(float) * R, ws));
-    return for_each_part(e, ws, [&](const b200_engine::Decode::Part& pt, cudaStream_t ps) -> int {
-      const int64_t r0 = static_cast<int64_t>(pt.b0) * beam;
-      const int Rp = pt.nb * beam;
-      float* logits = d.logits + r0 * V;
+    return with_parts(e, ws, [&](const PartStreams& ps) -> int {
+      const size_t P = ps.S.size();
+      std::vector<bf16*> x(P, nullptr);
       int cur = 0, cs = 0, n_tok = 1;
       for (int pos = 0; pos + 1 < max_len; ++pos) {
-        bf16* x = nullptr;
-        RC(decode_hidden(e, pt, cur, d.cur_tok, pos, &x, ps));
-        GemmProblem g;
-        g.M = Rp; g.N = V; g.K = E;
-        g.A = x; g.lda = E; g.B = e->ph + e->fc_w; g.ldb = E;
-        g.D = logits; g.ldd = V; g.d_fp32 = true; g.bias = e->pf + e->fc_b; g.split_k = 1;
-        RC(gemm_launch(g, ps));
-        RC(beam_topk(logits, d.scores[cs] + r0, d.fin[cs] + r0, pt.nb, beam, V, end_id, pos == 0, d.cur_tok + r0, d.parent + r0,
-                     d.scores[cs ^ 1] + r0, ps));
-        RC(beam_advance(d.seq[cs] + r0 * d.max_len, d.seq[cs ^ 1] + r0 * d.max_len, d.fin[cs] + r0, d.fin[cs ^ 1] + r0,
-                        d.cur_tok + r0, d.parent + r0, Rp, beam, d.max_len, pos, end_id, ps));
-        // the self-attention cache follows the surviving hypotheses
-        for (int l = 0; l < L; ++l) {
-          const int64_t off = (static_cast<int64_t>(l) * R + r0) * d.max_len * E;
-          RC(cache_reorder(d.kcache[cur] + off, d.vcache[cur] + off, d.kcache[cur ^ 1] + off, d.vcache[cur ^ 1] + off,
-                           d.parent + r0, pt.nb, beam, H, hd, d.max_len, pos, ps));
+        RC(decode_hidden_all(e, ps, cur, d.cur_tok, pos, x.data()));
+        for (size_t p = 0; p < P; ++p) {
+          const DecPart& v = ps.view[p];
+          const int64_t r0 = v.r0;
+          cudaStream_t st = ps.S[p];
+          float* logits = d.logits + r0 * V;
+          GemmProblem g;
+          g.M = v.R; g.N = V; g.K = E;
+          g.A = x[p]; g.lda = E; g.B = e->ph + e->fc_w; g.ldb = E;
+          g.D = logits; g.ldd = V; g.d_fp32 = true; g.bias = e->pf + e->fc_b; g.split_k = 1;
+          RC(gemm_launch(g, st));
+          RC(beam_topk(logits, d.scores[cs] + r0, d.fin[cs] + r0, v.B, beam, V, end_id, pos == 0, d.cur_tok + r0, d.parent + r0,
+                       d.scores[cs ^ 1] + r0, st));
+          RC(beam_advance(d.seq[cs] + r0 * d.max_len, d.seq[cs ^ 1] + r0 * d.max_len, d.fin[cs] + r0, d.fin[cs ^ 1] + r0,
+                          d.cur_tok + r0, d.parent + r0, v.R, beam, d.max_len, pos, end_id, st));
+          // the self-attention cache follows the surviving hypotheses
+          for (int l = 0; l < L; ++l) {
+            const int64_t off = (static_cast<int64_t>(l) * R + r0) * d.max_len * E;
+            RC(cache_reorder(d.kcache[cur] + off, d.vcache[cur] + off, d.kcache[cur ^ 1] + off, d.vcache[cur ^ 1] + off,
+                             d.parent + r0, v.B, beam, H, hd, d.max_len, pos, st));
+          }
         }
         cur ^= 1;
         cs ^= 1;
         ++n_tok;
       }
-      return beam_finalize(d.seq[cs] + r0 * d.max_len, d.scores[cs] + r0, pt.nb, beam, d.max_len, n_tok, end_id, c.pad_idx,
-                           d.out_tok + static_cast<int64_t>(pt.b0) * d.max_len, d.out_len + pt.b0, d.out_score + pt.b0, ps);
+      for (size_t p = 0; p < P; ++p) {
+        const DecPart& v = ps.view[p];
+        const int b0 = v.pt->b0;
+        RC(beam_finalize(d.seq[cs] + v.r0 * d.max_len, d.scores[cs] + v.r0, v.B, beam, d.max_len, n_tok, end_id, c.pad_idx,
+                         d.out_tok + static_cast<int64_t>(b0) * d.max_len, d.out_len + b0, d.out_score + b0, ps.S[p]));
+      }
+      return 0;
     });
   }));
   const int B = d.B;

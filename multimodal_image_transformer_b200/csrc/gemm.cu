@@ -41,6 +41,7 @@ struct GemmDev {
   const bf16* relu_mask; long long ldm;
   int act;
   int aux_mode;   // 0 none, 1 residual add, 2 relu mask (tile fetched by TMA through tmap_aux)
+  int b_evict_last;   // B tiles loaded with the L2 evict-last priority (CL == 1, K-major B)
   const long long* targets; long long ignore_index;
   float* part_max; float* part_sum; float* tgt_logit;
   const float* row_lse; const float* inv_count;
@@ -176,7 +177,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               load(sa + j * (BLOCK_K * 128), &tmap_a, m_blk * BLOCK_M + j * 64, kb * BLOCK_K);
           }
           if constexpr (!B_MN) {
-            load(sb, &tmap_b, kb * BLOCK_K, n_row0);
+            if constexpr (CL == 1) {
+              if (p.b_evict_last) tma_load_2d_hint(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_row0, l2_policy_evict_last());
+              else load(sb, &tmap_b, kb * BLOCK_K, n_row0);
+            } else {
+              load(sb, &tmap_b, kb * BLOCK_K, n_row0);
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < NSH / 64; ++j)
@@ -569,6 +575,14 @@ static int launch_instance(const CUtensorMap& ta, const CUtensorMap& tb, const C
   return 0;
 }
 
+static thread_local int g_grid_cap = 0;
+static thread_local bool g_b_evict_last = false;
+GemmGridCap::GemmGridCap(int max_ctas, bool b_evict_last) : prev_(g_grid_cap), prev_hint_(g_b_evict_last) {
+  g_grid_cap = max_ctas > 0 ? max_ctas : 0;
+  g_b_evict_last = b_evict_last;
+}
+GemmGridCap::~GemmGridCap() { g_grid_cap = prev_; g_b_evict_last = prev_hint_; }
+
 static double wave_eff(long long work, int sms) {
   long long waves = (work + sms - 1) / sms;
   return static_cast<double>(work) / static_cast<double>(waves * sms);
@@ -643,6 +657,7 @@ int gemm_launch(const GemmProblem& q, cudaStream_t stream, int* n_tiles_out) {
                "gemm: dropout needs the standard bf16 epilogue and M*N < 2^32");
   d.bias = q.bias; d.residual = q.residual; d.ldr = q.ldr; d.relu_mask = q.relu_mask; d.ldm = q.ldm;
   d.act = q.act;
+  d.b_evict_last = (q.b_evict_last || g_b_evict_last) ? 1 : 0;
   d.targets = reinterpret_cast<const long long*>(q.targets); d.ignore_index = q.ignore_index;
   d.part_max = q.part_max; d.part_sum = q.part_sum; d.tgt_logit = q.tgt_logit;
   d.row_lse = q.row_lse; d.inv_count = q.inv_count;
@@ -650,7 +665,7 @@ int gemm_launch(const GemmProblem& q, cudaStream_t stream, int* n_tiles_out) {
 
   // cluster of two CTAs sharing the B tile through TMA multicast whenever there are >= 2 M tiles
   static const bool no_cluster = getenv("B200_GEMM_NO_CLUSTER") != nullptr;
-  const int cl = (!no_cluster && d.num_m_tiles >= 2 && sms >= 2) ? 2 : 1;
+  const int cl = (!no_cluster && !q.single_cta && d.num_m_tiles >= 2 && sms >= 2) ? 2 : 1;
 
   CUtensorMap ta, tb;
   int rc;
@@ -680,7 +695,8 @@ int gemm_launch(const GemmProblem& q, cudaStream_t stream, int* n_tiles_out) {
   }
 
   const long long work = static_cast<long long>((d.num_m_tiles + cl - 1) / cl) * d.num_n_tiles * d.split_k;
-  const long long slots = sms / cl;
+  long long slots = sms / cl;
+  if (g_grid_cap > 0 && g_grid_cap / cl >= 1 && g_grid_cap / cl < slots) slots = g_grid_cap / cl;
   const int grid = static_cast<int>(work < slots ? work : slots) * cl;
 
 #define B200_GEMM_CASE(BN, AMN, BMN, EP)                                                  \

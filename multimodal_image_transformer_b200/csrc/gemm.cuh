@@ -23,6 +23,9 @@ struct GemmProblem {
   bool partials = false;
   int split_k = 1;   // 0 = auto
   int block_n = 0;   // 0 = auto
+  bool b_evict_last = false;  // load B (the weights) with the L2 evict-last priority: generation re-reads the same weights every
+                              // position while a read-once K/V stream passes through L2 (unpaired K-major B tiles only)
+  bool single_cta = false;   // never pair CTAs (cta_group::1 tiles): no cluster start-up for latency-bound skinny GEMMs
   // --- fused softmax-CE / argmax epilogues (LM head) ---
   GemmEpi epi = EPI_STD;
   const int64_t* targets = nullptr; long long ignore_index = 0;
@@ -36,6 +39,20 @@ struct GemmProblem {
 // Returns 0 / negative error. n_tiles_out (optional) = number of N tiles the launch used.
 int gemm_launch(const GemmProblem& p, cudaStream_t stream, int* n_tiles_out = nullptr);
 int gemm_check_launch(const GemmProblem& p, cudaStream_t stream);
+// Caps the persistent grid of every GEMM launched by the calling thread while the guard lives (0 = no cap):
+// generation with concurrent image partitions keeps its skinny GEMMs on the SMs the cross-attention
+// stream of another partition leaves free (a statically scheduled persistent grid larger than that would
+// wait for the stream to finish).
+// b_evict_last: every launch inside the scope loads its weights with the L2 evict-last priority (see GemmProblem).
+struct GemmGridCap {
+  explicit GemmGridCap(int max_ctas, bool b_evict_last = false);
+  ~GemmGridCap();
+  GemmGridCap(const GemmGridCap&) = delete;
+  GemmGridCap& operator=(const GemmGridCap&) = delete;
+ private:
+  int prev_;
+  bool prev_hint_;
+};
 int gemm_num_n_tiles(int N, int block_n);
 // number of non-empty K splits a launch with this (K, split_k) uses (= slabs written in partials mode)
 int gemm_effective_splits(int K, int split_k);
