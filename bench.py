@@ -453,6 +453,7 @@ def bench_decode(dec, c, dev, peaks, peak_src):
 
     for _ in range(2):
         run()
+    plan_greedy = eng.decode_plan_info()
     torch.cuda.synchronize()
     reps = 5
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -488,15 +489,16 @@ def bench_decode(dec, c, dev, peaks, peak_src):
                       "note": "beam search with 4 hypotheses per image, same 512 images, 47 steps"},
             "ms_per_batch": ms, "config": {"workload": "BASELINE configs[3]: greedy, batch 512, max_len 48 (47 steps, END "
                                                        "suppressed), cfg2 decoder, S=197, cross K/V precompute included",
-                                           "batch": B, "max_len": max_len},
+                                           "batch": B, "max_len": max_len, "schedule": plan_greedy},
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
                          "algorithmic_bytes": total, "peak_source": peak_src,
                          "traffic": tr["dram_bytes_per_launch"] if tr else None,
                          "traffic_note": (f"dominant kernel {tr['kernel']}: {tr['dram_bytes_per_launch'] / 1e6:.1f} MB DRAM vs "
                                           f"{tr['algorithmic_bytes_per_launch'] / 1e6:.1f} MB algorithmic per launch ({tr['source']})") if tr else None,
-                         "bound_note": "generation is a chain of ~75 dependent launches per position (6 layers x 11 kernels); the "
-                                       "HBM-bound cross-attention stream is ~45 % of the step, the rest is launch-latency bound "
-                                       "(DESIGN.md section 3.3)"}}
+                         "bound_note": "a position is a chain of ~75 dependent launches (6 layers x 11 kernels) around six HBM-bound "
+                                       "cross-attention streams; four image partitions run concurrently so that one partition's "
+                                       "stream (fat CTAs on 104 SMs) overlaps the other partitions' launch chains; what remains is "
+                                       "the per-partition launch latency (DESIGN.md section 3.3, profiles/r01_decode_sweeps.txt)"}}
 
 
 def main():

@@ -247,6 +247,12 @@ int64_t b200_engine_decode_workspace_bytes(const b200_engine* e, int32_t B, int3
 int b200_engine_decode_begin(b200_engine* e, const float* memory, const uint8_t* mem_pad, int32_t B,
                              int32_t beam, int32_t S, int32_t mem_dim, int32_t max_len, void* ws,
                              int64_t ws_bytes, void* stream);
+/* how the current decode plan is scheduled (after decode_begin): info[0] = concurrent image partitions,
+ * info[1] = SMs budgeted to the cross-attention K/V stream (0 = every SM), info[2] / info[3] = split-K of
+ * the E-deep / F-deep LayerNorm-fed GEMMs, info[4] = persistent-grid cap of the skinny GEMMs (0 = none),
+ * info[5] = hint flags (1 K/V stream evict-first, 2 16-row tail boxes, 4 weights evict-last).  Reporting
+ * only (bench.py); n = entries available in info. */
+int b200_engine_decode_plan_info(const b200_engine* e, int32_t* info, int32_t n);
 /* one position for every row: tokens_in [B*beam] at position pos -> argmax ids [B*beam]
  * (first index on ties, torch.argmax, model.py:233). */
 int b200_engine_decode_step(b200_engine* e, const int64_t* tokens_in, int32_t pos, int64_t* next_ids,

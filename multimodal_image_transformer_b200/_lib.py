@@ -104,6 +104,7 @@ SIGNATURES = {
     "b200_engine_backward_from_dlogits": (C.c_int, [_P, _P, _P, _P]),
     "b200_engine_grad_buckets": (_I32, [_P, _P, _P, _I32]),
     "b200_engine_decode_workspace_bytes": (_I64, [_P, _I32, _I32, _I32, _I32, _I32]),
+    "b200_engine_decode_plan_info": (C.c_int, [_P, _P, _I32]),
     "b200_engine_decode_begin": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P, _I64, _P]),
     "b200_engine_decode_step": (C.c_int, [_P, _P, _I32, _P, _P]),
     "b200_engine_generate_greedy": (C.c_int, [_P, _I64, _I64, _I32, _I32, _P, _P, _P]),

@@ -1137,6 +1137,15 @@ static int decode_argmax_part(b200_engine* e, const DecPart& v, const bf16* x, i
                             d.scratch + 2 * v.r0 * n_tiles, s);
 }
 
+int b200_engine_decode_plan_info(const b200_engine* e, int32_t* info, int32_t n) {
+  B200_REQUIRE(e && info && n >= 0, "decode_plan_info: null argument");
+  B200_REQUIRE(e->dec.ready, "decode_plan_info: call decode_begin first");
+  const auto& d = e->dec;
+  const int32_t v[6] = {static_cast<int32_t>(d.part.size()), d.attn_fat_grid, d.ksplit_e, d.ksplit_f, d.gemm_cap, d.kv_flags};
+  for (int i = 0; i < n && i < 6; ++i) info[i] = v[i];
+  return 0;
+}
+
 int b200_engine_decode_step(b200_engine* e, const int64_t* tokens_in, int32_t pos, int64_t* next_ids, void* stream) {
   B200_REQUIRE(e && tokens_in && next_ids, "decode_step: null argument");
   B200_REQUIRE(e->dec.ready, "decode_step: call decode_begin first");

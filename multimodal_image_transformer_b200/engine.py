@@ -302,6 +302,14 @@ class DecoderEngine:
                                                   max_len, L.ptr(self._dws), self._dws.numel(), L.cur_stream()),
                 "decode_begin")
 
+    def decode_plan_info(self) -> dict:
+        """How the current decode plan is scheduled (after decode_begin); reporting only."""
+        import ctypes
+        buf = (ctypes.c_int32 * 6)()
+        L.check(self.lib.b200_engine_decode_plan_info(self.handle, ctypes.addressof(buf), 6), "decode_plan_info")
+        keys = ("partitions", "attention_sms", "split_k_e", "split_k_f", "gemm_grid_cap", "hint_flags")
+        return dict(zip(keys, (int(v) for v in buf)))
+
     def decode_step(self, tokens_in: torch.Tensor, pos: int) -> torch.Tensor:
         tokens_in = tokens_in.to(self.device, torch.int64).contiguous()
         out = torch.empty_like(tokens_in)
