@@ -281,6 +281,10 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     launches0 = lib.b200_launch_count()
+    # roofline pass: every GEMM timed ALONE on the GPU.  The shipped step runs the bias-gradient column sums on a
+    # side stream next to the backward GEMMs (which then give up one pipeline stage); events around a GEMM would
+    # then also count the time its CTAs wait for SMs held by those sums, so this pass keeps the sums inline.
+    os.environ["B200_BIAS_INLINE"] = "1"
     L.check(lib.b200_gemm_profile_begin(min(1 << 20, 400 * args.steps + 64)), "profile_begin")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -294,6 +298,7 @@ def run_b200(args):
     cap = 400 * args.steps + 64
     pl_ms, pl_fl = (C.c_float * cap)(), (C.c_double * cap)()
     L.check(lib.b200_gemm_profile_end(C.byref(n_l), C.byref(tot_ms), C.byref(tot_fl), pl_ms, pl_fl, cap), "profile_end")
+    os.environ.pop("B200_BIAS_INLINE", None)
     if args.gemm_detail and rank == 0:
         per = n_l.value // args.steps
         with open(args.gemm_detail, "w") as f:
@@ -410,7 +415,9 @@ def run_b200(args):
                 "algorithmic_flops_per_step": tot_fl.value / args.steps,
                 "how": "2*M*N*K per launch summed over every GEMM launch of K eagerly launched timed steps / sum of their "
                        "CUDA-event durations on the launching stream (events cannot be read back from a graph replay, so "
-                       "the roofline pass is the eager one; ms_per_step_eager is its step time)",
+                       "the roofline pass is the eager one, with the bias-gradient sums inline so that each GEMM is alone "
+                       "on the GPU; ms_per_step_eager is its step time; the replayed step overlaps those sums with the "
+                       "backward GEMMs on a side stream)",
                 "traffic": None}
     tr = profiled_traffic("train_gemm")
     if tr is not None:

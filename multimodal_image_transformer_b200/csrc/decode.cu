@@ -335,10 +335,10 @@ __device__ __forceinline__ float dec_ex2(float x) {
 static constexpr int DECM_NQ = 4;       // rows of the partial-state exchange (nq <= 4)
 
 // bytes of one producer/consumer unit: ring + barriers + merge buffer, rounded to the swizzle alignment
-template <int HD, int DECM_STAGES>
+template <int HD, int DECM_STAGES, int NQR>
 __host__ __device__ constexpr size_t decm_unit_bytes() {
   return ((static_cast<size_t>(DECM_STAGES) * 2 * (HD / 64) * DEC_CK * 128 + (2 * DECM_STAGES + 2) * sizeof(uint64_t) +
-           static_cast<size_t>(2) * 4 * DECM_NQ * (HD + 2) * sizeof(float) + (DECM_STAGES + 4) * sizeof(int)) + 1023) / 1024 * 1024;
+           static_cast<size_t>(2) * 4 * NQR * (HD + 2) * sizeof(float) + (DECM_STAGES + 4) * sizeof(int)) + 1023) / 1024 * 1024;
 }
 
 // SUB = 1: the CTA is one unit (1 producer + 4 consumer warps), MINB CTAs per SM.
@@ -346,7 +346,9 @@ __host__ __device__ constexpr size_t decm_unit_bytes() {
 //          smaller than the SM count then leaves whole SMs to concurrently running kernels -- the launch
 //          chains of the other image partitions -- which a grid of small CTAs (spread over every SM by
 //          the block scheduler) cannot do.
-template <int HD, int DECM_STAGES, int MINB, int SUB>
+// NQR = query rows the partial-state exchange buffer holds (>= nq): 1 for greedy frees 6 KB per unit, which is
+// what lets four units with a 3-deep ring share one SM.
+template <int HD, int DECM_STAGES, int MINB, int SUB, int NQR>
 __global__ void __launch_bounds__(DEC_THREADS * SUB, SUB == 1 ? MINB : 1)
 attn_decode_mma_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
                        const __grid_constant__ CUtensorMap tmap_k16, const __grid_constant__ CUtensorMap tmap_v16,
@@ -360,11 +362,11 @@ attn_decode_mma_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
   const int ltid = (SUB == 1) ? static_cast<int>(threadIdx.x) : static_cast<int>(threadIdx.x) % DEC_THREADS;
   const int vcta = static_cast<int>(blockIdx.x) * SUB + sub;                           // unit index / count
   const int vgrid = static_cast<int>(gridDim.x) * SUB;
-  uint8_t* sm_decm = sm_decm_all + static_cast<size_t>(sub) * decm_unit_bytes<HD, DECM_STAGES>();
+  uint8_t* sm_decm = sm_decm_all + static_cast<size_t>(sub) * decm_unit_bytes<HD, DECM_STAGES, NQR>();
   uint64_t* full = reinterpret_cast<uint64_t*>(sm_decm + DECM_STAGES * STAGE);
   uint64_t* empty = full + DECM_STAGES;
-  float* red = reinterpret_cast<float*>(empty + DECM_STAGES + 2);   // [2][4][DECM_NQ][RED_STRIDE]
-  volatile int* item_ring = reinterpret_cast<volatile int*>(red + 2 * 4 * DECM_NQ * RED_STRIDE);   // [DECM_STAGES]: item whose first chunk is in the stage
+  float* red = reinterpret_cast<float*>(empty + DECM_STAGES + 2);   // [2][4][NQR][RED_STRIDE]
+  volatile int* item_ring = reinterpret_cast<volatile int*>(red + 2 * 4 * NQR * RED_STRIDE);   // [DECM_STAGES]: item whose first chunk is in the stage
   const bool dyn = a.sched != nullptr;
 
   const int warp = ltid >> 5, lane = ltid & 31;
@@ -473,16 +475,17 @@ attn_decode_mma_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
       }
     }
   };
+  if (!dyn) fetch_q(vcta);
   for (int item = vcta;; item += vgrid, par ^= 1) {
     if (dyn) {
       mbar_wait(&full[stage], phase);      // the item's first chunk (waited for again below: already complete)
       item = item_ring[stage];
       if (item < 0) break;
+      fetch_q(item);
     } else if (item >= n_items) {
       break;
     }
     const int grp = item / a.H, h = item % a.H;
-    fetch_q(item);
     // Q as mma A fragments: row g (< nq) = hypothesis g of this image, rows >= nq are zero
     uint32_t qa[HD / 16][4];
 #pragma unroll
@@ -490,6 +493,7 @@ attn_decode_mma_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
       qa[ks][0] = qn[ks][0]; qa[ks][2] = qn[ks][1];
       qa[ks][1] = qa[ks][3] = 0u;
     }
+    if (!dyn) fetch_q(item + vgrid);       // static stride: the next item's query travels while this item is processed
     float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
     float o[HD / 8][4];
 #pragma unroll
@@ -572,7 +576,7 @@ attn_decode_mma_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
 
     // ---- merge the four warps' states of rows < nq (row g of the tile lives in lanes 4g .. 4g+3)
     const float lsum = quad_sum_dec(l_run[0]);
-    float* rp = red + (par * 4 + warp) * DECM_NQ * RED_STRIDE;
+    float* rp = red + (par * 4 + warp) * NQR * RED_STRIDE;
     if (g < a.nq) {
 #pragma unroll
       for (int i = 0; i < HD / 8; ++i)
@@ -580,29 +584,30 @@ attn_decode_mma_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
       if (t == 0) { rp[g * RED_STRIDE + HD] = m_run[0]; rp[g * RED_STRIDE + HD + 1] = lsum; }
     }
     named_barrier_sync(1 + sub, 128);
-    const float* rb = red + par * 4 * DECM_NQ * RED_STRIDE;
+    const float* rb = red + par * 4 * NQR * RED_STRIDE;
     for (int idx = ltid; idx < a.nq * HD; idx += 128) {
       const int i = idx / HD, d = idx % HD;
       float mm = -INFINITY;
 #pragma unroll
-      for (int w = 0; w < 4; ++w) mm = fmaxf(mm, rb[(w * DECM_NQ + i) * RED_STRIDE + HD]);
+      for (int w = 0; w < 4; ++w) mm = fmaxf(mm, rb[(w * NQR + i) * RED_STRIDE + HD]);
       float ls = 0.f, val = 0.f;
 #pragma unroll
       for (int w = 0; w < 4; ++w) {
-        const float mw = rb[(w * DECM_NQ + i) * RED_STRIDE + HD];
+        const float mw = rb[(w * NQR + i) * RED_STRIDE + HD];
         const float cw = (mw == -INFINITY) ? 0.f : dec_ex2(mw - mm);
-        ls = fmaf(rb[(w * DECM_NQ + i) * RED_STRIDE + HD + 1], cw, ls);
-        val = fmaf(rb[(w * DECM_NQ + i) * RED_STRIDE + d], cw, val);
+        ls = fmaf(rb[(w * NQR + i) * RED_STRIDE + HD + 1], cw, ls);
+        val = fmaf(rb[(w * NQR + i) * RED_STRIDE + d], cw, val);
       }
       a.o[(static_cast<long long>(grp) * a.nq + i) * a.o_rs + h * HD + d] = __float2bfloat16(ls > 0.f ? val / ls : 0.f);
     }
   }
 }
 
-template <int HD, int DECM_STAGES, int MINB, int SUB>
+template <int HD, int DECM_STAGES, int MINB, int SUB, int NQR>
 static int launch_attn_decode_mma(const DecAttnArgs& a, int grid_cap, cudaStream_t s) {
-  auto kern = attn_decode_mma_kernel<HD, DECM_STAGES, MINB, SUB>;
-  const size_t unit = decm_unit_bytes<HD, DECM_STAGES>();
+  B200_REQUIRE(a.nq <= NQR, "attn_decode: %d query rows for an exchange buffer of %d", a.nq, NQR);
+  auto kern = attn_decode_mma_kernel<HD, DECM_STAGES, MINB, SUB, NQR>;
+  const size_t unit = decm_unit_bytes<HD, DECM_STAGES, NQR>();
   const size_t smem = unit * SUB + 1024;
   B200_REQUIRE(smem <= 227 * 1024, "attn_decode: %zu B of shared memory for %d units per CTA", smem, SUB);
   static bool configured = false;
@@ -654,8 +659,12 @@ int attn_decode(const bf16* q, long long q_rs, const bf16* k, const bf16* v, int
     // measured on B200 (512 images x 12 heads, S = 197): ring depth 2 with 4 CTAs per SM 0.82 ms per position,
     // depth 3 0.84, depth 4 (3 CTAs) 0.95, depth 1 0.92; 5-6 CTAs per SM (register cap 72 / 64, spills) 0.95-1.05
     // fat_grid > 0: one fat CTA per SM on at most fat_grid SMs (the other SMs stay free for concurrent kernels)
-    if (hd == 64) return fat_grid > 0 ? launch_attn_decode_mma<64, 2, 4, 4>(a, fat_grid, s) : launch_attn_decode_mma<64, 2, 4, 1>(a, 0, s);
-    if (hd == 128) return fat_grid > 0 ? launch_attn_decode_mma<128, 2, 2, 2>(a, fat_grid, s) : launch_attn_decode_mma<128, 2, 2, 1>(a, 0, s);
+    const bool deep = (flags & 8) != 0;
+    if (hd == 64) {
+      if (fat_grid > 0 && nq == 1 && deep) return launch_attn_decode_mma<64, 3, 4, 4, 1>(a, fat_grid, s);   // 4 units x 3-deep ring
+      return fat_grid > 0 ? launch_attn_decode_mma<64, 2, 4, 4, DECM_NQ>(a, fat_grid, s) : launch_attn_decode_mma<64, 2, 4, 1, DECM_NQ>(a, 0, s);
+    }
+    if (hd == 128) return fat_grid > 0 ? launch_attn_decode_mma<128, 2, 2, 2, DECM_NQ>(a, fat_grid, s) : launch_attn_decode_mma<128, 2, 2, 1, DECM_NQ>(a, 0, s);
   }
 #define B200_AD(HDV)                                              \
   do {                                                            \

@@ -11,7 +11,8 @@ int kv_to_head_major(const bf16* kv, bf16* k_hm, bf16* v_hm, int B, int S, int H
 // over the same nkeys keys.  q/o: [groups*nq, H*hd] rows; K/V: [groups][H][kv_len][hd], reading
 // the first nkeys rows.  key_pad: optional [groups, nkeys] uint8.  pf_k / pf_v / pf_bytes: optional L2
 // warm-up hint, the first pf_bytes of the K and V planes the NEXT call will stream; flags bit 0: load the
-// K/V stream with the L2 evict-first priority, bit 1: fetch a short last chunk as 16-row boxes
+// K/V stream with the L2 evict-first priority, bit 1: fetch a short last chunk as 16-row boxes, bit 3: 3-deep
+// rings in the fat-CTA shape (single query row per image only)
 // fat_grid > 0: run as at most fat_grid one-per-SM CTAs of several producer/consumer units each, leaving the
 // remaining SMs to concurrently running kernels; sched: optional two zeroed ints for dynamic (first come, first
 // served) item distribution, left zeroed again by the launch (all five: tensor-core kernel only).

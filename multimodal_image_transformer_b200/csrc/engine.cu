@@ -21,12 +21,14 @@ namespace {
 
 // Default size (MB over K and V together) of the L2 warm-up of the next layer's cross K/V stream during
 // generation; B200_DEC_PREFETCH_MB overrides.  0 = off.
+// TMA pipeline stages the backward GEMMs give up so that the bias-gradient sums fit next to them
+constexpr int kBwdStageDrop = 1;
 constexpr double kDecPrefetchMB = 0.0;
 constexpr bool kDecSingleCta = true;    // skinny generation GEMMs as unpaired CTAs (no cluster start-up); B200_DEC_SINGLE_CTA overrides
 constexpr bool kDecAttnDyn = false;         // dynamically scheduled cross attention; B200_DEC_ATTN_DYN overrides
 constexpr bool kDecAttnStream = false;      // cross attention of all partitions on one stream; B200_DEC_ATTN_STREAM overrides
 constexpr int kDecFatGridPct = 70;          // % of the SMs given to the cross-attention stream when partitions run concurrently (104 of 148); B200_DEC_ATTN_GRID overrides
-constexpr int kDecKvFlags = 3;          // attn_decode flags (decode.cuh); B200_DEC_KV_FLAGS overrides
+constexpr int kDecKvFlags = 11;          // attn_decode flags (decode.cuh); B200_DEC_KV_FLAGS overrides
 
 struct ParamInfo {
   std::string name;
@@ -98,6 +100,11 @@ struct b200_engine {
   const uint8_t* last_mem_pad = nullptr;
   long long last_ignore = 0;
   bool have_saved = false;
+  // Bias-gradient column sums of the training backward run on a side stream (no shared memory, few
+  // registers: they fit next to the resident GEMM CTAs and read dY while the dgrad / wgrad GEMMs stream the same
+  // tiles through L2); the branch is joined back before every gradient-bucket boundary.
+  cudaStream_t bias_stream = nullptr;
+  cudaEvent_t bias_fork = nullptr, bias_join = nullptr;
   // decode state (carved from the caller's decode workspace by decode_begin)
   struct Decode {
     int B = 0, beam = 0, R = 0, S = 0, max_len = 0;
@@ -126,7 +133,7 @@ struct b200_engine {
     std::vector<Part> part;
     int ksplit_e = 1, ksplit_f = 1;     // split-K of the E-deep / F-deep skinny GEMMs feeding a LayerNorm
     int64_t pf_bytes = 0;               // per K / V plane: head of the next layer's cross K/V warmed into L2 (0 = off)
-    int kv_flags = 0;                   // 1 = K/V stream evict-first in L2, 2 = 16-row tail boxes (attn_decode flags), 4 = weights evict-last
+    int kv_flags = 0;                   // 1 = K/V stream evict-first in L2, 2 = 16-row tail boxes (attn_decode flags), 4 = weights evict-last, 8 = 3-deep rings in fat CTAs
     bool single_cta = false;            // skinny GEMMs as unpaired CTAs
     int attn_fat_grid = 0;              // > 0: cross attention as <= this many one-per-SM fat CTAs (decode.cuh)
     int gemm_cap = 0;                   // > 0: persistent-grid cap of the generation GEMMs (the SMs left by the above)
@@ -250,12 +257,22 @@ int linear_dgrad(const bf16* dy, int64_t lddy, const bf16* W, int N_out, int K_i
   return gemm_launch(g, s);
 }
 // dW[N_out,K_in] += dy^T x ; db[N_out] += colsum(dy)
+// side != null: the bias sum runs on that stream behind `fork` (dy is complete at this point of s); the caller
+// joins the side stream before dy is overwritten and before the gradients are consumed
 int linear_wgrad(const bf16* dy, int64_t lddy, const bf16* x, int64_t ldx, float* dW, float* db, int M,
-                 int N_out, int K_in, cudaStream_t s) {
+                 int N_out, int K_in, cudaStream_t s, cudaStream_t side = nullptr, cudaEvent_t fork = nullptr,
+                 bool* side_used = nullptr) {
   GemmProblem g;
   g.M = N_out; g.N = K_in; g.K = M;
   g.A = dy; g.lda = lddy; g.a_mn = true; g.B = x; g.ldb = ldx; g.b_mn = true;
   g.D = dW; g.ldd = K_in; g.d_fp32 = true; g.accumulate = true; g.split_k = 0;
+  if (db && side) {
+    B200_CHECK_CUDA(cudaEventRecord(fork, s));
+    B200_CHECK_CUDA(cudaStreamWaitEvent(side, fork, 0));
+    if (side_used) *side_used = true;
+    if (int rc = colsum(dy, lddy, db, M, N_out, side)) return rc;
+    return gemm_launch(g, s);
+  }
   if (int rc = gemm_launch(g, s)) return rc;
   if (db) return colsum(dy, lddy, db, M, N_out, s);
   return 0;
@@ -365,8 +382,30 @@ int run_backward(b200_engine* e, bool have_dlogits, float* dmemory, void* const*
   const bool dropping = e->plan_dropout;
   auto site = [&](int id) { return dropping ? drop_site(e, id) : NO_DROP; };
   const float keep_scale = dropping ? 1.0f / (1.0f - e->drop_p) : 1.0f;
+  const bool bias_inline = getenv("B200_BIAS_INLINE") != nullptr;      // read per call: A/B switch and bench.py's roofline pass
+  cudaStream_t side = nullptr;
+  if (!bias_inline) {
+    if (!e->bias_stream) B200_CHECK_CUDA(cudaStreamCreateWithFlags(&e->bias_stream, cudaStreamNonBlocking));
+    if (!e->bias_fork) B200_CHECK_CUDA(cudaEventCreateWithFlags(&e->bias_fork, cudaEventDisableTiming));
+    if (!e->bias_join) B200_CHECK_CUDA(cudaEventCreateWithFlags(&e->bias_join, cudaEventDisableTiming));
+    side = e->bias_stream;
+  }
+  // one pipeline stage less while bias sums may be co-resident (B200_BWD_STAGE_DROP overrides)
+  static const int bwd_drop = getenv("B200_BWD_STAGE_DROP") ? atoi(getenv("B200_BWD_STAGE_DROP")) : kBwdStageDrop;
+  GemmStageCap stage_cap(side ? bwd_drop : 0);
+  bool side_used = false;
+  // every return path below goes through join_side (a captured graph must not be left forked)
+  auto join_side = [&](void) {
+    if (side && side_used) {
+      cudaEventRecord(e->bias_join, side);
+      cudaStreamWaitEvent(s, e->bias_join, 0);
+      side_used = false;
+    }
+  };
+  struct Joiner { decltype(join_side)& j; ~Joiner() { j(); } } joiner{join_side};
   int ev = 0;
   auto mark = [&](void) {
+    join_side();
     if (events && ev < n_events && events[ev]) cudaEventRecord(static_cast<cudaEvent_t>(events[ev]), s);
     ++ev;
   };
@@ -375,7 +414,7 @@ int run_backward(b200_engine* e, bool have_dlogits, float* dmemory, void* const*
   if (first_part <= 0) {
     if (need_dmemp) B200_CHECK_CUDA(cudaMemsetAsync(pl.dmemp, 0, static_cast<size_t>(Ms) * E * sizeof(float), s));
     // --- LM head
-    RC(linear_wgrad(pl.dlogits, V, pl.x_final, E, e->gf + e->fc_w, e->gf + e->fc_b, M, V, E, s));
+    RC(linear_wgrad(pl.dlogits, V, pl.x_final, E, e->gf + e->fc_w, e->gf + e->fc_b, M, V, E, s, side, e->bias_fork, &side_used));
     RC(linear_dgrad(pl.dlogits, V, e->ph + e->fc_w, V, E, dx, E, M, nullptr, 0, nullptr, 0, s));
     mark();
   }
@@ -400,7 +439,7 @@ int run_backward(b200_engine* e, bool have_dlogits, float* dmemory, void* const*
     RC(linear_wgrad(dz3, E, a.h, F, g + o.l2_w, nullptr, M, E, F, s));
     // h = dropout(relu(.)) is positive exactly where the unit is active AND kept
     RC(linear_dgrad(dz3, E, e->ph + o.l2_w, E, F, pl.dh, F, M, nullptr, 0, a.h, F, s, keep_scale));
-    RC(linear_wgrad(pl.dh, F, a.x2, E, g + o.l1_w, g + o.l1_b, M, F, E, s));
+    RC(linear_wgrad(pl.dh, F, a.x2, E, g + o.l1_w, g + o.l1_b, M, F, E, s, side, e->bias_fork, &side_used));
     bf16* dx2 = spare2;
     RC(linear_dgrad(pl.dh, F, e->ph + o.l1_w, F, E, dx2, E, M, dy3, E, nullptr, 0, s));
     // LN2
@@ -422,8 +461,8 @@ int run_backward(b200_engine* e, bool have_dlogits, float* dmemory, void* const*
     cg.dq = pl.dqc; cg.dq_bs = static_cast<long long>(T) * E; cg.dq_ts = E;
     cg.dk = pl.dkv; cg.dv = pl.dkv + E; cg.dk_bs = cg.dv_bs = static_cast<long long>(S) * 2 * E; cg.dk_ts = cg.dv_ts = 2 * E;
     RC(attn_bwd(ca, cg, s));
-    RC(linear_wgrad(pl.dqc, E, a.x1, E, g + o.ca_w, g + o.ca_b, M, E, E, s));
-    RC(linear_wgrad(pl.dkv, 2 * E, pl.memp, E, g + o.ca_w + static_cast<int64_t>(E) * E, g + o.ca_b + E, Ms, 2 * E, E, s));
+    RC(linear_wgrad(pl.dqc, E, a.x1, E, g + o.ca_w, g + o.ca_b, M, E, E, s, side, e->bias_fork, &side_used));
+    RC(linear_wgrad(pl.dkv, 2 * E, pl.memp, E, g + o.ca_w + static_cast<int64_t>(E) * E, g + o.ca_b + E, Ms, 2 * E, E, s, side, e->bias_fork, &side_used));
     if (need_dmemp) {
       GemmProblem gp;
       gp.M = Ms; gp.N = E; gp.K = 2 * E;
@@ -452,7 +491,7 @@ int run_backward(b200_engine* e, bool have_dlogits, float* dmemory, void* const*
     sg.dq = pl.dqkv; sg.dk = pl.dqkv + E; sg.dv = pl.dqkv + 2 * E;
     sg.dq_bs = sg.dk_bs = sg.dv_bs = static_cast<long long>(T) * 3 * E; sg.dq_ts = sg.dk_ts = sg.dv_ts = 3 * E;
     RC(attn_bwd(sa, sg, s));
-    RC(linear_wgrad(pl.dqkv, 3 * E, pl.xs[l], E, g + o.sa_w, g + o.sa_b, M, 3 * E, E, s));
+    RC(linear_wgrad(pl.dqkv, 3 * E, pl.xs[l], E, g + o.sa_w, g + o.sa_b, M, 3 * E, E, s, side, e->bias_fork, &side_used));
     bf16* dx_in = dx;     // dy2 is dead
     RC(linear_dgrad(pl.dqkv, 3 * E, e->ph + o.sa_w, 3 * E, E, dx_in, E, M, dy1, E, nullptr, 0, s));
     dx = dx_in;
@@ -462,7 +501,7 @@ int run_backward(b200_engine* e, bool have_dlogits, float* dmemory, void* const*
   RC(embed_bwd(e->last_tokens, dx, e->gf + e->emb, B, T, E, V, c.pad_idx, sqrtf(static_cast<float>(E)), s, site(0)));
   if (pl.mem_dim != E) {
     RC(cast_f32_to_bf16(pl.dmemp, pl.dmemp16, static_cast<long long>(Ms) * E, s));
-    RC(linear_wgrad(pl.dmemp16, E, pl.mem16, pl.mem_dim, e->gf + e->proj_w, e->gf + e->proj_b, Ms, E, pl.mem_dim, s));
+    RC(linear_wgrad(pl.dmemp16, E, pl.mem16, pl.mem_dim, e->gf + e->proj_w, e->gf + e->proj_b, Ms, E, pl.mem_dim, s, side, e->bias_fork, &side_used));
   } else if (dmemory) {
     B200_CHECK_CUDA(cudaMemcpyAsync(dmemory, pl.dmemp, static_cast<size_t>(Ms) * E * sizeof(float), cudaMemcpyDeviceToDevice, s));
   }
@@ -534,7 +573,7 @@ void build_decode_plan(const b200_engine* e, b200_engine::Decode* d, uint8_t* ba
     if (want > plane) want = plane;
     d->pf_bytes = want > 0 ? (want & ~static_cast<int64_t>(4095)) : 0;
     const char* fl_env = getenv("B200_DEC_KV_FLAGS");
-    d->kv_flags = fl_env ? (atoi(fl_env) & 7) : kDecKvFlags;
+    d->kv_flags = fl_env ? (atoi(fl_env) & 15) : kDecKvFlags;
   }
   // split-K of the LayerNorm-fed GEMMs: enough CTAs to cover the SMs
   const int rows_p = per * beam;
@@ -771,7 +810,7 @@ int with_parts(b200_engine* e, cudaStream_t s, Body body) {
 
 // the plan's tuning knobs, folded into the CUDA-graph cache keys (a sweep re-plans with different settings)
 uint64_t dec_tuning_key(const b200_engine::Decode& d) {
-  return static_cast<uint64_t>(d.pf_bytes) * 8ull + static_cast<uint64_t>(d.kv_flags) + (static_cast<uint64_t>(d.ksplit_e) << 40) +
+  return static_cast<uint64_t>(d.pf_bytes) * 16ull + static_cast<uint64_t>(d.kv_flags) + (static_cast<uint64_t>(d.ksplit_e) << 40) +
          (static_cast<uint64_t>(d.ksplit_f) << 46) + (static_cast<uint64_t>(d.single_cta ? 1 : 0) << 52) +
          (static_cast<uint64_t>(d.attn_fat_grid) << 53) + (static_cast<uint64_t>(d.use_att_stream ? 1 : 0) << 62) + (static_cast<uint64_t>(d.attn_dyn ? 1 : 0) << 61) ^
          (static_cast<uint64_t>(d.gemm_cap) * 0x9E3779B97F4A7C15ull);
@@ -881,6 +920,12 @@ void b200_engine_destroy(b200_engine* e) {
   if (e) {
     for (auto st : e->dec.side) cudaStreamDestroy(st);
     for (auto ev : e->dec.ev) cudaEventDestroy(ev);
+    for (auto ev : e->dec.evq) cudaEventDestroy(ev);
+    for (auto ev : e->dec.eva) cudaEventDestroy(ev);
+    if (e->dec.att_stream) cudaStreamDestroy(e->dec.att_stream);
+    if (e->bias_stream) cudaStreamDestroy(e->bias_stream);
+    if (e->bias_fork) cudaEventDestroy(e->bias_fork);
+    if (e->bias_join) cudaEventDestroy(e->bias_join);
   }
   delete e;
 }

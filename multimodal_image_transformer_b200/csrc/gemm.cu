@@ -42,6 +42,7 @@ struct GemmDev {
   int act;
   int aux_mode;   // 0 none, 1 residual add, 2 relu mask (tile fetched by TMA through tmap_aux)
   int b_evict_last;   // B tiles loaded with the L2 evict-last priority (CL == 1, K-major B)
+  int stage_drop;     // pipeline stages given up (frees shared memory for co-resident kernels of other streams)
   const long long* targets; long long ignore_index;
   float* part_max; float* part_sum; float* tgt_logit;
   const float* row_lse; const float* inv_count;
@@ -89,7 +90,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   constexpr uint32_t TMEM_COLS = ACC_STAGES * BLOCK_N;
   constexpr int NSH = BLOCK_N / CL;            // B rows (N) staged by this CTA
   const bool has_aux_smem = p.aux_mode != 0;
-  const int STAGES = L::stages(has_aux_smem);
+  const int STAGES = (L::stages(has_aux_smem) - p.stage_drop >= 2) ? L::stages(has_aux_smem) - p.stage_drop : 2;
 
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();   // 128-byte swizzle atoms need a 1024-byte aligned base
@@ -561,7 +562,10 @@ static int launch_instance(const CUtensorMap& ta, const CUtensorMap& tb, const C
                            const CUtensorMap& tx, const GemmDev& d, int grid, cudaStream_t stream) {
   auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, EPI, CL>;
   static bool configured = false;
-  const int smem = SmemLayout<BLOCK_N, CL>::total(d.aux_mode != 0);
+  using SL = SmemLayout<BLOCK_N, CL>;
+  const bool aux = d.aux_mode != 0;
+  const int n_stages = (SL::stages(aux) - d.stage_drop >= 2) ? SL::stages(aux) - d.stage_drop : 2;     // as in the kernel
+  const int smem = n_stages * SL::STAGE_BYTES + SL::epi_bytes(aux) + BAR_BYTES;
   if (!configured) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
     configured = true;
@@ -577,11 +581,14 @@ static int launch_instance(const CUtensorMap& ta, const CUtensorMap& tb, const C
 
 static thread_local int g_grid_cap = 0;
 static thread_local bool g_b_evict_last = false;
+static thread_local int g_stage_cap = 0;
 GemmGridCap::GemmGridCap(int max_ctas, bool b_evict_last) : prev_(g_grid_cap), prev_hint_(g_b_evict_last) {
   g_grid_cap = max_ctas > 0 ? max_ctas : 0;
   g_b_evict_last = b_evict_last;
 }
 GemmGridCap::~GemmGridCap() { g_grid_cap = prev_; g_b_evict_last = prev_hint_; }
+GemmStageCap::GemmStageCap(int drop) : prev_(g_stage_cap) { g_stage_cap = drop > 0 ? drop : 0; }
+GemmStageCap::~GemmStageCap() { g_stage_cap = prev_; }
 
 static double wave_eff(long long work, int sms) {
   long long waves = (work + sms - 1) / sms;
@@ -658,6 +665,7 @@ int gemm_launch(const GemmProblem& q, cudaStream_t stream, int* n_tiles_out) {
   d.bias = q.bias; d.residual = q.residual; d.ldr = q.ldr; d.relu_mask = q.relu_mask; d.ldm = q.ldm;
   d.act = q.act;
   d.b_evict_last = (q.b_evict_last || g_b_evict_last) ? 1 : 0;
+  d.stage_drop = g_stage_cap;
   d.targets = reinterpret_cast<const long long*>(q.targets); d.ignore_index = q.ignore_index;
   d.part_max = q.part_max; d.part_sum = q.part_sum; d.tgt_logit = q.tgt_logit;
   d.row_lse = q.row_lse; d.inv_count = q.inv_count;

@@ -53,6 +53,17 @@ struct GemmGridCap {
   int prev_;
   bool prev_hint_;
 };
+// Every GEMM launched by the calling thread while the guard lives gives up `drop` TMA pipeline stages (0 = as many
+// stages as fit): one stage less leaves 24-48 KB of shared memory for kernels of other streams to become resident
+// next to the persistent GEMM CTAs (the bias-gradient sums of the training backward).
+struct GemmStageCap {
+  explicit GemmStageCap(int drop);
+  ~GemmStageCap();
+  GemmStageCap(const GemmStageCap&) = delete;
+  GemmStageCap& operator=(const GemmStageCap&) = delete;
+ private:
+  int prev_;
+};
 int gemm_num_n_tiles(int N, int block_n);
 // number of non-empty K splits a launch with this (K, split_k) uses (= slabs written in partials mode)
 int gemm_effective_splits(int K, int split_k);

@@ -238,6 +238,18 @@ layernorm_reduce_fwd_kernel(const float* __restrict__ parts, int nsplit, long lo
       for (int j = 0; j < 8; ++j) sum += v[i][j];
     }
   }
+  // gamma / beta requested before the two warp reductions so that their latency hides behind them
+  float4 gq[NV][2], bq[NV][2];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      gq[i][0] = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+      gq[i][1] = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8) + 1);
+      bq[i][0] = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
+      bq[i][1] = __ldg(reinterpret_cast<const float4*>(beta + vi * 8) + 1);
+    }
+  }
   const float mu = warp_sum(sum) / E;
   float sq = 0.f;
 #pragma unroll
@@ -253,12 +265,8 @@ layernorm_reduce_fwd_kernel(const float* __restrict__ parts, int nsplit, long lo
   for (int i = 0; i < NV; ++i) {
     const int vi = lane + i * 32;
     if (vi < nvec) {
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8) + 1);
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8) + 1);
-      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      const float g[8] = {gq[i][0].x, gq[i][0].y, gq[i][0].z, gq[i][0].w, gq[i][1].x, gq[i][1].y, gq[i][1].z, gq[i][1].w};
+      const float b[8] = {bq[i][0].x, bq[i][0].y, bq[i][0].z, bq[i][0].w, bq[i][1].x, bq[i][1].y, bq[i][1].z, bq[i][1].w};
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mu) * rs * g[j] + b[j];
@@ -437,41 +445,53 @@ int layernorm_bwd(const bf16* dy, const bf16* x, const float* gamma, const float
 // ------------------------------------------------------------------------------------------
 // column sums (bias gradients): out[n] += sum_m x[m,n]
 // ------------------------------------------------------------------------------------------
+// No shared memory and <= 40 registers: the training backward runs these passes on a side stream, and a CTA
+// must fit next to a resident persistent GEMM CTA (which owns all but ~1 KB of the SM's shared memory).
+// Block = 256 columns x 256 rows: warp w owns the 64-column strip (w & 3) of row half (w >> 2); lane = 4 row
+// lanes x 8 column vectors (one full 128-byte line per row); the row lanes fold with two shuffles.
 __global__ void __launch_bounds__(256)
 colsum_kernel(const bf16* __restrict__ x, long long ldx, float* __restrict__ out, int M, int N) {
   pdl_wait();
   pdl_trigger();
-  __shared__ float red[8][256];
-  const int cv = threadIdx.x & 31;   // column vector within the block's 256-column strip
-  const int rl = threadIdx.x >> 5;   // row lane 0..7
-  const int col = blockIdx.x * 256 + cv * 8;
-  const int r0 = blockIdx.y * 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cv = lane & 7, rl = lane >> 3;
+  const int col = blockIdx.x * 256 + (warp & 3) * 64 + cv * 8;
+  const int r0 = blockIdx.y * 256 + (warp >> 2) * 128;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (col < N) {
     const int r1 = min(r0 + 128, M);
-    for (int r = r0 + rl; r < r1; r += 8) {
-      float f[8];
-      unpack8(ldg_nc_v4(x + static_cast<long long>(r) * ldx + col), f);
+    const bf16* base = x + col;
+    for (int r = r0 + rl; r < r1; r += 32) {       // eight 16-byte loads in flight per thread
+      uint4 u[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      for (int k = 0; k < 8; ++k) {
+        const int rr = r + 4 * k;
+        u[k] = (rr < r1) ? ldg_nc_v4(base + static_cast<long long>(rr) * ldx) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float f[8];
+        unpack8(u[k], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      }
     }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) red[rl][cv * 8 + j] = acc[j];
-  __syncthreads();
-  const int c = threadIdx.x;
-  if (blockIdx.x * 256 + c < N) {
-    float s = 0.f;
+  for (int j = 0; j < 8; ++j) {
+    acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
+    acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
+  }
+  if (rl == 0 && col < N) {
 #pragma unroll
-    for (int r = 0; r < 8; ++r) s += red[r][c];
-    atomicAdd(out + blockIdx.x * 256 + c, s);
+    for (int j = 0; j < 8; ++j) atomicAdd(out + col + j, acc[j]);
   }
 }
 
 int colsum(const bf16* x, long long ldx, float* out, int M, int N, cudaStream_t s) {
   B200_REQUIRE(N % 8 == 0 && ldx % 8 == 0, "colsum: N (%d) and ldx (%lld) must be multiples of 8", N, ldx);
   if (M == 0) return 0;
-  dim3 grid(cdiv(N, 256), cdiv(M, 128));
+  dim3 grid(cdiv(N, 256), cdiv(M, 256));
   B200_CHECK_CUDA(launch_kernel(colsum_kernel, grid, dim3(256), 0, s, true, 1, x, ldx, out, M, N));
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());

@@ -119,15 +119,32 @@ def _ignore_index(criterion) -> int:
     return int(getattr(criterion, "ignore_index", config.PAD_TOKEN_ID))
 
 
+_ZERO_STREAMS = {}
+
+
+def _zero_stream(device) -> "torch.cuda.Stream":
+    key = (device.type, device.index)
+    if key not in _ZERO_STREAMS:
+        _ZERO_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _ZERO_STREAMS[key]
+
+
 def fused_train_step(model, images, decoder_input_tokens, target_tokens, optimizer: B200AdamW, ignore_index: int,
                      grad_clip_value: float, dp: Optional[DataParallel] = None) -> torch.Tensor:
     """One optimisation step; returns the device tensor [loss, n_valid] (no host sync)."""
     decoder = model.decoder if hasattr(model, "decoder") else model
-    optimizer.zero_grad()
+    # the gradient arena is cleared on a side stream while the forward runs (the forward never touches it);
+    # fork / join through stream events, so the pattern is also valid under CUDA-graph capture
+    cur = torch.cuda.current_stream()
+    side = _zero_stream(cur.device)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        optimizer.zero_grad()
     if hasattr(model, "decoder"):
         out = model.loss(images, decoder_input_tokens, target_tokens, ignore_index, training=True)
     else:   # a bare decoder: `images` is the memory
         out = decoder.loss(decoder_input_tokens, target_tokens, images, None, ignore_index, training=True)
+    cur.wait_stream(side)
     if dp is not None and dp.world_size > 1:
         inv = dp.global_inv_count(out)                 # 1 / (non-PAD targets over all ranks)
         dp.backward_and_allreduce(inv)                 # bucketed all-reduce overlapped with backward

@@ -68,20 +68,26 @@ def main():
             for g in ((104,) if quick else (96, 104, 112, 120)):
                 for ast in (0, 1):
                     cfgs.append(dict(small, B200_DECODE_PARTS=parts, B200_DEC_ATTN_GRID=g, B200_DEC_ATTN_STREAM=ast))
-    # dynamic item scheduling of the cross attention, weights evict-last (flags bit 2)
-    best = dict(small, B200_DECODE_PARTS=4, B200_DEC_ATTN_GRID=104)
-    cfgs += [dict(best), dict(best, B200_DEC_ATTN_DYN=1), dict(best, B200_DEC_KV_FLAGS=7), dict(best, B200_DEC_ATTN_DYN=1, B200_DEC_KV_FLAGS=7),
-             dict(best, B200_DEC_ATTN_DYN=1, B200_DEC_KV_FLAGS=6), dict(best, B200_DEC_ATTN_DYN=1, B200_DEC_KV_FLAGS=0)]
-    cfgs += [dict(small, B200_DEC_ATTN_DYN=1), dict(small, B200_DEC_KV_FLAGS=7), dict(small, B200_DEC_ATTN_DYN=1, B200_DEC_KV_FLAGS=7)]
-    if not quick:
-        for parts in (2, 3, 4):
-            for g in (0, 88, 96, 104, 112, 120, 128):
-                c = dict(small, B200_DECODE_PARTS=parts, B200_DEC_ATTN_DYN=1)
-                if g:
-                    c["B200_DEC_ATTN_GRID"] = g
-                cfgs.append(c)
-                cfgs.append(dict(c, B200_DEC_KV_FLAGS=7))
-        cfgs += [dict(best, B200_DEC_ATTN_DYN=1, B200_DEC_ATTN_STREAM=1), dict(best, B200_DEC_ATTN_DYN=1, B200_DEC_ATTN_STREAM=1, B200_DEC_KV_FLAGS=7)]
+    if "--deep" in sys.argv:       # 3-deep rings in the fat-CTA attention (flags bit 3), SM budget, partitions
+        for parts in (4, 3, 2):
+            for g in (88, 96, 104, 112, 120):
+                for fl in (3, 11):
+                    cfgs.append({"B200_DECODE_PARTS": parts, "B200_DEC_ATTN_GRID": g, "B200_DEC_KV_FLAGS": fl})
+    if "--dyn" in sys.argv:
+        # dynamic item scheduling of the cross attention, weights evict-last (flags bit 2)
+        best = dict(small, B200_DECODE_PARTS=4, B200_DEC_ATTN_GRID=104)
+        cfgs += [dict(best), dict(best, B200_DEC_ATTN_DYN=1), dict(best, B200_DEC_KV_FLAGS=7), dict(best, B200_DEC_ATTN_DYN=1, B200_DEC_KV_FLAGS=7),
+                 dict(best, B200_DEC_ATTN_DYN=1, B200_DEC_KV_FLAGS=6), dict(best, B200_DEC_ATTN_DYN=1, B200_DEC_KV_FLAGS=0)]
+        cfgs += [dict(small, B200_DEC_ATTN_DYN=1), dict(small, B200_DEC_KV_FLAGS=7), dict(small, B200_DEC_ATTN_DYN=1, B200_DEC_KV_FLAGS=7)]
+        if not quick:
+            for parts in (2, 3, 4):
+                for g in (0, 88, 96, 104, 112, 120, 128):
+                    c = dict(small, B200_DECODE_PARTS=parts, B200_DEC_ATTN_DYN=1)
+                    if g:
+                        c["B200_DEC_ATTN_GRID"] = g
+                    cfgs.append(c)
+                    cfgs.append(dict(c, B200_DEC_KV_FLAGS=7))
+            cfgs += [dict(best, B200_DEC_ATTN_DYN=1, B200_DEC_ATTN_STREAM=1), dict(best, B200_DEC_ATTN_DYN=1, B200_DEC_ATTN_STREAM=1, B200_DEC_KV_FLAGS=7)]
     results = []
     for cfg in cfgs:
         try:
