@@ -477,3 +477,103 @@ def test_full_size_properties_cfg2(cuda_dev):
     perm = torch.randperm(c["B"], generator=torch.Generator().manual_seed(1))
     out_p = eng.forward_loss(tokd[perm], tgtd[perm], memd[perm], None, 0, training=False)
     assert abs(out_p[0].item() - loss) < 1e-5 * loss
+
+
+# ------------------------------------------------------------------ generation schedules / side streams
+_KNOBS = ("B200_DECODE_PARTS", "B200_DEC_ATTN_GRID", "B200_DEC_KV_FLAGS", "B200_DEC_ATTN_DYN", "B200_DEC_ATTN_STREAM",
+          "B200_DEC_PREFETCH_MB", "B200_DEC_SINGLE_CTA", "B200_DEC_KSPLIT_E", "B200_DEC_KSPLIT_F", "B200_DEC_GEMM_CTAS")
+
+
+@pytest.mark.parametrize("heads,beam", [(4, 1), (2, 1), (4, 3)])     # hd = 64 / 128: the tensor-core decode attention
+def test_decode_attention_schedules_are_equivalent(cuda_dev, heads, beam, monkeypatch):
+    """The cross-attention launch shapes of generation -- small CTAs on every SM, fat multi-unit CTAs on an SM
+    budget, 3-deep rings, 16-row tail boxes, eviction hints, L2 warm-up, dynamic item distribution, the dedicated
+    attention stream -- only move the same arithmetic around: token ids are identical to the plain schedule's."""
+    c = dict(V=1000, E=256, H=heads, L=2, F=512, ML=40, B=37, T=17, S=197)
+    p = O.init_params(c["V"], c["E"], c["H"], c["L"], c["F"], c["ML"], seed=5)
+    g = torch.Generator().manual_seed(6)
+    mem = torch.randn(c["B"], c["S"], c["E"], generator=g)
+    mpm = torch.zeros(c["B"], c["S"], dtype=torch.bool)
+    mpm[3, 150:] = True
+    eng = make_engine(c, p, cuda_dev)
+
+    def run(cfg):
+        for k in _KNOBS:
+            monkeypatch.delenv(k, raising=False)
+        for k, v in cfg.items():
+            monkeypatch.setenv(k, str(v))
+        outs = []
+        for rep in range(3):      # eager, capture, replay
+            eng.decode_begin(mem.to(cuda_dev), mpm.to(cuda_dev), beam=beam, max_len=10)
+            if beam == 1:
+                toks, lens = eng.generate_greedy(1, 2, 10, stop_check_interval=0)
+            else:
+                toks, lens, _ = eng.generate_beam(1, 2, 10)
+            outs.append((toks.cpu().clone(), lens.cpu().clone()))
+        for t, l in outs[1:]:
+            assert torch.equal(t, outs[0][0]) and torch.equal(l, outs[0][1]), cfg
+        return outs[0]
+
+    plain = {"B200_DECODE_PARTS": 1, "B200_DEC_KV_FLAGS": 0, "B200_DEC_SINGLE_CTA": 0}
+    base = run(plain)
+    variants = [
+        dict(plain, B200_DEC_KV_FLAGS=3),
+        dict(plain, B200_DEC_ATTN_GRID=7),                                        # fat CTAs, one partition
+        dict(plain, B200_DEC_ATTN_GRID=7, B200_DEC_KV_FLAGS=11),                 # + 3-deep rings (greedy, hd 64)
+        dict(plain, B200_DEC_ATTN_DYN=1),
+        dict(plain, B200_DEC_ATTN_GRID=5, B200_DEC_ATTN_DYN=1, B200_DEC_KV_FLAGS=2),
+        dict(plain, B200_DEC_PREFETCH_MB=1),
+        dict(plain, B200_DECODE_PARTS=3, B200_DEC_ATTN_GRID=9, B200_DEC_ATTN_STREAM=1),
+        dict(plain, B200_DECODE_PARTS=4, B200_DEC_ATTN_GRID=6, B200_DEC_ATTN_DYN=1, B200_DEC_ATTN_STREAM=1, B200_DEC_KV_FLAGS=15),
+        {},                                                                       # the shipped defaults
+    ]
+    for cfg in variants:
+        t, l = run(cfg)
+        assert torch.equal(t, base[0]) and torch.equal(l, base[1]), cfg
+
+
+def test_decode_plan_info_reports_the_schedule(cuda_dev, monkeypatch):
+    """b200_engine_decode_plan_info: greedy generation over a stream-heavy batch runs as four concurrent partitions
+    with the cross attention on 70 % of the SMs; beam search and small batches keep one partition."""
+    for k in _KNOBS:
+        monkeypatch.delenv(k, raising=False)
+    c = dict(V=264, E=768, H=12, L=1, F=256, ML=16, B=256, T=8, S=197)
+    p = O.init_params(c["V"], c["E"], c["H"], c["L"], c["F"], c["ML"], seed=3)
+    eng = make_engine(c, p, cuda_dev)
+    mem = torch.randn(c["B"], c["S"], c["E"], device=cuda_dev)
+    eng.decode_begin(mem, None, beam=1, max_len=8)
+    info = eng.decode_plan_info()
+    sms = torch.cuda.get_device_properties(cuda_dev).multi_processor_count
+    assert info["partitions"] == 4 and info["attention_sms"] == (sms * 70 + 50) // 100
+    assert info["gemm_grid_cap"] == sms - info["attention_sms"] and info["split_k_e"] == 2 and info["split_k_f"] == 1
+    toks, lens = eng.generate_greedy(1, 2, 8, 0)
+    assert toks.shape == (256, 8) and int(lens.min()) >= 1
+    eng.decode_begin(mem, None, beam=2, max_len=8)
+    assert eng.decode_plan_info()["partitions"] == 1
+    eng.decode_begin(mem[:8], None, beam=1, max_len=8)
+    info = eng.decode_plan_info()
+    assert info["partitions"] == 1 and info["attention_sms"] == 0 and info["gemm_grid_cap"] == 0
+
+
+@pytest.mark.parametrize("name", ["tiny", "cfg1"])
+def test_backward_bias_side_stream_matches_inline(cuda_dev, name, monkeypatch):
+    """The bias-gradient column sums run on a side stream next to the backward GEMMs (which give up a pipeline
+    stage); the gradients are those of the single-stream backward (atomics: equal up to summation order)."""
+    c, p, (tok, tgt, mem, _) = _case(name)
+    eng = make_engine(c, p, cuda_dev)
+    grads = []
+    for inline in (True, False, False):
+        if inline:
+            monkeypatch.setenv("B200_BIAS_INLINE", "1")
+        else:
+            monkeypatch.delenv("B200_BIAS_INLINE", raising=False)
+        eng.zero_grad()
+        eng.forward_loss(tok.to(cuda_dev), tgt.to(cuda_dev), mem.to(cuda_dev), None, 0, training=True)
+        eng.backward()
+        torch.cuda.synchronize()
+        grads.append(eng.grads.clone())
+    for g in grads[1:]:
+        assert rel_l2(g, grads[0]) < 1e-5
+        for k in ("fc_out.bias", "transformer_decoder.layers.0.linear1.bias", "transformer_decoder.layers.0.self_attn.in_proj_bias",
+                  "transformer_decoder.layers.1.multihead_attn.in_proj_bias"):
+            assert rel_l2(eng.view(k, g), eng.view(k, grads[0])) < 1e-5, k

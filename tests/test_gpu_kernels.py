@@ -142,12 +142,13 @@ def test_embedding_fwd_bwd(cuda_dev):
 
 def test_colsum_and_casts(cuda_dev):
     lib = L.lib()
-    M, N = 1000, 520
-    x = _rand((M, N), 1).bfloat16()
-    xd = x.to(cuda_dev)
-    out = torch.zeros(N, device=cuda_dev)
-    L.check(lib.b200_colsum(L.ptr(xd), N, L.ptr(out), M, N, L.cur_stream()))
-    assert rel_l2(out, x.float().sum(0)) < 1e-5
+    # ragged against the 256 x 256 block, the 64-column warp strips and the 4-row lanes; a strided view; accumulation
+    for M, N, ld in ((1000, 520, 520), (1, 8, 8), (257, 72, 72), (300, 264, 400), (12032, 768, 768)):
+        x = _rand((M, ld), 1 + M).bfloat16()
+        xd = x.to(cuda_dev)
+        out = torch.ones(N, device=cuda_dev)
+        L.check(lib.b200_colsum(L.ptr(xd), ld, L.ptr(out), M, N, L.cur_stream()))
+        assert rel_l2(out, 1.0 + x[:, :N].float().sum(0)) < 1e-5, (M, N, ld)
     f = _rand((1003,), 2).to(cuda_dev)
     h = torch.empty(1003, device=cuda_dev, dtype=torch.bfloat16)
     L.check(lib.b200_cast_f32_to_bf16(L.ptr(f), L.ptr(h), 1003, L.cur_stream()))
