@@ -611,8 +611,8 @@ attn_bwd_kernel(const AttnDev p) {
 //   step 2b  dS -> same smem;  dK[key tile] = dS^T Q  and  dQ[q-tile, half of hd] = dS K
 // 5 products instead of 7, 8 balanced warps, <= 128 registers, two CTAs per SM.
 // ------------------------------------------------------------------------------------------
-template <int HD, int NT, int MAXI>
-__global__ void __launch_bounds__(256, 2)
+template <int HD, int NT, int MAXI, int MINB, int NW>
+__global__ void __launch_bounds__(NW * 32, MINB)
 attn_bwd2_kernel(const AttnDev p) {
   pdl_wait();
   pdl_trigger();
@@ -651,7 +651,7 @@ attn_bwd2_kernel(const AttnDev p) {
   }
   cp_async_wait_all();
   __syncthreads();
-  for (int row = warp; row < p.TQP; row += 8) {
+  for (int row = warp; row < p.TQP; row += NW) {
     float acc = 0.f;
     for (int c = lane * 2; c < HD; c += 64) {
       const float2 a = unpack_bf16(*reinterpret_cast<const uint32_t*>(sPS + row * LD + c));
@@ -676,7 +676,7 @@ attn_bwd2_kernel(const AttnDev p) {
   for (int ii = 0; ii < MAXI; ++ii) {
 #pragma unroll
     for (int j = 0; j < NT; ++j) { pP[ii][j][0] = pP[ii][j][1] = 0u; pS[ii][j][0] = pS[ii][j][1] = 0u; }
-    const int item = warp + ii * 8;
+    const int item = warp + ii * NW;
     if (item < items) {
       const int mt = item / NB, kb = item % NB;
       const int row0 = mt * 16, key0 = kb * KB;
@@ -735,7 +735,7 @@ attn_bwd2_kernel(const AttnDev p) {
   auto stage = [&](const uint32_t (&src)[MAXI][NT][2]) {
 #pragma unroll
     for (int ii = 0; ii < MAXI; ++ii) {
-      const int item = warp + ii * 8;
+      const int item = warp + ii * NW;
       if (item < items) {
         const int mt = item / NB, kb = item % NB;
         const int row0 = mt * 16, key0 = kb * KB;
@@ -755,7 +755,7 @@ attn_bwd2_kernel(const AttnDev p) {
   stage(pP);
   __syncthreads();
   const int n_kt = p.TKP / 16;
-  for (int kt = warp; kt < n_kt; kt += 8) {
+  for (int kt = warp; kt < n_kt; kt += NW) {
     float acc[HD / 8][4];
 #pragma unroll
     for (int i = 0; i < HD / 8; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
@@ -788,7 +788,7 @@ attn_bwd2_kernel(const AttnDev p) {
   stage(pS);
   __syncthreads();
   const int n_dq = n_qt * 2;
-  for (int w = warp; w < n_dq + n_kt; w += 8) {
+  for (int w = warp; w < n_dq + n_kt; w += NW) {
     if (w < n_dq) {
       const int mt = w >> 1, half = w & 1;
       constexpr int NH = HD / 16;                  // n-tiles in one half of the head dim
@@ -907,7 +907,7 @@ static int launch_bwd(const AttnDev& d, cudaStream_t s) {
   return 0;
 }
 
-template <int HD, int NT, int MAXI>
+template <int HD, int NT, int MAXI, int MINB = 2, int NW = 8>
 static int launch_bwd2(const AttnDev& d, cudaStream_t s) {
   constexpr int LD = HD + 8;
   const int LDP = d.TKP + 8;
@@ -916,15 +916,18 @@ static int launch_bwd2(const AttnDev& d, cudaStream_t s) {
   B200_REQUIRE(smem <= 227 * 1024, "attention bwd: %zu B of shared memory needed (> 227 KB)", smem);
   static size_t configured = 48 * 1024;      // the default limit: never lower it
   if (smem > configured) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd2_kernel<HD, NT, MAXI>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    B200_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd2_kernel<HD, NT, MAXI, MINB, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = smem;
   }
-  B200_CHECK_CUDA(launch_kernel(attn_bwd2_kernel<HD, NT, MAXI>, dim3(d.H, d.B), dim3(256), smem, s, true, 1, d));
+  B200_CHECK_CUDA(launch_kernel(attn_bwd2_kernel<HD, NT, MAXI, MINB, NW>, dim3(d.H, d.B), dim3(NW * 32), smem, s, true, 1, d));
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
+static constexpr int kBwdShortMinB = 4;   // CTAs per SM the short-key staged backward is compiled for; B200_ATTN_BWD_MINB overrides
+// (long keys: 12 / 16 warps per CTA at 80 / 64 registers measured 188 / 178 us against 174 us for 8 warps at cfg2's
+// cross attention -- two CTAs per SM by shared memory either way, and the phases are not warp-count bound)
 // staged backward when its register-held work items fit (<= 8 warps x MAXI), else the two-phase one
 template <int HD>
 static int dispatch_bwd(const AttnDev& d, cudaStream_t s, int nt_fallback) {
@@ -937,6 +940,13 @@ static int dispatch_bwd(const AttnDev& d, cudaStream_t s, int nt_fallback) {
       if (items <= 24) return launch_bwd2<HD, 6, 3>(d, s);
     } else {
       const int items = n_qt * (d.TKP / 16);
+      if (items <= 16 && HD <= 64) {
+        // short keys (self attention of a caption): little shared memory, so the register cap decides how many
+        // CTAs share an SM; 3 fit without spills (80 registers), 4 with a few spilled words
+        static const int minb = getenv("B200_ATTN_BWD_MINB") ? atoi(getenv("B200_ATTN_BWD_MINB")) : kBwdShortMinB;
+        if (minb == 3) return launch_bwd2<HD, 2, 2, 3>(d, s);
+        if (minb == 4) return launch_bwd2<HD, 2, 2, 4>(d, s);
+      }
       if (items <= 16) return launch_bwd2<HD, 2, 2>(d, s);
       if (items <= 24) return launch_bwd2<HD, 2, 3>(d, s);
       const int items48 = n_qt * ((d.TKP + 47) / 48);
