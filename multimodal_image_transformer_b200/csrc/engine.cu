@@ -403,10 +403,15 @@ int run_backward(b200_engine* e, bool have_dlogits, float* dmemory, void* const*
     }
   };
   struct Joiner { decltype(join_side)& j; ~Joiner() { j(); } } joiner{join_side};
+  // Joins: (1) before a gradient-bucket event is recorded (data-parallel runs consume the bucket's bias gradients
+  // behind it), (2) in every layer right before the FFN dgrad rewrites pl.dh, the first buffer a pending sum of
+  // the previous layer may still be reading (by then those sums are long done: the wait is free), (3) at the end.
   int ev = 0;
   auto mark = [&](void) {
-    join_side();
-    if (events && ev < n_events && events[ev]) cudaEventRecord(static_cast<cudaEvent_t>(events[ev]), s);
+    if (events && ev < n_events && events[ev]) {
+      join_side();
+      cudaEventRecord(static_cast<cudaEvent_t>(events[ev]), s);
+    }
     ++ev;
   };
 
@@ -438,6 +443,7 @@ int run_backward(b200_engine* e, bool have_dlogits, float* dmemory, void* const*
     // FFN (linear2's bias gradient = column sums of dz3, produced by the LayerNorm backward above)
     RC(linear_wgrad(dz3, E, a.h, F, g + o.l2_w, nullptr, M, E, F, s));
     // h = dropout(relu(.)) is positive exactly where the unit is active AND kept
+    join_side();
     RC(linear_dgrad(dz3, E, e->ph + o.l2_w, E, F, pl.dh, F, M, nullptr, 0, a.h, F, s, keep_scale));
     RC(linear_wgrad(pl.dh, F, a.x2, E, g + o.l1_w, g + o.l1_b, M, F, E, s, side, e->bias_fork, &side_used));
     bf16* dx2 = spare2;

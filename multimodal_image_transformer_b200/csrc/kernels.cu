@@ -447,8 +447,9 @@ int layernorm_bwd(const bf16* dy, const bf16* x, const float* gamma, const float
 // ------------------------------------------------------------------------------------------
 // No shared memory and <= 40 registers: the training backward runs these passes on a side stream, and a CTA
 // must fit next to a resident persistent GEMM CTA (which owns all but ~1 KB of the SM's shared memory).
-// Block = 256 columns x 256 rows: warp w owns the 64-column strip (w & 3) of row half (w >> 2); lane = 4 row
-// lanes x 8 column vectors (one full 128-byte line per row); the row lanes fold with two shuffles.
+// Block = 256 columns x 64 rows: warp w owns the 64-column strip (w & 3) of row half (w >> 2); lane = 4 row
+// lanes x 8 column vectors (one full 128-byte line per row); every thread has its eight 16-byte loads in flight
+// at once, the row lanes fold with two shuffles, one atomic per column and warp.
 __global__ void __launch_bounds__(256)
 colsum_kernel(const bf16* __restrict__ x, long long ldx, float* __restrict__ out, int M, int N) {
   pdl_wait();
@@ -456,25 +457,22 @@ colsum_kernel(const bf16* __restrict__ x, long long ldx, float* __restrict__ out
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cv = lane & 7, rl = lane >> 3;
   const int col = blockIdx.x * 256 + (warp & 3) * 64 + cv * 8;
-  const int r0 = blockIdx.y * 256 + (warp >> 2) * 128;
+  const int r0 = blockIdx.y * 64 + (warp >> 2) * 32 + rl;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (col < N) {
-    const int r1 = min(r0 + 128, M);
     const bf16* base = x + col;
-    for (int r = r0 + rl; r < r1; r += 32) {       // eight 16-byte loads in flight per thread
-      uint4 u[8];
+    uint4 u[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int rr = r + 4 * k;
-        u[k] = (rr < r1) ? ldg_nc_v4(base + static_cast<long long>(rr) * ldx) : make_uint4(0u, 0u, 0u, 0u);
-      }
+    for (int k = 0; k < 8; ++k) {
+      const int rr = r0 + 4 * k;
+      u[k] = (rr < M) ? ldg_nc_v4(base + static_cast<long long>(rr) * ldx) : make_uint4(0u, 0u, 0u, 0u);
+    }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float f[8];
-        unpack8(u[k], f);
+    for (int k = 0; k < 8; ++k) {
+      float f[8];
+      unpack8(u[k], f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += f[j];
-      }
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
     }
   }
 #pragma unroll
@@ -491,7 +489,7 @@ colsum_kernel(const bf16* __restrict__ x, long long ldx, float* __restrict__ out
 int colsum(const bf16* x, long long ldx, float* out, int M, int N, cudaStream_t s) {
   B200_REQUIRE(N % 8 == 0 && ldx % 8 == 0, "colsum: N (%d) and ldx (%lld) must be multiples of 8", N, ldx);
   if (M == 0) return 0;
-  dim3 grid(cdiv(N, 256), cdiv(M, 256));
+  dim3 grid(cdiv(N, 256), cdiv(M, 64));
   B200_CHECK_CUDA(launch_kernel(colsum_kernel, grid, dim3(256), 0, s, true, 1, x, ldx, out, M, N));
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
