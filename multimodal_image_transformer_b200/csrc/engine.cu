@@ -960,6 +960,19 @@ int b200_engine_bind(b200_engine* e, float* params_f32, void* params_bf16, float
   B200_REQUIRE((reinterpret_cast<uintptr_t>(params_f32) & 255) == 0 && (reinterpret_cast<uintptr_t>(params_bf16) & 255) == 0 &&
                (reinterpret_cast<uintptr_t>(grads_f32) & 255) == 0, "engine_bind: arenas must be 256-byte aligned");
   e->pf = params_f32; e->ph = static_cast<bf16*>(params_bf16); e->gf = grads_f32; e->pe = pe_f32;
+  // the backward's side stream and its fork / join events are made here, on the device that owns the arenas and
+  // outside any stream capture (a first training step may already be captured into a CUDA graph)
+  if (grads_f32) {
+    cudaPointerAttributes at;
+    int dev = -1, cur = -1;
+    if (cudaPointerGetAttributes(&at, grads_f32) == cudaSuccess && at.type == cudaMemoryTypeDevice) dev = at.device;
+    cudaGetDevice(&cur);
+    if (dev >= 0 && dev != cur) cudaSetDevice(dev);
+    if (!e->bias_stream) B200_CHECK_CUDA(cudaStreamCreateWithFlags(&e->bias_stream, cudaStreamNonBlocking));
+    if (!e->bias_fork) B200_CHECK_CUDA(cudaEventCreateWithFlags(&e->bias_fork, cudaEventDisableTiming));
+    if (!e->bias_join) B200_CHECK_CUDA(cudaEventCreateWithFlags(&e->bias_join, cudaEventDisableTiming));
+    if (dev >= 0 && dev != cur) cudaSetDevice(cur);
+  }
   return 0;
 }
 

@@ -185,6 +185,7 @@ class GraphedTrainStep:
             if eng._lr_host != lr:
                 eng._lr_dev.fill_(lr)
                 eng._lr_host = lr
+            _zero_stream(torch.cuda.current_stream().device)   # made outside the capture
             torch.cuda.synchronize()
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
