@@ -445,52 +445,63 @@ int layernorm_bwd(const bf16* dy, const bf16* x, const float* gamma, const float
 // ------------------------------------------------------------------------------------------
 // column sums (bias gradients): out[n] += sum_m x[m,n]
 // ------------------------------------------------------------------------------------------
-// No shared memory and <= 40 registers: the training backward runs these passes on a side stream, and a CTA
-// must fit next to a resident persistent GEMM CTA (which owns all but ~1 KB of the SM's shared memory).
-// Block = 256 columns x 64 rows: warp w owns the 64-column strip (w & 3) of row half (w >> 2); lane = 4 row
-// lanes x 8 column vectors (one full 128-byte line per row); every thread has its eight 16-byte loads in flight
-// at once, the row lanes fold with two shuffles, one atomic per column and warp.
+// The training backward runs these passes on a side stream next to the persistent GEMM CTAs, which give up one
+// TMA stage for them (24-48 KB): 8 KB of shared memory and <= 40 registers per thread fit beside a GEMM CTA.
+// Block = 256 columns x `rows_per_cta` rows (a multiple of 64): warp = row lane, its 32 lanes cover one 512-byte row
+// segment; eight 16-byte loads in flight per thread; the eight row lanes fold through shared memory and every
+// column gets ONE atomic per CTA.  Same-address atomics serialise in L2 (a 50432-row matrix summed in 64-row
+// blocks spent 160 us on 1576 atomics per column), so the host sizes the row extent for ~3 CTAs per SM.
 __global__ void __launch_bounds__(256)
-colsum_kernel(const bf16* __restrict__ x, long long ldx, float* __restrict__ out, int M, int N) {
+colsum_kernel(const bf16* __restrict__ x, long long ldx, float* __restrict__ out, int M, int N, int rows_per_cta) {
   pdl_wait();
   pdl_trigger();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cv = lane & 7, rl = lane >> 3;
-  const int col = blockIdx.x * 256 + (warp & 3) * 64 + cv * 8;
-  const int r0 = blockIdx.y * 64 + (warp >> 2) * 32 + rl;
+  __shared__ float red[8][256];
+  const int cv = threadIdx.x & 31;   // column vector within the block's 256-column strip
+  const int rl = threadIdx.x >> 5;   // row lane 0..7
+  const int col = blockIdx.x * 256 + cv * 8;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (col < N) {
     const bf16* base = x + col;
-    uint4 u[8];
+    const int r_begin = blockIdx.y * rows_per_cta;
+    const int r_end = min(r_begin + rows_per_cta, M);
+    for (int r0 = r_begin + rl; r0 < r_end; r0 += 64) {
+      uint4 u[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int rr = r0 + 4 * k;
-      u[k] = (rr < M) ? ldg_nc_v4(base + static_cast<long long>(rr) * ldx) : make_uint4(0u, 0u, 0u, 0u);
-    }
+      for (int k = 0; k < 8; ++k) {
+        const int rr = r0 + 8 * k;
+        u[k] = (rr < r_end) ? ldg_nc_v4(base + static_cast<long long>(rr) * ldx) : make_uint4(0u, 0u, 0u, 0u);
+      }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float f[8];
-      unpack8(u[k], f);
+      for (int k = 0; k < 8; ++k) {
+        float f[8];
+        unpack8(u[k], f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      }
     }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
-    acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
-  }
-  if (rl == 0 && col < N) {
+  for (int j = 0; j < 8; ++j) red[rl][cv * 8 + j] = acc[j];
+  __syncthreads();
+  const int c = threadIdx.x;
+  if (blockIdx.x * 256 + c < N) {
+    float sum = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(out + col + j, acc[j]);
+    for (int r = 0; r < 8; ++r) sum += red[r][c];
+    atomicAdd(out + blockIdx.x * 256 + c, sum);
   }
 }
 
 int colsum(const bf16* x, long long ldx, float* out, int M, int N, cudaStream_t s) {
   B200_REQUIRE(N % 8 == 0 && ldx % 8 == 0, "colsum: N (%d) and ldx (%lld) must be multiples of 8", N, ldx);
   if (M == 0) return 0;
-  dim3 grid(cdiv(N, 256), cdiv(M, 64));
-  B200_CHECK_CUDA(launch_kernel(colsum_kernel, grid, dim3(256), 0, s, true, 1, x, ldx, out, M, N));
+  const int col_blocks = cdiv(N, 256);
+  // ~3 CTAs per SM over the whole grid, in whole 64-row slabs
+  const int want_row_blocks = max(1, (3 * 148) / col_blocks);
+  int rows_per_cta = cdiv(cdiv(M, want_row_blocks), 64) * 64;
+  if (rows_per_cta < 64) rows_per_cta = 64;
+  dim3 grid(col_blocks, cdiv(M, rows_per_cta));
+  B200_CHECK_CUDA(launch_kernel(colsum_kernel, grid, dim3(256), 0, s, true, 1, x, ldx, out, M, N, rows_per_cta));
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
