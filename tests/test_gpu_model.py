@@ -119,3 +119,29 @@ def test_bf16_memory_and_feature_cache(cuda_dev):
     l_cached = m.loss(None, tok, tgt, memory=a, training=False)[0].item()
     l_direct = m.loss(images, tok, tgt, training=False)[0].item()
     assert abs(l_cached - l_direct) < 2e-3 * l_direct
+
+
+def test_train_one_epoch_and_evaluate_loops_vs_reference(cuda_dev):
+    """train.train_one_epoch / train.evaluate (reference train.py:62-151) driven with the reference's batch dicts
+    (dataset.collate_fn keys): evaluate returns the golden loss, one epoch of three identical batches returns the mean
+    of the golden 3-step trajectory -- with the fused optimizer and with a stock torch.optim.AdamW through logits."""
+    from multimodal_image_transformer_b200.train import B200AdamW, evaluate, train_one_epoch
+    g = torch.load(GOLDEN, weights_only=True)
+    crit = torch.nn.CrossEntropyLoss(ignore_index=0)
+    batch = {"images": _images(g), "decoder_input_tokens": g["tokens"], "target_tokens": g["targets"], "image_paths": ["-"] * g["config"]["B"]}
+    loader = [batch, batch, batch]
+    want = sum(g["train_losses"]) / 3
+    m = _build(cuda_dev, g)
+    assert abs(evaluate(m, [batch], crit, cuda_dev) - g["loss"]) < 1e-3 * g["loss"]
+    opt = B200AdamW(m, lr=1e-4, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-5)
+    got = train_one_epoch(m, loader, opt, crit, cuda_dev, 5.0, None, 0, 50, None)
+    assert abs(got - want) < 2e-3 * want, (got, want)
+    assert m.training                                      # the loop leaves the model in train mode, like the reference
+    # the reference's own optimizer type: forward -> logits -> criterion -> backward -> clip -> step
+    m2 = _build(cuda_dev, g)
+    opt2 = torch.optim.AdamW([p for p in m2.parameters() if p.requires_grad], lr=1e-4, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-5)
+    got2 = train_one_epoch(m2, loader, opt2, crit, cuda_dev, 5.0, None, 0, 50, None)
+    assert abs(got2 - want) < 2e-3 * want, (got2, want)
+    # after three steps both optimizers have moved the evaluation loss the same way
+    e1, e2 = evaluate(m, [batch], crit, cuda_dev), evaluate(m2, [batch], crit, cuda_dev)
+    assert e1 < g["loss"] and abs(e1 - e2) < 2e-3 * e1, (e1, e2, g["loss"])
