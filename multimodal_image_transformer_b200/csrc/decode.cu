@@ -60,9 +60,9 @@ struct DecAttnArgs {
   const unsigned char* key_pad;     // [groups][nkeys] or null
   float scale;
   // optional L2 warm-up for the NEXT cross-attention launch (the following layer's K / V planes): the
-  // producer warp, once its own stream is issued, requests the first pf_bytes of each plane into L2.
-  // Between two cross-attention launches HBM is nearly idle (a chain of ~10 small launches), so the
-  // head of the next stream is fetched in that shadow.  Hint only: results do not depend on it.
+  // producer warp, once its own stream is issued, requests the first pf_bytes of each plane into L2
+  // (cp.async.bulk.prefetch.L2).  Hint only: results do not depend on it.  Measured on B200: no gain at any
+  // size (the requests queue in front of the launch chain's own weight loads), so the engine leaves it off.
   const bf16* pf_k; const bf16* pf_v; long long pf_bytes;
   int stream_evict_first;           // 1: the K/V stream is loaded with the L2 evict-first priority (read once)
   int tail16;                       // 1: a last chunk of < 64 keys is fetched as 16-row boxes

@@ -19,16 +19,16 @@ using namespace b200;
 
 namespace {
 
-// Default size (MB over K and V together) of the L2 warm-up of the next layer's cross K/V stream during
-// generation; B200_DEC_PREFETCH_MB overrides.  0 = off.
-// TMA pipeline stages the backward GEMMs give up so that the bias-gradient sums fit next to them
-constexpr int kBwdStageDrop = 1;
-constexpr double kDecPrefetchMB = 0.0;
-constexpr bool kDecSingleCta = true;    // skinny generation GEMMs as unpaired CTAs (no cluster start-up); B200_DEC_SINGLE_CTA overrides
-constexpr bool kDecAttnDyn = false;         // dynamically scheduled cross attention; B200_DEC_ATTN_DYN overrides
-constexpr bool kDecAttnStream = false;      // cross attention of all partitions on one stream; B200_DEC_ATTN_STREAM overrides
-constexpr int kDecFatGridPct = 70;          // % of the SMs given to the cross-attention stream when partitions run concurrently (104 of 148); B200_DEC_ATTN_GRID overrides
-constexpr int kDecKvFlags = 11;          // attn_decode flags (decode.cuh); B200_DEC_KV_FLAGS overrides
+// ---- measured defaults (B200, BASELINE cfg2 / cfg4 shapes; profiles/r01_decode_sweeps.txt, DESIGN.md sections 3.3 and 5);
+// ---- every one has an environment override, listed in INTEGRATION.md
+constexpr int kBwdStageDrop = 1;         // TMA stages the backward GEMMs give up so that the bias-gradient sums fit next to them (B200_BWD_STAGE_DROP)
+constexpr bool kDecSingleCta = true;     // skinny generation GEMMs as unpaired CTAs: no cluster start-up (B200_DEC_SINGLE_CTA)
+constexpr int kDecFatGridPct = 70;       // % of the SMs given to the cross-attention stream when partitions run concurrently: 104 of 148 (B200_DEC_ATTN_GRID)
+constexpr int kDecKvFlags = 11;          // attn_decode flags, decode.cuh: K/V evict-first + 16-row tail boxes + 3-deep rings (B200_DEC_KV_FLAGS)
+// measured negative, kept switchable for the next round's re-measurement:
+constexpr double kDecPrefetchMB = 0.0;   // MB (K + V) of the next layer's cross K/V warmed into L2 by the attention producer (B200_DEC_PREFETCH_MB)
+constexpr bool kDecAttnDyn = false;      // atomic work counter for the attention items (B200_DEC_ATTN_DYN)
+constexpr bool kDecAttnStream = false;   // cross attention of all partitions on one dedicated stream (B200_DEC_ATTN_STREAM)
 
 struct ParamInfo {
   std::string name;

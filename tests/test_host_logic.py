@@ -51,3 +51,18 @@ def test_no_cpu_fallback():
         from multimodal_image_transformer_b200.decoder import TransformerDecoder
         with pytest.raises(Exception):
             TransformerDecoder(264, 64, 2, 2, 128, 40, dropout=0.0)
+
+
+def test_every_tuning_switch_is_documented():
+    """Every B200_* environment variable the CUDA sources read appears in INTEGRATION.md's table of switches."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csrc = os.path.join(root, "multimodal_image_transformer_b200", "csrc")
+    names = set()
+    for fn in os.listdir(csrc):
+        if fn.endswith((".cu", ".cuh")):
+            names |= set(re.findall(r'getenv\("(B200_[A-Z0-9_]+)"\)', open(os.path.join(csrc, fn)).read()))
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    missing = sorted(n for n in names if n not in doc)
+    assert names and not missing, missing
