@@ -115,6 +115,64 @@ def trim_batch(decoder_input_tokens: torch.Tensor, target_tokens: torch.Tensor, 
     return decoder_input_tokens[:, :n], target_tokens[:, :n]
 
 
+def caption_lengths(tokens: torch.Tensor, pad_idx: int) -> torch.Tensor:
+    """Number of columns up to and including the last non-PAD token of every row of a padded caption matrix
+    (what tokenizer.py:293-313 produces: every caption padded / truncated to MAX_SEQ_LEN)."""
+    live = tokens != pad_idx
+    pos = torch.arange(1, tokens.shape[1] + 1, device=tokens.device)
+    return (live * pos).amax(dim=1)
+
+
+class LengthBucketBatchSampler:
+    """`batch_sampler` for `torch.utils.data.DataLoader` (reference train.py:282-289 uses shuffle=True over captions
+    that are all padded to MAX_SEQ_LEN): every epoch the indices are shuffled, cut into pools of `pool_batches`
+    batches, sorted by caption length inside a pool and cut into batches, whose order is shuffled again.  The
+    samples of a batch then have similar lengths, so `trim_batch` removes most of the PAD columns the random
+    batches of the reference would keep (a batch is as wide as its longest caption) -- same samples per epoch, same
+    loss definition, a fraction of the decoder work.  With `world_size` > 1 every rank takes the batches
+    `rank, rank + world_size, ...` of the same seeded order (the data-parallel step reduces over ranks, so the
+    ranks of a step should see similar widths: consecutive batches of a pool are given to consecutive ranks)."""
+
+    def __init__(self, lengths, batch_size: int, pool_batches: int = 50, shuffle: bool = True, seed: int = 0,
+                 drop_last: bool = False, rank: int = 0, world_size: int = 1):
+        self.lengths = torch.as_tensor(lengths).to(torch.int64).cpu()
+        assert self.lengths.dim() == 1 and batch_size >= 1 and pool_batches >= 1 and 0 <= rank < world_size
+        self.batch_size, self.pool_batches, self.shuffle, self.seed = batch_size, pool_batches, shuffle, seed
+        self.drop_last, self.rank, self.world_size = drop_last, rank, world_size
+        self.epoch = 0
+
+    def set_epoch(self, epoch: int) -> None:
+        self.epoch = epoch
+
+    def _batches(self):
+        n = self.lengths.numel()
+        g = torch.Generator().manual_seed(self.seed + self.epoch)
+        order = torch.randperm(n, generator=g) if self.shuffle else torch.arange(n)
+        pool = self.batch_size * self.pool_batches * self.world_size
+        batches = []
+        for p0 in range(0, n, pool):
+            idx = order[p0:p0 + pool]
+            idx = idx[torch.argsort(self.lengths[idx], stable=True)]
+            chunk = [idx[i:i + self.batch_size] for i in range(0, idx.numel(), self.batch_size)]
+            if chunk and chunk[-1].numel() < self.batch_size and self.drop_last:
+                chunk.pop()
+            # keep groups of world_size consecutive (similar-length) batches together, shuffle the groups
+            groups = [chunk[i:i + self.world_size] for i in range(0, len(chunk), self.world_size)]
+            if self.shuffle and len(groups) > 1:
+                perm = torch.randperm(len(groups), generator=g).tolist()
+                groups = [groups[i] for i in perm]
+            for grp in groups:
+                batches.extend(grp)
+        usable = len(batches) - len(batches) % self.world_size     # every rank runs the same number of steps
+        return [b.tolist() for b in batches[:usable][self.rank::self.world_size]] if self.world_size > 1 else [b.tolist() for b in batches]
+
+    def __iter__(self):
+        return iter(self._batches())
+
+    def __len__(self) -> int:
+        return len(self._batches())
+
+
 def _ignore_index(criterion) -> int:
     return int(getattr(criterion, "ignore_index", config.PAD_TOKEN_ID))
 
