@@ -102,3 +102,42 @@ def test_length_bucket_sampler_covers_the_epoch_and_cuts_padding():
     widths = [(max(lens[x].tolist()), max(lens[y].tolist())) for x, y in zip(*shards)]
     diffs = sorted(abs(p - q) for p, q in widths)
     assert diffs[len(diffs) // 2] <= 3, widths               # median gap (the 99-token outliers land in one batch per pool)
+
+
+def test_config_constants_follow_the_reference():
+    """config.py keeps the reference's names and values for everything the hot path reads (reference config.py:10-145);
+    checked against the live reference when it is mounted, against the values recorded here otherwise."""
+    import importlib.util
+    import os
+    from multimodal_image_transformer_b200 import config as ours
+    expect = dict(RANDOM_SEED=42, VOCAB_SIZE=10000, MAX_SEQ_LEN=100, DECODER_EMBED_DIM=512, DECODER_LAYERS=6, DECODER_HEADS=8,
+                  DECODER_FF_DIM=2048, DECODER_DROPOUT=0.1, LEARNING_RATE=1e-4, WEIGHT_DECAY=1e-5, GRAD_CLIP_VALUE=5.0,
+                  ADAM_BETA1=0.9, ADAM_BETA2=0.98, ADAM_EPS=1e-9, LOG_INTERVAL=50, PAD_TOKEN_ID=0, START_TOKEN_ID=1,
+                  END_TOKEN_ID=2, UNK_TOKEN_ID=3, PAD_TOKEN="<PAD>", START_TOKEN="<START>", END_TOKEN="<END>", UNK_TOKEN="<UNK>")
+    for k, v in expect.items():
+        assert getattr(ours, k) == v, k
+    ref_path = "/root/reference/config.py"
+    if os.path.exists(ref_path):
+        spec = importlib.util.spec_from_file_location("_ref_config", ref_path)
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+        for k in expect:
+            if hasattr(ref, k):
+                assert getattr(ref, k) == getattr(ours, k), (k, getattr(ref, k), getattr(ours, k))
+
+
+def test_trim_batch_on_the_host():
+    """trim_batch keeps every live column (rounded up to the multiple), never more than the input width, at least one."""
+    from multimodal_image_transformer_b200.train import trim_batch
+    tok = torch.zeros(4, 100, dtype=torch.int64)
+    tgt = torch.zeros(4, 100, dtype=torch.int64)
+    tok[0, :19] = 5
+    tgt[1, :21] = 7                       # the target side can be the longer one (shifted by one position)
+    a, b = trim_batch(tok, tgt, 0)
+    assert a.shape == b.shape == (4, 24) and torch.equal(a, tok[:, :24]) and torch.equal(b, tgt[:, :24])
+    a, b = trim_batch(tok, tgt, 0, multiple=1)
+    assert a.shape[1] == 21
+    tok[2, 99] = 3
+    assert trim_batch(tok, tgt, 0)[0].shape[1] == 100
+    z = torch.zeros(2, 16, dtype=torch.int64)
+    assert trim_batch(z, z, 0)[0].shape[1] == 8           # all PAD: one (rounded) column block survives
