@@ -2,7 +2,7 @@
 (decoder.TransformerDecoder, nn.CrossEntropyLoss, clip_grad_norm_, torch.optim.AdamW and the greedy
 loop of model.py:216-242) on seeded synthetic inputs.  Run in the build container only:
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [case ...]        (default: every case)
 
 The reference cannot travel to the GPU box, the fixtures do.  Weights are NOT stored: they are
 reproduced from the seed by oracle.decoder_oracle.init_params, which constructs the same torch.nn
@@ -25,6 +25,8 @@ CASES = {
     # name: V, E, H, L, F, max_len, B, T, S, full (store everything) or subsampled
     "nano": dict(V=264, E=64, H=2, L=2, F=128, ML=40, B=3, T=17, S=13, full=True),
     "cfg1": dict(V=10000, E=512, H=8, L=4, F=2048, ML=100, B=8, T=31, S=50, full=False),
+    # BASELINE configs[1] decoder (the headline shape: ViT-B/16 features 197 x 768, 6 layers, d = 768, 12 heads) at batch 4
+    "cfg2": dict(V=10000, E=768, H=12, L=6, F=3072, ML=100, B=4, T=47, S=197, full=False),
 }
 
 
@@ -47,7 +49,8 @@ def synth(c, seed):
 
 def main():
     torch.set_num_threads(8)
-    for name, c in CASES.items():
+    for name in (sys.argv[1:] or list(CASES)):
+        c = CASES[name]
         seed = 42
         torch.manual_seed(seed)
         model = refdec.TransformerDecoder(c["V"], c["E"], c["H"], c["L"], c["F"], c["ML"], dropout=0.0, pad_idx=0)

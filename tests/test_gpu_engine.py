@@ -56,7 +56,7 @@ def test_forward_logits_and_loss_vs_oracle(cuda_dev, name):
     assert lg[1].item() == (tgt != 0).sum().item()
 
 
-@pytest.mark.parametrize("name", ["nano", "cfg1"])
+@pytest.mark.parametrize("name", ["nano", "cfg1", "cfg2"])
 def test_forward_vs_reference_golden(cuda_dev, name):
     g = load_golden(name)
     c = g["config"]
@@ -293,6 +293,8 @@ def test_dropin_module_state_dict_and_autograd(cuda_dev):
 
 def test_greedy_vs_reference_golden_and_oracle(cuda_dev):
     from multimodal_image_transformer_b200.decoder import TransformerDecoder  # noqa: F401
+    # (the cfg2 golden is not used here: with random-init weights its four 12-token captions contain a bf16 near-tie
+    # of the arg-max; the forward / loss test above pins that shape)
     for name in ("nano", "cfg1"):
         g = load_golden(name)
         c = g["config"]
