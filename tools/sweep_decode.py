@@ -4,7 +4,7 @@ fraction of token ids identical to the default setting's (hints must not change 
 
   python tools/sweep_decode.py [--beam 4] [--quick]
 """
-import itertools, json, os, sys, time
+import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from multimodal_image_transformer_b200.engine import DecoderEngine
