@@ -2,7 +2,11 @@
 prints one JSON line per setting: ms per 512-caption batch (min over graph replays), ms per position, and the
 fraction of token ids identical to the default setting's (hints must not change results).
 
-  python tools/sweep_decode.py [--beam 4] [--quick]
+  python tools/sweep_decode.py [--beam 4] [--quick] [--l2] [--fat1] [--stream] [--deep] [--dyn]
+
+Without a mode flag only the split-K / unpaired-GEMM settings are swept; --l2: L2 warm-up and eviction hints, --fat1: the
+fat-CTA attention on one partition, --stream: partitions x SM budget x dedicated attention stream, --deep: 3-deep rings,
+--dyn: dynamic item scheduling and weights evict-last (the four sweeps of profiles/r01_decode_sweeps.txt).
 """
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
