@@ -692,7 +692,8 @@ template <int HD>
 __global__ void __launch_bounds__(128)
 attn_decode_self_kernel(const bf16* __restrict__ qkv, long long rs, bf16* __restrict__ kcache,
                         bf16* __restrict__ vcache, int max_len, int pos, bf16* __restrict__ o, long long o_rs,
-                        int n_items, int H, float scale) {
+                        int n_items, int H, float scale, const int64_t* __restrict__ seq, long long seq_ld,
+                        long long pad_idx) {
   constexpr int GL = (HD <= 32) ? 4 : (HD <= 64 ? 8 : 16);
   constexpr int KPW = 32 / GL;
   constexpr int UNR = 8;
@@ -709,6 +710,9 @@ attn_decode_self_kernel(const bf16* __restrict__ qkv, long long rs, bf16* __rest
   const int gl = lane % GL, kg = lane / GL;
   const int d0 = gl * 8;
   const bool active = d0 < HD;
+  // key padding of the reference (decoder.py:162: tgt_key_padding_mask = tokens == pad_idx, rebuilt from the
+  // whole prefix on every generate() step, model.py:224-228): a PAD id in the prefix is never attended to
+  const int64_t* seq_r = seq ? seq + static_cast<long long>(r) * seq_ld : nullptr;
   const bf16* qp = qkv + static_cast<long long>(r) * rs + h * HD + d0;
   bf16* kb = kcache + static_cast<long long>(item) * max_len * HD + d0;
   bf16* vb = vcache + static_cast<long long>(item) * max_len * HD + d0;
@@ -746,13 +750,14 @@ attn_decode_self_kernel(const bf16* __restrict__ qkv, long long rs, bf16* __rest
       for (int e = 0; e < 8; ++e) part = fmaf(qf[e], kf[e], part);
 #pragma unroll
       for (int off = GL / 2; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
-      if (gl == 0 && j < nkeys) sc[j] = part;
+      if (gl == 0 && j < nkeys) sc[j] = (seq_r && seq_r[j] == pad_idx) ? -INFINITY : part;
     }
   }
   __syncwarp();
   float mx = -INFINITY;
   for (int j = lane; j < nkeys; j += 32) mx = fmaxf(mx, sc[j]);
   mx = warp_max(mx);
+  if (mx == -INFINITY) mx = 0.f;      // every key is PAD (PAD at position 0): the row is 0, not NaN
   float sum = 0.f;
   for (int j = lane; j < nkeys; j += 32) {
     const float p = __expf(sc[j] - mx);
@@ -787,7 +792,7 @@ attn_decode_self_kernel(const bf16* __restrict__ qkv, long long rs, bf16* __rest
 #pragma unroll
     for (int off = GL; off < 32; off <<= 1) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], off);
   if (kg == 0 && active) {
-    const float inv = 1.f / sum;
+    const float inv = sum > 0.f ? 1.f / sum : 0.f;
     uint4 out;
     out.x = pack_bf16(acc[0] * inv, acc[1] * inv); out.y = pack_bf16(acc[2] * inv, acc[3] * inv);
     out.z = pack_bf16(acc[4] * inv, acc[5] * inv); out.w = pack_bf16(acc[6] * inv, acc[7] * inv);
@@ -796,14 +801,15 @@ attn_decode_self_kernel(const bf16* __restrict__ qkv, long long rs, bf16* __rest
 }
 
 int attn_decode_append(const bf16* qkv, long long qkv_rs, bf16* kcache, bf16* vcache, int max_len, int pos, bf16* o,
-                       long long o_rs, int R, int H, int hd, float scale, cudaStream_t s) {
+                       long long o_rs, int R, int H, int hd, float scale, cudaStream_t s, const int64_t* seq,
+                       long long seq_ld, long long pad_idx) {
   B200_REQUIRE(pos >= 0 && pos < max_len, "attn_decode_append: position %d outside the cache (%d rows)", pos, max_len);
   B200_REQUIRE(max_len <= 4096, "attn_decode_append: cache rows %d > 4096", max_len);
   const int items = R * H;
   const size_t smem = static_cast<size_t>(4) * (pos + 1) * sizeof(float);
 #define B200_AS(HDV)                                                                                              \
   B200_CHECK_CUDA(launch_kernel(attn_decode_self_kernel<HDV>, dim3(cdiv(items, 4)), dim3(128), smem, s, true, 1, \
-                                qkv, qkv_rs, kcache, vcache, max_len, pos, o, o_rs, items, H, scale))
+                                qkv, qkv_rs, kcache, vcache, max_len, pos, o, o_rs, items, H, scale, seq, seq_ld, pad_idx))
   switch (hd) {
     case 32: B200_AS(32); break;
     case 64: B200_AS(64); break;
@@ -1041,6 +1047,19 @@ __global__ void fill_col_i64_kernel(int64_t* p, long long n, long long stride, l
 }
 int fill_col_i64(int64_t* p, long long n, long long stride, long long v, cudaStream_t s) {
   B200_CHECK_CUDA(launch_kernel(fill_col_i64_kernel, dim3(cdiv(n, 256)), dim3(256), 0, s, true, 1, p, n, stride, v));
+  note_launch();
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void store_col_i64_kernel(int64_t* p, const int64_t* __restrict__ src, long long n, long long stride, long long col) {
+  pdl_wait();
+  pdl_trigger();
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i < n) p[i * stride + col] = src[i];
+}
+int store_col_i64(int64_t* p, const int64_t* src, long long n, long long stride, long long col, cudaStream_t s) {
+  B200_CHECK_CUDA(launch_kernel(store_col_i64_kernel, dim3(cdiv(n, 256)), dim3(256), 0, s, true, 1, p, src, n, stride, col));
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;

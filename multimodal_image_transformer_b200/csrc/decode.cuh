@@ -23,8 +23,13 @@ int attn_decode(const bf16* q, long long q_rs, const bf16* k, const bf16* v, int
 // self attention of one decode position with the cache append fused in: q/k/v of the current position
 // are the three E-wide column blocks of qkv [R, 3E]; k/v are written to cache row `pos` of
 // [R][H][max_len][hd] and attended together with rows [0,pos).
+// seq (optional): [R, seq_ld] token ids of the hypotheses, columns [0, pos] valid; keys whose token == pad_idx are
+// masked (the reference's tgt_key_padding_mask, decoder.py:162, rebuilt from the prefix on every generate() step).
 int attn_decode_append(const bf16* qkv, long long qkv_rs, bf16* kcache, bf16* vcache, int max_len, int pos, bf16* o,
-                       long long o_rs, int R, int H, int hd, float scale, cudaStream_t s);
+                       long long o_rs, int R, int H, int hd, float scale, cudaStream_t s,
+                       const int64_t* seq = nullptr, long long seq_ld = 0, long long pad_idx = 0);
+// p[r * stride + col] = src[r]
+int store_col_i64(int64_t* p, const int64_t* src, long long n, long long stride, long long col, cudaStream_t s);
 // greedy bookkeeping after a step: finished rows emit pad_id, END marks a row finished
 int greedy_update(const int64_t* next_ids, int64_t* cur_tokens, int64_t* out_tokens, int* out_len,
                   unsigned char* finished, int* n_finished, int R, int max_len, int pos, long long end_id,

@@ -11,6 +11,7 @@
 #include "kernels.cuh"
 #include <math.h>
 #include <stdlib.h>
+#include <nvtx3/nvToolsExt.h>
 #include <initializer_list>
 #include <string>
 #include <vector>
@@ -29,6 +30,20 @@ constexpr int kDecKvFlags = 11;          // attn_decode flags, decode.cuh: K/V e
 constexpr double kDecPrefetchMB = 0.0;   // MB (K + V) of the next layer's cross K/V warmed into L2 by the attention producer (B200_DEC_PREFETCH_MB)
 constexpr bool kDecAttnDyn = false;      // atomic work counter for the attention items (B200_DEC_ATTN_DYN)
 constexpr bool kDecAttnStream = false;   // cross attention of all partitions on one dedicated stream (B200_DEC_ATTN_STREAM)
+
+// NVTX ranges (the reference has no tracing at all) around the pieces of a step / a generation call,
+// switched on with B200_NVTX=1; the Python layer (engine.py, dp.py) adds the ranges of the calls it makes.
+struct NvtxRange {
+  bool on;
+  explicit NvtxRange(const char* name) {
+    static const bool enabled = getenv("B200_NVTX") != nullptr && atoi(getenv("B200_NVTX")) != 0;
+    on = enabled;
+    if (on) nvtxRangePushA(name);
+  }
+  ~NvtxRange() { if (on) nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 struct ParamInfo {
   std::string name;
@@ -304,6 +319,7 @@ int run_forward(b200_engine* e, const int64_t* tokens, const float* memory, cons
   Plan& pl = e->plan;
   const int M = B * T, Ms = B * S;
   const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+  NvtxRange nvtx_fwd("b200.decoder.forward");
 
   // dropout only in training mode (model.train(), train.py:64); eval / generation never drop
   const bool dropping = training && e->drop_p > 0.f;
@@ -327,6 +343,7 @@ int run_forward(b200_engine* e, const int64_t* tokens, const float* memory, cons
   RC(embed_pe_fwd(tokens, e->pf + e->emb, e->pe, pl.xs[0], B, T, E, c.vocab_size, sqrtf(static_cast<float>(E)), s, 0, site(0)));
 
   for (int l = 0; l < L; ++l) {
+    NvtxRange nvtx_layer("b200.decoder.forward.layer");
     const LayerOff& o = e->lo[l];
     LayerAct& a = pl.act[training ? l : 0];
     const bf16* x = pl.xs[l];
@@ -415,8 +432,10 @@ int run_backward(b200_engine* e, bool have_dlogits, float* dmemory, void* const*
     ++ev;
   };
 
+  NvtxRange nvtx_bwd("b200.decoder.backward");
   bf16* dx = pl.dxa;      // gradient of the residual stream at every part boundary lives in dxa
   if (first_part <= 0) {
+    NvtxRange nvtx_part("b200.decoder.backward.lm_head");
     if (need_dmemp) B200_CHECK_CUDA(cudaMemsetAsync(pl.dmemp, 0, static_cast<size_t>(Ms) * E * sizeof(float), s));
     // --- LM head
     RC(linear_wgrad(pl.dlogits, V, pl.x_final, E, e->gf + e->fc_w, e->gf + e->fc_b, M, V, E, s, side, e->bias_fork, &side_used));
@@ -429,6 +448,7 @@ int run_backward(b200_engine* e, bool have_dlogits, float* dmemory, void* const*
   for (int l = L - 1; l >= 0; --l) {
     const int part = L - l;
     if (part < first_part || part > last_part) continue;
+    NvtxRange nvtx_part("b200.decoder.backward.layer");
     const LayerOff& o = e->lo[l];
     LayerAct& a = pl.act[l];
     float* g = e->gf;
@@ -678,7 +698,8 @@ int dec_embed(b200_engine* e, const DecPart& v, const int64_t* tokens, int pos, 
                       sqrtf(static_cast<float>(c.embed_dim)), s, pos);
 }
 // self attention block + the cross-attention query:  QKV, attention over the cache (+ append), out-proj + LN1, Q
-int dec_pre(b200_engine* e, const DecPart& v, int l, int cur, int pos, cudaStream_t s) {
+// seq: [R, max_len] token ids of the hypotheses (columns [0, pos] valid): keys whose token is PAD are masked
+int dec_pre(b200_engine* e, const DecPart& v, int l, int cur, int pos, const int64_t* seq, cudaStream_t s) {
   const auto& c = e->cfg;
   auto& d = e->dec;
   const int E = c.embed_dim, H = c.num_heads, hd = E / H;
@@ -688,7 +709,8 @@ int dec_pre(b200_engine* e, const DecPart& v, int l, int cur, int pos, cudaStrea
   bf16* vc_l = d.vcache[cur] + l * self_stride + v.self_off;
   bf16* x = dec_x_in(v, l);
   RC(linear_dec(x, E, e->ph + o.sa_w, e->pf + o.sa_b, v.qkv, 3 * E, v.R, 3 * E, E, 0, s, d.single_cta));
-  RC(attn_decode_append(v.qkv, 3 * E, kc_l, vc_l, d.max_len, pos, v.attn, E, v.R, H, hd, 1.0f / sqrtf(static_cast<float>(hd)), s));
+  RC(attn_decode_append(v.qkv, 3 * E, kc_l, vc_l, d.max_len, pos, v.attn, E, v.R, H, hd, 1.0f / sqrtf(static_cast<float>(hd)), s,
+                        seq ? seq + v.r0 * d.max_len : nullptr, d.max_len, c.pad_idx));
   RC(linear_ln_fwd(v.attn, E, e->ph + o.sa_ow, e->pf + o.sa_ob, x, e->pf + o.n1_w, e->pf + o.n1_b, v.pt->parts, d.ksplit_e,
                    v.x1, v.R, E, E, c.ln_eps, s, d.single_cta));
   return linear_dec(v.x1, E, e->ph + o.ca_w, e->pf + o.ca_b, v.qc, E, v.R, E, E, 0, s, d.single_cta);
@@ -776,14 +798,16 @@ void parts_join(b200_engine* e, cudaStream_t s, const PartStreams& ps) {
 // (`cur` = live copy of the self-attention cache).  Launch order: per layer, every partition's self-attention
 // block, then every partition's cross attention, then every partition's FFN block, so that the attention
 // stream (if any) sees the partitions round robin.
-int decode_hidden_all(b200_engine* e, const PartStreams& ps, int cur, const int64_t* tokens, int pos, bf16** x_out) {
+int decode_hidden_all(b200_engine* e, const PartStreams& ps, int cur, const int64_t* tokens, int pos, bf16** x_out,
+                      const int64_t* seq) {
   auto& d = e->dec;
   const int L = e->cfg.num_layers;
   const int P = static_cast<int>(ps.S.size());
+  NvtxRange nvtx_pos("b200.decode.position");
   for (int p = 0; p < P; ++p) RC(dec_embed(e, ps.view[p], tokens, pos, ps.S[p]));
   for (int l = 0; l < L; ++l) {
     for (int p = 0; p < P; ++p) {
-      RC(dec_pre(e, ps.view[p], l, cur, pos, ps.S[p]));
+      RC(dec_pre(e, ps.view[p], l, cur, pos, seq, ps.S[p]));
       if (ps.SA) B200_CHECK_CUDA(cudaEventRecord(d.evq[p], ps.S[p]));
     }
     for (int p = 0; p < P; ++p) {
@@ -1217,7 +1241,12 @@ int b200_engine_decode_step(b200_engine* e, const int64_t* tokens_in, int32_t po
   GemmGridCap grid_cap(e->dec.gemm_cap, (e->dec.kv_flags & 4) != 0);
   return with_parts(e, s, [&](const PartStreams& ps) -> int {
     std::vector<bf16*> x(ps.S.size(), nullptr);
-    RC(decode_hidden_all(e, ps, e->dec.cur, tokens_in, pos, x.data()));
+    // the caller feeds one column at a time: keep the prefix (for the PAD-key mask) in the plan's sequence buffer
+    for (size_t p = 0; p < ps.S.size(); ++p) {
+      const DecPart& v = ps.view[p];
+      RC(store_col_i64(e->dec.seq[0] + v.r0 * e->dec.max_len, tokens_in + v.r0, v.R, e->dec.max_len, pos, ps.S[p]));
+    }
+    RC(decode_hidden_all(e, ps, e->dec.cur, tokens_in, pos, x.data(), e->dec.seq[0]));
     for (size_t p = 0; p < ps.S.size(); ++p) RC(decode_argmax_part(e, ps.view[p], x[p], next_ids, ps.S[p]));
     return 0;
   });
@@ -1248,7 +1277,7 @@ int b200_engine_generate_greedy(b200_engine* e, int64_t start_id, int64_t end_id
   auto steps = [&](const PartStreams& ps, int p0, int p1) -> int {
     std::vector<bf16*> x(ps.S.size(), nullptr);
     for (int pos = p0; pos < p1; ++pos) {
-      RC(decode_hidden_all(e, ps, 0, d.cur_tok, pos, x.data()));
+      RC(decode_hidden_all(e, ps, 0, d.cur_tok, pos, x.data(), toks));
       for (size_t p = 0; p < ps.S.size(); ++p) {
         const DecPart& v = ps.view[p];
         RC(decode_argmax_part(e, v, x[p], d.ids, ps.S[p]));
@@ -1317,7 +1346,7 @@ int b200_engine_generate_beam(b200_engine* e, int64_t start_id, int64_t end_id, 
       std::vector<bf16*> x(P, nullptr);
       int cur = 0, cs = 0, n_tok = 1;
       for (int pos = 0; pos + 1 < max_len; ++pos) {
-        RC(decode_hidden_all(e, ps, cur, d.cur_tok, pos, x.data()));
+        RC(decode_hidden_all(e, ps, cur, d.cur_tok, pos, x.data(), d.seq[cs]));
         for (size_t p = 0; p < P; ++p) {
           const DecPart& v = ps.view[p];
           const int64_t r0 = v.r0;

@@ -82,12 +82,10 @@ class _DecoderFunction(torch.autograd.Function):
         if eng._generation != ctx.generation:
             raise RuntimeError("b200 decoder: the activations of this forward were overwritten by a later "
                                "forward; only one graph per decoder can be alive at a time")
-        saved = eng.grads.clone()          # keep whatever the fused path may have accumulated
-        eng.grads.zero_()
         want_dmem = ctx.memory_needs_grad and ctx.mem_dim == eng.embed_dim
-        dmem = eng.backward_from_dlogits(dlogits, want_dmemory=want_dmem)
-        grads = tuple(eng.view(name, eng.grads).clone() for name in module._param_names)
-        eng.grads.copy_(saved)
+        with eng.scratch_grads() as sg:    # whatever the fused path accumulated in eng.grads stays untouched
+            dmem = eng.backward_from_dlogits(dlogits, want_dmemory=want_dmem)
+        grads = tuple(eng.view(name, sg) for name in module._param_names)
         return (None, None, dmem, None) + grads
 
 
@@ -155,6 +153,13 @@ class TransformerDecoder(nn.Module):
             raise RuntimeError("b200 TransformerDecoder lives on its CUDA device in fp32 master / bf16 compute; "
                                "moving or casting it is not supported (no CPU fallback)")
         return self
+
+    def train(self, mode: bool = True):
+        """Mode switches are where foreign code typically edits weights through `p.data` (EMA swaps, re-inits):
+        the bf16 shadow is re-cast and no longer trusted until the next fused optimizer step (engine.sync_shadow)."""
+        if mode != self.training:
+            self.engine._shadow_fresh = False
+        return super().train(mode)
 
     def _flat_params(self):
         return [self.get_parameter(n) for n in self._param_names]

@@ -14,6 +14,8 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 import torch.distributed as dist
 
+from .engine import nvtx_range
+
 
 def shard_range(n_items: int, rank: int, world_size: int) -> Tuple[int, int]:
     """Contiguous [begin, end) slice of a global batch owned by `rank` (sizes differ by at most 1)."""
@@ -77,7 +79,7 @@ class DataParallel:
         """Replicas must start identical (rank 0 wins)."""
         if self.world_size > 1:
             dist.broadcast(self.engine.params, src=0, group=self.group)
-            self.engine.sync_shadow(force=True)
+            self.engine.mark_weights_changed()
 
     def global_inv_count(self, loss_and_count: torch.Tensor) -> torch.Tensor:
         """Device scalar 1 / sum_over_ranks(n_valid): the scale of dlogits on every rank."""
@@ -101,7 +103,7 @@ class DataParallel:
         for i, ((off, cnt), ev) in enumerate(zip(self.buckets, self.events)):
             self.engine.backward_parts(i, i, inv_count)
             ev.record(cur)
-            with torch.cuda.stream(self.comm_stream):
+            with torch.cuda.stream(self.comm_stream), nvtx_range("b200.dp.allreduce_bucket"):
                 self.comm_stream.wait_event(ev)
                 dist.all_reduce(g[off:off + cnt], op=dist.ReduceOp.SUM, group=self.group)
         cur.wait_stream(self.comm_stream)

@@ -12,6 +12,17 @@ import torch
 
 from . import _lib as L
 
+import contextlib
+import os
+
+
+def nvtx_range(name: str):
+    """NVTX range around one engine call when B200_NVTX=1 (the C++ engine adds the per-layer / per-part /
+    per-position ranges inside).  A no-op context manager otherwise."""
+    if os.environ.get("B200_NVTX", "0") not in ("", "0"):
+        return torch.cuda.nvtx.range(name)
+    return contextlib.nullcontext()
+
 
 def sinusoid_table(max_len: int, d_model: int) -> torch.Tensor:
     """The `pe` buffer of decoder.PositionalEncodingBatchFirst (reference decoder.py:34-51)."""
@@ -73,6 +84,9 @@ class DecoderEngine:
         self._ws = None
         self._ws_key = None
         self._shadow_version = -1
+        self._shadow_fresh = False      # True while the last writer of the master weights was the fused AdamW kernel
+        self._graph_pins = set()        # captured CUDA graphs holding raw pointers into the workspace / dropout state
+        self._scratch_grads = None
         L.check(self.lib.b200_engine_bind(self.handle, L.ptr(self.params), L.ptr(self.params_bf16),
                                           L.ptr(self.grads), L.ptr(self.pe)), "engine_bind")
 
@@ -91,8 +105,15 @@ class DecoderEngine:
         element), so the device state [seed, counter] is all that is kept."""
         p = float(p)
         if p > 0:
-            self._drop_state = torch.tensor([seed & 0x7FFFFFFF, 0], device=self.device, dtype=torch.int32)
+            if getattr(self, "_graph_pins", None) and getattr(self, "_drop_state", None) is not None:
+                # a captured graph reads this buffer: re-seed in place instead of reallocating it
+                self._drop_state.copy_(torch.tensor([seed & 0x7FFFFFFF, 0], dtype=torch.int32))
+            else:
+                self._drop_state = torch.tensor([seed & 0x7FFFFFFF, 0], device=self.device, dtype=torch.int32)
         else:
+            if getattr(self, "_graph_pins", None) and getattr(self, "dropout_p", 0.0) > 0:
+                raise RuntimeError("b200 engine: a captured CUDA graph uses the dropout state; release it "
+                                   "(GraphedTrainStep.release()) before disabling dropout")
             self._drop_state = None
         self.dropout_p = p
         self._drop_active = None
@@ -154,23 +175,78 @@ class DecoderEngine:
             for k, v in tensors.items():
                 if k in self.layout:
                     self.view(k).copy_(v.to(self.device, torch.float32))
-        self.sync_shadow(force=True)
+        self.mark_weights_changed()
 
     def sync_shadow(self, force: bool = False) -> None:
-        """Refresh the bf16 weight shadow if the fp32 master was modified through torch."""
+        """Refresh the bf16 weight shadow (what every GEMM reads) from the fp32 master.
+
+        In-place edits of a parameter tensor itself bump the arena's version counter and are detected;
+        edits through `p.data` (p.data.copy_/mul_, EMA swaps, dist.broadcast(p.data), HF-style init
+        utilities) are invisible to any counter.  Policy: the shadow is trusted only while the last
+        writer of the master was the fused AdamW kernel (`_shadow_fresh`, which writes master and
+        shadow together) -- i.e. inside the fused training loop; every other entry point
+        (eval-mode forwards, generation, train()/eval() switches, load) re-casts, one pass over the
+        arena.  After editing `p.data` in the middle of a fused training loop, call
+        `engine.sync_shadow(force=True)`."""
         ver = self.params._version
-        if force or ver != self._shadow_version:
+        if force or not self._shadow_fresh or ver != self._shadow_version:
             L.check(self.lib.b200_cast_f32_to_bf16(L.ptr(self.params), L.ptr(self.params_bf16),
                                                    C.c_int64(self.total), L.cur_stream()), "cast")
             self._shadow_version = ver
 
+    def mark_weights_changed(self) -> None:
+        """The fp32 master may have been edited behind the engine's back: re-cast now and stop trusting the shadow."""
+        self._shadow_fresh = False
+        self.sync_shadow(force=True)
+
+    # ------------------------------------------------------------------ CUDA-graph pins
+    def pin_for_graph(self, owner) -> None:
+        self._graph_pins.add(id(owner))
+
+    def unpin_for_graph(self, owner) -> None:
+        self._graph_pins.discard(id(owner))
+
+    def reserve_workspace(self, B: int, T: int, S: int, mem_dim: int, training: bool) -> None:
+        """Grow the activation workspace to fit this shape now (call before capturing a CUDA graph
+        when a larger evaluation / logits shape will run between replays)."""
+        self._ensure_ws(B, T, S, mem_dim, training)
+
     def zero_grad(self) -> None:
         self.grads.zero_()
+
+    def _bind(self, grads: torch.Tensor) -> None:
+        L.check(self.lib.b200_engine_bind(self.handle, L.ptr(self.params), L.ptr(self.params_bf16),
+                                          L.ptr(grads), L.ptr(self.pe)), "engine_bind")
+
+    def scratch_grads(self):
+        """Context manager: the engine's backward accumulates into a zeroed scratch arena instead of
+        `self.grads` (the autograd bridge returns per-parameter views of it, so whatever the fused
+        path accumulated in `self.grads` is neither cloned nor disturbed).  The scratch arena is
+        reused by the next call: tensors obtained through torch.autograd.grad alias it until then."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def cm():
+            if self._scratch_grads is None:
+                self._scratch_grads = torch.zeros_like(self.grads)
+            else:
+                self._scratch_grads.zero_()
+            self._bind(self._scratch_grads)
+            try:
+                yield self._scratch_grads
+            finally:
+                self._bind(self.grads)
+        return cm()
 
     # ------------------------------------------------------------------ workspace
     def _ensure_ws(self, B: int, T: int, S: int, mem_dim: int, training: bool) -> None:
         need = int(self.lib.b200_engine_workspace_bytes(self.handle, B, T, S, mem_dim, int(training)))
         if self._ws is None or self._ws.numel() < need:
+            if self._graph_pins:
+                raise RuntimeError(
+                    "b200 engine: this forward needs a %d-byte workspace but a captured CUDA graph holds pointers into "
+                    "the current %d-byte one; call engine.reserve_workspace(B, T, S, mem_dim, training) for the largest "
+                    "shape before capturing, or GraphedTrainStep.release() first" % (need, 0 if self._ws is None else self._ws.numel()))
             self._ws = None
             self._ws = torch.empty(need, device=self.device, dtype=torch.uint8)
             L.check(self.lib.b200_engine_set_workspace(self.handle, L.ptr(self._ws), C.c_int64(self._ws.numel())),
@@ -203,9 +279,10 @@ class DecoderEngine:
         self._ensure_ws(B, T, S, mem_dim, training)
         logits = torch.empty(B, T, self.vocab_size, device=self.device, dtype=torch.float32)
         self._keep = (tokens, memory, mem_pad)
-        L.check(self.lib.b200_engine_forward_logits(self.handle, L.ptr(tokens), L.ptr(memory), L.ptr(mem_pad),
-                                                    B, T, S, mem_dim, int(training), L.ptr(logits),
-                                                    L.cur_stream()), "forward_logits")
+        with nvtx_range("b200.forward_logits"):
+            L.check(self.lib.b200_engine_forward_logits(self.handle, L.ptr(tokens), L.ptr(memory), L.ptr(mem_pad),
+                                                        B, T, S, mem_dim, int(training), L.ptr(logits),
+                                                        L.cur_stream()), "forward_logits")
         return logits
 
     def forward_loss(self, tokens, targets, memory, mem_pad=None, ignore_index: int = 0,
@@ -219,9 +296,10 @@ class DecoderEngine:
         self._ensure_ws(B, T, S, mem_dim, training)
         out = torch.empty(2, device=self.device, dtype=torch.float32)
         self._keep = (tokens, memory, mem_pad, targets)
-        L.check(self.lib.b200_engine_forward_loss(self.handle, L.ptr(tokens), L.ptr(targets), L.ptr(memory),
-                                                  L.ptr(mem_pad), B, T, S, mem_dim, C.c_int64(ignore_index),
-                                                  int(training), L.ptr(out), L.cur_stream()), "forward_loss")
+        with nvtx_range("b200.forward_loss"):
+            L.check(self.lib.b200_engine_forward_loss(self.handle, L.ptr(tokens), L.ptr(targets), L.ptr(memory),
+                                                      L.ptr(mem_pad), B, T, S, mem_dim, C.c_int64(ignore_index),
+                                                      int(training), L.ptr(out), L.cur_stream()), "forward_loss")
         return out
 
     def backward(self, inv_count: Optional[torch.Tensor] = None, want_dmemory: bool = False,
@@ -233,22 +311,25 @@ class DecoderEngine:
         if events:
             n_ev = len(events)
             ev_arr = (C.c_void_p * n_ev)(*[C.c_void_p(e.cuda_event) for e in events])
-        L.check(self.lib.b200_engine_backward(self.handle, L.ptr(inv_count), L.ptr(dmem), ev_arr, n_ev,
-                                              L.cur_stream()), "backward")
+        with nvtx_range("b200.backward"):
+            L.check(self.lib.b200_engine_backward(self.handle, L.ptr(inv_count), L.ptr(dmem), ev_arr, n_ev,
+                                                  L.cur_stream()), "backward")
         return dmem
 
     def backward_parts(self, first: int, last: int, inv_count: Optional[torch.Tensor] = None) -> None:
         """Parts [first, last] of backward (0 = LM head, k = layer L-k, L+1 = embedding/projection)."""
-        L.check(self.lib.b200_engine_backward_parts(self.handle, L.ptr(inv_count), None, first, last, L.cur_stream()),
-                "backward_parts")
+        with nvtx_range("b200.backward_part"):
+            L.check(self.lib.b200_engine_backward_parts(self.handle, L.ptr(inv_count), None, first, last, L.cur_stream()),
+                    "backward_parts")
 
     def backward_from_dlogits(self, dlogits: torch.Tensor, want_dmemory: bool = False) -> Optional[torch.Tensor]:
         dlogits = dlogits.to(torch.float32).contiguous()
         dmem = None
         if want_dmemory:
             dmem = torch.empty_like(self._keep[1], dtype=torch.float32)
-        L.check(self.lib.b200_engine_backward_from_dlogits(self.handle, L.ptr(dlogits), L.ptr(dmem),
-                                                           L.cur_stream()), "backward_from_dlogits")
+        with nvtx_range("b200.backward_from_dlogits"):
+            L.check(self.lib.b200_engine_backward_from_dlogits(self.handle, L.ptr(dlogits), L.ptr(dmem),
+                                                               L.cur_stream()), "backward_from_dlogits")
         return dmem
 
     def grad_buckets(self) -> List[Tuple[int, int]]:
@@ -272,13 +353,16 @@ class DecoderEngine:
         sumsq = self._scal[0:1]
         sumsq.zero_()
         st = L.cur_stream()
-        L.check(self.lib.b200_grad_sumsq(L.ptr(self.grads), C.c_int64(self.total), L.ptr(sumsq), st), "grad_sumsq")
-        L.check(self.lib.b200_adamw_step_dev(L.ptr(self.params), L.ptr(self.params_bf16), L.ptr(self.grads),
-                                             L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq), C.c_int64(self.total),
-                                             L.ptr(sumsq), C.c_float(max_norm), L.ptr(self._lr_dev),
-                                             C.c_float(betas[0]), C.c_float(betas[1]), C.c_float(eps),
-                                             C.c_float(weight_decay), L.ptr(self._step_dev), st), "adamw_step")
+        with nvtx_range("b200.optimizer.grad_norm"):
+            L.check(self.lib.b200_grad_sumsq(L.ptr(self.grads), C.c_int64(self.total), L.ptr(sumsq), st), "grad_sumsq")
+        with nvtx_range("b200.optimizer.clip_adamw"):
+            L.check(self.lib.b200_adamw_step_dev(L.ptr(self.params), L.ptr(self.params_bf16), L.ptr(self.grads),
+                                                 L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq), C.c_int64(self.total),
+                                                 L.ptr(sumsq), C.c_float(max_norm), L.ptr(self._lr_dev),
+                                                 C.c_float(betas[0]), C.c_float(betas[1]), C.c_float(eps),
+                                                 C.c_float(weight_decay), L.ptr(self._step_dev), st), "adamw_step")
         # the kernel wrote both the fp32 master and the bf16 shadow: nothing to re-sync
+        self._shadow_fresh = True
         return sumsq
 
     # ------------------------------------------------------------------ KV-cached generation
@@ -298,9 +382,10 @@ class DecoderEngine:
             self._dws = torch.empty(need, device=self.device, dtype=torch.uint8)
         self._dkeep = (memory, mem_pad)
         self._dshape = (B, beam, max_len)
-        L.check(self.lib.b200_engine_decode_begin(self.handle, L.ptr(memory), L.ptr(mem_pad), B, beam, S, mem_dim,
-                                                  max_len, L.ptr(self._dws), self._dws.numel(), L.cur_stream()),
-                "decode_begin")
+        with nvtx_range("b200.decode_begin"):
+            L.check(self.lib.b200_engine_decode_begin(self.handle, L.ptr(memory), L.ptr(mem_pad), B, beam, S, mem_dim,
+                                                      max_len, L.ptr(self._dws), self._dws.numel(), L.cur_stream()),
+                    "decode_begin")
 
     def decode_plan_info(self) -> dict:
         """How the current decode plan is scheduled (after decode_begin); reporting only."""
@@ -323,8 +408,9 @@ class DecoderEngine:
         assert beam == 1
         toks = torch.empty(B, max_len, device=self.device, dtype=torch.int64)
         lens = torch.empty(B, device=self.device, dtype=torch.int32)
-        L.check(self.lib.b200_engine_generate_greedy(self.handle, start_id, end_id, max_len, stop_check_interval,
-                                                     L.ptr(toks), L.ptr(lens), L.cur_stream()), "generate_greedy")
+        with nvtx_range("b200.generate_greedy"):
+            L.check(self.lib.b200_engine_generate_greedy(self.handle, start_id, end_id, max_len, stop_check_interval,
+                                                         L.ptr(toks), L.ptr(lens), L.cur_stream()), "generate_greedy")
         return toks, lens
 
     def generate_beam(self, start_id: int, end_id: int, max_len: int):
@@ -333,6 +419,7 @@ class DecoderEngine:
         toks = torch.empty(B, plan_len, device=self.device, dtype=torch.int64)
         lens = torch.empty(B, device=self.device, dtype=torch.int32)
         score = torch.empty(B, device=self.device, dtype=torch.float32)
-        L.check(self.lib.b200_engine_generate_beam(self.handle, start_id, end_id, max_len, L.ptr(toks), L.ptr(lens),
-                                                   L.ptr(score), L.cur_stream()), "generate_beam")
+        with nvtx_range("b200.generate_beam"):
+            L.check(self.lib.b200_engine_generate_beam(self.handle, start_id, end_id, max_len, L.ptr(toks), L.ptr(lens),
+                                                       L.ptr(score), L.cur_stream()), "generate_beam")
         return toks, lens, score

@@ -51,27 +51,59 @@ class FeatureCache:
     the images whose key (e.g. the dataset's image path) is new, and returns the batch's features
     as one bf16 device tensor that the engine consumes in place (half the host->device bytes of fp32)."""
 
-    def __init__(self, model: "ImageToTextModel"):
+    def __init__(self, model: "ImageToTextModel", capacity: int = 1024):
         self.model = model
-        self.store = {}
+        self.slot = {}              # key -> row of the pinned slab
+        self.slab = None            # [capacity, S, enc_dim] bf16, pinned; doubled when full
+        self.capacity = capacity
+        self._stage = [None, None]  # two pinned staging batches (the H2D copy of one overlaps the gather of the next)
+        self._flip = 0
+        self._ev = [None, None]     # H2D copy out of each staging batch: waited for before the batch is refilled
         self.hits = 0
         self.misses = 0
+
+    @property
+    def store(self):
+        return {k: self.slab[i] for k, i in self.slot.items()}
+
+    def _grow(self, shape, need: int) -> None:
+        if self.slab is not None and need <= self.slab.shape[0]:
+            return
+        cap = max(self.capacity, need, 2 * (0 if self.slab is None else self.slab.shape[0]))
+        new = torch.empty((cap,) + tuple(shape), dtype=torch.bfloat16).pin_memory()
+        if self.slab is not None:
+            new[:self.slab.shape[0]].copy_(self.slab)
+        self.slab = new
 
     @torch.no_grad()
     def get(self, keys, pixel_values: torch.Tensor) -> torch.Tensor:
         dev = self.model.decoder.engine.device
-        missing = [i for i, k in enumerate(keys) if k not in self.store]
+        missing = [i for i, k in enumerate(keys) if k not in self.slot]
         if missing:
             feats = self.model.encode(pixel_values[missing].to(dev)).to(torch.bfloat16).cpu()
-            for j, i in enumerate(missing):
-                self.store[keys[i]] = feats[j].clone().pin_memory()
+            self._grow(feats.shape[1:], len(self.slot) + len(missing))
+            rows = []
+            for i in missing:
+                if keys[i] not in self.slot:
+                    self.slot[keys[i]] = len(self.slot)
+                rows.append(self.slot[keys[i]])
+            self.slab[torch.tensor(rows)] = feats
         self.misses += len(missing)
         self.hits += len(keys) - len(missing)
-        first = self.store[keys[0]]
-        stage = torch.empty((len(keys),) + tuple(first.shape), dtype=torch.bfloat16).pin_memory()
-        for i, k in enumerate(keys):
-            stage[i].copy_(self.store[k])
-        return stage.to(dev, non_blocking=True)
+        idx = torch.tensor([self.slot[k] for k in keys], dtype=torch.int64)
+        st = self._stage[self._flip]
+        if st is None or st.shape[0] != len(keys) or st.shape[1:] != self.slab.shape[1:]:
+            st = torch.empty((len(keys),) + tuple(self.slab.shape[1:]), dtype=torch.bfloat16).pin_memory()
+            self._stage[self._flip] = st
+        flip = self._flip
+        self._flip ^= 1
+        if self._ev[flip] is not None:
+            self._ev[flip].synchronize()
+        torch.index_select(self.slab, 0, idx, out=st)        # one vectorised gather instead of a Python loop of copies
+        out = st.to(dev, non_blocking=True)
+        self._ev[flip] = torch.cuda.Event()
+        self._ev[flip].record(torch.cuda.current_stream(dev))
+        return out
 
 
 class ImageToTextModel(nn.Module):
@@ -96,7 +128,9 @@ class ImageToTextModel(nn.Module):
         self.decoder_embed_dim = decoder_embed_dim
         self.decoder_pad_idx = decoder_pad_idx
         self.memory_mode = memory_mode or config.MEMORY_MODE
-        # RNG order of the reference: projection (nn.Linear default init) before the decoder
+        # RNG order AND registration order of the reference (model.py:97-114): projection before the decoder, so that
+        # model.parameters() lists encoder, projection, decoder and a stock torch.optim state_dict maps by position
+        self.register_module("projection", None)
         proj_init = None
         if self.encoder_output_dim != decoder_embed_dim:
             lin = nn.Linear(self.encoder_output_dim, decoder_embed_dim)
@@ -189,12 +223,10 @@ class _ProjectedDecoderFunction(torch.autograd.Function):
         eng = model.decoder.engine
         if eng._generation != ctx.generation:
             raise RuntimeError("b200 decoder: activations of this forward were overwritten by a later forward")
-        saved = eng.grads.clone()
-        eng.grads.zero_()
-        eng.backward_from_dlogits(dlogits)
+        with eng.scratch_grads() as sg:
+            eng.backward_from_dlogits(dlogits)
         names = ["projection.weight", "projection.bias"] + model.decoder._param_names
-        grads = tuple(eng.view(n, eng.grads).clone() for n in names)
-        eng.grads.copy_(saved)
+        grads = tuple(eng.view(n, sg) for n in names)
         return (None, None, None) + grads
 
 

@@ -12,27 +12,36 @@ from . import config
 from .dp import DataParallel
 
 
-class B200AdamW:
+class B200AdamW(torch.optim.Optimizer):
     """torch.optim.AdamW-compatible facade over the engine's fused clip + AdamW kernel
-    (reference train.py:96-100, 319-325; torch AdamW semantics)."""
+    (reference train.py:96-100, 319-325; torch AdamW semantics).
+
+    It IS a torch.optim.Optimizer (param_groups / defaults / initial_lr), so the reference's optional
+    warm-up schedule -- transformers.get_linear_schedule_with_warmup, a LambdaLR, reference
+    train.py:331-341 -- drives it: the scheduler writes param_groups[0]["lr"], step() hands that
+    value to the device-resident learning rate the (possibly CUDA-graph-replayed) kernel reads."""
 
     def __init__(self, model, lr=config.LEARNING_RATE, betas=(config.ADAM_BETA1, config.ADAM_BETA2),
                  eps=config.ADAM_EPS, weight_decay=config.WEIGHT_DECAY, max_grad_norm: float = 0.0):
         self.model_ref = model
         self.decoder = model.decoder if hasattr(model, "decoder") else model
         self.engine = self.decoder.engine
-        self.param_groups = [dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
-                                  params=[p for p in model.parameters() if p.requires_grad])]
+        params = [p for p in model.parameters() if p.requires_grad]
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self.max_grad_norm = max_grad_norm
         self.last_grad_sumsq: Optional[torch.Tensor] = None
 
     def zero_grad(self, set_to_none: bool = False) -> None:
         self.engine.zero_grad()          # the arena stays allocated; .grad views keep pointing at it
 
-    def step(self, max_grad_norm: Optional[float] = None) -> None:
+    def step(self, closure=None, max_grad_norm: Optional[float] = None) -> None:
+        if closure is not None and not callable(closure):      # step(5.0): positional clip value (round-1 signature)
+            max_grad_norm, closure = float(closure), None
+        if closure is not None:
+            raise RuntimeError("B200AdamW.step does not take a closure (the fused step runs forward and backward itself)")
         g = self.param_groups[0]
         mn = self.max_grad_norm if max_grad_norm is None else max_grad_norm
-        self.last_grad_sumsq = self.engine.adamw_step(lr=g["lr"], betas=g["betas"], eps=g["eps"],
+        self.last_grad_sumsq = self.engine.adamw_step(lr=float(g["lr"]), betas=g["betas"], eps=g["eps"],
                                                       weight_decay=g["weight_decay"], max_norm=mn)
 
     # ---- checkpoint compatibility (reference train.py:351-357, 424): torch.optim.AdamW layout
@@ -54,7 +63,7 @@ class B200AdamW:
         checkpoint written here resumes in the reference and vice versa; torch_format=False returns
         the flat-arena form."""
         e = self.engine
-        groups = [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]
+        groups = [{k: (float(v) if k == "lr" else v) for k, v in g.items() if k != "params"} for g in self.param_groups]
         if not torch_format:
             return {"step": e.opt_step, "exp_avg": None if e.exp_avg is None else e.exp_avg.clone(),
                     "exp_avg_sq": None if e.exp_avg_sq is None else e.exp_avg_sq.clone(), "param_groups": groups}
@@ -90,7 +99,7 @@ class B200AdamW:
                 e.opt_step = steps.pop() if steps else 0
                 e._step_dev.fill_(e.opt_step)
             for g, s_ in zip(self.param_groups, sd["param_groups"]):
-                g.update({k: v for k, v in s_.items() if k in ("lr", "betas", "eps", "weight_decay")})
+                g.update({k: v for k, v in s_.items() if k in ("lr", "betas", "eps", "weight_decay", "initial_lr")})
             return
         e.opt_step = int(sd["step"])
         e._step_dev.fill_(e.opt_step)
@@ -98,7 +107,7 @@ class B200AdamW:
             e.exp_avg = sd["exp_avg"].to(e.device).clone()
             e.exp_avg_sq = sd["exp_avg_sq"].to(e.device).clone()
         for g, s in zip(self.param_groups, sd["param_groups"]):
-            g.update(s)
+            g.update({k: v for k, v in s.items() if k != "params"})
 
 
 def trim_batch(decoder_input_tokens: torch.Tensor, target_tokens: torch.Tensor, pad_idx: int, multiple: int = 8):
@@ -239,7 +248,7 @@ class GraphedTrainStep:
             # tensors (e.g. a staging slot refilled by an H2D copy) replay without any extra copy
             self.static_in = (images, tokens, targets)
             eng = (self.model.decoder if hasattr(self.model, "decoder") else self.model).engine
-            lr = self.optimizer.param_groups[0]["lr"]
+            lr = float(self.optimizer.param_groups[0]["lr"])
             if eng._lr_host != lr:
                 eng._lr_dev.fill_(lr)
                 eng._lr_host = lr
@@ -248,19 +257,29 @@ class GraphedTrainStep:
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self.static_out = self._eager(*self.static_in)
+            # the graph holds raw pointers into the workspace and the dropout state: the engine refuses to
+            # reallocate either from now on (a larger eval batch must be reserved BEFORE capture, engine.reserve_workspace)
+            eng.pin_for_graph(self)
             self.graph.replay()
             return self.static_out
         for d, s in zip(self.static_in, (images, tokens, targets)):
             if d.data_ptr() != s.data_ptr():
                 d.copy_(s, non_blocking=True)
         eng = (self.model.decoder if hasattr(self.model, "decoder") else self.model).engine
-        lr = self.optimizer.param_groups[0]["lr"]
+        lr = float(self.optimizer.param_groups[0]["lr"])     # a scheduler may have moved it since the last replay
         if eng._lr_host != lr:
             eng._lr_dev.fill_(lr)
             eng._lr_host = lr
         eng.opt_step += 1
+        eng._shadow_fresh = True          # the replayed AdamW kernel rewrites the bf16 shadow
         self.graph.replay()
         return self.static_out
+
+    def release(self) -> None:
+        """Drop the captured graph (and the engine's allocation pin with it)."""
+        eng = (self.model.decoder if hasattr(self.model, "decoder") else self.model).engine
+        self.graph = None
+        eng.unpin_for_graph(self)
 
 
 def train_one_epoch(model, dataloader, optimizer, criterion, device, grad_clip_value, scheduler, epoch,

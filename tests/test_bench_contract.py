@@ -41,12 +41,19 @@ def test_committed_bench_line_has_the_contract_keys():
 
 
 def test_reference_arm_runs_on_the_host_cores():
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
-                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--ref-budget-s", "12"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-800:]
     d = _last_json_line(out.stdout)
     for k in BASE_KEYS + ("e2e", "cpu_baseline"):
         assert k in d, k
     assert d["impl"] == "reference" and d["metric"] == "decoder train tokens/sec" and d["value"] > 0
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
-    assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    sys.path.insert(0, ROOT)
+    from oracle import ref_loader
+    # the unmodified reference (oracle/_ref, copied by oracle/make_ref.sh) whenever it is present, else the oracle port
+    want_kind = "reference" if ref_loader.available() else "port"
+    assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["kind"] == want_kind and d["cpu_baseline"]["cores"] >= 1
+    assert d["steps"] == 1 and d["warmup"] == 1 and 8 <= d["cpu_baseline"]["sample_batch"] <= 256
+    if want_kind == "reference":
+        assert ref_loader.verify_manifest() and "MANIFEST MISMATCH" not in d["cpu_baseline"]["sample"]

@@ -66,6 +66,30 @@ def test_model_forward_loss_and_train_steps_vs_reference(cuda_dev):
     assert all(p.grad is None for p in m2.encoder.parameters())
 
 
+def test_parameter_order_matches_the_reference_for_stock_optimizers(cuda_dev):
+    """model.parameters() lists encoder, projection, decoder like the reference (model.py:34-114 registers them in
+    that order; train.py:319 builds AdamW over model.parameters()), so a stock torch.optim.AdamW state_dict --
+    which maps state by POSITION -- round-trips between the two models."""
+    g = torch.load(GOLDEN, weights_only=True)
+    m = _build(cuda_dev, g)
+    names = [n for n, _ in m.named_parameters()]
+    first = [n.split(".")[0] for n in names]
+    blocks = [k for i, k in enumerate(first) if i == 0 or first[i - 1] != k]
+    assert blocks == ["encoder", "projection", "decoder"], blocks
+    dec_names = [n[len("decoder."):] for n in names if n.startswith("decoder.")]
+    assert dec_names == [n for n in m.decoder.engine.layout if not n.startswith("projection.")]
+    assert dec_names[0] == "token_embedding.weight" and dec_names[-1] == "fc_out.bias"
+    trainable = [p for p in m.parameters() if p.requires_grad]
+    opt = torch.optim.AdamW(trainable, lr=1e-4)
+    for p in trainable:
+        p.grad = torch.zeros_like(p)
+    opt.step()
+    sd = opt.state_dict()
+    shapes = [tuple(sd["state"][i]["exp_avg"].shape) for i in range(len(trainable))]
+    assert shapes[0] == (g["config"]["E"], 768) and shapes[1] == (g["config"]["E"],)          # projection first
+    assert shapes[2] == (g["config"]["V"], g["config"]["E"])                                    # then the embedding
+
+
 def test_model_generate_vs_reference(cuda_dev):
     from PIL import Image
     g = torch.load(GOLDEN, weights_only=True)

@@ -43,6 +43,49 @@ def test_mask_helpers_match_oracle():
     assert torch.equal(utils.create_padding_mask(seq, 0), O.padding_mask(seq, 0))
 
 
+def test_b200_adamw_is_a_torch_optimizer_driven_by_lambda_lr():
+    """The reference's optional warm-up schedule (train.py:331-341: get_linear_schedule_with_warmup, a LambdaLR)
+    must be constructible over the fused optimizer and drive the learning rate its kernel receives.  Host logic
+    only: the engine is a stub that records what step() hands to the kernel launcher."""
+    from multimodal_image_transformer_b200.train import B200AdamW
+
+    class _Eng:
+        def __init__(self):
+            self.lrs, self.opt_step, self.exp_avg, self.exp_avg_sq = [], 0, None, None
+
+        def adamw_step(self, lr, betas, eps, weight_decay, max_norm):
+            self.lrs.append((lr, max_norm))
+            return None
+
+        def zero_grad(self):
+            pass
+
+    class _Dec(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(4))
+            self.engine = _Eng()
+
+    dec = _Dec()
+    opt = B200AdamW(dec, lr=1e-3, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-5)
+    assert isinstance(opt, torch.optim.Optimizer) and opt.param_groups[0]["lr"] == 1e-3
+    warm, total = 3, 10
+    sched = torch.optim.lr_scheduler.LambdaLR(
+        opt, lambda s: (s / warm) if s < warm else max(0.0, (total - s) / (total - warm)))     # HF linear warm-up / decay
+    want = []
+    for step in range(6):
+        want.append(sched.get_last_lr()[0])
+        opt.step(max_grad_norm=5.0)
+        sched.step()
+    got = [lr for lr, _ in dec.engine.lrs]
+    assert got == pytest.approx(want) and got[0] == 0.0 and got[3] == pytest.approx(1e-3)
+    assert all(mn == 5.0 for _, mn in dec.engine.lrs)
+    opt.step(2.5)                                   # positional clip value (round-1 call style)
+    assert dec.engine.lrs[-1][1] == 2.5
+    sd = opt.state_dict(torch_format=False)
+    assert sd["param_groups"][0]["lr"] == pytest.approx(sched.get_last_lr()[0])
+
+
 def test_no_cpu_fallback():
     from multimodal_image_transformer_b200.engine import DecoderEngine
     with pytest.raises(RuntimeError):

@@ -1,0 +1,99 @@
+"""Race-evidence substitute for compute-sanitizer (closed on this GPU pool): >= 1000 back-to-back
+launches of the hand-rolled mbarrier / TMEM / TMA protocols -- mixed-shape tcgen05 GEMMs (K- and MN-major operands,
+paired and unpaired CTAs, split-K accumulate, fused residual / ReLU-mask epilogues), the training attention kernels
+and whole generation calls (graph replay included) -- with every result hashed.  A protocol race shows up as a hash
+that differs between repetitions of the same launch, between a run with and without programmatic dependent launch
+(B200_NO_PDL=1), or as an mbarrier time-out trap.  Prints one JSON line {"launches", "hash", "mismatches"}.
+
+    python tools/stress_launches.py [--reps N]          (tests/test_gpu_stress.py runs it with PDL on and off)
+"""
+import argparse
+import hashlib
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+
+def digest(t):
+    return hashlib.sha256(t.detach().contiguous().cpu().view(torch.uint8).numpy().tobytes()).hexdigest()[:16]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reps", type=int, default=6)
+    args = ap.parse_args()
+    from multimodal_image_transformer_b200 import _lib as L
+    from multimodal_image_transformer_b200 import ops
+    from oracle import decoder_oracle as O
+    from tests.helpers import CFGS, make_engine, synth
+    dev = torch.device("cuda", 0)
+    lib = L.lib()
+    n0 = lib.b200_launch_count()
+    g = torch.Generator().manual_seed(7)
+    shapes = [(128, 128, 64), (129, 136, 72), (257, 264, 192), (1000, 768, 768), (4096, 3072, 768), (4096, 768, 3072),
+              (333, 10000, 512), (12032, 768, 768), (64, 2304, 768), (5000, 1536, 768)]
+    hashes, mism = [], 0
+
+    def check(tag, fn):
+        nonlocal mism
+        first = None
+        for _ in range(args.reps):
+            h = fn()
+            if first is None:
+                first = h
+            elif h != first:
+                mism += 1
+                print("MISMATCH", tag, first, h, file=sys.stderr)
+        hashes.append(first)
+
+    # ---- GEMM family: forward (K,K), dgrad (K,MN), wgrad (MN,MN) with split-K atomics (order-dependent fp32 sums are
+    # compared after rounding to bf16, everything else bit for bit)
+    for (M, N, K) in shapes:
+        a = torch.randn(M, K, generator=g).to(dev, torch.bfloat16)
+        w = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev, torch.bfloat16)
+        bias = torch.randn(N, generator=g).to(dev)
+        res = torch.randn(M, N, generator=g).to(dev, torch.bfloat16)
+        dy = torch.randn(M, N, generator=g).to(dev, torch.bfloat16)
+        check(f"fwd{M}x{N}x{K}", lambda: digest(ops.gemm(a, w, bias=bias, act=1, residual=None)))
+        check(f"res{M}x{N}x{K}", lambda: digest(ops.gemm(a, w, bias=bias, residual=res)))
+        check(f"dgrad{M}x{N}x{K}", lambda: digest(ops.gemm(dy, w, b_mn=True)))
+        check(f"mask{M}x{N}x{K}", lambda: digest(ops.gemm(dy, w, b_mn=True, relu_mask=a)))
+        check(f"wgrad{M}x{N}x{K}", lambda: digest(ops.gemm(dy, a, a_mn=True, b_mn=True, out_fp32=True, accumulate=True, split_k=0).to(torch.bfloat16)))
+    # ---- whole engine: train steps (all kernels incl. attention fwd / bwd, LayerNorm, CE) and generation
+    for name in ("tiny", "cfg1"):
+        c = CFGS[name]
+        p = O.init_params(c["V"], c["E"], c["H"], c["L"], c["F"], c["ML"], seed=42)
+        tok, tgt, mem, _ = synth(c, 43)
+        eng = make_engine(c, p, dev)
+        tokd, tgtd, memd = tok.to(dev), tgt.to(dev), mem.to(dev)
+
+        def train():
+            eng.zero_grad()
+            out = eng.forward_loss(tokd, tgtd, memd, None, 0, training=True)
+            eng.backward()
+            return digest(out) + digest(eng.grads.to(torch.bfloat16))       # atomics: summation order only
+
+        def gen(beam):
+            eng.decode_begin(memd, None, beam=beam, max_len=12)
+            if beam == 1:
+                t, l = eng.generate_greedy(1, 2, 12, 0)
+            else:
+                t, l, _ = eng.generate_beam(1, 2, 12)
+            return digest(t) + digest(l)
+        check("loss" + name, lambda: digest(eng.forward_loss(tokd, tgtd, memd, None, 0, training=False)))
+        check("logits" + name, lambda: digest(eng.forward_logits(tokd, memd, None)))
+        check("train" + name, train)
+        check("greedy" + name, lambda: gen(1))
+        check("beam" + name, lambda: gen(3))
+    torch.cuda.synchronize()
+    total = hashlib.sha256("".join(hashes).encode()).hexdigest()[:16]
+    print(json.dumps({"launches": int(lib.b200_launch_count() - n0), "hash": total, "mismatches": mism,
+                      "pdl": os.environ.get("B200_NO_PDL") is None, "cases": len(hashes)}))
+    sys.exit(0 if mism == 0 else 1)
+
+
+if __name__ == "__main__":
+    main()
