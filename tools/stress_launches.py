@@ -38,6 +38,7 @@ def main():
     hashes, mism = [], 0
 
     def check(tag, fn):
+        """bit-exact cases: every repetition must hash identically"""
         nonlocal mism
         first = None
         for _ in range(args.reps):
@@ -48,6 +49,21 @@ def main():
                 mism += 1
                 print("MISMATCH", tag, first, h, file=sys.stderr)
         hashes.append(first)
+
+    def check_close(tag, fn, tol=2e-5):
+        """results accumulated with fp32 atomics (split-K wgrad, bias sums): the summation order differs between runs,
+        so repetitions are compared by relative L2 distance instead of by hash"""
+        nonlocal mism
+        first = None
+        for _ in range(args.reps):
+            t = fn().float()
+            if first is None:
+                first = t.clone()
+            else:
+                d = ((t - first).norm() / first.norm().clamp_min(1e-30)).item()
+                if not d < tol:
+                    mism += 1
+                    print("MISMATCH", tag, d, file=sys.stderr)
 
     # ---- GEMM family: forward (K,K), dgrad (K,MN), wgrad (MN,MN) with split-K atomics (order-dependent fp32 sums are
     # compared after rounding to bf16, everything else bit for bit)
@@ -61,7 +77,7 @@ def main():
         check(f"res{M}x{N}x{K}", lambda: digest(ops.gemm(a, w, bias=bias, residual=res)))
         check(f"dgrad{M}x{N}x{K}", lambda: digest(ops.gemm(dy, w, b_mn=True)))
         check(f"mask{M}x{N}x{K}", lambda: digest(ops.gemm(dy, w, b_mn=True, relu_mask=a)))
-        check(f"wgrad{M}x{N}x{K}", lambda: digest(ops.gemm(dy, a, a_mn=True, b_mn=True, out_fp32=True, accumulate=True, split_k=0).to(torch.bfloat16)))
+        check_close(f"wgrad{M}x{N}x{K}", lambda: ops.gemm(dy, a, a_mn=True, b_mn=True, out_fp32=True, accumulate=True, split_k=0))
     # ---- whole engine: train steps (all kernels incl. attention fwd / bwd, LayerNorm, CE) and generation
     for name in ("tiny", "cfg1"):
         c = CFGS[name]
@@ -72,9 +88,9 @@ def main():
 
         def train():
             eng.zero_grad()
-            out = eng.forward_loss(tokd, tgtd, memd, None, 0, training=True)
+            eng.forward_loss(tokd, tgtd, memd, None, 0, training=True)
             eng.backward()
-            return digest(out) + digest(eng.grads.to(torch.bfloat16))       # atomics: summation order only
+            return eng.grads
 
         def gen(beam):
             eng.decode_begin(memd, None, beam=beam, max_len=12)
@@ -85,7 +101,7 @@ def main():
             return digest(t) + digest(l)
         check("loss" + name, lambda: digest(eng.forward_loss(tokd, tgtd, memd, None, 0, training=False)))
         check("logits" + name, lambda: digest(eng.forward_logits(tokd, memd, None)))
-        check("train" + name, train)
+        check_close("train" + name, train)
         check("greedy" + name, lambda: gen(1))
         check("beam" + name, lambda: gen(3))
     torch.cuda.synchronize()
