@@ -140,6 +140,10 @@ typedef struct {
   void* dv; int64_t dv_bs, dv_ts;
 } b200_attn_bwd_args;
 int b200_attn_bwd(const b200_attn_bwd_args* a, void* stream);
+/* Bring-up instrument of the tcgen05 attention kernels (head dim 64, Tq <= 64: the shapes b200_attn_fwd / _bwd route to
+   csrc/attention_tc.cu): device buffer of 32 x 16 int64 that CTA 0 of the following launches fills with clock64 stamps of
+   its pipeline events (producer issue, S issued, P seen, PV issued, softmax phases ...); NULL switches it off. */
+int b200_attn_tc_trace(void* stamps_dev);
 
 /* ---- optimizer (train.py:96-100, 319-325): global-norm clip + AdamW over one flat arena ---- */
 /* sumsq[0] += sum g^2 ; caller zero-fills. */

@@ -83,6 +83,7 @@ SIGNATURES = {
     "b200_cast_bf16_to_f32": (C.c_int, [_P, _P, _I64, _P]),
     "b200_attn_fwd": (C.c_int, [C.POINTER(AttnFwdArgs), _P]),
     "b200_attn_bwd": (C.c_int, [C.POINTER(AttnBwdArgs), _P]),
+    "b200_attn_tc_trace": (C.c_int, [_P]),
     "b200_grad_sumsq": (C.c_int, [_P, _I64, _P, _P]),
     "b200_adamw_step": (C.c_int, [_P, _P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _F, _F, _I32, _P]),
     "b200_adamw_step_dev": (C.c_int, [_P, _P, _P, _P, _P, _I64, _P, _F, _P, _F, _F, _F, _F, _P, _P]),

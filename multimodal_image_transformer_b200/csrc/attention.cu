@@ -11,6 +11,7 @@
 // Backward recomputes P from the saved log-sum-exp: phase 1 produces dQ per query tile, phase 2
 // produces dK/dV per key tile (no atomics, deterministic).
 #include "attention.cuh"
+#include "attention_tc.cuh"
 #include <math.h>
 #include <stdlib.h>
 
@@ -997,6 +998,7 @@ static int try_launch_fwd_split(const AttnDev& d, cudaStream_t s) {
 
 int attn_fwd(const AttnArgs& a, cudaStream_t s) {
   if (int rc = check_common(a)) return rc;
+  if (attn_tc_supported(a)) return attn_tc_fwd(a, s);      // tcgen05 / TMEM path (attention_tc.cu)
   AttnDev d;
   fill_dev(a, &d);
   {

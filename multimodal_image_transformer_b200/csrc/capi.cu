@@ -4,6 +4,7 @@
 #include "gemm.cuh"
 #include "kernels.cuh"
 #include "attention.cuh"
+#include "attention_tc.cuh"
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -181,6 +182,11 @@ int b200_attn_bwd(const b200_attn_bwd_args* a, void* stream) {
   g.dk = BF(a->dk); g.dk_bs = a->dk_bs; g.dk_ts = a->dk_ts;
   g.dv = BF(a->dv); g.dv_bs = a->dv_bs; g.dv_ts = a->dv_ts;
   return attn_bwd(o, g, S_(stream));
+}
+
+int b200_attn_tc_trace(void* stamps_dev) {
+  attn_tc_set_trace(static_cast<long long*>(stamps_dev));
+  return 0;
 }
 
 int b200_grad_sumsq(const float* grad, int64_t n, float* sumsq, void* stream) {
