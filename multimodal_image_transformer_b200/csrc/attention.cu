@@ -1027,6 +1027,7 @@ int attn_bwd(const AttnArgs& a, const AttnGrads& gr, cudaStream_t s) {
   };
   B200_REQUIRE(ok(gr.d_o, gr.do_bs, gr.do_ts) && ok(gr.dq, gr.dq_bs, gr.dq_ts) && ok(gr.dk, gr.dk_bs, gr.dk_ts) && ok(gr.dv, gr.dv_bs, gr.dv_ts),
                "attention bwd: dO/dQ/dK/dV must be non-null, 16-byte aligned, strides multiples of 8");
+  if (attn_tc_bwd_supported(a, gr)) return attn_tc_bwd(a, gr, s);   // tcgen05 / TMEM path (attention_tc.cu)
   AttnDev d;
   fill_dev(a, &d);
   d.d_o = gr.d_o; d.do_bs = gr.do_bs; d.do_ts = gr.do_ts;

@@ -41,40 +41,65 @@ constexpr int ROW_BYTES = TC_HD * 2;       // 128: one swizzle row
 constexpr int Q_BYTES = 64 * ROW_BYTES;    // 8 KB
 constexpr int SLAB_BYTES64 = 64 * ROW_BYTES;   // one 64-key slab of P: 64 query rows x 128 B
 
-// mbar_wait of common.cuh inlines its time-out report (printf argument marshalling) at every call site; these kernels
-// wait in ~20 places, so the report lives out of line and the wait itself is a handful of instructions
-__device__ __noinline__ void tc_wait_timeout(uint32_t parity) {
-  printf("b200: attention mbarrier timeout block %d thread %d parity %u\n", blockIdx.x, threadIdx.x, parity);
-  __trap();
-}
-__device__ int g_tc_wait_mode = 0;      // experiment switch (B200_ATTN_TC_WAIT): 0 spin, 1 nanosleep back-off, 2 suspend-time hint
-__device__ __forceinline__ bool tc_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
-      : "memory");
-  return ok != 0;
-}
+// Bounded mbarrier wait in SEVEN instructions.  These kernels wait in ~25 inlined places and run six different warp
+// roles at once: their hot loops have to fit the 32 KB L1.5 instruction cache together (measured on the backward
+// kernel: with the clock64 / printf time-out of common.cuh's mbar_wait inlined everywhere, trace stamps and unrolled
+// role bodies the binary was 61 KB and stall_no_inst was 58 % of the non-waiting samples of the elementwise warps).
+// A protocol bug still surfaces as a trap (after 2^24 polls: >= 0.3 s), never as a hung GPU.
 __device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const int mode = g_tc_wait_mode;
-  const long long t0 = clock64();
-  while (true) {
-    if (mode == 2) { if (tc_try_wait_hint(bar, parity, 1000000u)) return; }
-    else if (mbar_try_wait(bar, parity)) return;
-    if (mode == 1) __nanosleep(100);
-    if (clock64() - t0 > 4000000000LL) tc_wait_timeout(parity);
-  }
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .u32 n;\n\t"
+      "mov.u32 n, 0;\n\t"
+      "TC_WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra TC_WAIT_DONE;\n\t"
+      "add.u32 n, n, 1;\n\t"
+      "setp.lt.u32 p, n, 16777216;\n\t"
+      "@p bra TC_WAIT_LOOP;\n\t"
+      "trap;\n\t"
+      "TC_WAIT_DONE:\n\t"
+      "}"
+      :
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
 }
 
 __device__ __forceinline__ float ex2f(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// explicit shared-space accesses: pointers computed as `smem + runtime offset` otherwise compile to GENERIC LD.E / ST.E
+// (measured on the first version of the backward kernel: the generic accesses were its top stall, stall_lg / long scoreboard)
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float lds_f1(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+// global loads that stay where they are written (a prefetch an item ahead must not sink below the next barrier wait)
+__device__ __forceinline__ uint4 ldg_v4_here(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ float ldg_f1_here(const float* p) {
+  float r;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(r) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void sts_f1(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 
 // ---- TMEM loads: 32 lanes x N consecutive 32-bit columns (thread = lane)
@@ -102,6 +127,16 @@ __device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&r)[32]) {
                  "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
                  "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
                  "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+// the same for two 16-register loads
+__device__ __forceinline__ void tmem_ld_wait_dep16x2(uint32_t (&a)[16], uint32_t (&b)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
+                 "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]),
+                 "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]),
+                 "+r"(b[8]), "+r"(b[9]), "+r"(b[10]), "+r"(b[11]), "+r"(b[12]), "+r"(b[13]), "+r"(b[14]), "+r"(b[15])
                :
                : "memory");
 }
@@ -292,9 +327,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     }
   } else if (warp == 9) {
     // ============================ S = Q K^T issuer =========================
-    // one thread: everything per instruction is an add on a precomputed descriptor (the address field of a shared-
-    // memory descriptor is its low 14 bits in 16-byte units, and shared memory ends below 2^18 bytes)
-    if (lane == 0) {
+    // everything per instruction is an add on a precomputed descriptor (the address field of a shared-memory
+    // descriptor is its low 14 bits in 16-byte units, and shared memory ends below 2^18 bytes); the whole warp walks the
+    // loop so that this arithmetic stays warp-uniform (uniform registers), one elected lane issues
+    {
       const uint32_t idesc_s = make_idesc_bf16(64, half, false, false);
       const uint64_t dq0 = make_smem_desc_sw128(smem_u32(smem), 16, 1024);
       const uint64_t dk0 = make_smem_desc_sw128(smem_u32(smem) + p.k_off, 16, 1024);
@@ -308,21 +344,24 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         const uint64_t dq = dq0 + slot_u * s;
         const uint64_t dk = dk0 + slot_u * s;
         const uint32_t d = tmem_base + t * half;
+        if (elect_one()) {
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
+          for (int hf = 0; hf < 2; ++hf) {
 #pragma unroll
-          for (int k = 0; k < TC_HD / 16; ++k)
-            umma_bf16(d + (static_cast<uint32_t>(hf * 16) << 16), dq + static_cast<uint64_t>(k * 2),
-                      dk + half_u * hf + static_cast<uint64_t>(k * 2), idesc_s, k > 0 ? 1u : 0u);
+            for (int k = 0; k < TC_HD / 16; ++k)
+              umma_bf16(d + (static_cast<uint32_t>(hf * 16) << 16), dq + static_cast<uint64_t>(k * 2),
+                        dk + half_u * hf + static_cast<uint64_t>(k * 2), idesc_s, k > 0 ? 1u : 0u);
+          }
+          umma_commit(&s_full[t]);
+          umma_commit(&qk_empty[s]);
+          tc_stamp(p, i, 1);
         }
-        umma_commit(&s_full[t]);
-        umma_commit(&qk_empty[s]);
-        tc_stamp(p, i, 1);
+        __syncwarp();
       }
     }
   } else if (warp == 10) {
     // ============================ O = P V issuer ===========================
-    if (lane == 0) {
+    {
       const uint32_t idesc_o = make_idesc_bf16(64, TC_HD, false, true);
       const uint64_t dp0 = make_smem_desc_sw128(smem_u32(smem) + p.p_base, 16, 1024);              // K-major P buffer
       const uint64_t dv0 = make_smem_desc_sw128(smem_u32(smem) + p.v_base, 64 * ROW_BYTES, 1024);  // MN-major V tile
@@ -334,23 +373,26 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         tc_wait(&v_full[sv], static_cast<uint32_t>(i / p.nv) & 1u);
         tc_wait(&p_full[g], static_cast<uint32_t>(i / p.n_p) & 1u);
         tc_fence_after();
-        tc_stamp(p, i, 2);
         const uint64_t dp = dp0 + pbuf_u * g;
         const uint64_t dv = dv0 + vbuf_u * sv;
         const uint32_t d = tmem_o + t * TC_HD;
-        for (int sl = 0; sl < nslab; ++sl) {
+        if (elect_one()) {
+          tc_stamp(p, i, 2);
+          for (int sl = 0; sl < nslab; ++sl) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int kk = sl * 4 + q;
-            if (kk < ksteps)
-              umma_bf16(d, dp + static_cast<uint64_t>(sl * (SLAB_BYTES64 >> 4) + q * 2),
-                        dv + static_cast<uint64_t>(kk * ((16 * ROW_BYTES) >> 4)), idesc_o, kk > 0 ? 1u : 0u);
+            for (int q = 0; q < 4; ++q) {
+              const int kk = sl * 4 + q;
+              if (kk < ksteps)
+                umma_bf16(d, dp + static_cast<uint64_t>(sl * (SLAB_BYTES64 >> 4) + q * 2),
+                          dv + static_cast<uint64_t>(kk * ((16 * ROW_BYTES) >> 4)), idesc_o, kk > 0 ? 1u : 0u);
+            }
           }
+          umma_commit(&o_full[t]);
+          umma_commit(&v_empty[sv]);
+          umma_commit(&p_empty[i & 1]);                // by parity of the item: each softmax group is the only waiter of "its" barrier
+          tc_stamp(p, i, 3);
         }
-        umma_commit(&o_full[t]);
-        umma_commit(&v_empty[sv]);
-        umma_commit(&p_empty[i & 1]);                // by parity of the item: each softmax group is the only waiter of "its" barrier
-        tc_stamp(p, i, 3);
+        __syncwarp();
       }
     }
   } else {
@@ -404,11 +446,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       const int item = first + i * stride;
       const int t = i % ns;
       const uint32_t ph_t = static_cast<uint32_t>(i / ns) & 1u;
-      const float* bias = reinterpret_cast<const float*>(smem + p.bias_off) + grp * 2 * half + hf * half;
+      const uint32_t bias = smem_u32(smem + p.bias_off) + static_cast<uint32_t>(grp * 2 * half + hf * half) * 4u;   // shared-space address of this thread's key bias
       if (MASKED && p.has_bias) {
         // key bias of this item (0 / -inf per key), written by the group's 128 threads between two group barriers: the
         // first one says every thread has finished reading the previous item's bias
-        float* bw = reinterpret_cast<float*>(smem + p.bias_off) + grp * 2 * half;
+        const uint32_t bw = smem_u32(smem + p.bias_off) + static_cast<uint32_t>(grp * 2 * half) * 4u;
         const int e = (warp - 1 - 4 * grp) * 32 + lane;
         const int bb = item / p.H;
         bool mk[3];
@@ -423,7 +465,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         named_barrier_sync(1 + grp, 128);
 #pragma unroll
         for (int k = 0; k < 3; ++k)
-          if (e + k * 128 < p.Tk16) bw[e + k * 128] = mk[k] ? -INFINITY : 0.f;
+          if (e + k * 128 < p.Tk16) sts_f1(bw + static_cast<uint32_t>(e + k * 128) * 4u, mk[k] ? -INFINITY : 0.f);
         named_barrier_sync(1 + grp, 128);
       }
       tc_wait(&s_full[t], ph_t);
@@ -432,14 +474,14 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       const uint32_t t_s = tmem_base + t * half + lane_addr;
       const int key_base = hf * half;                // first key of this thread's half
       const int pb = i % p.n_p;
-      uint8_t* sP = smem + p.p_base + pb * p.p_bytes;
+      const uint32_t sP = smem_u32(smem + p.p_base + pb * p.p_bytes);
       const int bh = item;
       float mx = -INFINITY, sum = 0.f, m2;
 
       // score of local column c (already a float) -> masked value for the maximum
       auto masked_raw = [&](float v, int c) __attribute__((always_inline)) {
         const int key = key_base + c;
-        if (MASKED && p.has_bias) v += bias[c];      // 0 / -inf: the additive form keeps the scale out of the max pass
+        if (MASKED && p.has_bias) v += lds_f1(bias + static_cast<uint32_t>(c) * 4u);      // 0 / -inf: the additive form keeps the scale out of the max pass
         if (key >= p.Tk || (MASKED && p.causal && key > row)) v = -INFINITY;
         return v;
       };
@@ -455,7 +497,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float a = fmaf(__uint_as_float(r[g * 8 + j]), p.sl2, -m2);
-            if (MASKED && p.has_bias) a += bias[c0 + j];
+            if (MASKED && p.has_bias) a += lds_f1(bias + static_cast<uint32_t>(c0 + j) * 4u);
             if (key0 + j >= p.Tk || (MASKED && p.causal && key0 + j > row)) a = -INFINITY;
             pv[j] = ex2f(a);
           }
@@ -471,7 +513,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         u.y = pack_bf16(pv[2], pv[3]);
         u.z = pack_bf16(pv[4], pv[5]);
         u.w = pack_bf16(pv[6], pv[7]);
-        *reinterpret_cast<uint4*>(sP + p_unit_off(row, key0)) = u;
+        sts_v4(sP + p_unit_off(row, key0), u);
       };
 
       // Both passes are COMPACT runtime loops: straight-line blocks of 32 columns (enough independent work per block
@@ -543,6 +585,456 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ==========================================================================================
+// backward
+// ==========================================================================================
+// Everything is computed TRANSPOSED (thread = key) so that the softmax statistics are per COLUMN and arrive as
+// broadcast shared-memory reads (no cross-lane reduction anywhere), and the unit of work is one 128-key tile of one
+// (image, head) item:
+//   S^T  = K_t Q^T      [128 keys x NQ rows]   A = K tile (K-major), B = Q (K-major)            -> TMEM, NQ columns
+//   dP^T = V_t dO^T     [128 x NQ]             A = V tile,            B = dO                     -> TMEM, NQ columns
+//   elementwise (thread = key): P^T = exp2(S^T * scale*log2e - lse2[row]), dS^T = P^T * (dP^T - delta[row]),
+//                       both as bf16 into shared memory, one 128-byte swizzle row per key ([keys][rows])
+//   dV_t = P^T dO       [128 keys x 64]        A = P^T (K-major), B = dO as stored (MN-major)    -> TMEM, 64 columns
+//   dK_t = dS^T Q       [128 keys x 64]        A = dS^T (K-major), B = Q as stored (MN-major)    -> TMEM, 64 columns
+//   dQ  += dS K_t       [64 rows x 64]         A = dS^T read MN-major, B = K tile MN-major       -> TMEM, 64 columns,
+//                                              accumulated over the key tiles of the item
+// TMEM: 2 stages x (48 + 48 + 64 + 64) + 64 = 512 columns, which is why this path takes NQ <= 48 query rows (the
+// caption length 48 of every BASELINE config gives T = 47); longer targets keep the mma.sync kernels.
+// Warps (512 threads): 0-3 / 4-7 the two elementwise groups (units alternate), 8-11 the output group (dQ of the item,
+// dV and dK tiles: TMEM -> bf16 -> per-warp swizzled staging tile -> TMA store through 3-D tensor maps that clip at the
+// sample's last row), 12 TMA producer, 13 row statistics (lse * log2e and delta = rowsum(dO * O) per item, from the
+// TMA-loaded dO and O tiles) + TMEM allocation, 14 issuer of the S^T / dP^T products, 15 issuer of the dV / dK / dQ
+// products.
+// History (cfg2 cross attention, 256 x 12 items of 47 x 197; mma.sync kernel: 171 us):
+//   128 us  one output group that also computed the statistics from global memory, rows stored with per-thread 16-byte
+//           stores (32 different lines per instruction: the LSU was the bottleneck, and it slowed the elementwise
+//           groups' shared-memory traffic with it);
+//   108 us  statistics on their own warp; MMA issue by an elected lane of a CONVERGED warp (descriptor arithmetic in
+//           uniform registers instead of an ELECT / 5 x R2UR "waterfall" loop per instruction);
+//    96 us  output through staging tiles + TMA stores;
+//   then every added feature (trace stamps, unrolled / pipelined role bodies, more statistics warps, schedule knobs)
+//   made ALL roles slower: the binary had grown to 61 KB and stall_no_inst dominated -- six roles run six different
+//   loops at once and share a 32 KB L1.5 instruction cache.  This version is the same schedule on a code diet:
+//   seven-instruction waits, trace stamps compiled out (template), one loop body per role.
+struct TcBwdDev {
+  int B, H, Tq, Tk, NQ, NT, tail16, n_items;
+  int causal, has_mask;
+  int kring_off, vring_off, o_off, pds_off, stage_off, stat_off, bar_off;   // byte offsets (Q | dO slots start at 0)
+  const long long* key_tokens; long long pad_idx;
+  const unsigned char* key_pad_mask;
+  float scale, sl2;
+  const float* lse;
+  long long* trace;                               // bring-up instrument: [unit][16] clock64 stamps of CTA 0 (null = off)
+};
+
+namespace {
+constexpr int BW_THREADS = 512;
+constexpr int BW_TILE = 128;                          // keys per unit
+constexpr int BW_TILE_BYTES = BW_TILE * ROW_BYTES;    // 16 KB: one K or V tile, one P^T or dS^T buffer
+constexpr int BW_STAGE_COLS = 224;                    // S^T 0, dP^T 48, dV 96, dK 160
+constexpr int BW_DQ_COL = 448;
+constexpr int BW_RK = 3, BW_RV = 2;                   // K ring / V ring entries (V is dead after dP^T: its ring is short)
+constexpr int BW_NSLOT = 3;                           // Q | dO slots and row-statistics slots (items in flight)
+constexpr int BW_QROWS_BYTES = 48 * ROW_BYTES;        // 6 KB: the <= 48 rows of Q, dO or O of one item
+constexpr int BW_SLOT_BYTES = 2 * BW_QROWS_BYTES;     // Q | dO
+constexpr int BW_STAGING_BYTES = 32 * ROW_BYTES;      // 4 KB: one [32 rows][128 B] tile; two per output warp
+// stamps of CTA 0's first 32 units: 0 K load issued, 1 S^T / dP^T issued, 2 st_full seen, 3 P / dS buffers free,
+// 4 P / dS published, 5 output products: operands ready, 6 ... issued, 7 out_full seen, 8 tiles stored, 9 statistics done
+template <bool TRACE>
+__device__ __forceinline__ void bw_stamp(const TcBwdDev& p, int u, int slot) {
+  if constexpr (TRACE) {
+    if (blockIdx.x == 0 && u < 32) p.trace[u * 16 + slot] = clock64();
+  }
+}
+}  // namespace
+
+template <bool TRACE>
+__global__ void __launch_bounds__(BW_THREADS, 1)
+attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
+                   const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_k,
+                   const __grid_constant__ CUtensorMap tmap_k_tail, const __grid_constant__ CUtensorMap tmap_v,
+                   const __grid_constant__ CUtensorMap tmap_v_tail, const __grid_constant__ CUtensorMap tmap_dq,
+                   const __grid_constant__ CUtensorMap tmap_dk, const __grid_constant__ CUtensorMap tmap_dv,
+                   const TcBwdDev p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.bar_off);
+  uint64_t* qdo_full = bars;                 // [3] Q and dO of the item landed
+  uint64_t* qdo_empty = qdo_full + 4;        // [3] every product of the item has read them
+  uint64_t* k_full = qdo_empty + 4;          // [3] K tile landed
+  uint64_t* k_empty = k_full + 4;            // [3] S^T and dQ of the unit have read it
+  uint64_t* v_full = k_empty + 4;            // [2] V tile landed
+  uint64_t* v_empty = v_full + 4;            // [2] dP^T of the unit has read it
+  uint64_t* st_full = v_empty + 4;           // [2] S^T and dP^T complete in TMEM
+  uint64_t* st_empty = st_full + 2;          // [2] ... and read
+  uint64_t* pds_full = st_empty + 2;         // [2] P^T and dS^T written to shared memory
+  uint64_t* pds_empty = pds_full + 2;        // [2] ... and read by the output products
+  uint64_t* out_full = pds_empty + 2;        // [2] dV and dK tile complete in TMEM
+  uint64_t* out_empty = out_full + 2;        // [2] ... and read
+  uint64_t* dq_full = out_empty + 2;         // [1]
+  uint64_t* dq_empty = dq_full + 1;          // [1]
+  uint64_t* stat_full = dq_empty + 1;        // [3] row statistics of the item written
+  uint64_t* stat_empty = stat_full + 4;      // [3] ... and read by all its units
+  uint64_t* o_full = stat_empty + 4;         // [1] O of the item landed (one slot: it lives only until the statistics are done)
+  uint64_t* o_empty = o_full + 1;            // [1]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // shared memory starts out as zeros: K / V rows past the last key, P^T / dS^T row slots past NQ and the tail of a
+  // short last tile are multiplied by zeros later, so they have to be finite
+  for (int i = threadIdx.x; i < p.stat_off / 16; i += BW_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async();
+  if (warp == 13) {
+    tmem_alloc(tmem_ptr_smem, 512);
+    tmem_relinquish();
+  }
+  if (warp == 12 && lane == 0) {
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&qdo_full[i], 1);
+      mbar_init(&qdo_empty[i], 1);
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&stat_full[i], 32);
+      mbar_init(&stat_empty[i], 128 * p.NT);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&st_full[i], 1);
+      mbar_init(&st_empty[i], 128);
+      mbar_init(&pds_full[i], 128);
+      mbar_init(&pds_empty[i], 1);
+      mbar_init(&out_full[i], 1);
+      mbar_init(&out_empty[i], 128);
+    }
+    mbar_init(dq_full, 1);
+    mbar_init(dq_empty, 128);
+    mbar_init(o_full, 1);
+    mbar_init(o_empty, 32);
+    fence_barrier_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+  pdl_trigger();
+
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int n_local = (p.n_items > first) ? (p.n_items - first + stride - 1) / stride : 0;
+  const int NT = p.NT;
+  const int n_units = n_local * NT;
+  const int qsteps = p.NQ / 16;
+  uint8_t* const kring = smem + p.kring_off;
+  uint8_t* const vring = smem + p.vring_off;
+  uint8_t* const pds = smem + p.pds_off;
+  const uint32_t stat_u = smem_u32(smem + p.stat_off);       // [3][lse2 64 | delta 64]
+
+  if (warp == 12) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      int u = 0;
+      for (int i = 0; i < n_local; ++i) {
+        const int item = first + i * stride;
+        const int b = item / p.H, h = item % p.H;
+        const int sl = i % BW_NSLOT;
+        tc_wait(&qdo_empty[sl], (static_cast<uint32_t>(i / BW_NSLOT) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&qdo_full[sl], 2 * p.NQ * ROW_BYTES);
+        tma_load_2d(smem + sl * BW_SLOT_BYTES, &tmap_q, &qdo_full[sl], h * TC_HD, b * p.Tq);
+        tma_load_2d(smem + sl * BW_SLOT_BYTES + BW_QROWS_BYTES, &tmap_do, &qdo_full[sl], h * TC_HD, b * p.Tq);
+        tc_wait(o_empty, (static_cast<uint32_t>(i) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(o_full, p.NQ * ROW_BYTES);
+        tma_load_2d(smem + p.o_off, &tmap_o, o_full, h * TC_HD, b * p.Tq);
+        for (int kt = 0; kt < NT; ++kt, ++u) {
+          const int rk = u % BW_RK, rv = u % BW_RV;
+          const bool tail = kt == NT - 1;
+          const int rows = tail ? p.tail16 : BW_TILE;
+          tc_wait(&k_empty[rk], (static_cast<uint32_t>(u / BW_RK) & 1u) ^ 1u);
+          bw_stamp<TRACE>(p, u, 0);
+          mbar_arrive_expect_tx(&k_full[rk], rows * ROW_BYTES);
+          tma_load_2d(kring + rk * BW_TILE_BYTES, tail ? &tmap_k_tail : &tmap_k, &k_full[rk], h * TC_HD, b * p.Tk + kt * BW_TILE);
+          tc_wait(&v_empty[rv], (static_cast<uint32_t>(u / BW_RV) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&v_full[rv], rows * ROW_BYTES);
+          tma_load_2d(vring + rv * BW_TILE_BYTES, tail ? &tmap_v_tail : &tmap_v, &v_full[rv], h * TC_HD, b * p.Tk + kt * BW_TILE);
+        }
+      }
+    }
+  } else if (warp == 14) {
+    // ============================ S^T = K Q^T and dP^T = V dO^T ============
+    // The WHOLE warp walks the loop (waits, descriptor arithmetic: warp-uniform, so it stays in uniform registers) and
+    // one elected lane issues.  Issuing from inside an `if (lane == 0)` region made every tcgen05.mma a ~19-instruction
+    // sequence: 64-bit adds in vector registers plus an ELECT / 5 x R2UR "waterfall" loop per instruction.
+    const uint32_t idesc = make_idesc_bf16(128, p.NQ, false, false);
+    const uint64_t d_q0 = make_smem_desc_sw128(smem_u32(smem), 16, 1024);
+    const uint64_t d_k0 = make_smem_desc_sw128(smem_u32(kring), 16, 1024);
+    const uint64_t d_v0 = make_smem_desc_sw128(smem_u32(vring), 16, 1024);
+    int i = 0, kt = 0;
+    for (int u = 0; u < n_units; ++u) {
+      const int g = u & 1, rk = u % BW_RK, rv = u % BW_RV;
+      if (kt == 0) tc_wait(&qdo_full[i % BW_NSLOT], static_cast<uint32_t>(i / BW_NSLOT) & 1u);
+      tc_wait(&k_full[rk], static_cast<uint32_t>(u / BW_RK) & 1u);
+      tc_wait(&v_full[rv], static_cast<uint32_t>(u / BW_RV) & 1u);
+      tc_wait(&st_empty[g], (static_cast<uint32_t>(u >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint64_t dq = d_q0 + static_cast<uint64_t>((i % BW_NSLOT) * (BW_SLOT_BYTES >> 4));
+      const uint64_t ddo = dq + static_cast<uint64_t>(BW_QROWS_BYTES >> 4);
+      const uint64_t dk = d_k0 + static_cast<uint64_t>(rk * (BW_TILE_BYTES >> 4));
+      const uint64_t dv = d_v0 + static_cast<uint64_t>(rv * (BW_TILE_BYTES >> 4));
+      const uint32_t t_s = tmem_base + g * BW_STAGE_COLS;
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < TC_HD / 16; ++k) umma_bf16(t_s, dk + static_cast<uint64_t>(k * 2), dq + static_cast<uint64_t>(k * 2), idesc, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < TC_HD / 16; ++k) umma_bf16(t_s + 48, dv + static_cast<uint64_t>(k * 2), ddo + static_cast<uint64_t>(k * 2), idesc, k > 0 ? 1u : 0u);
+        umma_commit(&st_full[g]);
+        umma_commit(&v_empty[rv]);
+        bw_stamp<TRACE>(p, u, 1);
+      }
+      __syncwarp();
+      if (++kt == NT) { kt = 0; ++i; }
+    }
+  } else if (warp == 15) {
+    // ============================ dV = P^T dO, dK = dS^T Q, dQ += dS K ======
+    const uint32_t idesc_kv = make_idesc_bf16(128, TC_HD, false, true);
+    const uint32_t idesc_dq = make_idesc_bf16(64, TC_HD, true, true);
+    const uint64_t d_p0 = make_smem_desc_sw128(smem_u32(pds), 16, 1024);                          // K-major P^T / dS^T
+    const uint64_t d_pm0 = make_smem_desc_sw128(smem_u32(pds), 64 * ROW_BYTES, 1024);             // the same bytes, MN-major
+    const uint64_t d_qm0 = make_smem_desc_sw128(smem_u32(smem), 64 * ROW_BYTES, 1024);            // Q / dO as stored (MN-major)
+    const uint64_t d_km0 = make_smem_desc_sw128(smem_u32(kring), 64 * ROW_BYTES, 1024);           // K tile as stored
+    constexpr uint64_t KSTEP_MN = (16 * ROW_BYTES) >> 4;                                            // 16 rows of 128 B
+    int i = 0, kt = 0;
+    for (int u = 0; u < n_units; ++u) {
+      const int g = u & 1, rk = u % BW_RK;
+      tc_wait(&pds_full[g], static_cast<uint32_t>(u >> 1) & 1u);
+      tc_wait(&out_empty[g], (static_cast<uint32_t>(u >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      bw_stamp<TRACE>(p, u, 5);
+      const uint64_t dp = d_p0 + static_cast<uint64_t>(g * ((2 * BW_TILE_BYTES) >> 4));
+      const uint64_t dds = dp + static_cast<uint64_t>(BW_TILE_BYTES >> 4);
+      const uint64_t dds_m = d_pm0 + static_cast<uint64_t>(g * ((2 * BW_TILE_BYTES) >> 4) + (BW_TILE_BYTES >> 4));
+      const uint64_t dq_m = d_qm0 + static_cast<uint64_t>((i % BW_NSLOT) * (BW_SLOT_BYTES >> 4));
+      const uint64_t ddo_m = dq_m + static_cast<uint64_t>(BW_QROWS_BYTES >> 4);
+      const uint64_t dk_m = d_km0 + static_cast<uint64_t>(rk * (BW_TILE_BYTES >> 4));
+      const uint32_t t_v = tmem_base + g * BW_STAGE_COLS + 96, t_k = t_v + 64, t_q = tmem_base + BW_DQ_COL;
+      const int ksteps = (kt == NT - 1 ? p.tail16 : BW_TILE) / 16;
+      const bool last = kt == NT - 1;
+      if (elect_one()) {
+        for (int k = 0; k < qsteps; ++k) umma_bf16(t_v, dp + static_cast<uint64_t>(k * 2), ddo_m + KSTEP_MN * k, idesc_kv, k > 0 ? 1u : 0u);
+        for (int k = 0; k < qsteps; ++k) umma_bf16(t_k, dds + static_cast<uint64_t>(k * 2), dq_m + KSTEP_MN * k, idesc_kv, k > 0 ? 1u : 0u);
+        umma_commit(&out_full[g]);                     // the output group drains dV / dK while dQ is still being accumulated
+      }
+      __syncwarp();
+      // the dQ accumulator of the previous item has been drained (only the item's first dQ product has to wait for that)
+      if (kt == 0) {
+        tc_wait(dq_empty, (static_cast<uint32_t>(i) & 1u) ^ 1u);
+        tc_fence_after();
+      }
+      if (elect_one()) {
+        for (int k = 0; k < ksteps; ++k) umma_bf16(t_q, dds_m + KSTEP_MN * k, dk_m + KSTEP_MN * k, idesc_dq, (kt > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&pds_empty[g]);
+        umma_commit(&k_empty[rk]);
+        bw_stamp<TRACE>(p, u, 6);
+        if (last) {
+          umma_commit(dq_full);
+          umma_commit(&qdo_empty[i % BW_NSLOT]);
+        }
+      }
+      __syncwarp();
+      if (++kt == NT) { kt = 0; ++i; }
+    }
+  } else if (warp < 8) {
+    // ============================ elementwise groups ========================
+    const int g = warp >> 2, w4 = warp & 3;
+    const int j = w4 * 32 + lane;                    // key inside the tile = TMEM lane
+    const uint32_t lane_addr = static_cast<uint32_t>(w4 * 32) << 16;
+    const uint32_t rowP = smem_u32(pds + g * 2 * BW_TILE_BYTES + j * ROW_BYTES);
+    const int sw = j & 7;
+    int prev_i = -1;
+    for (int u = g; u < n_units; u += 2) {
+      const int i = u / NT, kt = u - i * NT;
+      const int key = kt * BW_TILE + j;
+      bool valid = key < p.Tk;
+      if (p.has_mask && valid) {
+        const long long off = static_cast<long long>((first + i * stride) / p.H) * p.Tk + key;
+        if (p.key_tokens) valid = p.key_tokens[off] != p.pad_idx;
+        if (valid && p.key_pad_mask) valid = p.key_pad_mask[off] == 0;
+      }
+      if (i != prev_i) {
+        tc_wait(&stat_full[i % BW_NSLOT], static_cast<uint32_t>(i / BW_NSLOT) & 1u);
+        prev_i = i;
+      }
+      tc_wait(&st_full[g], static_cast<uint32_t>(u >> 1) & 1u);
+      tc_fence_after();
+      if (j == 0) bw_stamp<TRACE>(p, u, 2);
+      tc_wait(&pds_empty[g], (static_cast<uint32_t>(u >> 1) & 1u) ^ 1u);
+      if (j == 0) bw_stamp<TRACE>(p, u, 3);
+      const uint32_t lse2 = stat_u + static_cast<uint32_t>(i % BW_NSLOT) * 512u;      // [64] lse * log2e, then [64] delta
+      const uint32_t t_s = tmem_base + g * BW_STAGE_COLS + lane_addr;
+      const int lim = (p.causal && valid) ? key : (valid ? 0 : 0x7fffffff);   // rows below `lim` get P = 0 (causal: key > row)
+      // 16 rows per trip: S^T and dP^T -> P^T, dS^T -> two 16-byte units of this key's row in each buffer (ONE loop body)
+#pragma unroll 1
+      for (int c = 0; c < qsteps; ++c) {
+        uint32_t rs[16], rd[16];
+        tmem_ld_32x16(t_s + c * 16, rs);
+        tmem_ld_32x16(t_s + 48 + c * 16, rd);
+        tmem_ld_wait();
+        uint32_t pk[8], dk[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 l = lds_f4(lse2 + static_cast<uint32_t>(c * 4 + q) * 16u), d = lds_f4(lse2 + 256u + static_cast<uint32_t>(c * 4 + q) * 16u);
+          const float la[4] = {l.x, l.y, l.z, l.w}, da[4] = {d.x, d.y, d.z, d.w};
+          float pv[4], ds[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int idx = q * 4 + e;
+            float pr = ex2f(fmaf(__uint_as_float(rs[idx]), p.sl2, -la[e]));
+            if (c * 16 + idx < lim) pr = 0.f;
+            pv[e] = pr;
+            ds[e] = pr * (__uint_as_float(rd[idx]) - da[e]);
+          }
+          pk[q * 2] = pack_bf16(pv[0], pv[1]); pk[q * 2 + 1] = pack_bf16(pv[2], pv[3]);
+          dk[q * 2] = pack_bf16(ds[0], ds[1]); dk[q * 2 + 1] = pack_bf16(ds[2], ds[3]);
+        }
+        const uint32_t u0 = static_cast<uint32_t>(((2 * c) ^ sw) << 4), u1 = static_cast<uint32_t>(((2 * c + 1) ^ sw) << 4);
+        sts_v4(rowP + u0, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+        sts_v4(rowP + u1, make_uint4(pk[4], pk[5], pk[6], pk[7]));
+        sts_v4(rowP + BW_TILE_BYTES + u0, make_uint4(dk[0], dk[1], dk[2], dk[3]));
+        sts_v4(rowP + BW_TILE_BYTES + u1, make_uint4(dk[4], dk[5], dk[6], dk[7]));
+      }
+      tc_fence_before();
+      mbar_arrive(&st_empty[g]);
+      fence_proxy_async();
+      mbar_arrive(&pds_full[g]);
+      mbar_arrive(&stat_empty[i % BW_NSLOT]);
+      if (j == 0) bw_stamp<TRACE>(p, u, 4);
+    }
+  } else if (warp < 12) {
+    // ============================ output group ==============================
+    const int w4 = warp & 3;
+    const uint32_t lane_addr = static_cast<uint32_t>(w4 * 32) << 16;
+    uint8_t* const stg = smem + p.stage_off + w4 * 2 * BW_STAGING_BYTES;     // this warp's two [32 rows][128 B] swizzled staging tiles
+    const uint32_t stg_row = smem_u32(stg) + static_cast<uint32_t>(lane * ROW_BYTES);
+    const int sw = lane & 7;
+    int n_tiles = 0;                                  // staging tiles written so far: tile n uses buffer n % 2
+    int i = 0, kt = 0;
+    for (int u = 0; u < n_units; ++u) {
+      const int g = u & 1;
+      const int item = first + i * stride;
+      const int b = item / p.H, h = item % p.H;
+      tc_wait(&out_full[g], static_cast<uint32_t>(u >> 1) & 1u);
+      tc_fence_after();
+      if (w4 == 0 && lane == 0) bw_stamp<TRACE>(p, u, 7);
+      const bool last = kt == NT - 1;
+      const int key0 = kt * BW_TILE + w4 * 32;          // first key of this warp's 32 rows
+      // tiles of the unit: 0 = dQ of the item (after its last unit; FIRST, the next item's dQ products wait for the
+      // accumulator), 1 = dV, 2 = dK: 64 fp32 columns of this thread's TMEM lane -> one bf16 row of the staging tile
+      // -> TMA store (ONE loop body)
+#pragma unroll 1
+      for (int t = last ? 0 : 1; t < 3; ++t) {
+        if (t == 0) {
+          tc_wait(dq_full, static_cast<uint32_t>(i) & 1u);
+          tc_fence_after();
+        }
+        // M = 64 accumulator (dQ): rows 16w .. 16w+15 live in lanes 32w + 0..15 -> 16 staging rows per warp
+        const bool active = t == 0 ? (w4 * 16 < p.Tq) : (key0 < p.Tk);
+        if (active) {
+          const uint32_t taddr = (t == 0 ? tmem_base + BW_DQ_COL : tmem_base + g * BW_STAGE_COLS + 96 + (t - 1) * 64) + lane_addr;
+          const float sc = t == 1 ? 1.f : p.scale;
+          uint32_t ra[32], rb[32];
+          tmem_ld_32x32(taddr, ra);
+          tmem_ld_32x32(taddr + 32, rb);
+          // the buffer may be rewritten once the store issued two tiles ago has READ it (one store may still be in flight)
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+          tmem_ld_wait();
+          if (t != 0 || lane < 16) {
+            const uint32_t dst_row = stg_row + static_cast<uint32_t>(n_tiles & 1) * BW_STAGING_BYTES;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 v;
+              v.x = pack_bf16(__uint_as_float(ra[q * 8 + 0]) * sc, __uint_as_float(ra[q * 8 + 1]) * sc);
+              v.y = pack_bf16(__uint_as_float(ra[q * 8 + 2]) * sc, __uint_as_float(ra[q * 8 + 3]) * sc);
+              v.z = pack_bf16(__uint_as_float(ra[q * 8 + 4]) * sc, __uint_as_float(ra[q * 8 + 5]) * sc);
+              v.w = pack_bf16(__uint_as_float(ra[q * 8 + 6]) * sc, __uint_as_float(ra[q * 8 + 7]) * sc);
+              sts_v4(dst_row + ((q ^ sw) << 4), v);
+              v.x = pack_bf16(__uint_as_float(rb[q * 8 + 0]) * sc, __uint_as_float(rb[q * 8 + 1]) * sc);
+              v.y = pack_bf16(__uint_as_float(rb[q * 8 + 2]) * sc, __uint_as_float(rb[q * 8 + 3]) * sc);
+              v.z = pack_bf16(__uint_as_float(rb[q * 8 + 4]) * sc, __uint_as_float(rb[q * 8 + 5]) * sc);
+              v.w = pack_bf16(__uint_as_float(rb[q * 8 + 6]) * sc, __uint_as_float(rb[q * 8 + 7]) * sc);
+              sts_v4(dst_row + (((4 + q) ^ sw) << 4), v);
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(t == 0 ? &tmap_dq : (t == 1 ? &tmap_dv : &tmap_dk), stg + (n_tiles & 1) * BW_STAGING_BYTES, h * TC_HD,
+                         t == 0 ? w4 * 16 : key0, b);
+            bulk_commit();
+          }
+          ++n_tiles;
+        }
+        if (t == 0) {
+          tc_fence_before();
+          mbar_arrive(dq_empty);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&out_empty[g]);
+      if (last) { kt = 0; ++i; } else ++kt;
+      if (w4 == 0 && lane == 0) bw_stamp<TRACE>(p, u, 8);
+    }
+    if (lane == 0) bulk_wait_all();
+    __syncwarp();
+  } else if (warp == 13) {
+    // ============================ row statistics ============================
+    // lse * log2(e) (+inf for rows past Tq and for fully masked rows: P = 0) and delta = rowsum(dO * O): lane = row
+    // (then row + 32), from the 128-byte-swizzled dO and O tiles of the item.  Compact loops on purpose (see the header).
+    for (int i = 0; i < n_local; ++i) {
+      const int item = first + i * stride;
+      const int sl = i % BW_NSLOT;
+      tc_wait(&qdo_full[sl], static_cast<uint32_t>(i / BW_NSLOT) & 1u);
+      tc_wait(o_full, static_cast<uint32_t>(i) & 1u);
+      tc_wait(&stat_empty[sl], (static_cast<uint32_t>(i / BW_NSLOT) & 1u) ^ 1u);
+      const uint32_t s_do = smem_u32(smem + sl * BW_SLOT_BYTES + BW_QROWS_BYTES), s_o = smem_u32(smem + p.o_off);
+#pragma unroll 1
+      for (int rr = 0; rr < 2; ++rr) {
+        const int row = lane + 32 * rr;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, l = INFINITY;
+        if (row < p.Tq) {
+          const float x = p.lse[static_cast<long long>(item) * p.Tq + row];
+          l = (x == -INFINITY) ? INFINITY : x * LOG2E;
+#pragma unroll 2
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t off = static_cast<uint32_t>(row * ROW_BYTES + ((c ^ (row & 7)) << 4));
+            const float4 o4 = lds_f4(s_o + off), d4 = lds_f4(s_do + off);
+            float2 x0 = unpack_bf16(__float_as_uint(o4.x)), y0 = unpack_bf16(__float_as_uint(d4.x));
+            float2 x1 = unpack_bf16(__float_as_uint(o4.y)), y1 = unpack_bf16(__float_as_uint(d4.y));
+            float2 x2 = unpack_bf16(__float_as_uint(o4.z)), y2 = unpack_bf16(__float_as_uint(d4.z));
+            float2 x3 = unpack_bf16(__float_as_uint(o4.w)), y3 = unpack_bf16(__float_as_uint(d4.w));
+            a0 = fmaf(x0.x, y0.x, a0); a1 = fmaf(x0.y, y0.y, a1);
+            a2 = fmaf(x1.x, y1.x, a2); a3 = fmaf(x1.y, y1.y, a3);
+            a0 = fmaf(x2.x, y2.x, a0); a1 = fmaf(x2.y, y2.y, a1);
+            a2 = fmaf(x3.x, y3.x, a2); a3 = fmaf(x3.y, y3.y, a3);
+          }
+        }
+        sts_f1(stat_u + static_cast<uint32_t>(sl * 128 + row) * 4u, l);
+        sts_f1(stat_u + static_cast<uint32_t>(sl * 128 + 64 + row) * 4u, (a0 + a1) + (a2 + a3));
+      }
+      mbar_arrive(o_empty);
+      mbar_arrive(&stat_full[sl]);
+      if (lane == 0) bw_stamp<TRACE>(p, i * NT, 9);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 13) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -631,14 +1123,6 @@ int attn_tc_fwd(const AttnArgs& a, cudaStream_t s) {
   const int sms = device_sm_count();
   const int grid = d.n_items < sms ? d.n_items : sms;
   d.trace = g_tc_trace;
-  {
-    static bool mode_set = false;
-    if (!mode_set) {
-      const int mode = getenv("B200_ATTN_TC_WAIT") ? atoi(getenv("B200_ATTN_TC_WAIT")) : 0;
-      B200_CHECK_CUDA(cudaMemcpyToSymbol(g_tc_wait_mode, &mode, sizeof(int)));
-      mode_set = true;
-    }
-  }
   const bool masked = d.has_bias || d.causal, drop = d.drop.thr != 0;
   typedef void (*Kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcDev);
   static const Kern kerns[4] = {attn_tc_fwd_kernel<false, false>, attn_tc_fwd_kernel<true, false>,
@@ -650,6 +1134,81 @@ int attn_tc_fwd(const AttnArgs& a, cudaStream_t s) {
   }
   Kern kern = kerns[(masked ? 1 : 0) + (drop ? 2 : 0)];
   B200_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(TC_THREADS), static_cast<size_t>(smem), s, true, 1, tq, tk, tv, d));
+  note_launch();
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static bool tc_bwd_enabled() {
+  static const bool on = !(getenv("B200_ATTN_TC_BWD") && atoi(getenv("B200_ATTN_TC_BWD")) == 0);
+  return on;
+}
+
+bool attn_tc_bwd_supported(const AttnArgs& a, const AttnGrads& g) {
+  if (!tc_enabled() || !tc_bwd_enabled()) return false;
+  if (a.hd != TC_HD || a.Tq > 48 || a.Tq < 1 || a.Tk < 1 || a.drop.thr != 0) return false;
+  // short key ranges (the caption's self attention, Tk = Tq <= 48) stay on the mma.sync kernel: one 128-key tile per
+  // item leaves the tcgen05 pipeline latency-bound (measured 66 us against 58 us at cfg2)
+  static const int min_tk = getenv("B200_ATTN_TC_BWD_MIN_TK") ? atoi(getenv("B200_ATTN_TC_BWD_MIN_TK")) : 65;
+  if (a.Tk < min_tk) return false;
+  auto out_ok = [](const void* ptr, long long ts) { return ptr != nullptr && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ts % 8 == 0; };
+  return tc_layout_ok(a.q, a.q_bs, a.q_ts, a.Tq) && tc_layout_ok(a.k, a.k_bs, a.k_ts, a.Tk) && tc_layout_ok(a.v, a.v_bs, a.v_ts, a.Tk) &&
+         tc_layout_ok(g.d_o, g.do_bs, g.do_ts, a.Tq) && tc_layout_ok(a.o, a.o_bs, a.o_ts, a.Tq) && a.lse != nullptr &&
+         out_ok(g.dq, g.dq_ts) && out_ok(g.dk, g.dk_ts) && out_ok(g.dv, g.dv_ts) && g.dq_bs % 8 == 0 && g.dk_bs % 8 == 0 && g.dv_bs % 8 == 0;
+}
+
+int attn_tc_bwd(const AttnArgs& a, const AttnGrads& g, cudaStream_t s) {
+  TcBwdDev d;
+  memset(&d, 0, sizeof(d));
+  d.B = a.B; d.H = a.H; d.Tq = a.Tq; d.Tk = a.Tk;
+  d.NQ = (a.Tq + 15) / 16 * 16;
+  const int tk16 = (a.Tk + 15) / 16 * 16;
+  d.NT = (tk16 + BW_TILE - 1) / BW_TILE;
+  d.tail16 = tk16 - (d.NT - 1) * BW_TILE;
+  d.n_items = a.B * a.H;
+  d.causal = a.causal;
+  d.has_mask = (a.key_tokens != nullptr || a.key_pad_mask != nullptr) ? 1 : 0;
+  d.key_tokens = reinterpret_cast<const long long*>(a.key_tokens); d.pad_idx = a.pad_idx;
+  d.key_pad_mask = a.key_pad_mask;
+  d.scale = a.scale; d.sl2 = a.scale * LOG2E;
+  d.lse = a.lse;
+  // shared memory: 3 x (Q | dO), 3 K tiles, 2 V tiles, O, 2 x (P^T | dS^T), 4 x 2 staging tiles, row statistics, barriers
+  d.kring_off = BW_NSLOT * BW_SLOT_BYTES;
+  d.vring_off = d.kring_off + BW_RK * BW_TILE_BYTES;
+  d.o_off = d.vring_off + BW_RV * BW_TILE_BYTES;
+  d.pds_off = d.o_off + BW_QROWS_BYTES;
+  d.stage_off = d.pds_off + 2 * 2 * BW_TILE_BYTES;
+  d.stat_off = d.stage_off + 4 * 2 * BW_STAGING_BYTES;
+  d.bar_off = d.stat_off + BW_NSLOT * 512;
+  const int smem = d.bar_off + 512 + 1024;
+  B200_REQUIRE(smem <= 227 * 1024, "attention backward (tcgen05): %d B of shared memory", smem);
+
+  CUtensorMap tq, tdo, to, tk, tkt, tv, tvt, tdq, tdk, tdv;
+  const uint64_t cols = static_cast<uint64_t>(a.H) * TC_HD;
+  if (int rc = make_tmap_2d_bf16(&tq, a.q, cols, static_cast<uint64_t>(a.B) * a.Tq, a.q_ts * 2, TC_HD, d.NQ)) return rc;
+  if (int rc = make_tmap_2d_bf16(&tdo, g.d_o, cols, static_cast<uint64_t>(a.B) * a.Tq, g.do_ts * 2, TC_HD, d.NQ)) return rc;
+  if (int rc = make_tmap_2d_bf16(&to, a.o, cols, static_cast<uint64_t>(a.B) * a.Tq, a.o_ts * 2, TC_HD, d.NQ)) return rc;
+  if (int rc = make_tmap_2d_bf16(&tkt, a.k, cols, static_cast<uint64_t>(a.B) * a.Tk, a.k_ts * 2, TC_HD, d.tail16)) return rc;
+  if (int rc = make_tmap_2d_bf16(&tvt, a.v, cols, static_cast<uint64_t>(a.B) * a.Tk, a.v_ts * 2, TC_HD, d.tail16)) return rc;
+  tk = tkt; tv = tvt;
+  if (d.NT > 1) {
+    if (int rc = make_tmap_2d_bf16(&tk, a.k, cols, static_cast<uint64_t>(a.B) * a.Tk, a.k_ts * 2, TC_HD, BW_TILE)) return rc;
+    if (int rc = make_tmap_2d_bf16(&tv, a.v, cols, static_cast<uint64_t>(a.B) * a.Tk, a.v_ts * 2, TC_HD, BW_TILE)) return rc;
+  }
+  if (int rc = make_tmap_3d_bf16(&tdq, g.dq, cols, a.Tq, a.B, g.dq_ts * 2, g.dq_bs * 2, TC_HD, 16)) return rc;
+  if (int rc = make_tmap_3d_bf16(&tdk, g.dk, cols, a.Tk, a.B, g.dk_ts * 2, g.dk_bs * 2, TC_HD, 32)) return rc;
+  if (int rc = make_tmap_3d_bf16(&tdv, g.dv, cols, a.Tk, a.B, g.dv_ts * 2, g.dv_bs * 2, TC_HD, 32)) return rc;
+  const int sms = device_sm_count();
+  const int grid = d.n_items < sms ? d.n_items : sms;
+  d.trace = g_tc_trace;
+  static bool configured = false;
+  if (!configured) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B200_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  auto kern = d.trace != nullptr ? attn_tc_bwd_kernel<true> : attn_tc_bwd_kernel<false>;
+  B200_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(BW_THREADS), static_cast<size_t>(smem), s, true, 1, tq, tdo, to, tk, tkt, tv, tvt, tdq, tdk, tdv, d));
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -253,11 +253,23 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
       : "memory");
 }
 
+// warm a 2-D tile into L2 (no shared memory, no completion): latency hiding that does not cost ring entries
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0),
+               "r"(c1)
+               : "memory");
+}
 // ---- TMA stores (shared -> global), bulk async-group completion
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int32_t c0, int32_t c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(map)),
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
 // element-wise fp32 add of the tile into global memory (split-K / gradient accumulation)
@@ -425,5 +437,9 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64
                       uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer);
 int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
                      uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer);
+// 3-D bf16 tensor [d2][d1][d0] (d0 contiguous), box = (box0, box1, 1), 128-byte swizzle: rows past d1 are clipped per
+// d2 slice (per-sample [T, columns] views whose tiles must not spill into the next sample)
+int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                      uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1);
 
 }  // namespace b200

@@ -529,6 +529,22 @@ static int make_tmap_2d(CUtensorMap* out, CUtensorMapDataType dt, const void* ba
                (unsigned long long)outer_stride_bytes, box_inner, box_outer);
   return 0;
 }
+int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                      uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1) {
+  PFN_encodeTiled enc = get_encode_fn();
+  B200_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (stride1_bytes & 15) == 0 && (stride2_bytes & 15) == 0,
+               "TMA (3-D) base / strides not 16-byte aligned");
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d", (int)r);
+  return 0;
+}
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
                       uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
   return make_tmap_2d(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, inner, outer, outer_stride_bytes, box_inner, box_outer);

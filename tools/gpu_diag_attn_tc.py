@@ -92,7 +92,8 @@ def case(B, H, Tq, Tk, causal, mask, bwd=True, reps=0, seed=0):
         o_ref.backward(do.float())
         errs = []
         for name, got, ref in (("dq", dq, qr.grad), ("dk", dk, kr.grad), ("dv", dv, vr.grad)):
-            rel = ((got.float() - ref).norm() / ref.norm().clamp_min(1e-20)).item()
+            # relative to the gradient's own norm, with a floor (a one-key softmax has dS = 0 exactly: dq = dk = 0)
+            rel = ((got.float() - ref).norm() / ref.norm().clamp_min(1e-3 * do.float().norm())).item()
             errs.append(rel)
             msg += f" {name} rel {rel:.3e}"
             ok = ok and rel < 1e-2 and not torch.isnan(got.float()).any()
@@ -142,8 +143,50 @@ def trace(B, H, Tq, Tk, causal):
         print(f"  {i:2d}: {r[0]:7d} {r[1]:7d} {r[2]:7d} {r[3]:7d} | {r[4]:7d} {r[5]:7d} {r[6]:7d} {r[7]:7d} {r[8]:7d} | P published by quarter 0-3: {r[9]:7d} {r[10]:7d} {r[11]:7d} {r[12]:7d}")
 
 
+def trace_bwd(B, H, Tq, Tk, causal):
+    """per-unit (128-key tile) pipeline timeline of CTA 0 of the backward kernel"""
+    E = H * hd
+    q, do = (torch.randn(B, Tq, E, device=dev).bfloat16() for _ in range(2))
+    k, v = (torch.randn(B, Tk, E, device=dev).bfloat16() for _ in range(2))
+    o = torch.zeros_like(q)
+    lse = torch.zeros(B, H, Tq, device=dev)
+    a = L.AttnFwdArgs()
+    a.q, a.q_bs, a.q_ts = q.data_ptr(), Tq * E, E
+    a.k, a.k_bs, a.k_ts = k.data_ptr(), Tk * E, E
+    a.v, a.v_bs, a.v_ts = v.data_ptr(), Tk * E, E
+    a.o, a.o_bs, a.o_ts = o.data_ptr(), Tq * E, E
+    a.lse, a.B, a.H, a.Tq, a.Tk, a.hd, a.causal = lse.data_ptr(), B, H, Tq, Tk, hd, causal
+    a.key_tokens, a.pad_idx, a.key_pad_mask, a.scale = None, 0, None, 1 / math.sqrt(hd)
+    L.check(lib.b200_attn_fwd(C.byref(a), L.cur_stream()), "attn_fwd")
+    dq, dk, dv = (torch.zeros_like(t) for t in (q, k, v))
+    bw = L.AttnBwdArgs()
+    bw.f = a
+    bw.d_o, bw.do_bs, bw.do_ts = do.data_ptr(), Tq * E, E
+    bw.dq, bw.dq_bs, bw.dq_ts = dq.data_ptr(), Tq * E, E
+    bw.dk, bw.dk_bs, bw.dk_ts = dk.data_ptr(), Tk * E, E
+    bw.dv, bw.dv_bs, bw.dv_ts = dv.data_ptr(), Tk * E, E
+    for _ in range(3):
+        L.check(lib.b200_attn_bwd(C.byref(bw), L.cur_stream()), "attn_bwd")
+    buf = torch.zeros(32, 16, dtype=torch.int64, device=dev)
+    L.check(lib.b200_attn_tc_trace(buf.data_ptr()), "trace")
+    L.check(lib.b200_attn_bwd(C.byref(bw), L.cur_stream()), "attn_bwd")
+    torch.cuda.synchronize()
+    L.check(lib.b200_attn_tc_trace(None), "trace")
+    t = buf.cpu()
+    t0 = int(t[0, 0])
+    print(f"bwd trace Tq{Tq} Tk{Tk} causal{causal}: unit: load_issue S_issued | st_full_seen pds_free published | out_ready out_issued | out_full_seen stored | stats")
+    for u in range(32):
+        r = [int(x) - t0 if int(x) else -1 for x in t[u, :16]]
+        print(f"  {u:2d}: {r[0]:7d} {r[1]:7d} | {r[2]:7d} {r[3]:7d} {r[4]:7d} | {r[5]:7d} {r[6]:7d} | {r[7]:7d} {r[8]:7d} | {r[9]:7d}"
+              f" || V load issue {r[14]:7d}; S issuer: at unit {r[10]:7d} K seen {r[11]:7d} V seen {r[12]:7d} stage free {r[13]:7d}")
+
+
 def main():
     bwd = "--no-bwd" not in sys.argv
+    if "--trace-bwd" in sys.argv:
+        trace_bwd(256, 12, 47, 197, 0)
+        trace_bwd(256, 12, 47, 47, 1)
+        return
     if "--bench" in sys.argv:          # one big case only (ncu captures): --bench cross|self|cfg5
         which = sys.argv[sys.argv.index("--bench") + 1]
         shp = {"cross": (256, 12, 47, 197, 0, None), "self": (256, 12, 47, 47, 1, "tokens"), "cfg5": (64, 16, 47, 257, 0, None)}[which]

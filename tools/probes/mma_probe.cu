@@ -5,7 +5,7 @@
 #include <stdio.h>
 using namespace b200;
 
-__global__ void __launch_bounds__(128, 1) probe(int M, int N, int nmma, int same_d, long long* out) {
+__global__ void __launch_bounds__(128, 1) probe(int M, int N, int nmma, int same_d, long long* out, int a_mn = 0, int b_mn = 0) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   __shared__ uint64_t bar;
@@ -20,9 +20,10 @@ __global__ void __launch_bounds__(128, 1) probe(int M, int N, int nmma, int same
   tc_fence_after();
   const uint32_t tbase = tptr;
   if (threadIdx.x == 32) {
-    const uint32_t idesc = make_idesc_bf16(M, N, false, false);
-    const uint64_t da = make_smem_desc_sw128(smem_u32(smem), 16, 1024);
-    const uint64_t db = make_smem_desc_sw128(smem_u32(smem) + 32 * 1024, 16, 1024);
+    const uint32_t idesc = make_idesc_bf16(M, N, a_mn != 0, b_mn != 0);
+    const uint64_t da = a_mn ? make_smem_desc_sw128(smem_u32(smem), 8192, 1024) : make_smem_desc_sw128(smem_u32(smem), 16, 1024);
+    const uint64_t db = b_mn ? make_smem_desc_sw128(smem_u32(smem) + 32 * 1024, 8192, 1024) : make_smem_desc_sw128(smem_u32(smem) + 32 * 1024, 16, 1024);
+    const uint64_t sa = a_mn ? 128 : 2, sb = b_mn ? 128 : 2;     // per-k-step advance in 16-byte units
     // warm-up
     for (int i = 0; i < 4; ++i) umma_bf16(tbase, da, db, idesc, i > 0);
     umma_commit(&bar);
@@ -30,7 +31,7 @@ __global__ void __launch_bounds__(128, 1) probe(int M, int N, int nmma, int same
     tc_fence_after();
     const long long t0 = clock64();
     for (int i = 0; i < nmma; ++i)
-      umma_bf16(tbase + (same_d ? 0 : (i & 1) * 256), da + static_cast<uint64_t>((i & 3) * 2), db + static_cast<uint64_t>((i & 3) * 2), idesc, (i > 1) ? 1u : 0u);
+      umma_bf16(tbase + (same_d ? 0 : (i & 1) * 256), da + sa * static_cast<uint64_t>(i & 3), db + sb * static_cast<uint64_t>(i & 3), idesc, (i > 1) ? 1u : 0u);
     const long long t1 = clock64();
     umma_commit(&bar);
     mbar_wait(&bar, 1);
@@ -131,6 +132,19 @@ int main() {
   long long* d;
   cudaMalloc(&d, 64);
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  {
+    struct { int M, N, a, b; } cs[] = {{128, 48, 0, 0}, {128, 64, 0, 1}, {64, 64, 1, 1}, {64, 64, 0, 1}, {64, 64, 0, 0}, {128, 64, 1, 1}};
+    for (auto c : cs)
+      for (int nm : {4, 8, 16}) {
+        cudaMemset(d, 0, 64);
+        probe<<<1, 128, 100 * 1024>>>(c.M, c.N, nm, 1, d, c.a, c.b);
+        cudaError_t e = cudaDeviceSynchronize();
+        long long h[8];
+        cudaMemcpy(h, d, 64, cudaMemcpyDeviceToHost);
+        printf("M %3d N %3d A %s B %s n %2d: issue %6lld cyc (%5.1f / mma)  done %6lld cyc (%5.1f / mma) %s\n", c.M, c.N, c.a ? "MN" : "K ",
+               c.b ? "MN" : "K ", nm, h[0], (double)h[0] / nm, h[1], (double)h[1] / nm, e == cudaSuccess ? "" : cudaGetErrorString(e));
+      }
+  }
   const int Ms[2] = {64, 128};
   const int Ns[5] = {24, 64, 104, 208, 256};
   for (int same = 1; same >= 0; --same)
