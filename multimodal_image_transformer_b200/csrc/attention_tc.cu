@@ -178,6 +178,24 @@ __device__ __forceinline__ void tmem_sweep(uint32_t taddr, int n, F&& f) {
   }
 }
 
+// ring position without a division per trip (code size: see tc_wait)
+struct RingPos {
+  int idx = 0;
+  uint32_t ph = 0;
+  __device__ __forceinline__ void advance(int n) {
+    if (++idx == n) { idx = 0; ph ^= 1u; }
+  }
+};
+// (image, head) of the CTA's items: item = first + i * stride, b = item / H, h = item % H
+struct ItemPos {
+  int b, h, db, dh, H;
+  __device__ __forceinline__ ItemPos(int first, int stride, int H_) : b(first / H_), h(first % H_), db(stride / H_), dh(stride % H_), H(H_) {}
+  __device__ __forceinline__ void advance() {
+    b += db; h += dh;
+    if (h >= H) { h -= H; ++b; }
+  }
+};
+
 struct TcDev {
   int B, H, Tq, Tk, Tk16, half, nslab;
   int n_items;
@@ -201,8 +219,11 @@ struct TcDev {
 
 // stamps of CTA 0's first 32 items: 0 producer issue, 1 S issued, 2 p_full seen, 3 PV issued, 4 s_full seen (softmax),
 // 5 pass 1 done, 6 pass 2 done (P published), 7 o_full seen, 8 epilogue done
+template <bool TRACE>
 __device__ __forceinline__ void tc_stamp(const TcDev& p, int i, int slot) {
-  if (p.trace != nullptr && blockIdx.x == 0 && i < 32) p.trace[i * 16 + slot] = clock64();
+  if constexpr (TRACE) {
+    if (blockIdx.x == 0 && i < 32) p.trace[i * 16 + slot] = clock64();
+  }
 }
 
 __device__ __forceinline__ uint32_t tc_drop_pair(const TcDev& p, int bh, int row, int key) {
@@ -228,7 +249,7 @@ __device__ __forceinline__ uint32_t p_unit_off(int row, int key) {
 // one in-order issuer as warp 1, S(i+2) waited behind P(i) and every tcgen05.mma took ~150 cycles to issue next to
 // two busy softmax warps on its scheduler (55 cycles alone, tools/probes/mma_probe.cu).  A group publishes P(i) and only
 // then finishes item i-2 (its previous one), so the P V product never sits on its critical path.
-template <bool MASKED, bool DROP>
+template <bool MASKED, bool DROP, bool TRACE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                    const __grid_constant__ CUtensorMap tmap_v, const TcDev p) {
@@ -296,14 +317,16 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   if (warp == 0) {
     // ============================ TMA producer ============================
     if (lane == 0) {
-      for (int i = 0; i < n_local; ++i) {
-        const int item = first + i * stride;
-        const int b = item / p.H, h = item % p.H;
+      RingPos rq;
+      ItemPos it(first, stride, p.H);
+#pragma unroll 1
+      for (int i = 0; i < n_local; ++i, rq.advance(p.nslot), it.advance()) {
+        const int b = it.b, h = it.h;
         // the Q | K entry is free again as soon as S = Q K^T of its previous item is complete, the V entry once that
         // item's P V is: Q / K run nslot items ahead of the S products, V nv items ahead of the P V products
-        const int s = i % p.nslot;
-        tc_wait(&qk_empty[s], (static_cast<uint32_t>(i / p.nslot) & 1u) ^ 1u);
-        tc_stamp(p, i, 0);
+        const int s = rq.idx;
+        tc_wait(&qk_empty[s], rq.ph ^ 1u);
+        tc_stamp<TRACE>(p, i, 0);
         uint8_t* slot = smem + s * p.slot_bytes;
         mbar_arrive_expect_tx(&qk_full[s], Q_BYTES + 2 * half * ROW_BYTES);
         tma_load_2d(slot, &tmap_q, &qk_full[s], h * TC_HD, b * p.Tq);
@@ -314,11 +337,13 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   } else if (warp == 11) {
     // ============================ V TMA producer ==========================
     if (lane == 0) {
-      for (int i = 0; i < n_local; ++i) {
-        const int item = first + i * stride;
-        const int b = item / p.H, h = item % p.H;
-        const int sv = i % p.nv;
-        tc_wait(&v_empty[sv], (static_cast<uint32_t>(i / p.nv) & 1u) ^ 1u);
+      RingPos rv;
+      ItemPos it(first, stride, p.H);
+#pragma unroll 1
+      for (int i = 0; i < n_local; ++i, rv.advance(p.nv), it.advance()) {
+        const int b = it.b, h = it.h;
+        const int sv = rv.idx;
+        tc_wait(&v_empty[sv], rv.ph ^ 1u);
         uint8_t* vbuf = smem + p.v_base + sv * p.v_bytes;
         mbar_arrive_expect_tx(&v_full[sv], 2 * half * ROW_BYTES);
         tma_load_2d(vbuf, &tmap_v, &v_full[sv], h * TC_HD, b * p.Tk);
@@ -336,10 +361,12 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       const uint64_t dk0 = make_smem_desc_sw128(smem_u32(smem) + p.k_off, 16, 1024);
       const uint64_t slot_u = static_cast<uint64_t>(p.slot_bytes >> 4);
       const uint64_t half_u = static_cast<uint64_t>((half * ROW_BYTES) >> 4);
-      for (int i = 0; i < n_local; ++i) {
-        const int s = i % p.nslot, t = i % ns;
-        tc_wait(&qk_full[s], static_cast<uint32_t>(i / p.nslot) & 1u);
-        tc_wait(&s_empty[t], (static_cast<uint32_t>(i / ns) & 1u) ^ 1u);
+      RingPos rq, rt;
+#pragma unroll 1
+      for (int i = 0; i < n_local; ++i, rq.advance(p.nslot), rt.advance(ns)) {
+        const int s = rq.idx, t = rt.idx;
+        tc_wait(&qk_full[s], rq.ph);
+        tc_wait(&s_empty[t], rt.ph ^ 1u);
         tc_fence_after();
         const uint64_t dq = dq0 + slot_u * s;
         const uint64_t dk = dk0 + slot_u * s;
@@ -354,7 +381,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           }
           umma_commit(&s_full[t]);
           umma_commit(&qk_empty[s]);
-          tc_stamp(p, i, 1);
+          tc_stamp<TRACE>(p, i, 1);
         }
         __syncwarp();
       }
@@ -367,17 +394,19 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       const uint64_t dv0 = make_smem_desc_sw128(smem_u32(smem) + p.v_base, 64 * ROW_BYTES, 1024);  // MN-major V tile
       const uint64_t pbuf_u = static_cast<uint64_t>(p.p_bytes >> 4), vbuf_u = static_cast<uint64_t>(p.v_bytes >> 4);
       const int nslab = p.nslab, ksteps = p.Tk16 / 16;
-      for (int i = 0; i < n_local; ++i) {
-        const int g = i % p.n_p, sv = i % p.nv, t = i % no;
-        tc_wait(&o_empty[t], (static_cast<uint32_t>(i / no) & 1u) ^ 1u);
-        tc_wait(&v_full[sv], static_cast<uint32_t>(i / p.nv) & 1u);
-        tc_wait(&p_full[g], static_cast<uint32_t>(i / p.n_p) & 1u);
+      RingPos rp, rv, ro;
+#pragma unroll 1
+      for (int i = 0; i < n_local; ++i, rp.advance(p.n_p), rv.advance(p.nv), ro.advance(no)) {
+        const int g = rp.idx, sv = rv.idx, t = ro.idx;
+        tc_wait(&o_empty[t], ro.ph ^ 1u);
+        tc_wait(&v_full[sv], rv.ph);
+        tc_wait(&p_full[g], rp.ph);
         tc_fence_after();
         const uint64_t dp = dp0 + pbuf_u * g;
         const uint64_t dv = dv0 + vbuf_u * sv;
         const uint32_t d = tmem_o + t * TC_HD;
         if (elect_one()) {
-          tc_stamp(p, i, 2);
+          tc_stamp<TRACE>(p, i, 2);
           for (int sl = 0; sl < nslab; ++sl) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -390,7 +419,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           umma_commit(&o_full[t]);
           umma_commit(&v_empty[sv]);
           umma_commit(&p_empty[i & 1]);                // by parity of the item: each softmax group is the only waiter of "its" barrier
-          tc_stamp(p, i, 3);
+          tc_stamp<TRACE>(p, i, 3);
         }
         __syncwarp();
       }
@@ -413,7 +442,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       const int t = i % no;
       tc_wait(&o_full[t], static_cast<uint32_t>(i / no) & 1u);
       tc_fence_after();
-      if (stamper) tc_stamp(p, i, 7);
+      if (stamper) tc_stamp<TRACE>(p, i, 7);
       const uint32_t t_o = tmem_o + t * TC_HD + lane_addr;
       uint32_t ro[2][32];
       tmem_ld_32x32(t_o, ro[0]);
@@ -437,12 +466,17 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         }
         if (p.lse) p.lse[static_cast<long long>(item) * p.Tq + row] = lse;
       }
-      if (stamper) tc_stamp(p, i, 8);
+      if (stamper) tc_stamp<TRACE>(p, i, 8);
     };
 
     float prev_inv = 0.f, prev_lse = 0.f;
     int prev_i = -1;
-    for (int i = grp; i < n_local; i += 2) {
+    // (one `finish` call site: the loop runs one trip past the group's last item -- code size, see tc_wait)
+#pragma unroll 1
+    for (int i = grp;; i += 2) {
+      const bool have = i < n_local;
+      float cur_inv = 0.f, cur_lse = 0.f;
+      if (have) {
       const int item = first + i * stride;
       const int t = i % ns;
       const uint32_t ph_t = static_cast<uint32_t>(i / ns) & 1u;
@@ -470,7 +504,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       }
       tc_wait(&s_full[t], ph_t);
       tc_fence_after();
-      if (stamper) tc_stamp(p, i, 4);
+      if (stamper) tc_stamp<TRACE>(p, i, 4);
       const uint32_t t_s = tmem_base + t * half + lane_addr;
       const int key_base = hf * half;                // first key of this thread's half
       const int pb = i % p.n_p;
@@ -548,7 +582,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       });
       mx = fmaxf(mxa, mxb);
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
-      if (stamper) tc_stamp(p, i, 5);
+      if (stamper) tc_stamp<TRACE>(p, i, 5);
       m2 = (mx == -INFINITY) ? 0.f : mx * p.sl2;       // fully masked row: P = 0, O = 0, lse = -inf
       // the P V product that last read this P buffer is complete: item i - 2 (this group's previous one) with two
       // buffers, item i - 1 (the other group's) with one.  P V(i) signals p_empty[i & 1], so every barrier has ONE
@@ -571,15 +605,18 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       sum += __shfl_xor_sync(0xffffffffu, sum, 16);
       fence_proxy_async();                            // P (generic-proxy stores) -> visible to the tensor core's reads
       mbar_arrive(&p_full[pb]);
-      if (stamper) tc_stamp(p, i, 6);
-      if (lane == 0) tc_stamp(p, i, 9 + w4);          // per-warp publication time (slots 9-12, by TMEM lane quarter)
+      if (stamper) tc_stamp<TRACE>(p, i, 6);
+      if (lane == 0) tc_stamp<TRACE>(p, i, 9 + w4);          // per-warp publication time (slots 9-12, by TMEM lane quarter)
+      cur_inv = sum > 0.f ? 1.f / sum : 0.f;
+      cur_lse = (sum > 0.f) ? m2 * LN2 + logf(sum) : -INFINITY;
+      }
       // ---- finish the PREVIOUS item of this group while the tensor core works on this one
       if (prev_i >= 0) finish(prev_i, prev_inv, prev_lse);
+      if (!have) break;
       prev_i = i;
-      prev_inv = sum > 0.f ? 1.f / sum : 0.f;
-      prev_lse = (sum > 0.f) ? m2 * LN2 + logf(sum) : -INFINITY;
+      prev_inv = cur_inv;
+      prev_lse = cur_lse;
     }
-    if (prev_i >= 0) finish(prev_i, prev_inv, prev_lse);
   }
 
   tc_fence_before();
@@ -740,6 +777,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     // ============================ TMA producer ============================
     if (lane == 0) {
       int u = 0;
+#pragma unroll 1
       for (int i = 0; i < n_local; ++i) {
         const int item = first + i * stride;
         const int b = item / p.H, h = item % p.H;
@@ -751,6 +789,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         tc_wait(o_empty, (static_cast<uint32_t>(i) & 1u) ^ 1u);
         mbar_arrive_expect_tx(o_full, p.NQ * ROW_BYTES);
         tma_load_2d(smem + p.o_off, &tmap_o, o_full, h * TC_HD, b * p.Tq);
+#pragma unroll 1
         for (int kt = 0; kt < NT; ++kt, ++u) {
           const int rk = u % BW_RK, rv = u % BW_RV;
           const bool tail = kt == NT - 1;
@@ -775,6 +814,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     const uint64_t d_k0 = make_smem_desc_sw128(smem_u32(kring), 16, 1024);
     const uint64_t d_v0 = make_smem_desc_sw128(smem_u32(vring), 16, 1024);
     int i = 0, kt = 0;
+#pragma unroll 1
     for (int u = 0; u < n_units; ++u) {
       const int g = u & 1, rk = u % BW_RK, rv = u % BW_RV;
       if (kt == 0) tc_wait(&qdo_full[i % BW_NSLOT], static_cast<uint32_t>(i / BW_NSLOT) & 1u);
@@ -809,6 +849,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     const uint64_t d_km0 = make_smem_desc_sw128(smem_u32(kring), 64 * ROW_BYTES, 1024);           // K tile as stored
     constexpr uint64_t KSTEP_MN = (16 * ROW_BYTES) >> 4;                                            // 16 rows of 128 B
     int i = 0, kt = 0;
+#pragma unroll 1
     for (int u = 0; u < n_units; ++u) {
       const int g = u & 1, rk = u % BW_RK;
       tc_wait(&pds_full[g], static_cast<uint32_t>(u >> 1) & 1u);
@@ -825,7 +866,9 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       const int ksteps = (kt == NT - 1 ? p.tail16 : BW_TILE) / 16;
       const bool last = kt == NT - 1;
       if (elect_one()) {
+#pragma unroll 1
         for (int k = 0; k < qsteps; ++k) umma_bf16(t_v, dp + static_cast<uint64_t>(k * 2), ddo_m + KSTEP_MN * k, idesc_kv, k > 0 ? 1u : 0u);
+#pragma unroll 1
         for (int k = 0; k < qsteps; ++k) umma_bf16(t_k, dds + static_cast<uint64_t>(k * 2), dq_m + KSTEP_MN * k, idesc_kv, k > 0 ? 1u : 0u);
         umma_commit(&out_full[g]);                     // the output group drains dV / dK while dQ is still being accumulated
       }
@@ -836,6 +879,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         tc_fence_after();
       }
       if (elect_one()) {
+#pragma unroll 1
         for (int k = 0; k < ksteps; ++k) umma_bf16(t_q, dds_m + KSTEP_MN * k, dk_m + KSTEP_MN * k, idesc_dq, (kt > 0 || k > 0) ? 1u : 0u);
         umma_commit(&pds_empty[g]);
         umma_commit(&k_empty[rk]);
@@ -856,6 +900,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     const uint32_t rowP = smem_u32(pds + g * 2 * BW_TILE_BYTES + j * ROW_BYTES);
     const int sw = j & 7;
     int prev_i = -1;
+#pragma unroll 1
     for (int u = g; u < n_units; u += 2) {
       const int i = u / NT, kt = u - i * NT;
       const int key = kt * BW_TILE + j;
@@ -923,6 +968,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     const int sw = lane & 7;
     int n_tiles = 0;                                  // staging tiles written so far: tile n uses buffer n % 2
     int i = 0, kt = 0;
+#pragma unroll 1
     for (int u = 0; u < n_units; ++u) {
       const int g = u & 1;
       const int item = first + i * stride;
@@ -995,6 +1041,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     // ============================ row statistics ============================
     // lse * log2(e) (+inf for rows past Tq and for fully masked rows: P = 0) and delta = rowsum(dO * O): lane = row
     // (then row + 32), from the 128-byte-swizzled dO and O tiles of the item.  Compact loops on purpose (see the header).
+#pragma unroll 1
     for (int i = 0; i < n_local; ++i) {
       const int item = first + i * stride;
       const int sl = i % BW_NSLOT;
@@ -1060,6 +1107,10 @@ bool attn_tc_supported(const AttnArgs& a) {
   if (!tc_enabled()) return false;
   if (a.hd != TC_HD || a.Tq > 64 || a.Tk > 288 || a.Tq < 1 || a.Tk < 1) return false;
   if (a.causal && a.Tk > a.Tq + 64) return false;
+  // short key ranges (the caption's self attention, Tk = Tq <= 64) stay on the mma.sync kernel: the per-item pipeline
+  // overhead of this kernel exceeds the work (measured 38 us against 19 us at cfg2)
+  static const int min_tk = getenv("B200_ATTN_TC_MIN_TK") ? atoi(getenv("B200_ATTN_TC_MIN_TK")) : 65;
+  if (a.Tk < min_tk) return false;
   return tc_layout_ok(a.q, a.q_bs, a.q_ts, a.Tq) && tc_layout_ok(a.k, a.k_bs, a.k_ts, a.Tk) &&
          tc_layout_ok(a.v, a.v_bs, a.v_ts, a.Tk) && (reinterpret_cast<uintptr_t>(a.o) & 15) == 0 && a.o_ts % 8 == 0;
 }
@@ -1125,14 +1176,15 @@ int attn_tc_fwd(const AttnArgs& a, cudaStream_t s) {
   d.trace = g_tc_trace;
   const bool masked = d.has_bias || d.causal, drop = d.drop.thr != 0;
   typedef void (*Kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcDev);
-  static const Kern kerns[4] = {attn_tc_fwd_kernel<false, false>, attn_tc_fwd_kernel<true, false>,
-                                attn_tc_fwd_kernel<false, true>, attn_tc_fwd_kernel<true, true>};
+  static const Kern kerns[5] = {attn_tc_fwd_kernel<false, false, false>, attn_tc_fwd_kernel<true, false, false>,
+                                attn_tc_fwd_kernel<false, true, false>, attn_tc_fwd_kernel<true, true, false>,
+                                attn_tc_fwd_kernel<true, true, true>};     // the trace build takes the general path
   static bool configured = false;
   if (!configured) {
-    for (int i = 0; i < 4; ++i) B200_CHECK_CUDA(cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    for (int i = 0; i < 5; ++i) B200_CHECK_CUDA(cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  Kern kern = kerns[(masked ? 1 : 0) + (drop ? 2 : 0)];
+  Kern kern = d.trace != nullptr ? kerns[4] : kerns[(masked ? 1 : 0) + (drop ? 2 : 0)];
   B200_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(TC_THREADS), static_cast<size_t>(smem), s, true, 1, tq, tk, tv, d));
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
