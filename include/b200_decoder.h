@@ -129,6 +129,13 @@ typedef struct {
   const int64_t* key_tokens; int64_t pad_idx;   /* self: key padding from token ids (or NULL) */
   const uint8_t* key_pad_mask;                  /* cross: [B,Tk] or NULL */
   float scale;                                  /* 1/sqrt(hd) */
+  /* Packed (var-len) sequences -- the reference pads every caption to MAX_SEQ_LEN (tokenizer.py:293-313,
+   * dataset.py:176-206); packing drops the PAD rows.  cu_q / cu_k: device int32 [B+1] row offsets of every sample in
+   * the q-side (q, o, dO, dq) / k-side (k, v, dk, dv) tensors, sample b owns rows [cu[b], cu[b+1]); total_q / total_k =
+   * cu[B].  Tq / Tk are then the LARGEST per-sample lengths, lse stays [B,H,Tq], batch strides of packed tensors are
+   * ignored.  NULL (the default) = regular [B, T] batches. */
+  const int32_t* cu_q; const int32_t* cu_k;
+  int32_t total_q, total_k;
 } b200_attn_fwd_args;
 int b200_attn_fwd(const b200_attn_fwd_args* a, void* stream);
 
@@ -219,6 +226,17 @@ int b200_engine_forward_loss(b200_engine* e, const int64_t* tokens, const int64_
                              const float* memory, const uint8_t* mem_pad, int32_t B, int32_t T,
                              int32_t S, int32_t mem_dim, int64_t ignore_index, int32_t training,
                              float* loss_out, void* stream);
+/* The same on a PACKED (var-len) batch.  The reference pads every caption to MAX_SEQ_LEN (tokenizer.py:293-313,
+ * dataset.py:176-206), so 75-85 % of the positions of a real batch are PAD; here sample b keeps only its first
+ * cu_seqlens[b+1] - cu_seqlens[b] positions (its non-PAD prefix) and every GEMM / LayerNorm / CE row-wise kernel runs on
+ * total_rows = cu_seqlens[B] rows; the attention kernels index per-sample offsets.  tokens / targets stay [B,T] (the
+ * engine gathers them), cu_seqlens is a device int32 [B+1] the caller keeps alive until backward is done.  Loss and
+ * gradients equal the padded call's (PAD targets are ignored and PAD keys masked there).  The backward entry points
+ * below run unchanged on the packed activations. */
+int b200_engine_forward_loss_packed(b200_engine* e, const int64_t* tokens, const int64_t* targets,
+                                    const float* memory, const uint8_t* mem_pad, int32_t B, int32_t T, int32_t S,
+                                    int32_t mem_dim, int64_t ignore_index, int32_t training,
+                                    const int32_t* cu_seqlens, int32_t total_rows, float* loss_out, void* stream);
 /* backward of the last forward_loss(training=1) into the bound gradient arena (accumulating:
  * the caller zero-fills, as optimizer.zero_grad() does in train.py:80).
  * inv_count_dev: optional device scalar replacing 1/valid_count (data-parallel global mean).

@@ -34,6 +34,8 @@ class AttnFwdArgs(C.Structure):
         ("key_tokens", C.c_void_p), ("pad_idx", C.c_int64),
         ("key_pad_mask", C.c_void_p),
         ("scale", C.c_float),
+        ("cu_q", C.c_void_p), ("cu_k", C.c_void_p),
+        ("total_q", C.c_int32), ("total_k", C.c_int32),
     ]
 
 
@@ -100,6 +102,7 @@ SIGNATURES = {
     "b200_engine_set_workspace": (C.c_int, [_P, _P, _I64]),
     "b200_engine_forward_logits": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P, _P]),
     "b200_engine_forward_loss": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I64, _I32, _P, _P]),
+    "b200_engine_forward_loss_packed": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I64, _I32, _P, _I32, _P, _P]),
     "b200_engine_backward": (C.c_int, [_P, _P, _P, _P, _I32, _P]),
     "b200_engine_backward_parts": (C.c_int, [_P, _P, _P, _I32, _I32, _P]),
     "b200_engine_backward_from_dlogits": (C.c_int, [_P, _P, _P, _P]),

@@ -52,6 +52,8 @@ struct AttnDev {
   long long q_bs, q_ts, k_bs, k_ts, v_bs, v_ts, o_bs, o_ts, do_bs, do_ts, dq_bs, dq_ts, dk_bs, dk_ts, dv_bs, dv_ts;
   float* lse;
   int B, H, Tq, Tk, TQP, TKP;
+  int lse_ld, TqS, TkS;          // row pitch of lse and the (row, key) strides of the dropout counter: the LARGEST lengths
+  const int32_t *cu_q, *cu_k;    // packed sequences (attention.cuh); the kernels then patch Tq / Tk / base pointers per sample
   int causal;
   const long long* key_tokens; long long pad_idx;
   const unsigned char* key_pad_mask;
@@ -61,8 +63,18 @@ struct AttnDev {
 
 // keep-decision of probability (row i, key j) of head bh; see common.cuh for the element order
 __device__ __forceinline__ uint32_t attn_drop_pair(const AttnDev& p, int bh, int row, int key) {
-  return (static_cast<uint32_t>(bh) * p.Tq + row) * static_cast<uint32_t>((p.Tk + 1) >> 1) + (static_cast<uint32_t>(key) >> 1);
+  return (static_cast<uint32_t>(bh) * p.TqS + row) * static_cast<uint32_t>((p.TkS + 1) >> 1) + (static_cast<uint32_t>(key) >> 1);
 }
+// packed sequences: this CTA's sample owns rows [cu[b], cu[b+1]) -- Tq / Tk shrink to the sample's own lengths (the tile
+// sizes TQP / TKP stay those of the longest sample).  The ROW OFFSETS are not patched into the struct: the kernels index
+// the packed tensors as  base + bq * q_bs  with bq = cu_q[b] and q_bs = q_ts (set on the host), see VARLEN_ROWS.
+// (A first version shifted the base pointers in the struct copy; nvcc 12.9 dropped the update of the FIRST field --
+// later reads went back to the kernel parameter -- so the offsets are explicit locals now.)
+__device__ __forceinline__ void attn_varlen_patch(AttnDev& p, int b) {
+  if (p.cu_q) p.Tq = p.cu_q[b + 1] - p.cu_q[b];
+  if (p.cu_k) p.Tk = p.cu_k[b + 1] - p.cu_k[b];
+}
+#define VARLEN_ROWS(p, b) const long long bq = (p).cu_q ? (p).cu_q[b] : (b), bk = (p).cu_k ? (p).cu_k[b] : (b); (void)bq; (void)bk
 __device__ __forceinline__ bool attn_drop_keep(uint32_t r, int key, uint32_t thr) {
   return ((key & 1) ? (r >> 16) : (r & 0xFFFFu)) >= thr;
 }
@@ -164,9 +176,11 @@ __device__ __forceinline__ void fill_key_bias(float* sBias, const AttnDev& p, in
 // ------------------------------------------------------------------------------------------
 template <int HD, int NT>
 __global__ void __launch_bounds__(128)
-attn_fwd_kernel(const AttnDev p) {
+attn_fwd_kernel(const AttnDev pin) {
   pdl_wait();
   pdl_trigger();
+  AttnDev p = pin;
+  attn_varlen_patch(p, blockIdx.y);
   constexpr int LD = HD + 8;
   extern __shared__ __align__(16) uint8_t smem_attn[];
   bf16* sQ = reinterpret_cast<bf16*>(smem_attn);
@@ -175,12 +189,13 @@ attn_fwd_kernel(const AttnDev p) {
   float* sBias = reinterpret_cast<float*>(sV + p.TKP * LD);
 
   const int h = blockIdx.x, b = blockIdx.y;
+  VARLEN_ROWS(p, b);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
 
-  load_rows<HD>(sQ, p.q + b * p.q_bs + h * HD, p.q_ts, p.Tq, p.TQP);
-  load_rows<HD>(sK, p.k + b * p.k_bs + h * HD, p.k_ts, p.Tk, p.TKP);
-  load_rows<HD>(sV, p.v + b * p.v_bs + h * HD, p.v_ts, p.Tk, p.TKP);
+  load_rows<HD>(sQ, p.q + bq * p.q_bs + h * HD, p.q_ts, p.Tq, p.TQP);
+  load_rows<HD>(sK, p.k + bk * p.k_bs + h * HD, p.k_ts, p.Tk, p.TKP);
+  load_rows<HD>(sV, p.v + bk * p.v_bs + h * HD, p.v_ts, p.Tk, p.TKP);
   fill_key_bias(sBias, p, b);
   cp_async_wait_all();
   __syncthreads();
@@ -253,12 +268,12 @@ attn_fwd_kernel(const AttnDev p) {
       const int row = row0 + g + r * 8;
       const float inv = l > 0.f ? 1.f / l : 0.f;
       if (row < p.Tq) {
-        bf16* orow = p.o + b * p.o_bs + row * p.o_ts + h * HD;
+        bf16* orow = p.o + bq * p.o_bs + row * p.o_ts + h * HD;
 #pragma unroll
         for (int i = 0; i < HD / 8; ++i)
           *reinterpret_cast<uint32_t*>(orow + i * 8 + 2 * t) = pack_bf16(o[i][2 * r] * inv, o[i][2 * r + 1] * inv);
         if (p.lse && t == 0)
-          p.lse[(static_cast<long long>(b) * p.H + h) * p.Tq + row] = (l > 0.f) ? m_run[r] * LN2 + logf(l) : -INFINITY;
+          p.lse[(static_cast<long long>(b) * p.H + h) * p.lse_ld + row] = (l > 0.f) ? m_run[r] * LN2 + logf(l) : -INFINITY;
       }
     }
   }
@@ -281,9 +296,11 @@ __device__ __forceinline__ float ex2_ftz(float x) {
 // ------------------------------------------------------------------------------------------
 template <int HD, int NT>
 __global__ void __launch_bounds__(512)
-attn_fwd_split_kernel(const AttnDev p, int KS) {
+attn_fwd_split_kernel(const AttnDev pin, int KS) {
   pdl_wait();
   pdl_trigger();
+  AttnDev p = pin;
+  attn_varlen_patch(p, blockIdx.y);
   constexpr int LD = HD + 8;
   constexpr int LDO = HD + 4;                       // fp32 partial-O row pitch
   extern __shared__ __align__(16) uint8_t smem_attn[];
@@ -295,13 +312,14 @@ attn_fwd_split_kernel(const AttnDev p, int KS) {
   float* sO = reinterpret_cast<float*>(sK);         // [items][16][LDO] partial O, aliases K/V
 
   const int h = blockIdx.x, b = blockIdx.y;
+  VARLEN_ROWS(p, b);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int n_kt = p.TKP / 16;
 
-  load_rows<HD>(sQ, p.q + b * p.q_bs + h * HD, p.q_ts, p.Tq, p.TQP);
-  load_rows<HD>(sK, p.k + b * p.k_bs + h * HD, p.k_ts, p.Tk, p.TKP);
-  load_rows<HD>(sV, p.v + b * p.v_bs + h * HD, p.v_ts, p.Tk, p.TKP);
+  load_rows<HD>(sQ, p.q + bq * p.q_bs + h * HD, p.q_ts, p.Tq, p.TQP);
+  load_rows<HD>(sK, p.k + bk * p.k_bs + h * HD, p.k_ts, p.Tk, p.TKP);
+  load_rows<HD>(sV, p.v + bk * p.v_bs + h * HD, p.v_ts, p.Tk, p.TKP);
   fill_key_bias(sBias, p, b);
   cp_async_wait_all();
   __syncthreads();
@@ -379,12 +397,12 @@ attn_fwd_split_kernel(const AttnDev p, int KS) {
       const int row = row0 + g + r * 8;
       const float inv = l_loc[r] > 0.f ? 1.f / l_loc[r] : 0.f;
       if (row < p.Tq) {
-        bf16* orow = p.o + b * p.o_bs + row * p.o_ts + h * HD;
+        bf16* orow = p.o + bq * p.o_bs + row * p.o_ts + h * HD;
 #pragma unroll
         for (int i = 0; i < HD / 8; ++i)
           *reinterpret_cast<uint32_t*>(orow + i * 8 + 2 * t) = pack_bf16(o[i][2 * r] * inv, o[i][2 * r + 1] * inv);
         if (p.lse && t == 0)
-          p.lse[(static_cast<long long>(b) * p.H + h) * p.Tq + row] = (l_loc[r] > 0.f) ? m_loc[r] * LN2 + logf(l_loc[r]) : -INFINITY;
+          p.lse[(static_cast<long long>(b) * p.H + h) * p.lse_ld + row] = (l_loc[r] > 0.f) ? m_loc[r] * LN2 + logf(l_loc[r]) : -INFINITY;
       }
     }
     return;
@@ -427,9 +445,9 @@ attn_fwd_split_kernel(const AttnDev p, int KS) {
       uint4 out;
       out.x = pack_bf16(acc[0] * inv, acc[1] * inv); out.y = pack_bf16(acc[2] * inv, acc[3] * inv);
       out.z = pack_bf16(acc[4] * inv, acc[5] * inv); out.w = pack_bf16(acc[6] * inv, acc[7] * inv);
-      *reinterpret_cast<uint4*>(p.o + b * p.o_bs + row * p.o_ts + h * HD + cs) = out;
+      *reinterpret_cast<uint4*>(p.o + bq * p.o_bs + row * p.o_ts + h * HD + cs) = out;
       if (p.lse && cs == 0)
-        p.lse[(static_cast<long long>(b) * p.H + h) * p.Tq + row] = (L > 0.f) ? M * LN2 + logf(L) : -INFINITY;
+        p.lse[(static_cast<long long>(b) * p.H + h) * p.lse_ld + row] = (L > 0.f) ? M * LN2 + logf(L) : -INFINITY;
     }
   }
 }
@@ -439,9 +457,11 @@ attn_fwd_split_kernel(const AttnDev p, int KS) {
 // ------------------------------------------------------------------------------------------
 template <int HD, int NT>
 __global__ void __launch_bounds__(128)
-attn_bwd_kernel(const AttnDev p) {
+attn_bwd_kernel(const AttnDev pin) {
   pdl_wait();
   pdl_trigger();
+  AttnDev p = pin;
+  attn_varlen_patch(p, blockIdx.y);
   constexpr int LD = HD + 8;
   extern __shared__ __align__(16) uint8_t smem_attn[];
   bf16* sQ = reinterpret_cast<bf16*>(smem_attn);
@@ -454,19 +474,20 @@ attn_bwd_kernel(const AttnDev p) {
   float* sD = sLse + p.TQP;
 
   const int h = blockIdx.x, b = blockIdx.y;
+  VARLEN_ROWS(p, b);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
 
-  load_rows<HD>(sQ, p.q + b * p.q_bs + h * HD, p.q_ts, p.Tq, p.TQP);
-  load_rows<HD>(sdO, p.d_o + b * p.do_bs + h * HD, p.do_ts, p.Tq, p.TQP);
-  load_rows<HD>(sK, p.k + b * p.k_bs + h * HD, p.k_ts, p.Tk, p.TKP);
-  load_rows<HD>(sV, p.v + b * p.v_bs + h * HD, p.v_ts, p.Tk, p.TKP);
-  load_rows<HD>(sO, p.o_in + b * p.o_bs + h * HD, p.o_ts, p.Tq, p.TQP);
+  load_rows<HD>(sQ, p.q + bq * p.q_bs + h * HD, p.q_ts, p.Tq, p.TQP);
+  load_rows<HD>(sdO, p.d_o + bq * p.do_bs + h * HD, p.do_ts, p.Tq, p.TQP);
+  load_rows<HD>(sK, p.k + bk * p.k_bs + h * HD, p.k_ts, p.Tk, p.TKP);
+  load_rows<HD>(sV, p.v + bk * p.v_bs + h * HD, p.v_ts, p.Tk, p.TKP);
+  load_rows<HD>(sO, p.o_in + bq * p.o_bs + h * HD, p.o_ts, p.Tq, p.TQP);
   fill_key_bias(sBias, p, b);
   for (int row = threadIdx.x; row < p.TQP; row += blockDim.x) {
     float l = INFINITY;
     if (row < p.Tq) {
-      l = p.lse[(static_cast<long long>(b) * p.H + h) * p.Tq + row];
+      l = p.lse[(static_cast<long long>(b) * p.H + h) * p.lse_ld + row];
       l = (l == -INFINITY) ? INFINITY : l * LOG2E;   // fully masked row: P = 0
     }
     sLse[row] = l;
@@ -532,7 +553,7 @@ attn_bwd_kernel(const AttnDev p) {
     for (int r = 0; r < 2; ++r) {
       const int row = row0 + g + r * 8;
       if (row < p.Tq) {
-        bf16* drow = p.dq + b * p.dq_bs + row * p.dq_ts + h * HD;
+        bf16* drow = p.dq + bq * p.dq_bs + row * p.dq_ts + h * HD;
 #pragma unroll
         for (int i = 0; i < HD / 8; ++i)
           *reinterpret_cast<uint32_t*>(drow + i * 8 + 2 * t) = pack_bf16(dq[i][2 * r], dq[i][2 * r + 1]);
@@ -591,8 +612,8 @@ attn_bwd_kernel(const AttnDev p) {
     for (int r = 0; r < 2; ++r) {
       const int key = key0 + g + r * 8;
       if (key < p.Tk) {
-        bf16* krow = p.dk + b * p.dk_bs + key * p.dk_ts + h * HD;
-        bf16* vrow = p.dv + b * p.dv_bs + key * p.dv_ts + h * HD;
+        bf16* krow = p.dk + bk * p.dk_bs + key * p.dk_ts + h * HD;
+        bf16* vrow = p.dv + bk * p.dv_bs + key * p.dv_ts + h * HD;
 #pragma unroll
         for (int i = 0; i < HD / 8; ++i) {
           *reinterpret_cast<uint32_t*>(krow + i * 8 + 2 * t) = pack_bf16(dk[i][2 * r], dk[i][2 * r + 1]);
@@ -614,9 +635,11 @@ attn_bwd_kernel(const AttnDev p) {
 // ------------------------------------------------------------------------------------------
 template <int HD, int NT, int MAXI, int MINB, int NW>
 __global__ void __launch_bounds__(NW * 32, MINB)
-attn_bwd2_kernel(const AttnDev p) {
+attn_bwd2_kernel(const AttnDev pin) {
   pdl_wait();
   pdl_trigger();
+  AttnDev p = pin;
+  attn_varlen_patch(p, blockIdx.y);
   constexpr int LD = HD + 8;
   constexpr int KB = NT * 8;
   extern __shared__ __align__(16) uint8_t smem_attn[];
@@ -632,20 +655,21 @@ attn_bwd2_kernel(const AttnDev p) {
   float* sD = sLse + p.TQP;
 
   const int h = blockIdx.x, b = blockIdx.y;
+  VARLEN_ROWS(p, b);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int mi = lane >> 3, r8 = lane & 7;
 
-  load_rows<HD>(sQ, p.q + b * p.q_bs + h * HD, p.q_ts, p.Tq, p.TQP);
-  load_rows<HD>(sdO, p.d_o + b * p.do_bs + h * HD, p.do_ts, p.Tq, p.TQP);
-  load_rows<HD>(sK, p.k + b * p.k_bs + h * HD, p.k_ts, p.Tk, p.TKP);
-  load_rows<HD>(sV, p.v + b * p.v_bs + h * HD, p.v_ts, p.Tk, p.TKP);
-  load_rows<HD>(sPS, p.o_in + b * p.o_bs + h * HD, p.o_ts, p.Tq, p.TQP);   // O, row pitch LD
+  load_rows<HD>(sQ, p.q + bq * p.q_bs + h * HD, p.q_ts, p.Tq, p.TQP);
+  load_rows<HD>(sdO, p.d_o + bq * p.do_bs + h * HD, p.do_ts, p.Tq, p.TQP);
+  load_rows<HD>(sK, p.k + bk * p.k_bs + h * HD, p.k_ts, p.Tk, p.TKP);
+  load_rows<HD>(sV, p.v + bk * p.v_bs + h * HD, p.v_ts, p.Tk, p.TKP);
+  load_rows<HD>(sPS, p.o_in + bq * p.o_bs + h * HD, p.o_ts, p.Tq, p.TQP);   // O, row pitch LD
   fill_key_bias(sBias, p, b);
   for (int row = threadIdx.x; row < p.TQP; row += blockDim.x) {
     float l = INFINITY;
     if (row < p.Tq) {
-      l = p.lse[(static_cast<long long>(b) * p.H + h) * p.Tq + row];
+      l = p.lse[(static_cast<long long>(b) * p.H + h) * p.lse_ld + row];
       l = (l == -INFINITY) ? INFINITY : l * LOG2E;
     }
     sLse[row] = l;
@@ -776,7 +800,7 @@ attn_bwd2_kernel(const AttnDev p) {
     for (int r = 0; r < 2; ++r) {
       const int key = kt * 16 + g + r * 8;
       if (key < p.Tk) {
-        bf16* vrow = p.dv + b * p.dv_bs + key * p.dv_ts + h * HD;
+        bf16* vrow = p.dv + bk * p.dv_bs + key * p.dv_ts + h * HD;
 #pragma unroll
         for (int i = 0; i < HD / 8; ++i)
           *reinterpret_cast<uint32_t*>(vrow + i * 8 + 2 * t) = pack_bf16(acc[i][2 * r], acc[i][2 * r + 1]);
@@ -812,7 +836,7 @@ attn_bwd2_kernel(const AttnDev p) {
       for (int r = 0; r < 2; ++r) {
         const int row = mt * 16 + g + r * 8;
         if (row < p.Tq) {
-          bf16* drow = p.dq + b * p.dq_bs + row * p.dq_ts + h * HD + half * (HD / 2);
+          bf16* drow = p.dq + bq * p.dq_bs + row * p.dq_ts + h * HD + half * (HD / 2);
 #pragma unroll
           for (int i = 0; i < NH; ++i)
             *reinterpret_cast<uint32_t*>(drow + i * 8 + 2 * t) = pack_bf16(acc[i][2 * r], acc[i][2 * r + 1]);
@@ -839,7 +863,7 @@ attn_bwd2_kernel(const AttnDev p) {
       for (int r = 0; r < 2; ++r) {
         const int key = kt * 16 + g + r * 8;
         if (key < p.Tk) {
-          bf16* krow = p.dk + b * p.dk_bs + key * p.dk_ts + h * HD;
+          bf16* krow = p.dk + bk * p.dk_bs + key * p.dk_ts + h * HD;
 #pragma unroll
           for (int i = 0; i < HD / 8; ++i)
             *reinterpret_cast<uint32_t*>(krow + i * 8 + 2 * t) = pack_bf16(acc[i][2 * r], acc[i][2 * r + 1]);
@@ -856,6 +880,7 @@ static int check_common(const AttnArgs& a) {
   B200_REQUIRE(a.B > 0 && a.H > 0 && a.Tq > 0 && a.Tk > 0, "attention: empty problem");
   B200_REQUIRE(a.hd == 32 || a.hd == 64 || a.hd == 96 || a.hd == 128, "attention: head dim %d not in {32,64,96,128}", a.hd);
   B200_REQUIRE(a.Tq <= 512 && a.Tk <= 512, "attention: Tq/Tk (%d/%d) above the 512 resident-tile limit", a.Tq, a.Tk);
+  B200_REQUIRE(!(a.cu_k && (a.key_tokens || a.key_pad_mask)), "attention: packed keys carry no padding, a key mask cannot be combined with cu_k");
   auto ok = [](const void* ptr, long long bs, long long ts) {
     return ptr != nullptr && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && bs % 8 == 0 && ts % 8 == 0;
   };
@@ -872,6 +897,10 @@ static void fill_dev(const AttnArgs& a, AttnDev* d) {
   d->lse = a.lse;
   d->B = a.B; d->H = a.H; d->Tq = a.Tq; d->Tk = a.Tk;
   d->TQP = (a.Tq + 15) / 16 * 16; d->TKP = (a.Tk + 15) / 16 * 16;
+  d->lse_ld = a.Tq; d->TqS = a.Tq; d->TkS = a.Tk;
+  d->cu_q = a.cu_q; d->cu_k = a.cu_k;
+  if (a.cu_q) { d->q_bs = a.q_ts; d->o_bs = a.o_ts; }      // packed: "batch index" = first row of the sample (VARLEN_ROWS)
+  if (a.cu_k) { d->k_bs = a.k_ts; d->v_bs = a.v_ts; }
   d->causal = a.causal;
   d->key_tokens = reinterpret_cast<const long long*>(a.key_tokens); d->pad_idx = a.pad_idx;
   d->key_pad_mask = a.key_pad_mask;
@@ -1034,6 +1063,8 @@ int attn_bwd(const AttnArgs& a, const AttnGrads& gr, cudaStream_t s) {
   d.dq = gr.dq; d.dq_bs = gr.dq_bs; d.dq_ts = gr.dq_ts;
   d.dk = gr.dk; d.dk_bs = gr.dk_bs; d.dk_ts = gr.dk_ts;
   d.dv = gr.dv; d.dv_bs = gr.dv_bs; d.dv_ts = gr.dv_ts;
+  if (a.cu_q) { d.do_bs = gr.do_ts; d.dq_bs = gr.dq_ts; }
+  if (a.cu_k) { d.dk_bs = gr.dk_ts; d.dv_bs = gr.dv_ts; }
   switch (a.hd) {
     case 32: return dispatch_bwd<32>(d, s, 8);
     case 64: return dispatch_bwd<64>(d, s, 8);

@@ -17,6 +17,12 @@ struct AttnArgs {
   const unsigned char* key_pad_mask = nullptr;
   float scale = 1.f;
   DropCfg drop = DropCfg{nullptr, 0u, 0u, 1.f};           // dropout on the probabilities (functional.py:6682)
+  // Packed (var-len) sequences: cu_q / cu_k = int32 [B + 1] row offsets of every sample in q / o / dO / dq (resp.
+  // k / v / dk / dv); sample b owns rows [cu[b], cu[b+1]).  Tq / Tk are then the LARGEST per-sample lengths (they size
+  // the tiles and the [B, H, Tq] log-sum-exp rows) and the batch strides of those tensors are ignored.
+  const int32_t* cu_q = nullptr;
+  const int32_t* cu_k = nullptr;
+  int total_q = 0, total_k = 0;                             // packed: rows of the whole q-side / k-side tensors (= cu[B])
 };
 struct AttnGrads {
   const bf16* d_o = nullptr; long long do_bs = 0, do_ts = 0;

@@ -206,6 +206,7 @@ struct TcDev {
   int bias_off, bar_off;                 // byte offsets from the (aligned) shared-memory base
   const long long* key_tokens; long long pad_idx;
   const unsigned char* key_pad_mask;
+  const int32_t* cu_q;                   // packed query rows (attention.cuh): sample b owns rows [cu_q[b], cu_q[b+1]); Tq = the largest
   float scale, sl2;                      // softmax scale and scale * log2(e)
   bf16* o; long long o_bs, o_ts;
   float* lse;
@@ -329,7 +330,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         tc_stamp<TRACE>(p, i, 0);
         uint8_t* slot = smem + s * p.slot_bytes;
         mbar_arrive_expect_tx(&qk_full[s], Q_BYTES + 2 * half * ROW_BYTES);
-        tma_load_2d(slot, &tmap_q, &qk_full[s], h * TC_HD, b * p.Tq);
+        tma_load_2d(slot, &tmap_q, &qk_full[s], h * TC_HD, p.cu_q ? p.cu_q[b] : b * p.Tq);
         tma_load_2d(slot + p.k_off, &tmap_k, &qk_full[s], h * TC_HD, b * p.Tk);
         tma_load_2d(slot + p.k_off + half * ROW_BYTES, &tmap_k, &qk_full[s], h * TC_HD, b * p.Tk + half);
       }
@@ -433,7 +434,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     const bool stamper = (w4 == 3) && lane == 0;
     const uint32_t lane_addr = static_cast<uint32_t>(w4 * 32) << 16;
     const uint32_t dkey = DROP ? drop_key(p.drop) : 0u;
-    const bool writer = hf == 0 && row < p.Tq;       // O rows live in the lower 16 lanes of every quarter
+    const bool writer = hf == 0 && row < p.Tq;       // O rows live in the lower 16 lanes of every quarter (packed: checked per sample)
 
     // O of local item i (TMEM stage i % no) -> rows scaled by 1 / row sum -> global memory; log-sum-exp
     auto finish = [&](int i, float inv, float lse) {
@@ -450,8 +451,14 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&o_empty[t]);
-      if (writer) {
-        bf16* orow = p.o + static_cast<long long>(b) * p.o_bs + static_cast<long long>(row) * p.o_ts + h * TC_HD;
+      long long row0 = 0;                              // packed: first row of the sample, and its own row count
+      bool wr = writer;
+      if (p.cu_q) {
+        row0 = p.cu_q[b];
+        wr = writer && row < p.cu_q[b + 1] - static_cast<int>(row0);
+      }
+      if (wr) {
+        bf16* orow = p.o + static_cast<long long>(b) * p.o_bs + (row0 + row) * p.o_ts + h * TC_HD;
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
 #pragma unroll
@@ -667,6 +674,8 @@ struct TcBwdDev {
   const unsigned char* key_pad_mask;
   float scale, sl2;
   const float* lse;
+  const int32_t* cu_q;                            // packed query rows (attention.cuh); dQ then leaves through plain row stores
+  bf16* dq; long long dq_ts;
   long long* trace;                               // bring-up instrument: [unit][16] clock64 stamps of CTA 0 (null = off)
 };
 
@@ -784,11 +793,12 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         const int sl = i % BW_NSLOT;
         tc_wait(&qdo_empty[sl], (static_cast<uint32_t>(i / BW_NSLOT) & 1u) ^ 1u);
         mbar_arrive_expect_tx(&qdo_full[sl], 2 * p.NQ * ROW_BYTES);
-        tma_load_2d(smem + sl * BW_SLOT_BYTES, &tmap_q, &qdo_full[sl], h * TC_HD, b * p.Tq);
-        tma_load_2d(smem + sl * BW_SLOT_BYTES + BW_QROWS_BYTES, &tmap_do, &qdo_full[sl], h * TC_HD, b * p.Tq);
+        const int qrow0 = p.cu_q ? p.cu_q[b] : b * p.Tq;
+        tma_load_2d(smem + sl * BW_SLOT_BYTES, &tmap_q, &qdo_full[sl], h * TC_HD, qrow0);
+        tma_load_2d(smem + sl * BW_SLOT_BYTES + BW_QROWS_BYTES, &tmap_do, &qdo_full[sl], h * TC_HD, qrow0);
         tc_wait(o_empty, (static_cast<uint32_t>(i) & 1u) ^ 1u);
         mbar_arrive_expect_tx(o_full, p.NQ * ROW_BYTES);
-        tma_load_2d(smem + p.o_off, &tmap_o, o_full, h * TC_HD, b * p.Tq);
+        tma_load_2d(smem + p.o_off, &tmap_o, o_full, h * TC_HD, qrow0);
 #pragma unroll 1
         for (int kt = 0; kt < NT; ++kt, ++u) {
           const int rk = u % BW_RK, rv = u % BW_RV;
@@ -989,7 +999,29 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         }
         // M = 64 accumulator (dQ): rows 16w .. 16w+15 live in lanes 32w + 0..15 -> 16 staging rows per warp
         const bool active = t == 0 ? (w4 * 16 < p.Tq) : (key0 < p.Tk);
-        if (active) {
+        if (active && t == 0 && p.cu_q != nullptr) {
+          // packed rows: a 16-row TMA box would spill into the next sample, so dQ leaves through per-thread row stores
+          const int r0 = p.cu_q[b], nq = p.cu_q[b + 1] - r0;
+          const int row = w4 * 16 + (lane & 15);
+          uint32_t ra[32];
+#pragma unroll 1
+          for (int hc = 0; hc < 2; ++hc) {
+            tmem_ld_32x32(tmem_base + BW_DQ_COL + lane_addr + hc * 32, ra);
+            tmem_ld_wait();
+            if (lane < 16 && row < nq) {
+              bf16* dst = p.dq + static_cast<long long>(r0 + row) * p.dq_ts + h * TC_HD + hc * 32;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 v;
+                v.x = pack_bf16(__uint_as_float(ra[q * 8 + 0]) * p.scale, __uint_as_float(ra[q * 8 + 1]) * p.scale);
+                v.y = pack_bf16(__uint_as_float(ra[q * 8 + 2]) * p.scale, __uint_as_float(ra[q * 8 + 3]) * p.scale);
+                v.z = pack_bf16(__uint_as_float(ra[q * 8 + 4]) * p.scale, __uint_as_float(ra[q * 8 + 5]) * p.scale);
+                v.w = pack_bf16(__uint_as_float(ra[q * 8 + 6]) * p.scale, __uint_as_float(ra[q * 8 + 7]) * p.scale);
+                *reinterpret_cast<uint4*>(dst + q * 8) = v;
+              }
+            }
+          }
+        } else if (active) {
           const uint32_t taddr = (t == 0 ? tmem_base + BW_DQ_COL : tmem_base + g * BW_STAGE_COLS + 96 + (t - 1) * 64) + lane_addr;
           const float sc = t == 1 ? 1.f : p.scale;
           uint32_t ra[32], rb[32];
@@ -1045,6 +1077,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     for (int i = 0; i < n_local; ++i) {
       const int item = first + i * stride;
       const int sl = i % BW_NSLOT;
+      const int nq = p.cu_q ? p.cu_q[item / p.H + 1] - p.cu_q[item / p.H] : p.Tq;     // rows of this sample
       tc_wait(&qdo_full[sl], static_cast<uint32_t>(i / BW_NSLOT) & 1u);
       tc_wait(o_full, static_cast<uint32_t>(i) & 1u);
       tc_wait(&stat_empty[sl], (static_cast<uint32_t>(i / BW_NSLOT) & 1u) ^ 1u);
@@ -1053,7 +1086,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       for (int rr = 0; rr < 2; ++rr) {
         const int row = lane + 32 * rr;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, l = INFINITY;
-        if (row < p.Tq) {
+        if (row < nq) {
           const float x = p.lse[static_cast<long long>(item) * p.Tq + row];
           l = (x == -INFINITY) ? INFINITY : x * LOG2E;
 #pragma unroll 2
@@ -1098,20 +1131,23 @@ static bool tc_enabled() {
   return on;
 }
 
-static bool tc_layout_ok(const void* ptr, long long bs, long long ts, int T) {
+static bool tc_layout_ok(const void* ptr, long long bs, long long ts, int T, bool packed = false) {
   // the TMA view is a plain 2-D [B * T rows][columns] tensor: batch stride = T rows, 16-byte aligned pitch
-  return ptr != nullptr && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ts % 8 == 0 && bs == static_cast<long long>(T) * ts;
+  // (packed rows: [total rows][columns], the batch stride is not used)
+  return ptr != nullptr && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ts % 8 == 0 && (packed || bs == static_cast<long long>(T) * ts);
 }
 
 bool attn_tc_supported(const AttnArgs& a) {
   if (!tc_enabled()) return false;
   if (a.hd != TC_HD || a.Tq > 64 || a.Tk > 288 || a.Tq < 1 || a.Tk < 1) return false;
   if (a.causal && a.Tk > a.Tq + 64) return false;
+  if (a.cu_k != nullptr) return false;             // packed KEYS (self attention) stay on the mma.sync kernels
+  if (a.cu_q != nullptr && a.total_q < 1) return false;
   // short key ranges (the caption's self attention, Tk = Tq <= 64) stay on the mma.sync kernel: the per-item pipeline
   // overhead of this kernel exceeds the work (measured 38 us against 19 us at cfg2)
   static const int min_tk = getenv("B200_ATTN_TC_MIN_TK") ? atoi(getenv("B200_ATTN_TC_MIN_TK")) : 65;
   if (a.Tk < min_tk) return false;
-  return tc_layout_ok(a.q, a.q_bs, a.q_ts, a.Tq) && tc_layout_ok(a.k, a.k_bs, a.k_ts, a.Tk) &&
+  return tc_layout_ok(a.q, a.q_bs, a.q_ts, a.Tq, a.cu_q != nullptr) && tc_layout_ok(a.k, a.k_bs, a.k_ts, a.Tk) &&
          tc_layout_ok(a.v, a.v_bs, a.v_ts, a.Tk) && (reinterpret_cast<uintptr_t>(a.o) & 15) == 0 && a.o_ts % 8 == 0;
 }
 
@@ -1127,7 +1163,8 @@ static void tc_fill_common(const AttnArgs& a, TcDev* d) {
   d->key_tokens = reinterpret_cast<const long long*>(a.key_tokens); d->pad_idx = a.pad_idx;
   d->key_pad_mask = a.key_pad_mask;
   d->scale = a.scale; d->sl2 = a.scale * LOG2E;
-  d->o = a.o; d->o_bs = a.o_bs; d->o_ts = a.o_ts; d->lse = a.lse;
+  d->o = a.o; d->o_bs = a.cu_q ? 0 : a.o_bs; d->o_ts = a.o_ts; d->lse = a.lse;
+  d->cu_q = a.cu_q;
   d->drop = a.drop;
 }
 
@@ -1167,7 +1204,8 @@ int attn_tc_fwd(const AttnArgs& a, cudaStream_t s) {
   B200_REQUIRE(smem <= 227 * 1024, "attention (tcgen05): %d B of shared memory", smem);
 
   CUtensorMap tq, tk, tv;
-  if (int rc = make_tmap_2d_bf16(&tq, a.q, static_cast<uint64_t>(a.H) * TC_HD, static_cast<uint64_t>(a.B) * a.Tq, a.q_ts * 2, TC_HD, 64)) return rc;
+  const uint64_t q_rows = a.cu_q ? static_cast<uint64_t>(a.total_q) : static_cast<uint64_t>(a.B) * a.Tq;
+  if (int rc = make_tmap_2d_bf16(&tq, a.q, static_cast<uint64_t>(a.H) * TC_HD, q_rows, a.q_ts * 2, TC_HD, 64)) return rc;
   if (int rc = make_tmap_2d_bf16(&tk, a.k, static_cast<uint64_t>(a.H) * TC_HD, static_cast<uint64_t>(a.B) * a.Tk, a.k_ts * 2, TC_HD, d.half)) return rc;
   if (int rc = make_tmap_2d_bf16(&tv, a.v, static_cast<uint64_t>(a.H) * TC_HD, static_cast<uint64_t>(a.B) * a.Tk, a.v_ts * 2, TC_HD, d.half)) return rc;
 
@@ -1198,14 +1236,15 @@ static bool tc_bwd_enabled() {
 
 bool attn_tc_bwd_supported(const AttnArgs& a, const AttnGrads& g) {
   if (!tc_enabled() || !tc_bwd_enabled()) return false;
-  if (a.hd != TC_HD || a.Tq > 48 || a.Tq < 1 || a.Tk < 1 || a.drop.thr != 0) return false;
+  if (a.hd != TC_HD || a.Tq > 48 || a.Tq < 1 || a.Tk < 1 || a.drop.thr != 0 || a.cu_k != nullptr) return false;
   // short key ranges (the caption's self attention, Tk = Tq <= 48) stay on the mma.sync kernel: one 128-key tile per
   // item leaves the tcgen05 pipeline latency-bound (measured 66 us against 58 us at cfg2)
   static const int min_tk = getenv("B200_ATTN_TC_BWD_MIN_TK") ? atoi(getenv("B200_ATTN_TC_BWD_MIN_TK")) : 65;
   if (a.Tk < min_tk) return false;
   auto out_ok = [](const void* ptr, long long ts) { return ptr != nullptr && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ts % 8 == 0; };
-  return tc_layout_ok(a.q, a.q_bs, a.q_ts, a.Tq) && tc_layout_ok(a.k, a.k_bs, a.k_ts, a.Tk) && tc_layout_ok(a.v, a.v_bs, a.v_ts, a.Tk) &&
-         tc_layout_ok(g.d_o, g.do_bs, g.do_ts, a.Tq) && tc_layout_ok(a.o, a.o_bs, a.o_ts, a.Tq) && a.lse != nullptr &&
+  const bool pk = a.cu_q != nullptr;
+  return tc_layout_ok(a.q, a.q_bs, a.q_ts, a.Tq, pk) && tc_layout_ok(a.k, a.k_bs, a.k_ts, a.Tk) && tc_layout_ok(a.v, a.v_bs, a.v_ts, a.Tk) &&
+         tc_layout_ok(g.d_o, g.do_bs, g.do_ts, a.Tq, pk) && tc_layout_ok(a.o, a.o_bs, a.o_ts, a.Tq, pk) && a.lse != nullptr &&
          out_ok(g.dq, g.dq_ts) && out_ok(g.dk, g.dk_ts) && out_ok(g.dv, g.dv_ts) && g.dq_bs % 8 == 0 && g.dk_bs % 8 == 0 && g.dv_bs % 8 == 0;
 }
 
@@ -1224,6 +1263,7 @@ int attn_tc_bwd(const AttnArgs& a, const AttnGrads& g, cudaStream_t s) {
   d.key_pad_mask = a.key_pad_mask;
   d.scale = a.scale; d.sl2 = a.scale * LOG2E;
   d.lse = a.lse;
+  d.cu_q = a.cu_q; d.dq = g.dq; d.dq_ts = g.dq_ts;
   // shared memory: 3 x (Q | dO), 3 K tiles, 2 V tiles, O, 2 x (P^T | dS^T), 4 x 2 staging tiles, row statistics, barriers
   d.kring_off = BW_NSLOT * BW_SLOT_BYTES;
   d.vring_off = d.kring_off + BW_RK * BW_TILE_BYTES;
@@ -1237,9 +1277,10 @@ int attn_tc_bwd(const AttnArgs& a, const AttnGrads& g, cudaStream_t s) {
 
   CUtensorMap tq, tdo, to, tk, tkt, tv, tvt, tdq, tdk, tdv;
   const uint64_t cols = static_cast<uint64_t>(a.H) * TC_HD;
-  if (int rc = make_tmap_2d_bf16(&tq, a.q, cols, static_cast<uint64_t>(a.B) * a.Tq, a.q_ts * 2, TC_HD, d.NQ)) return rc;
-  if (int rc = make_tmap_2d_bf16(&tdo, g.d_o, cols, static_cast<uint64_t>(a.B) * a.Tq, g.do_ts * 2, TC_HD, d.NQ)) return rc;
-  if (int rc = make_tmap_2d_bf16(&to, a.o, cols, static_cast<uint64_t>(a.B) * a.Tq, a.o_ts * 2, TC_HD, d.NQ)) return rc;
+  const uint64_t q_rows = a.cu_q ? static_cast<uint64_t>(a.total_q) : static_cast<uint64_t>(a.B) * a.Tq;
+  if (int rc = make_tmap_2d_bf16(&tq, a.q, cols, q_rows, a.q_ts * 2, TC_HD, d.NQ)) return rc;
+  if (int rc = make_tmap_2d_bf16(&tdo, g.d_o, cols, q_rows, g.do_ts * 2, TC_HD, d.NQ)) return rc;
+  if (int rc = make_tmap_2d_bf16(&to, a.o, cols, q_rows, a.o_ts * 2, TC_HD, d.NQ)) return rc;
   if (int rc = make_tmap_2d_bf16(&tkt, a.k, cols, static_cast<uint64_t>(a.B) * a.Tk, a.k_ts * 2, TC_HD, d.tail16)) return rc;
   if (int rc = make_tmap_2d_bf16(&tvt, a.v, cols, static_cast<uint64_t>(a.B) * a.Tk, a.v_ts * 2, TC_HD, d.tail16)) return rc;
   tk = tkt; tv = tvt;
@@ -1247,9 +1288,12 @@ int attn_tc_bwd(const AttnArgs& a, const AttnGrads& g, cudaStream_t s) {
     if (int rc = make_tmap_2d_bf16(&tk, a.k, cols, static_cast<uint64_t>(a.B) * a.Tk, a.k_ts * 2, TC_HD, BW_TILE)) return rc;
     if (int rc = make_tmap_2d_bf16(&tv, a.v, cols, static_cast<uint64_t>(a.B) * a.Tk, a.v_ts * 2, TC_HD, BW_TILE)) return rc;
   }
-  if (int rc = make_tmap_3d_bf16(&tdq, g.dq, cols, a.Tq, a.B, g.dq_ts * 2, g.dq_bs * 2, TC_HD, 16)) return rc;
+  if (!a.cu_q) {
+    if (int rc = make_tmap_3d_bf16(&tdq, g.dq, cols, a.Tq, a.B, g.dq_ts * 2, g.dq_bs * 2, TC_HD, 16)) return rc;
+  }
   if (int rc = make_tmap_3d_bf16(&tdk, g.dk, cols, a.Tk, a.B, g.dk_ts * 2, g.dk_bs * 2, TC_HD, 32)) return rc;
   if (int rc = make_tmap_3d_bf16(&tdv, g.dv, cols, a.Tk, a.B, g.dv_ts * 2, g.dv_bs * 2, TC_HD, 32)) return rc;
+  if (a.cu_q) tdq = tdk;                                // packed rows: dQ leaves through plain stores, the map is not used
   const int sms = device_sm_count();
   const int grid = d.n_items < sms ? d.n_items : sms;
   d.trace = g_tc_trace;

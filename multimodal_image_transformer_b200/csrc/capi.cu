@@ -165,6 +165,7 @@ static void to_attn(const b200_attn_fwd_args* a, AttnArgs* o) {
   o->lse = a->lse; o->B = a->B; o->H = a->H; o->Tq = a->Tq; o->Tk = a->Tk; o->hd = a->hd;
   o->causal = a->causal; o->key_tokens = a->key_tokens; o->pad_idx = a->pad_idx;
   o->key_pad_mask = a->key_pad_mask; o->scale = a->scale;
+  o->cu_q = a->cu_q; o->cu_k = a->cu_k; o->total_q = a->total_q; o->total_k = a->total_k;
 }
 int b200_attn_fwd(const b200_attn_fwd_args* a, void* stream) {
   B200_REQUIRE(a, "attn_fwd: null args");

@@ -63,6 +63,12 @@ struct LayerAct {   // activations of one layer kept for backward
 
 struct Plan {
   int B = 0, T = 0, S = 0, mem_dim = 0, training = 0;
+  // rows of the decoder-side activations: B * T, or -- packed (var-len) batches -- the number of kept (non-PAD) positions,
+  // sample b owning rows [cu[b], cu[b+1]) (tokenizer.py:293-313 pads every caption; packing drops those rows)
+  int M = 0;
+  const int32_t* cu = nullptr;     // device [B+1], caller-owned; null = regular [B, T] layout
+  int64_t *ptok = nullptr, *ptgt = nullptr;   // packed token / target ids [M]
+  int32_t* ppos = nullptr;                    // position of every packed row [M]
   int64_t bytes = 0;
   bf16* mem16 = nullptr;      // [B*S, mem_dim]
   bf16* memp = nullptr;       // [B*S, E] projected memory (== mem16 when no projection)
@@ -176,12 +182,13 @@ int64_t add_param(b200_engine* e, const std::string& name, int64_t numel) {
   return off;
 }
 
-void build_plan(const b200_engine* e, Plan* pl, uint8_t* base, int B, int T, int S, int mem_dim, int training) {
+void build_plan(const b200_engine* e, Plan* pl, uint8_t* base, int B, int T, int S, int mem_dim, int training, int rows = 0) {
   const auto& c = e->cfg;
   const int64_t E = c.embed_dim, F = c.ff_dim, V = c.vocab_size, H = c.num_heads, L = c.num_layers;
-  const int64_t M = static_cast<int64_t>(B) * T, Ms = static_cast<int64_t>(B) * S;
+  const int64_t M = rows > 0 ? rows : static_cast<int64_t>(B) * T, Ms = static_cast<int64_t>(B) * S;
   Bump b(base);
-  pl->B = B; pl->T = T; pl->S = S; pl->mem_dim = mem_dim; pl->training = training;
+  pl->B = B; pl->T = T; pl->S = S; pl->mem_dim = mem_dim; pl->training = training; pl->M = static_cast<int>(M);
+  pl->ptok = b.take<int64_t>(M); pl->ptgt = b.take<int64_t>(M); pl->ppos = b.take<int32_t>(M);
   pl->mem16 = b.take<bf16>(Ms * mem_dim);
   pl->memp = (mem_dim != E) ? b.take<bf16>(Ms * E) : pl->mem16;
   // residual stream: training keeps every layer input (xs[l]) for backward, inference ping-pongs
@@ -305,19 +312,22 @@ DropCfg drop_site(const b200_engine* e, int id) {
 }
 
 int run_forward(b200_engine* e, const int64_t* tokens, const float* memory, const uint8_t* mem_pad, int B,
-                int T, int S, int mem_dim, int training, cudaStream_t s) {
+                int T, int S, int mem_dim, int training, cudaStream_t s, const int32_t* cu = nullptr, int rows = 0,
+                const int64_t* targets = nullptr) {
   const auto& c = e->cfg;
   const int E = c.embed_dim, F = c.ff_dim, H = c.num_heads, L = c.num_layers, hd = E / H;
   B200_REQUIRE(e->pf && e->ph, "engine: parameters not bound");
   B200_REQUIRE(B > 0 && T > 0 && S > 0, "engine: empty batch (B=%d T=%d S=%d)", B, T, S);
   B200_REQUIRE(T <= c.max_seq_len, "engine: T=%d exceeds max_seq_len=%d (positional table too short, decoder.py:71)", T, c.max_seq_len);
   B200_REQUIRE(mem_dim == E || (mem_dim == c.enc_dim && e->proj_w >= 0), "engine: memory width %d matches neither embed_dim %d nor enc_dim %d", mem_dim, E, c.enc_dim);
+  B200_REQUIRE(cu == nullptr || (rows > 0 && rows <= B * T), "engine: packed batch with %d rows (B*T = %d)", rows, B * T);
   Plan probe;
-  build_plan(e, &probe, nullptr, B, T, S, mem_dim, training);
+  build_plan(e, &probe, nullptr, B, T, S, mem_dim, training, cu ? rows : 0);
   B200_REQUIRE(e->ws && probe.bytes <= e->ws_bytes, "engine: workspace too small (%lld needed, %lld bound)", (long long)probe.bytes, (long long)e->ws_bytes);
-  build_plan(e, &e->plan, e->ws, B, T, S, mem_dim, training);
+  build_plan(e, &e->plan, e->ws, B, T, S, mem_dim, training, cu ? rows : 0);
   Plan& pl = e->plan;
-  const int M = B * T, Ms = B * S;
+  pl.cu = cu;
+  const int M = pl.M, Ms = B * S;
   const float scale = 1.0f / sqrtf(static_cast<float>(hd));
   NvtxRange nvtx_fwd("b200.decoder.forward");
 
@@ -340,7 +350,13 @@ int run_forward(b200_engine* e, const int64_t* tokens, const float* memory, cons
   if (mem_dim != E)
     RC(linear_fwd(pl.mem16, mem_dim, e->ph + e->proj_w, e->pf + e->proj_b, pl.memp, E, Ms, E, mem_dim, 0, nullptr, 0, s));
 
-  RC(embed_pe_fwd(tokens, e->pf + e->emb, e->pe, pl.xs[0], B, T, E, c.vocab_size, sqrtf(static_cast<float>(E)), s, 0, site(0)));
+  if (cu) {
+    // gather the kept positions: packed token / target ids and the position of every packed row
+    RC(pack_rows(tokens, targets, cu, B, T, pl.ptok, pl.ptgt, pl.ppos, s));
+    RC(embed_pe_fwd(pl.ptok, e->pf + e->emb, e->pe, pl.xs[0], M, 1, E, c.vocab_size, sqrtf(static_cast<float>(E)), s, 0, site(0), pl.ppos));
+  } else {
+    RC(embed_pe_fwd(tokens, e->pf + e->emb, e->pe, pl.xs[0], B, T, E, c.vocab_size, sqrtf(static_cast<float>(E)), s, 0, site(0)));
+  }
 
   for (int l = 0; l < L; ++l) {
     NvtxRange nvtx_layer("b200.decoder.forward.layer");
@@ -355,7 +371,8 @@ int run_forward(b200_engine* e, const int64_t* tokens, const float* memory, cons
     sa.q_bs = sa.k_bs = sa.v_bs = static_cast<long long>(T) * 3 * E; sa.q_ts = sa.k_ts = sa.v_ts = 3 * E;
     sa.o = a.attn_o; sa.o_bs = static_cast<long long>(T) * E; sa.o_ts = E;
     sa.lse = a.lse_s; sa.B = B; sa.H = H; sa.Tq = T; sa.Tk = T; sa.hd = hd; sa.causal = 1;
-    sa.key_tokens = tokens; sa.pad_idx = c.pad_idx; sa.scale = scale; sa.drop = site(1 + 6 * l + 0);
+    sa.key_tokens = cu ? nullptr : tokens; sa.pad_idx = c.pad_idx; sa.scale = scale; sa.drop = site(1 + 6 * l + 0);
+    sa.cu_q = sa.cu_k = cu; sa.total_q = sa.total_k = M;      // packed: no PAD keys exist, every sample has its own length
     RC(attn_fwd(sa, s));
     RC(linear_fwd(a.attn_o, E, e->ph + o.sa_ow, e->pf + o.sa_ob, a.y1, E, M, E, E, 0, x, E, s, site(1 + 6 * l + 1)));
     RC(layernorm_fwd(a.y1, e->pf + o.n1_w, e->pf + o.n1_b, a.x1, a.mean1, a.rstd1, M, E, c.ln_eps, s));
@@ -368,6 +385,7 @@ int run_forward(b200_engine* e, const int64_t* tokens, const float* memory, cons
     ca.o = a.attn_c; ca.o_bs = static_cast<long long>(T) * E; ca.o_ts = E;
     ca.lse = a.lse_c; ca.B = B; ca.H = H; ca.Tq = T; ca.Tk = S; ca.hd = hd; ca.causal = 0;
     ca.key_pad_mask = mem_pad; ca.scale = scale; ca.drop = site(1 + 6 * l + 2);
+    ca.cu_q = cu; ca.total_q = M;
     RC(attn_fwd(ca, s));
     RC(linear_fwd(a.attn_c, E, e->ph + o.ca_ow, e->pf + o.ca_ob, a.y2, E, M, E, E, 0, a.x1, E, s, site(1 + 6 * l + 3)));
     RC(layernorm_fwd(a.y2, e->pf + o.n2_w, e->pf + o.n2_b, a.x2, a.mean2, a.rstd2, M, E, c.ln_eps, s));
@@ -391,7 +409,8 @@ int run_backward(b200_engine* e, bool have_dlogits, float* dmemory, void* const*
   B200_REQUIRE(e->gf, "engine: gradient arena not bound");
   B200_REQUIRE(c.act == B200_ACT_RELU, "engine: backward is implemented for the reference activation (ReLU) only");
   const int B = pl.B, T = pl.T, S = pl.S;
-  const int M = B * T, Ms = B * S;
+  const int M = pl.M, Ms = B * S;
+  const int32_t* cu = pl.cu;
   const float scale = 1.0f / sqrtf(static_cast<float>(hd));
   const bool need_dmemp = (pl.mem_dim != E) || dmemory != nullptr;
   B200_REQUIRE(!(dmemory && pl.mem_dim != E), "engine: dmemory is only available when memory is already embed_dim wide");
@@ -482,6 +501,7 @@ int run_backward(b200_engine* e, bool have_dlogits, float* dmemory, void* const*
     ca.o = a.attn_c; ca.o_bs = static_cast<long long>(T) * E; ca.o_ts = E;
     ca.lse = a.lse_c; ca.B = B; ca.H = H; ca.Tq = T; ca.Tk = S; ca.hd = hd; ca.causal = 0;
     ca.key_pad_mask = e->last_mem_pad; ca.scale = scale; ca.drop = site(1 + 6 * l + 2);
+    ca.cu_q = cu; ca.total_q = M;
     AttnGrads cg;
     cg.d_o = pl.dattn; cg.do_bs = static_cast<long long>(T) * E; cg.do_ts = E;
     cg.dq = pl.dqc; cg.dq_bs = static_cast<long long>(T) * E; cg.dq_ts = E;
@@ -511,7 +531,8 @@ int run_backward(b200_engine* e, bool have_dlogits, float* dmemory, void* const*
     sa.q_bs = sa.k_bs = sa.v_bs = static_cast<long long>(T) * 3 * E; sa.q_ts = sa.k_ts = sa.v_ts = 3 * E;
     sa.o = a.attn_o; sa.o_bs = static_cast<long long>(T) * E; sa.o_ts = E;
     sa.lse = a.lse_s; sa.B = B; sa.H = H; sa.Tq = T; sa.Tk = T; sa.hd = hd; sa.causal = 1;
-    sa.key_tokens = e->last_tokens; sa.pad_idx = c.pad_idx; sa.scale = scale; sa.drop = site(1 + 6 * l + 0);
+    sa.key_tokens = cu ? nullptr : e->last_tokens; sa.pad_idx = c.pad_idx; sa.scale = scale; sa.drop = site(1 + 6 * l + 0);
+    sa.cu_q = sa.cu_k = cu; sa.total_q = sa.total_k = M;
     AttnGrads sg;
     sg.d_o = pl.dattn; sg.do_bs = static_cast<long long>(T) * E; sg.do_ts = E;
     sg.dq = pl.dqkv; sg.dk = pl.dqkv + E; sg.dv = pl.dqkv + 2 * E;
@@ -524,7 +545,8 @@ int run_backward(b200_engine* e, bool have_dlogits, float* dmemory, void* const*
     mark();
   }
   if (last_part < L + 1) return 0;
-  RC(embed_bwd(e->last_tokens, dx, e->gf + e->emb, B, T, E, V, c.pad_idx, sqrtf(static_cast<float>(E)), s, site(0)));
+  if (cu) RC(embed_bwd(pl.ptok, dx, e->gf + e->emb, M, 1, E, V, c.pad_idx, sqrtf(static_cast<float>(E)), s, site(0)));
+  else RC(embed_bwd(e->last_tokens, dx, e->gf + e->emb, B, T, E, V, c.pad_idx, sqrtf(static_cast<float>(E)), s, site(0)));
   if (pl.mem_dim != E) {
     RC(cast_f32_to_bf16(pl.dmemp, pl.dmemp16, static_cast<long long>(Ms) * E, s));
     RC(linear_wgrad(pl.dmemp16, E, pl.mem16, pl.mem_dim, e->gf + e->proj_w, e->gf + e->proj_b, Ms, E, pl.mem_dim, s, side, e->bias_fork, &side_used));
@@ -1046,16 +1068,18 @@ int b200_engine_forward_logits(b200_engine* e, const int64_t* tokens, const floa
   return gemm_launch(g, s);
 }
 
-int b200_engine_forward_loss(b200_engine* e, const int64_t* tokens, const int64_t* targets, const float* memory,
+static int forward_loss_impl(b200_engine* e, const int64_t* tokens, const int64_t* targets, const float* memory,
                              const uint8_t* mem_pad, int32_t B, int32_t T, int32_t S, int32_t mem_dim,
-                             int64_t ignore_index, int32_t training, float* loss_out, void* stream) {
+                             int64_t ignore_index, int32_t training, const int32_t* cu, int32_t rows, float* loss_out,
+                             void* stream) {
   B200_REQUIRE(e && tokens && targets && memory && loss_out, "forward_loss: null argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  RC(run_forward(e, tokens, memory, mem_pad, B, T, S, mem_dim, training, s));
+  RC(run_forward(e, tokens, memory, mem_pad, B, T, S, mem_dim, training, s, cu, rows, targets));
+  Plan& pl = e->plan;
+  if (cu) targets = pl.ptgt;                          // the packed copies (run_forward gathered them)
   e->last_tokens = tokens; e->last_targets = targets; e->last_mem_pad = mem_pad; e->last_ignore = ignore_index;
   e->have_saved = training != 0;
-  Plan& pl = e->plan;
-  const int E = e->cfg.embed_dim, V = e->cfg.vocab_size, M = B * T;
+  const int E = e->cfg.embed_dim, V = e->cfg.vocab_size, M = pl.M;
   B200_CHECK_CUDA(cudaMemsetAsync(pl.scalars, 0, 16 * sizeof(float), s));
   RC(b200_lmhead_ce_fwd(pl.x_final, E, e->ph + e->fc_w, E, e->pf + e->fc_b, targets, M, V, E, ignore_index,
                         pl.row_lse, pl.row_loss, pl.scalars, pl.scalars + 1, pl.ce_scratch, stream));
@@ -1064,13 +1088,28 @@ int b200_engine_forward_loss(b200_engine* e, const int64_t* tokens, const int64_
   return 0;
 }
 
+int b200_engine_forward_loss(b200_engine* e, const int64_t* tokens, const int64_t* targets, const float* memory,
+                             const uint8_t* mem_pad, int32_t B, int32_t T, int32_t S, int32_t mem_dim,
+                             int64_t ignore_index, int32_t training, float* loss_out, void* stream) {
+  return forward_loss_impl(e, tokens, targets, memory, mem_pad, B, T, S, mem_dim, ignore_index, training, nullptr, 0, loss_out, stream);
+}
+
+int b200_engine_forward_loss_packed(b200_engine* e, const int64_t* tokens, const int64_t* targets, const float* memory,
+                                    const uint8_t* mem_pad, int32_t B, int32_t T, int32_t S, int32_t mem_dim,
+                                    int64_t ignore_index, int32_t training, const int32_t* cu_seqlens, int32_t total_rows,
+                                    float* loss_out, void* stream) {
+  B200_REQUIRE(cu_seqlens && total_rows > 0, "forward_loss_packed: cu_seqlens / total_rows missing");
+  return forward_loss_impl(e, tokens, targets, memory, mem_pad, B, T, S, mem_dim, ignore_index, training, cu_seqlens, total_rows,
+                           loss_out, stream);
+}
+
 int b200_engine_backward(b200_engine* e, const float* inv_count_dev, float* dmemory, void* const* bucket_events,
                          int32_t num_bucket_events, void* stream) {
   B200_REQUIRE(e, "backward: null engine");
   B200_REQUIRE(e->have_saved && e->last_targets, "backward: call forward_loss(training=1) first");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   Plan& pl = e->plan;
-  const int E = e->cfg.embed_dim, V = e->cfg.vocab_size, M = pl.B * pl.T;
+  const int E = e->cfg.embed_dim, V = e->cfg.vocab_size, M = pl.M;
   const float* inv = inv_count_dev ? inv_count_dev : pl.scalars + 6;
   RC(b200_lmhead_ce_bwd(pl.x_final, E, e->ph + e->fc_w, E, e->pf + e->fc_b, e->last_targets, M, V, E, e->last_ignore,
                         pl.row_lse, inv, pl.dlogits, V, stream));
@@ -1085,7 +1124,7 @@ int b200_engine_backward_parts(b200_engine* e, const float* inv_count_dev, float
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   Plan& pl = e->plan;
   if (first_part == 0) {
-    const int E = e->cfg.embed_dim, V = e->cfg.vocab_size, M = pl.B * pl.T;
+    const int E = e->cfg.embed_dim, V = e->cfg.vocab_size, M = pl.M;
     const float* inv = inv_count_dev ? inv_count_dev : pl.scalars + 6;
     RC(b200_lmhead_ce_bwd(pl.x_final, E, e->ph + e->fc_w, E, e->pf + e->fc_b, e->last_targets, M, V, E, e->last_ignore,
                           pl.row_lse, inv, pl.dlogits, V, stream));

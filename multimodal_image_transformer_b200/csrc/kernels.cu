@@ -25,7 +25,8 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // ------------------------------------------------------------------------------------------
 __global__ void embed_pe_fwd_kernel(const int64_t* __restrict__ tokens, const float* __restrict__ emb,
                                     const float* __restrict__ pe, bf16* __restrict__ x, int rows,
-                                    int T, int E, int V, float scale, int t0, const DropCfg dc) {
+                                    int T, int E, int V, float scale, int t0, const DropCfg dc,
+                                    const int32_t* __restrict__ pos) {
   pdl_wait();
   pdl_trigger();
   const int vec_per_row = E >> 3;
@@ -35,7 +36,7 @@ __global__ void embed_pe_fwd_kernel(const int64_t* __restrict__ tokens, const fl
   const int c = static_cast<int>(idx % vec_per_row) << 3;
   long long tok = tokens[row];
   tok = tok < 0 ? 0 : (tok >= V ? V - 1 : tok);
-  const int t = row % T + t0;
+  const int t = pos ? pos[row] : row % T + t0;
   const float4* e4 = reinterpret_cast<const float4*>(emb + tok * E + c);
   const float4* p4 = reinterpret_cast<const float4*>(pe + static_cast<long long>(t) * E + c);
   const float4 e0 = __ldg(e4), e1 = __ldg(e4 + 1), p0 = __ldg(p4), p1 = __ldg(p4 + 1);
@@ -51,10 +52,33 @@ __global__ void embed_pe_fwd_kernel(const int64_t* __restrict__ tokens, const fl
 }
 
 int embed_pe_fwd(const int64_t* tokens, const float* emb, const float* pe, bf16* x, int B, int T,
-                 int E, int V, float scale, cudaStream_t s, int t0, DropCfg dc) {
+                 int E, int V, float scale, cudaStream_t s, int t0, DropCfg dc, const int32_t* pos) {
   B200_REQUIRE(E % 8 == 0, "embed: E (%d) must be a multiple of 8", E);
   const long long n = static_cast<long long>(B) * T * (E / 8);
-  B200_CHECK_CUDA(launch_kernel(embed_pe_fwd_kernel, dim3(cdiv(n, 256)), dim3(256), 0, s, true, 1, tokens, emb, pe, x, B * T, T, E, V, scale, t0, dc));
+  B200_CHECK_CUDA(launch_kernel(embed_pe_fwd_kernel, dim3(cdiv(n, 256)), dim3(256), 0, s, true, 1, tokens, emb, pe, x, B * T, T, E, V, scale, t0, dc, pos));
+  note_launch();
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void pack_rows_kernel(const int64_t* __restrict__ tokens, const int64_t* __restrict__ targets,
+                                 const int32_t* __restrict__ cu, int B, int T, int64_t* __restrict__ ptok,
+                                 int64_t* __restrict__ ptgt, int32_t* __restrict__ ppos) {
+  pdl_wait();
+  pdl_trigger();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * T) return;
+  const int b = idx / T, t = idx - b * T;
+  const int r0 = cu[b];
+  if (t >= cu[b + 1] - r0) return;
+  ptok[r0 + t] = tokens[idx];
+  if (targets) ptgt[r0 + t] = targets[idx];
+  ppos[r0 + t] = t;
+}
+int pack_rows(const int64_t* tokens, const int64_t* targets, const int32_t* cu, int B, int T, int64_t* ptok,
+              int64_t* ptgt, int32_t* ppos, cudaStream_t s) {
+  B200_CHECK_CUDA(launch_kernel(pack_rows_kernel, dim3(cdiv(static_cast<long long>(B) * T, 256)), dim3(256), 0, s, true, 1, tokens,
+                                targets, cu, B, T, ptok, ptgt, ppos));
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -6,8 +6,14 @@
 namespace b200 {
 
 // position of row r is (r % T) + t0  (t0 > 0: single-position decode steps)
+// pos (optional): position of every row (packed / var-len batches)
 int embed_pe_fwd(const int64_t* tokens, const float* emb, const float* pe, bf16* x, int B, int T,
-                 int E, int V, float scale, cudaStream_t s, int t0 = 0, DropCfg dc = DropCfg{nullptr, 0u, 0u, 1.f});
+                 int E, int V, float scale, cudaStream_t s, int t0 = 0, DropCfg dc = DropCfg{nullptr, 0u, 0u, 1.f},
+                 const int32_t* pos = nullptr);
+// packed (var-len) batches: sample b keeps its first cu[b+1]-cu[b] positions as rows [cu[b], cu[b+1]);
+// ptok / ptgt / ppos = token id, target id and position of every kept row
+int pack_rows(const int64_t* tokens, const int64_t* targets, const int32_t* cu, int B, int T, int64_t* ptok,
+              int64_t* ptgt, int32_t* ppos, cudaStream_t s);
 int embed_bwd(const int64_t* tokens, const bf16* dx, float* demb, int B, int T, int E, int V,
               long long pad_idx, float scale, cudaStream_t s, DropCfg dc = DropCfg{nullptr, 0u, 0u, 1.f});
 // advances the dropout step counter (state[1]) on the stream

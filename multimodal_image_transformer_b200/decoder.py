@@ -192,13 +192,17 @@ class TransformerDecoder(nn.Module):
 
     # ------------------------------------------------------------------ fused fast path
     def loss(self, tgt_tokens, target_tokens, memory, memory_padding_mask=None, ignore_index: int = 0,
-             training: Optional[bool] = None) -> torch.Tensor:
+             training: Optional[bool] = None, lengths=None) -> torch.Tensor:
         """mean CE over targets != ignore_index with the LM head fused into the loss (logits are
-        never materialised).  Returns a device tensor [loss, n_valid]; no host sync."""
+        never materialised).  Returns a device tensor [loss, n_valid]; no host sync.
+
+        lengths (host, B ints; e.g. DecoderEngine.packed_lengths(cpu_tokens)): packed / var-len path -- only the non-PAD
+        prefix of every caption is computed (the reference pads to MAX_SEQ_LEN, tokenizer.py:293-313); same loss and
+        gradients as the padded call."""
         training = self.training if training is None else training
         self.engine.dropout_active(self.training and training)
         return self.engine.forward_loss(tgt_tokens, target_tokens, memory, self._mask(memory_padding_mask),
-                                        ignore_index, training=training)
+                                        ignore_index, training=training, lengths=lengths)
 
     def backward(self, inv_count=None, events=None):
         """Backward of the last loss(training=True) into the flat gradient arena (accumulates)."""

@@ -286,8 +286,13 @@ class DecoderEngine:
         return logits
 
     def forward_loss(self, tokens, targets, memory, mem_pad=None, ignore_index: int = 0,
-                     training: bool = False) -> torch.Tensor:
-        """Returns a device tensor [mean_loss, n_valid_targets]."""
+                     training: bool = False, lengths=None) -> torch.Tensor:
+        """Returns a device tensor [mean_loss, n_valid_targets].
+
+        lengths (optional, host list / CPU tensor of B ints): PACKED (var-len) forward -- sample b keeps only its first
+        lengths[b] positions (its non-PAD prefix: the reference pads every caption to MAX_SEQ_LEN, tokenizer.py:293-313,
+        dataset.py:176-206) and every row-wise kernel runs on sum(lengths) rows instead of B * T.  Loss and gradients
+        equal the padded call's.  `packed_lengths()` derives the lengths from the token ids."""
         tokens, memory, mem_pad = self._prep(tokens, memory, mem_pad)
         targets = targets.contiguous()
         B, T = tokens.shape
@@ -296,11 +301,37 @@ class DecoderEngine:
         self._ensure_ws(B, T, S, mem_dim, training)
         out = torch.empty(2, device=self.device, dtype=torch.float32)
         self._keep = (tokens, memory, mem_pad, targets)
+        if lengths is not None:
+            lens = torch.as_tensor(lengths, dtype=torch.int32, device="cpu").reshape(-1)
+            if lens.numel() != B or int(lens.min()) < 1 or int(lens.max()) > T:
+                raise ValueError("forward_loss: lengths must hold B values in [1, T]")
+            cu = torch.zeros(B + 1, dtype=torch.int32)
+            cu[1:] = torch.cumsum(lens, 0)
+            total = int(cu[-1])
+            cu_dev = cu.to(self.device, non_blocking=True)
+            self._keep = self._keep + (cu_dev,)
+            with nvtx_range("b200.forward_loss_packed"):
+                L.check(self.lib.b200_engine_forward_loss_packed(
+                    self.handle, L.ptr(tokens), L.ptr(targets), L.ptr(memory), L.ptr(mem_pad), B, T, S, mem_dim,
+                    C.c_int64(ignore_index), int(training), L.ptr(cu_dev), total, L.ptr(out), L.cur_stream()),
+                    "forward_loss_packed")
+            return out
         with nvtx_range("b200.forward_loss"):
             L.check(self.lib.b200_engine_forward_loss(self.handle, L.ptr(tokens), L.ptr(targets), L.ptr(memory),
                                                       L.ptr(mem_pad), B, T, S, mem_dim, C.c_int64(ignore_index),
                                                       int(training), L.ptr(out), L.cur_stream()), "forward_loss")
         return out
+
+    @staticmethod
+    def packed_lengths(tokens: torch.Tensor, pad_idx: int = 0):
+        """Per-sample length of the non-PAD prefix of [B, T] token ids (on the host), or None when some caption has a
+        PAD *inside* it (the packed path keeps prefixes only; such a batch has to take the padded path, where PAD keys
+        are masked like the reference does, decoder.py:158-162)."""
+        nonpad = (tokens != pad_idx)
+        prefix = nonpad.long().cumprod(1).sum(1)
+        if not torch.equal(prefix, nonpad.sum(1)) or int(prefix.min()) < 1:
+            return None
+        return prefix.to("cpu", torch.int32)
 
     def backward(self, inv_count: Optional[torch.Tensor] = None, want_dmemory: bool = False,
                  events: Optional[List[torch.cuda.Event]] = None) -> Optional[torch.Tensor]:

@@ -164,13 +164,13 @@ class ImageToTextModel(nn.Module):
         return _forward_with_projection(self, tgt_tokens, memory)
 
     def loss(self, image_tensors, tgt_tokens, target_tokens, ignore_index: int = 0, training=None,
-             memory: Optional[torch.Tensor] = None) -> torch.Tensor:
+             memory: Optional[torch.Tensor] = None, lengths=None) -> torch.Tensor:
         """Fused path: encoder -> (projection + decoder + LM head + CE) without logits.  `memory`
-        (e.g. from a FeatureCache) skips the frozen encoder."""
+        (e.g. from a FeatureCache) skips the frozen encoder; `lengths` selects the packed / var-len decoder path."""
         if memory is None:
             memory = self.encode(image_tensors)
         return self.decoder.loss(tgt_tokens.to(memory.device), target_tokens.to(memory.device), memory, None,
-                                 ignore_index, training)
+                                 ignore_index, training, lengths=lengths)
 
     @torch.no_grad()
     def generate(self, image, start_token_id, end_token_id, max_len=100, method="greedy", beam_size=3) -> List[int]:

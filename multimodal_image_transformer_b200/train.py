@@ -6,6 +6,8 @@ with any other optimizer / criterion it degrades to the reference's own loop ove
 autograd-compatible forward."""
 from typing import Optional
 
+import os
+
 import torch
 
 from . import config
@@ -110,6 +112,10 @@ class B200AdamW(torch.optim.Optimizer):
             g.update({k: v for k, v in s.items() if k != "params"})
 
 
+# train_one_epoch packs the captions' non-PAD prefixes (var-len path of the engine) unless B200_PACKED=0
+PACKED_BATCHES = os.environ.get("B200_PACKED", "1") != "0"
+
+
 def trim_batch(decoder_input_tokens: torch.Tensor, target_tokens: torch.Tensor, pad_idx: int, multiple: int = 8):
     """Drop the all-PAD tail columns of a collated batch.  The reference pads every caption to
     MAX_SEQ_LEN (tokenizer.py:306, dataset.py:195-197), so most columns of a real batch are PAD for
@@ -197,8 +203,9 @@ def _zero_stream(device) -> "torch.cuda.Stream":
 
 
 def fused_train_step(model, images, decoder_input_tokens, target_tokens, optimizer: B200AdamW, ignore_index: int,
-                     grad_clip_value: float, dp: Optional[DataParallel] = None) -> torch.Tensor:
-    """One optimisation step; returns the device tensor [loss, n_valid] (no host sync)."""
+                     grad_clip_value: float, dp: Optional[DataParallel] = None, lengths=None) -> torch.Tensor:
+    """One optimisation step; returns the device tensor [loss, n_valid] (no host sync).
+    lengths (host, B ints): packed / var-len step -- PAD positions are not computed at all (see decoder.loss)."""
     decoder = model.decoder if hasattr(model, "decoder") else model
     # the gradient arena is cleared on a side stream while the forward runs (the forward never touches it);
     # fork / join through stream events, so the pattern is also valid under CUDA-graph capture
@@ -208,9 +215,9 @@ def fused_train_step(model, images, decoder_input_tokens, target_tokens, optimiz
     with torch.cuda.stream(side):
         optimizer.zero_grad()
     if hasattr(model, "decoder"):
-        out = model.loss(images, decoder_input_tokens, target_tokens, ignore_index, training=True)
+        out = model.loss(images, decoder_input_tokens, target_tokens, ignore_index, training=True, lengths=lengths)
     else:   # a bare decoder: `images` is the memory
-        out = decoder.loss(decoder_input_tokens, target_tokens, images, None, ignore_index, training=True)
+        out = decoder.loss(decoder_input_tokens, target_tokens, images, None, ignore_index, training=True, lengths=lengths)
     cur.wait_stream(side)
     if dp is not None and dp.world_size > 1:
         inv = dp.global_inv_count(out)                 # 1 / (non-PAD targets over all ranks)
@@ -292,13 +299,19 @@ def train_one_epoch(model, dataloader, optimizer, criterion, device, grad_clip_v
     for i, batch in enumerate(dataloader):
         images = batch["images"].to(device, non_blocking=True)
         tokens, targets = batch["decoder_input_tokens"], batch["target_tokens"]
+        lengths = None
         if fused and _ignore_index(criterion) == pad:
             tokens, targets = trim_batch(tokens, targets, pad)      # on the host tensors: no device sync
+            # var-len: the captions' non-PAD prefixes only (tokenizer.py:293-313 pads every caption to MAX_SEQ_LEN);
+            # B200_PACKED=0 keeps the padded rectangle.  None when a caption has a PAD inside it.
+            if PACKED_BATCHES and tokens.device.type == "cpu":
+                from .engine import DecoderEngine
+                lengths = DecoderEngine.packed_lengths(tokens, pad)
         tokens = tokens.to(device, non_blocking=True)
         targets = targets.to(device, non_blocking=True)
         if fused:
             out = fused_train_step(model, images, tokens, targets, optimizer, _ignore_index(criterion),
-                                   grad_clip_value, dp)
+                                   grad_clip_value, dp, lengths=lengths)
             batch_loss = float(out[0].item())
         else:
             optimizer.zero_grad()

@@ -873,3 +873,64 @@ def test_backward_bias_side_stream_matches_inline(cuda_dev, name, monkeypatch):
         for k in ("fc_out.bias", "transformer_decoder.layers.0.linear1.bias", "transformer_decoder.layers.0.self_attn.in_proj_bias",
                   "transformer_decoder.layers.1.multihead_attn.in_proj_bias"):
             assert rel_l2(eng.view(k, g), eng.view(k, grads[0])) < 1e-5, k
+
+
+def _varlen_case(name, seed=7, lo=12):
+    """A batch whose captions have U[lo, T] real tokens followed by PAD (the reference's padded batches,
+    tokenizer.py:293-313 / dataset.py:176-206)."""
+    c = CFGS[name]
+    p = O.init_params(c["V"], c["E"], c["H"], c["L"], c["F"], c["ML"], seed=seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    B, T, S, V = c["B"], c["T"], c["S"], c["V"]
+    cap = torch.randint(4, V, (B, T + 1), generator=g)
+    cap[:, 0] = 1
+    lens = torch.randint(min(lo, T), T + 1, (B,), generator=g)          # tokens of the INPUT (caption[:-1]) that are real
+    lens[0] = T                                                         # one full-length caption
+    for b in range(B):
+        n = int(lens[b])
+        if n < T + 1:
+            cap[b, n] = 2 if n < T + 1 else cap[b, n]                  # END closes the caption ...
+            cap[b, n + 1:] = 0                                          # ... PAD after it
+    tok, tgt = cap[:, :-1].contiguous(), cap[:, 1:].contiguous()
+    mem = torch.randn(B, S, c["E"], generator=g)
+    return c, p, tok, tgt, mem
+
+
+@pytest.mark.parametrize("name", ["nano", "hd96", "cfg1", "cfg2s"])
+def test_packed_varlen_path_equals_padded_path(cuda_dev, name):
+    """f4: the packed / var-len engine path (cu_seqlens, rows = sum of lengths) gives the padded path's
+    loss and gradients on captions of U[12, T] tokens, and both match the fp32 oracle (= the reference's padded math)."""
+    from multimodal_image_transformer_b200.engine import DecoderEngine
+    c, p, tok, tgt, mem = _varlen_case(name)
+    lengths = DecoderEngine.packed_lengths(tok, 0)
+    assert lengths is not None and int(lengths.sum()) < tok.numel()
+    eng = make_engine(c, p, cuda_dev)
+    td, gd, md = tok.to(cuda_dev), tgt.to(cuda_dev), mem.to(cuda_dev)
+    eng.zero_grad()
+    out_pad = eng.forward_loss(td, gd, md, None, 0, training=True).cpu()
+    eng.backward()
+    g_pad = eng.grads.clone()
+    eng.zero_grad()
+    out_pk = eng.forward_loss(td, gd, md, None, 0, training=True, lengths=lengths).cpu()
+    eng.backward()
+    g_pk = eng.grads.clone()
+    torch.cuda.synchronize()
+    assert out_pk[1].item() == out_pad[1].item() == (tgt != 0).sum().item()
+    # same kernels on the same rows (only the attention tiling differs): loss to 1e-6 relative, gradients to 2e-3
+    assert abs(out_pk[0].item() - out_pad[0].item()) <= 1e-6 * abs(out_pad[0].item()) + 1e-7
+    assert rel_l2(g_pk, g_pad) < 2e-3
+    for k in ("fc_out.weight", "token_embedding.weight", "transformer_decoder.layers.0.self_attn.in_proj_weight",
+              "transformer_decoder.layers.0.multihead_attn.in_proj_weight", "transformer_decoder.layers.0.linear1.weight"):
+        assert rel_l2(eng.view(k, g_pk), eng.view(k, g_pad)) < 2e-3, k
+    # and against the oracle (the reference's padded computation)
+    lref, gref = O.loss_and_grads(p, tok, tgt, mem, None, c["H"])
+    assert abs(out_pk[0].item() - lref.item()) < 1e-3 * lref.item()
+    assert _grad_close(eng.view("fc_out.weight", g_pk), gref["fc_out.weight"], rel=1.5e-2, cos=0.9995)
+    assert _grad_close(eng.view("token_embedding.weight", g_pk), gref["token_embedding.weight"])
+
+
+def test_packed_lengths_rejects_inner_pad():
+    from multimodal_image_transformer_b200.engine import DecoderEngine
+    tok = torch.tensor([[1, 5, 6, 2, 0, 0], [1, 7, 0, 8, 2, 0]])
+    assert DecoderEngine.packed_lengths(tok, 0) is None
+    assert DecoderEngine.packed_lengths(tok[:1], 0).tolist() == [4]
