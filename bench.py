@@ -509,7 +509,41 @@ def run_b200(args):
                                           f"1 warm-up + 3 timed steps, {threads} threads; the full-batch run is `--impl reference`"}
     if world == 1 and not args.no_decode:
         line["decode"] = bench_decode(dec, c, dev, peaks, peak_src)
+    if world == 1 and not args.no_varlen:
+        line["varlen"] = bench_varlen(dec, opt, c, dev, args.steps)
     print(json.dumps(line))
+
+
+def bench_varlen(dec, opt, c, dev, steps):
+    """Extra object: the same train step on captions of U[12, T] real tokens (SURVEY 8d's padded run; the reference pads
+    every caption, tokenizer.py:293-313) -- the padded [B, T] rectangle against the packed / var-len engine path
+    (b200_engine_forward_loss_packed), both launched eagerly (the packed row count changes per batch, so it is not
+    graph-replayed).  Throughput is counted in REAL (non-PAD) input tokens."""
+    from multimodal_image_transformer_b200.engine import DecoderEngine
+    from multimodal_image_transformer_b200.train import fused_train_step
+    host = [synth_batch(c, 5000 + i, full_length=False) for i in range(2)]
+    lens = [DecoderEngine.packed_lengths(b[0], 0) for b in host]
+    batches = [(b[0].to(dev), b[1].to(dev), b[2].to(dev, torch.bfloat16)) for b in host]
+    real = sum(int(l.sum()) for l in lens) / len(lens)
+    out = {"padding": f"U[12,{c['T']}] real tokens per caption, PAD after", "real_tokens_per_step": real,
+           "real_fraction": real / (c["B"] * c["T"]), "launch_mode": "eager launches (both arms)"}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for name, use_len in (("padded", False), ("packed", True)):
+        def step(i):
+            tok, tgt, mem = batches[i % 2]
+            return fused_train_step(dec, mem, tok, tgt, opt, 0, 5.0, None, lengths=lens[i % 2] if use_len else None)
+        for i in range(3):
+            res = step(i)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(steps):
+            res = step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out[name] = {"ms_per_step": ms, "real_tokens_per_s": real / (ms / 1e3), "loss": float(res[0].item())}
+    out["speedup_packed_over_padded"] = out["padded"]["ms_per_step"] / out["packed"]["ms_per_step"]
+    return out
 
 
 def bench_decode(dec, c, dev, peaks, peak_src):
@@ -586,6 +620,7 @@ def main():
                     help="--impl reference: wall-clock budget; the per-step sample (never the step count) shrinks to fit it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--no-varlen", action="store_true", help="skip the extra padded-vs-packed (var-len) train-step comparison")
     ap.add_argument("--no-graph", action="store_true", help="time the eager launch sequence instead of the CUDA-graph replay")
     ap.add_argument("--gemm-detail", default=None, help="write per-launch GEMM timings of one step to this CSV")
     args = ap.parse_args()

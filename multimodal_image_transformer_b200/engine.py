@@ -305,10 +305,21 @@ class DecoderEngine:
             lens = torch.as_tensor(lengths, dtype=torch.int32, device="cpu").reshape(-1)
             if lens.numel() != B or int(lens.min()) < 1 or int(lens.max()) > T:
                 raise ValueError("forward_loss: lengths must hold B values in [1, T]")
-            cu = torch.zeros(B + 1, dtype=torch.int32)
-            cu[1:] = torch.cumsum(lens, 0)
-            total = int(cu[-1])
-            cu_dev = cu.to(self.device, non_blocking=True)
+            # row offsets travel through a small ring of pinned staging buffers: a pageable H2D copy would block the
+            # host until the stream drains and expose the launch time of the whole eager step
+            ring = getattr(self, "_cu_ring", None)
+            if ring is None or ring[0][0].numel() < B + 1:
+                ring = [(torch.empty(B + 1, dtype=torch.int32).pin_memory(),
+                         torch.empty(B + 1, dtype=torch.int32, device=self.device), torch.cuda.Event()) for _ in range(4)]
+                self._cu_ring, self._cu_next = ring, 0
+            cu, cu_dev, ev = ring[self._cu_next]
+            self._cu_next = (self._cu_next + 1) % len(ring)
+            ev.synchronize()                      # the copy that last used this staging buffer has finished
+            cu[0] = 0
+            torch.cumsum(lens, 0, out=cu[1:B + 1])
+            total = int(cu[B])
+            cu_dev[:B + 1].copy_(cu[:B + 1], non_blocking=True)
+            ev.record()
             self._keep = self._keep + (cu_dev,)
             with nvtx_range("b200.forward_loss_packed"):
                 L.check(self.lib.b200_engine_forward_loss_packed(
