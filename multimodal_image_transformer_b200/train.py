@@ -344,9 +344,13 @@ def evaluate(model, dataloader, criterion, device):
         for batch in dataloader:
             images = batch["images"].to(device, non_blocking=True)
             tokens, targets = batch["decoder_input_tokens"], batch["target_tokens"]
+            lengths = None
             if ii == pad:
                 tokens, targets = trim_batch(tokens, targets, pad)
+                if PACKED_BATCHES and tokens.device.type == "cpu":      # var-len path, as in train_one_epoch
+                    from .engine import DecoderEngine
+                    lengths = DecoderEngine.packed_lengths(tokens, pad)
             tokens = tokens.to(device, non_blocking=True)
             targets = targets.to(device, non_blocking=True)
-            total_loss += float(model.loss(images, tokens, targets, ii, training=False)[0].item())
+            total_loss += float(model.loss(images, tokens, targets, ii, training=False, lengths=lengths)[0].item())
     return total_loss / max(num_batches, 1)

@@ -934,3 +934,26 @@ def test_packed_lengths_rejects_inner_pad():
     tok = torch.tensor([[1, 5, 6, 2, 0, 0], [1, 7, 0, 8, 2, 0]])
     assert DecoderEngine.packed_lengths(tok, 0) is None
     assert DecoderEngine.packed_lengths(tok[:1], 0).tolist() == [4]
+
+
+def test_packed_path_with_dropout_and_eval(cuda_dev):
+    """The packed path in training mode with dropout (finite loss / gradients; masks are drawn per packed row, so only
+    the dropout-free quantities are compared) and in eval mode (identical to the padded eval loss)."""
+    from multimodal_image_transformer_b200.engine import DecoderEngine
+    c, p, tok, tgt, mem = _varlen_case("tiny", seed=11, lo=5)
+    lengths = DecoderEngine.packed_lengths(tok, 0)
+    eng = make_engine(c, p, cuda_dev)
+    td, gd, md = tok.to(cuda_dev), tgt.to(cuda_dev), mem.to(cuda_dev)
+    ev_pad = eng.forward_loss(td, gd, md, None, 0, training=False).cpu()
+    ev_pk = eng.forward_loss(td, gd, md, None, 0, training=False, lengths=lengths).cpu()
+    assert abs(ev_pk[0].item() - ev_pad[0].item()) <= 1e-6 * abs(ev_pad[0].item()) + 1e-7
+    eng.set_dropout(0.1, seed=3)
+    eng.dropout_active(True)
+    eng.zero_grad()
+    out = eng.forward_loss(td, gd, md, None, 0, training=True, lengths=lengths).cpu()
+    eng.backward()
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all() and torch.isfinite(eng.grads).all()
+    assert abs(out[0].item() - ev_pad[0].item()) < 0.2 * ev_pad[0].item()      # dropout moves the loss, not its scale
+    assert out[1].item() == (tgt != 0).sum().item()
+    eng.dropout_active(False)
