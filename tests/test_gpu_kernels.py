@@ -171,7 +171,12 @@ def _attn_ref(q, k, v, causal, keymask):
 
 @pytest.mark.parametrize("B,H,Tq,Tk,hd,causal", [(2, 2, 17, 17, 64, 1), (3, 4, 31, 31, 64, 1), (2, 3, 47, 197, 64, 0),
                                                  (2, 2, 31, 50, 64, 0), (2, 2, 47, 47, 96, 1), (2, 2, 47, 257, 128, 0),
-                                                 (1, 2, 99, 99, 128, 1), (2, 2, 20, 1, 64, 0), (2, 2, 33, 40, 32, 0)])
+                                                 (1, 2, 99, 99, 128, 1), (2, 2, 20, 1, 64, 0), (2, 2, 33, 40, 32, 0),
+                                                 # tcgen05 kernels (hd 64, Tk >= 65): three key tiles, an exact tile, one
+                                                 # query row, a 1-key tail tile, the longest forward, several items per CTA
+                                                 (2, 4, 47, 257, 64, 0), (3, 5, 48, 128, 64, 0), (2, 2, 1, 70, 64, 0),
+                                                 (5, 7, 33, 129, 64, 0), (2, 4, 47, 288, 64, 0), (32, 12, 47, 197, 64, 0),
+                                                 (2, 3, 64, 197, 64, 0)])
 def test_attention_fwd_bwd(cuda_dev, B, H, Tq, Tk, hd, causal):
     lib = L.lib()
     E = H * hd
