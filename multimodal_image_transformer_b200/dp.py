@@ -97,16 +97,23 @@ class DataParallel:
         """Backward one gradient bucket at a time; each bucket's all-reduce is launched on the comm
         stream behind a (torch) event recorded right after the bucket's last gradient write, so it
         overlaps the rest of backward.  Fork/join through torch events only: the whole sequence can
-        be captured in a CUDA graph (train.GraphedTrainStep)."""
+        be captured in a CUDA graph (train.GraphedTrainStep).  Returns True when the squared global gradient norm
+        has been accumulated along the way (engine.norm_add_bucket), so that the optimizer can skip its own pass."""
         g = self.engine.grads
         cur = torch.cuda.current_stream()
+        overlap_norm = self.engine.buckets_cover_arena() and os.environ.get("B200_OVERLAP_NORM", "1") != "0"
+        if overlap_norm:
+            self.engine.norm_begin()
         for i, ((off, cnt), ev) in enumerate(zip(self.buckets, self.events)):
             self.engine.backward_parts(i, i, inv_count)
             ev.record(cur)
             with torch.cuda.stream(self.comm_stream), nvtx_range("b200.dp.allreduce_bucket"):
                 self.comm_stream.wait_event(ev)
                 dist.all_reduce(g[off:off + cnt], op=dist.ReduceOp.SUM, group=self.group)
+                if overlap_norm:
+                    self.engine.norm_add_bucket(i)     # global norm of the REDUCED gradients, bucket by bucket
         cur.wait_stream(self.comm_stream)
+        return overlap_norm
 
     def allreduce_buckets(self) -> None:
         """Launch one all-reduce per bucket on the comm stream as soon as backward has finished

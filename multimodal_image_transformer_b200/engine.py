@@ -382,7 +382,29 @@ class DecoderEngine:
         return [(int(offs[i]), int(cnts[i])) for i in range(n)]
 
     # ------------------------------------------------------------------ optimizer
-    def adamw_step(self, lr=1e-4, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-5, max_norm=5.0) -> torch.Tensor:
+    def norm_begin(self) -> None:
+        """Start a per-bucket gradient-norm accumulation (see norm_add_bucket): zero the squared-norm scalar."""
+        self._scal[0:1].zero_()
+
+    def norm_add_bucket(self, index: int) -> None:
+        """sumsq += |g|^2 over gradient bucket `index` (readiness order of grad_buckets()) on the CURRENT stream.  Called
+        on a side stream behind the bucket's event, the global-norm pass of clip_grad_norm_ (train.py:97) overlaps the rest
+        of backward and reads every bucket while it is still in L2; adamw_step(norm_ready=True) then skips its own pass."""
+        off, cnt = self.grad_buckets()[index]
+        L.check(self.lib.b200_grad_sumsq(C.c_void_p(self.grads.data_ptr() + 4 * off), C.c_int64(cnt), L.ptr(self._scal[0:1]),
+                                         L.cur_stream()), "grad_sumsq")
+
+    def buckets_cover_arena(self) -> bool:
+        b = sorted(self.grad_buckets())
+        pos = 0
+        for off, cnt in b:
+            if off != pos:
+                return False
+            pos = off + cnt
+        return pos == self.total
+
+    def adamw_step(self, lr=1e-4, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-5, max_norm=5.0,
+                   norm_ready: bool = False) -> torch.Tensor:
         """clip_grad_norm_(max_norm) + AdamW over the whole arena (train.py:96-100, 319-325).
         Returns the device scalar holding the squared global gradient norm (pre-clip)."""
         if self.exp_avg is None:
@@ -393,10 +415,11 @@ class DecoderEngine:
             self._lr_dev.fill_(lr)   # lr lives on the device so that a captured step can be replayed
             self._lr_host = lr
         sumsq = self._scal[0:1]
-        sumsq.zero_()
         st = L.cur_stream()
-        with nvtx_range("b200.optimizer.grad_norm"):
-            L.check(self.lib.b200_grad_sumsq(L.ptr(self.grads), C.c_int64(self.total), L.ptr(sumsq), st), "grad_sumsq")
+        if not norm_ready:
+            sumsq.zero_()
+            with nvtx_range("b200.optimizer.grad_norm"):
+                L.check(self.lib.b200_grad_sumsq(L.ptr(self.grads), C.c_int64(self.total), L.ptr(sumsq), st), "grad_sumsq")
         with nvtx_range("b200.optimizer.clip_adamw"):
             L.check(self.lib.b200_adamw_step_dev(L.ptr(self.params), L.ptr(self.params_bf16), L.ptr(self.grads),
                                                  L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq), C.c_int64(self.total),

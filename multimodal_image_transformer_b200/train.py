@@ -36,7 +36,7 @@ class B200AdamW(torch.optim.Optimizer):
     def zero_grad(self, set_to_none: bool = False) -> None:
         self.engine.zero_grad()          # the arena stays allocated; .grad views keep pointing at it
 
-    def step(self, closure=None, max_grad_norm: Optional[float] = None) -> None:
+    def step(self, closure=None, max_grad_norm: Optional[float] = None, norm_ready: bool = False) -> None:
         if closure is not None and not callable(closure):      # step(5.0): positional clip value (round-1 signature)
             max_grad_norm, closure = float(closure), None
         if closure is not None:
@@ -44,7 +44,7 @@ class B200AdamW(torch.optim.Optimizer):
         g = self.param_groups[0]
         mn = self.max_grad_norm if max_grad_norm is None else max_grad_norm
         self.last_grad_sumsq = self.engine.adamw_step(lr=float(g["lr"]), betas=g["betas"], eps=g["eps"],
-                                                      weight_decay=g["weight_decay"], max_norm=mn)
+                                                      weight_decay=g["weight_decay"], max_norm=mn, norm_ready=norm_ready)
 
     # ---- checkpoint compatibility (reference train.py:351-357, 424): torch.optim.AdamW layout
     def _named_trainable(self):
@@ -195,6 +195,26 @@ def _ignore_index(criterion) -> int:
 _ZERO_STREAMS = {}
 
 
+# the gradient-norm pass runs per bucket on a side stream under the rest of backward (B200_OVERLAP_NORM=0: one pass at the end)
+OVERLAP_NORM = os.environ.get("B200_OVERLAP_NORM", "1") != "0"
+_NORM_STATE = {}
+
+
+def _norm_events(eng):
+    """(one event per gradient bucket, side stream) of an engine; created OUTSIDE any graph capture.  torch creates the
+    CUDA event lazily at the first record(), and the engine records these events through their raw handles, so every
+    event is recorded once here (a wait on a never-created event would be a silent no-op)."""
+    key = id(eng)
+    if key not in _NORM_STATE:
+        if torch.cuda.is_current_stream_capturing():
+            return None
+        evs = [torch.cuda.Event() for _ in eng.grad_buckets()]
+        for ev in evs:
+            ev.record()
+        _NORM_STATE[key] = (evs, torch.cuda.Stream(device=eng.device))
+    return _NORM_STATE[key]
+
+
 def _zero_stream(device) -> "torch.cuda.Stream":
     key = (device.type, device.index)
     if key not in _ZERO_STREAMS:
@@ -219,13 +239,27 @@ def fused_train_step(model, images, decoder_input_tokens, target_tokens, optimiz
     else:   # a bare decoder: `images` is the memory
         out = decoder.loss(decoder_input_tokens, target_tokens, images, None, ignore_index, training=True, lengths=lengths)
     cur.wait_stream(side)
+    eng = decoder.engine
+    norm_ready = False
     if dp is not None and dp.world_size > 1:
         inv = dp.global_inv_count(out)                 # 1 / (non-PAD targets over all ranks)
-        dp.backward_and_allreduce(inv)                 # bucketed all-reduce overlapped with backward
+        norm_ready = dp.backward_and_allreduce(inv)    # bucketed all-reduce (+ per-bucket norm) overlapped with backward
         out = dp.global_loss(out, inv)
+    elif OVERLAP_NORM and eng.buckets_cover_arena() and _norm_events(eng) is not None:
+        # the global gradient norm (clip_grad_norm_, train.py:97) bucket by bucket on a side stream, behind the event the
+        # engine records when a bucket's gradients are final: the 288 MB pass leaves the critical path
+        evs, nstream = _norm_events(eng)
+        eng.norm_begin()
+        decoder.backward(events=evs)
+        with torch.cuda.stream(nstream):
+            for i, ev in enumerate(evs):
+                nstream.wait_event(ev)
+                eng.norm_add_bucket(i)
+        cur.wait_stream(nstream)
+        norm_ready = True
     else:
         decoder.backward()
-    optimizer.step(max_grad_norm=grad_clip_value)
+    optimizer.step(max_grad_norm=grad_clip_value, norm_ready=norm_ready)
     return out
 
 
@@ -260,6 +294,7 @@ class GraphedTrainStep:
                 eng._lr_dev.fill_(lr)
                 eng._lr_host = lr
             _zero_stream(torch.cuda.current_stream().device)   # made outside the capture
+            _norm_events(eng)
             torch.cuda.synchronize()
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):

@@ -53,7 +53,7 @@ def test_b200_adamw_is_a_torch_optimizer_driven_by_lambda_lr():
         def __init__(self):
             self.lrs, self.opt_step, self.exp_avg, self.exp_avg_sq = [], 0, None, None
 
-        def adamw_step(self, lr, betas, eps, weight_decay, max_norm):
+        def adamw_step(self, lr, betas, eps, weight_decay, max_norm, norm_ready=False):
             self.lrs.append((lr, max_norm))
             return None
 
