@@ -195,7 +195,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else if (warp == 1) {
     // ============================ MMA issuer (leader CTA only) ==============================
-    if (lane == 0 && leader) {
+    // The WHOLE warp walks the loop (waits and descriptor arithmetic are warp-uniform and stay in uniform registers) and
+    // one elected lane issues: inside an `if (lane == 0)` region every tcgen05.mma cost ~21 instructions (vector-register
+    // descriptor math plus an ELECT / 5 x R2UR "waterfall" loop), measured in the attention kernels.
+    if (leader) {
       constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M * CL, BLOCK_N, A_MN, B_MN);
       constexpr uint16_t PAIR_MASK = static_cast<uint16_t>((1u << CL) - 1u);
       int stage = 0;
@@ -214,6 +217,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
           const uint32_t sb = sa + L::A_BYTES;
+          if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // K-major: 128-byte rows, 8-row groups 1024 B apart, 16 k-elements = +32 B.
@@ -229,11 +233,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           // frees this smem stage (in both CTAs of a pair) once the MMAs have read it
           if constexpr (CL == 1) umma_commit(&empty_bar[stage]);
           else umma_commit_pair(&empty_bar[stage], PAIR_MASK);
+          // accumulator complete: publish to the epilogue warps (of both CTAs)
+          if (kb == kb1 - 1) {
+            if constexpr (CL == 1) umma_commit(&tmem_full[acc]);
+            else umma_commit_pair(&tmem_full[acc], PAIR_MASK);
+          }
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        // accumulator complete: publish to the epilogue warps (of both CTAs)
-        if constexpr (CL == 1) umma_commit(&tmem_full[acc]);
-        else umma_commit_pair(&tmem_full[acc], PAIR_MASK);
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
     }
