@@ -676,6 +676,7 @@ struct TcBwdDev {
   const float* lse;
   const int32_t* cu_q;                            // packed query rows (attention.cuh); dQ then leaves through plain row stores
   bf16* dq; long long dq_ts;
+  DropCfg drop;                                   // dropout on the probabilities (functional.py:6682): same counter-based masks as the forward
   long long* trace;                               // bring-up instrument: [unit][16] clock64 stamps of CTA 0 (null = off)
 };
 
@@ -700,7 +701,7 @@ __device__ __forceinline__ void bw_stamp(const TcBwdDev& p, int u, int slot) {
 }
 }  // namespace
 
-template <bool TRACE>
+template <bool TRACE, bool DROP>
 __global__ void __launch_bounds__(BW_THREADS, 1)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
                    const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_k,
@@ -909,6 +910,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     const uint32_t lane_addr = static_cast<uint32_t>(w4 * 32) << 16;
     const uint32_t rowP = smem_u32(pds + g * 2 * BW_TILE_BYTES + j * ROW_BYTES);
     const int sw = j & 7;
+    const uint32_t dkey = DROP ? drop_key(p.drop) : 0u;
+    const uint32_t kpairs = static_cast<uint32_t>((p.Tk + 1) >> 1);    // dropout draws: one per pair of adjacent keys
     int prev_i = -1;
 #pragma unroll 1
     for (int u = g; u < n_units; u += 2) {
@@ -932,6 +935,9 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       const uint32_t lse2 = stat_u + static_cast<uint32_t>(i % BW_NSLOT) * 512u;      // [64] lse * log2e, then [64] delta
       const uint32_t t_s = tmem_base + g * BW_STAGE_COLS + lane_addr;
       const int lim = (p.causal && valid) ? key : (valid ? 0 : 0x7fffffff);   // rows below `lim` get P = 0 (causal: key > row)
+      // dropout (forward: O = dropout(P) V): the dV operand is dropout(P), dP is masked and rescaled before dS = P (dP - delta)
+      const uint32_t pair0 = DROP ? static_cast<uint32_t>(first + i * stride) * static_cast<uint32_t>(p.Tq) * kpairs + (static_cast<uint32_t>(key) >> 1) : 0u;
+      const uint32_t half_sh = (key & 1) ? 16u : 0u;
       // 16 rows per trip: S^T and dP^T -> P^T, dS^T -> two 16-byte units of this key's row in each buffer (ONE loop body)
 #pragma unroll 1
       for (int c = 0; c < qsteps; ++c) {
@@ -950,8 +956,15 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             const int idx = q * 4 + e;
             float pr = ex2f(fmaf(__uint_as_float(rs[idx]), p.sl2, -la[e]));
             if (c * 16 + idx < lim) pr = 0.f;
+            float dpe = __uint_as_float(rd[idx]);
             pv[e] = pr;
-            ds[e] = pr * (__uint_as_float(rd[idx]) - da[e]);
+            if constexpr (DROP) {
+              const uint32_t r = drop_rand(dkey, pair0 + static_cast<uint32_t>(c * 16 + idx) * kpairs);
+              const bool keep = ((r >> half_sh) & 0xFFFFu) >= p.drop.thr;
+              pv[e] = keep ? pr * p.drop.scale : 0.f;
+              dpe = keep ? dpe * p.drop.scale : 0.f;
+            }
+            ds[e] = pr * (dpe - da[e]);
           }
           pk[q * 2] = pack_bf16(pv[0], pv[1]); pk[q * 2 + 1] = pack_bf16(pv[2], pv[3]);
           dk[q * 2] = pack_bf16(ds[0], ds[1]); dk[q * 2 + 1] = pack_bf16(ds[2], ds[3]);
@@ -1236,7 +1249,7 @@ static bool tc_bwd_enabled() {
 
 bool attn_tc_bwd_supported(const AttnArgs& a, const AttnGrads& g) {
   if (!tc_enabled() || !tc_bwd_enabled()) return false;
-  if (a.hd != TC_HD || a.Tq > 48 || a.Tq < 1 || a.Tk < 1 || a.drop.thr != 0 || a.cu_k != nullptr) return false;
+  if (a.hd != TC_HD || a.Tq > 48 || a.Tq < 1 || a.Tk < 1 || a.cu_k != nullptr) return false;
   // short key ranges (the caption's self attention, Tk = Tq <= 48) stay on the mma.sync kernel: one 128-key tile per
   // item leaves the tcgen05 pipeline latency-bound (measured 66 us against 58 us at cfg2)
   static const int min_tk = getenv("B200_ATTN_TC_BWD_MIN_TK") ? atoi(getenv("B200_ATTN_TC_BWD_MIN_TK")) : 65;
@@ -1264,6 +1277,7 @@ int attn_tc_bwd(const AttnArgs& a, const AttnGrads& g, cudaStream_t s) {
   d.scale = a.scale; d.sl2 = a.scale * LOG2E;
   d.lse = a.lse;
   d.cu_q = a.cu_q; d.dq = g.dq; d.dq_ts = g.dq_ts;
+  d.drop = a.drop;
   // shared memory: 3 x (Q | dO), 3 K tiles, 2 V tiles, O, 2 x (P^T | dS^T), 4 x 2 staging tiles, row statistics, barriers
   d.kring_off = BW_NSLOT * BW_SLOT_BYTES;
   d.vring_off = d.kring_off + BW_RK * BW_TILE_BYTES;
@@ -1299,11 +1313,13 @@ int attn_tc_bwd(const AttnArgs& a, const AttnGrads& g, cudaStream_t s) {
   d.trace = g_tc_trace;
   static bool configured = false;
   if (!configured) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    B200_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B200_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B200_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B200_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  auto kern = d.trace != nullptr ? attn_tc_bwd_kernel<true> : attn_tc_bwd_kernel<false>;
+  const bool drop = d.drop.thr != 0;
+  auto kern = d.trace != nullptr ? attn_tc_bwd_kernel<true, true> : (drop ? attn_tc_bwd_kernel<false, true> : attn_tc_bwd_kernel<false, false>);
   B200_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(BW_THREADS), static_cast<size_t>(smem), s, true, 1, tq, tdo, to, tk, tkt, tv, tvt, tdq, tdk, tdv, d));
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());

@@ -188,13 +188,16 @@ def test_dp_bucket_path_equals_full_batch_backward(cuda_dev):
 _LONG = dict(V=264, E=128, H=2, L=2, F=256, ML=100, B=2, T=99, S=197)   # reference MAX_SEQ_LEN: two-phase attention backward
 
 
-@pytest.mark.parametrize("name", ["tiny", "hd96", "cfg1", "long"])
+_TCDROP = dict(V=1000, E=128, H=2, L=2, F=256, ML=100, B=3, T=47, S=197)   # head dim 64, S >= 65: the tcgen05 cross attention
+
+
+@pytest.mark.parametrize("name", ["tiny", "hd96", "cfg1", "long", "tcdrop"])
 def test_dropout_matches_oracle_with_same_masks(cuda_dev, name):
     """Dropout p=0.1 at the reference's 1 + 6 L sites (decoder.py:72; transformer.py:1175,1195,1199;
     attention probabilities, functional.py:6682).  torch's random stream cannot be reproduced, so
     the oracle applies torch's dropout SEMANTICS with the CUDA path's counter-based masks
     (oracle.DropSpec) and loss / logits / every gradient are compared as in the p=0 tests."""
-    c = _LONG if name == "long" else CFGS[name]
+    c = _LONG if name == "long" else (_TCDROP if name == "tcdrop" else CFGS[name])
     p = O.init_params(c["V"], c["E"], c["H"], c["L"], c["F"], c["ML"], seed=42)
     tok, tgt, mem, mpm = synth(c, 43)
     eng = make_engine(c, p, cuda_dev)
