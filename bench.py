@@ -303,7 +303,7 @@ def run_b200(args):
     lib = L.lib()
     c = CONFIGS[args.config]
     torch.manual_seed(42)
-    dec = TransformerDecoder(c["V"], c["E"], c["H"], c["L"], c["F"], c["ML"], dropout=0.0, pad_idx=0, device=dev)
+    dec = TransformerDecoder(c["V"], c["E"], c["H"], c["L"], c["F"], c["ML"], dropout=args.dropout, pad_idx=0, device=dev)
     dec.train()
     opt = B200AdamW(dec, lr=1e-4, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-5)
     dp = DataParallel(dec.engine) if world > 1 else None
@@ -492,7 +492,7 @@ def run_b200(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-        "data": "synthetic", "config": workload_config(c, world, dropout=0.0),
+        "data": "synthetic", "config": workload_config(c, world, dropout=args.dropout),
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         "step_model_tflops_per_gpu": step_tf, "step_model_frac_of_peak": step_tf / peak_tf,
         "step_model_frac_vs_burst": step_tf / peak_burst, "step_model_frac_vs_sustained": step_tf / peak_sus,
@@ -631,6 +631,8 @@ def main():
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS), help="cfg2 = the headline workload (default)")
     ap.add_argument("--ref-budget-s", type=float, default=240.0,
                     help="--impl reference: wall-clock budget; the per-step sample (never the step count) shrinks to fit it")
+    ap.add_argument("--dropout", type=float, default=0.0,
+                    help="decoder dropout of the B200 arm (headline: 0, like the parity runs; the reference trains with 0.1, config.py:69)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
     ap.add_argument("--no-varlen", action="store_true", help="skip the extra padded-vs-packed (var-len) train-step comparison")
