@@ -433,7 +433,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     const int row = w4 * 16 + (lane & 15);           // query row
     const bool stamper = (w4 == 3) && lane == 0;
     const uint32_t lane_addr = static_cast<uint32_t>(w4 * 32) << 16;
-    const uint32_t dkey = DROP ? drop_key(p.drop) : 0u;
+    const bool dropping = DROP && p.drop.thr != 0;   // (the trace build is the DROP variant: it must also run without dropout)
+    const uint32_t dkey = dropping ? drop_key(p.drop) : 0u;
     const bool writer = hf == 0 && row < p.Tq;       // O rows live in the lower 16 lanes of every quarter (packed: checked per sample)
 
     // O of local item i (TMEM stage i % no) -> rows scaled by 1 / row sum -> global memory; log-sum-exp
@@ -544,7 +545,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           }
         }
         sum += ((pv[0] + pv[1]) + (pv[2] + pv[3])) + ((pv[4] + pv[5]) + (pv[6] + pv[7]));
-        if (DROP) {                                   // the row sum keeps the undropped probabilities; P V sees dropout(P)
+        if (DROP && dropping) {                       // the row sum keeps the undropped probabilities; P V sees dropout(P)
           const uint32_t pair0 = tc_drop_pair(p, bh, row, key0);
 #pragma unroll
           for (int j = 0; j < 4; ++j) drop_apply2(pv[2 * j], pv[2 * j + 1], drop_rand(dkey, pair0 + j), p.drop.thr, p.drop.scale);
@@ -728,9 +729,9 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   uint64_t* dq_empty = dq_full + 1;          // [1]
   uint64_t* stat_full = dq_empty + 1;        // [3] row statistics of the item written
   uint64_t* stat_empty = stat_full + 4;      // [3] ... and read by all its units
-  uint64_t* o_full = stat_empty + 4;         // [1] O of the item landed (one slot: it lives only until the statistics are done)
-  uint64_t* o_empty = o_full + 1;            // [1]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_empty + 1);
+  uint64_t* o_full = stat_empty + 4;         // [2] O of the item landed (it lives only until the statistics are done; with ONE
+  uint64_t* o_empty = o_full + 2;            // [2] slot the chain stats(i) -> load O(i+1) -> stats(i+1) set the item period: 4.9 k cycles)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // shared memory starts out as zeros: K / V rows past the last key, P^T / dS^T row slots past NQ and the tail of a
@@ -762,8 +763,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     }
     mbar_init(dq_full, 1);
     mbar_init(dq_empty, 128);
-    mbar_init(o_full, 1);
-    mbar_init(o_empty, 32);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&o_full[i], 1);
+      mbar_init(&o_empty[i], 32);
+    }
     fence_barrier_init();
   }
   tc_fence_before();
@@ -797,9 +800,9 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         const int qrow0 = p.cu_q ? p.cu_q[b] : b * p.Tq;
         tma_load_2d(smem + sl * BW_SLOT_BYTES, &tmap_q, &qdo_full[sl], h * TC_HD, qrow0);
         tma_load_2d(smem + sl * BW_SLOT_BYTES + BW_QROWS_BYTES, &tmap_do, &qdo_full[sl], h * TC_HD, qrow0);
-        tc_wait(o_empty, (static_cast<uint32_t>(i) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(o_full, p.NQ * ROW_BYTES);
-        tma_load_2d(smem + p.o_off, &tmap_o, o_full, h * TC_HD, qrow0);
+        tc_wait(&o_empty[i & 1], (static_cast<uint32_t>(i >> 1) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&o_full[i & 1], p.NQ * ROW_BYTES);
+        tma_load_2d(smem + p.o_off + (i & 1) * BW_QROWS_BYTES, &tmap_o, &o_full[i & 1], h * TC_HD, qrow0);
 #pragma unroll 1
         for (int kt = 0; kt < NT; ++kt, ++u) {
           const int rk = u % BW_RK, rv = u % BW_RV;
@@ -910,7 +913,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     const uint32_t lane_addr = static_cast<uint32_t>(w4 * 32) << 16;
     const uint32_t rowP = smem_u32(pds + g * 2 * BW_TILE_BYTES + j * ROW_BYTES);
     const int sw = j & 7;
-    const uint32_t dkey = DROP ? drop_key(p.drop) : 0u;
+    const bool dropping = DROP && p.drop.thr != 0;   // (the trace build is the DROP variant: it must also run without dropout)
+    const uint32_t dkey = dropping ? drop_key(p.drop) : 0u;
     const uint32_t kpairs = static_cast<uint32_t>((p.Tk + 1) >> 1);    // dropout draws: one per pair of adjacent keys
     int prev_i = -1;
 #pragma unroll 1
@@ -958,7 +962,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             if (c * 16 + idx < lim) pr = 0.f;
             float dpe = __uint_as_float(rd[idx]);
             pv[e] = pr;
-            if constexpr (DROP) {
+            if (DROP && dropping) {
               const uint32_t r = drop_rand(dkey, pair0 + static_cast<uint32_t>(c * 16 + idx) * kpairs);
               const bool keep = ((r >> half_sh) & 0xFFFFu) >= p.drop.thr;
               pv[e] = keep ? pr * p.drop.scale : 0.f;
@@ -1092,9 +1096,9 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       const int sl = i % BW_NSLOT;
       const int nq = p.cu_q ? p.cu_q[item / p.H + 1] - p.cu_q[item / p.H] : p.Tq;     // rows of this sample
       tc_wait(&qdo_full[sl], static_cast<uint32_t>(i / BW_NSLOT) & 1u);
-      tc_wait(o_full, static_cast<uint32_t>(i) & 1u);
+      tc_wait(&o_full[i & 1], static_cast<uint32_t>(i >> 1) & 1u);
       tc_wait(&stat_empty[sl], (static_cast<uint32_t>(i / BW_NSLOT) & 1u) ^ 1u);
-      const uint32_t s_do = smem_u32(smem + sl * BW_SLOT_BYTES + BW_QROWS_BYTES), s_o = smem_u32(smem + p.o_off);
+      const uint32_t s_do = smem_u32(smem + sl * BW_SLOT_BYTES + BW_QROWS_BYTES), s_o = smem_u32(smem + p.o_off + (i & 1) * BW_QROWS_BYTES);
 #pragma unroll 1
       for (int rr = 0; rr < 2; ++rr) {
         const int row = lane + 32 * rr;
@@ -1119,7 +1123,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         sts_f1(stat_u + static_cast<uint32_t>(sl * 128 + row) * 4u, l);
         sts_f1(stat_u + static_cast<uint32_t>(sl * 128 + 64 + row) * 4u, (a0 + a1) + (a2 + a3));
       }
-      mbar_arrive(o_empty);
+      mbar_arrive(&o_empty[i & 1]);
       mbar_arrive(&stat_full[sl]);
       if (lane == 0) bw_stamp<TRACE>(p, i * NT, 9);
     }
@@ -1250,8 +1254,11 @@ static bool tc_bwd_enabled() {
 bool attn_tc_bwd_supported(const AttnArgs& a, const AttnGrads& g) {
   if (!tc_enabled() || !tc_bwd_enabled()) return false;
   if (a.hd != TC_HD || a.Tq > 48 || a.Tq < 1 || a.Tk < 1 || a.cu_k != nullptr) return false;
-  // short key ranges (the caption's self attention, Tk = Tq <= 48) stay on the mma.sync kernel: one 128-key tile per
-  // item leaves the tcgen05 pipeline latency-bound (measured 66 us against 58 us at cfg2)
+  // short key ranges (the caption's self attention, Tk = Tq = 47: ONE 128-key tile per item) stay on the mma.sync kernel
+  // by default.  Since the O tile got a second slot this kernel is the faster one in isolation (51 us against 60 us at
+  // cfg2; with one slot the chain statistics(i) -> load O(i+1) -> statistics(i+1) set the item period: 66 us), but the
+  // step time did not move in same-box A/Bs (8.28 vs 8.24 / 8.28 ms) and the packed (cu_k) self attention runs on the
+  // mma.sync kernel anyway: one kernel family for both layouts keeps packed and padded steps bit-identical per sample.
   static const int min_tk = getenv("B200_ATTN_TC_BWD_MIN_TK") ? atoi(getenv("B200_ATTN_TC_BWD_MIN_TK")) : 65;
   if (a.Tk < min_tk) return false;
   auto out_ok = [](const void* ptr, long long ts) { return ptr != nullptr && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ts % 8 == 0; };
@@ -1278,11 +1285,11 @@ int attn_tc_bwd(const AttnArgs& a, const AttnGrads& g, cudaStream_t s) {
   d.lse = a.lse;
   d.cu_q = a.cu_q; d.dq = g.dq; d.dq_ts = g.dq_ts;
   d.drop = a.drop;
-  // shared memory: 3 x (Q | dO), 3 K tiles, 2 V tiles, O, 2 x (P^T | dS^T), 4 x 2 staging tiles, row statistics, barriers
+  // shared memory: 3 x (Q | dO), 3 K tiles, 2 V tiles, 2 x O, 2 x (P^T | dS^T), 4 x 2 staging tiles, row statistics, barriers
   d.kring_off = BW_NSLOT * BW_SLOT_BYTES;
   d.vring_off = d.kring_off + BW_RK * BW_TILE_BYTES;
   d.o_off = d.vring_off + BW_RV * BW_TILE_BYTES;
-  d.pds_off = d.o_off + BW_QROWS_BYTES;
+  d.pds_off = d.o_off + 2 * BW_QROWS_BYTES;
   d.stage_off = d.pds_off + 2 * 2 * BW_TILE_BYTES;
   d.stat_off = d.stage_off + 4 * 2 * BW_STAGING_BYTES;
   d.bar_off = d.stat_off + BW_NSLOT * 512;
