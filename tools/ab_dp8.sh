@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B of data-parallel settings on ONE 8-GPU box: each argument is a set of env assignments
 for cfg in "$@"; do
-  out=$(env $cfg python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 20 --warmup 5 2>/dev/null | tail -1)
+  out=$(env $cfg python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 20 --warmup 5 --no-decode --no-cpu-baseline 2>/dev/null | tail -1)
   python - "$cfg" "$out" <<'PY'
 import json, sys
 d = json.loads(sys.argv[2])
