@@ -184,3 +184,19 @@ def test_trim_batch_on_the_host():
     assert trim_batch(tok, tgt, 0)[0].shape[1] == 100
     z = torch.zeros(2, 16, dtype=torch.int64)
     assert trim_batch(z, z, 0)[0].shape[1] == 8           # all PAD: one (rounded) column block survives
+
+
+def test_packed_lengths_host_rules():
+    """Var-len path: lengths = non-PAD prefix per caption; a PAD inside a caption (or an empty caption)
+    disqualifies the batch (it then takes the padded path, where PAD keys are masked like decoder.py:158-162)."""
+    import torch
+    from multimodal_image_transformer_b200.engine import DecoderEngine
+    tok = torch.tensor([[1, 5, 6, 2, 0, 0], [1, 7, 8, 9, 2, 0], [1, 4, 4, 4, 4, 2]])
+    assert DecoderEngine.packed_lengths(tok, 0).tolist() == [4, 5, 6]
+    assert DecoderEngine.packed_lengths(tok, 0).dtype == torch.int32
+    inner = torch.tensor([[1, 5, 6, 2, 0, 0], [1, 7, 0, 8, 2, 0]])
+    assert DecoderEngine.packed_lengths(inner, 0) is None
+    empty = torch.tensor([[1, 5, 2], [0, 0, 0]])
+    assert DecoderEngine.packed_lengths(empty, 0) is None
+    # a different PAD id
+    assert DecoderEngine.packed_lengths(torch.tensor([[1, 5, 9, 9]]), 9).tolist() == [2]
