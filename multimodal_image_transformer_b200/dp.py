@@ -60,6 +60,18 @@ class DataParallel:
         self.events = [torch.cuda.Event() for _ in self.buckets]
         self.comm_stream = torch.cuda.Stream(device=engine.device)
         self._cnt = torch.zeros(1, device=engine.device, dtype=torch.float32)
+        # Optional second communicator with few CTAs for the EARLY buckets (B200_DP_SLOW_CTAS = its maxCTAs, 0 = off): their
+        # all-reduces have the whole rest of backward to hide under, so they may be slow, and every SM NCCL does not hold
+        # is an SM the statically scheduled persistent GEMMs do not wait for; the last `fast_tail` buckets (exposed after
+        # backward ends) keep the default communicator.
+        self.slow_group = None
+        self.fast_tail = int(os.environ.get("B200_DP_FAST_TAIL", "2"))
+        slow_ctas = int(os.environ.get("B200_DP_SLOW_CTAS", "0"))
+        if slow_ctas > 0 and self.world_size > 1 and dist.get_backend(group) == "nccl":
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.config.max_ctas = slow_ctas
+            opts.config.min_ctas = 1
+            self.slow_group = dist.new_group(ranks=list(range(self.world_size)), pg_options=opts)
 
     @staticmethod
     def init_from_env(backend: str = "nccl") -> Tuple[int, int, int]:
@@ -107,9 +119,10 @@ class DataParallel:
         for i, ((off, cnt), ev) in enumerate(zip(self.buckets, self.events)):
             self.engine.backward_parts(i, i, inv_count)
             ev.record(cur)
+            grp = self.slow_group if (self.slow_group is not None and i < len(self.buckets) - self.fast_tail) else self.group
             with torch.cuda.stream(self.comm_stream), nvtx_range("b200.dp.allreduce_bucket"):
                 self.comm_stream.wait_event(ev)
-                dist.all_reduce(g[off:off + cnt], op=dist.ReduceOp.SUM, group=self.group)
+                dist.all_reduce(g[off:off + cnt], op=dist.ReduceOp.SUM, group=grp)
                 if overlap_norm:
                     self.engine.norm_add_bucket(i)     # global norm of the REDUCED gradients, bucket by bucket
         cur.wait_stream(self.comm_stream)
