@@ -126,6 +126,10 @@ struct b200_engine {
   // tiles through L2); the branch is joined back before every gradient-bucket boundary.
   cudaStream_t bias_stream = nullptr;
   cudaEvent_t bias_fork = nullptr, bias_join = nullptr;
+  // B200_WGRAD_SIDE: the weight-gradient GEMMs ride the same side stream; one completion event per wgrad site of a layer
+  // (+ LM head, projection) orders the main stream's next overwrite of the dY buffer that wgrad reads
+  static constexpr int W_SITES = 9;
+  cudaEvent_t wdone[W_SITES] = {};
   // decode state (carved from the caller's decode workspace by decode_begin)
   struct Decode {
     int B = 0, beam = 0, R = 0, S = 0, max_len = 0;
@@ -280,20 +284,25 @@ int linear_dgrad(const bf16* dy, int64_t lddy, const bf16* W, int N_out, int K_i
 }
 // dW[N_out,K_in] += dy^T x ; db[N_out] += colsum(dy)
 // side != null: the bias sum runs on that stream behind `fork` (dy is complete at this point of s); the caller
-// joins the side stream before dy is overwritten and before the gradients are consumed
+// joins the side stream before dy is overwritten and before the gradients are consumed.  done != null: the wgrad GEMM
+// rides the side stream too (dW is needed only at the bucket boundary, so it fills the SMs the main stream's
+// HBM-bound kernels and GEMM tails leave idle) and `done` is recorded behind it.
 int linear_wgrad(const bf16* dy, int64_t lddy, const bf16* x, int64_t ldx, float* dW, float* db, int M,
                  int N_out, int K_in, cudaStream_t s, cudaStream_t side = nullptr, cudaEvent_t fork = nullptr,
-                 bool* side_used = nullptr) {
+                 bool* side_used = nullptr, cudaEvent_t done = nullptr) {
   GemmProblem g;
   g.M = N_out; g.N = K_in; g.K = M;
   g.A = dy; g.lda = lddy; g.a_mn = true; g.B = x; g.ldb = ldx; g.b_mn = true;
   g.D = dW; g.ldd = K_in; g.d_fp32 = true; g.accumulate = true; g.split_k = 0;
-  if (db && side) {
+  if (side && (db || done)) {
     B200_CHECK_CUDA(cudaEventRecord(fork, s));
     B200_CHECK_CUDA(cudaStreamWaitEvent(side, fork, 0));
     if (side_used) *side_used = true;
-    if (int rc = colsum(dy, lddy, db, M, N_out, side)) return rc;
-    return gemm_launch(g, s);
+    if (db) { if (int rc = colsum(dy, lddy, db, M, N_out, side)) return rc; }
+    if (!done) return gemm_launch(g, s);
+    if (int rc = gemm_launch(g, side)) return rc;
+    B200_CHECK_CUDA(cudaEventRecord(done, side));
+    return 0;
   }
   if (int rc = gemm_launch(g, s)) return rc;
   if (db) return colsum(dy, lddy, db, M, N_out, s);
@@ -424,19 +433,40 @@ int run_backward(b200_engine* e, bool have_dlogits, float* dmemory, void* const*
     if (!e->bias_stream) B200_CHECK_CUDA(cudaStreamCreateWithFlags(&e->bias_stream, cudaStreamNonBlocking));
     if (!e->bias_fork) B200_CHECK_CUDA(cudaEventCreateWithFlags(&e->bias_fork, cudaEventDisableTiming));
     if (!e->bias_join) B200_CHECK_CUDA(cudaEventCreateWithFlags(&e->bias_join, cudaEventDisableTiming));
+    for (auto& w : e->wdone) if (!w) B200_CHECK_CUDA(cudaEventCreateWithFlags(&w, cudaEventDisableTiming));
     side = e->bias_stream;
   }
   // one pipeline stage less while bias sums may be co-resident (B200_BWD_STAGE_DROP overrides)
   static const int bwd_drop = getenv("B200_BWD_STAGE_DROP") ? atoi(getenv("B200_BWD_STAGE_DROP")) : kBwdStageDrop;
   GemmStageCap stage_cap(side ? bwd_drop : 0);
   bool side_used = false;
+  // B200_WGRAD_SIDE=1 (read per call: A/B switch): the wgrad GEMMs ride the side stream as well; wpend[site] = a wgrad of
+  // that site is in flight, wwait(site) orders the main stream behind it (and, the side stream being in order, behind
+  // everything launched on it before)
+  enum { W_L2 = 0, W_L1, W_CAO, W_CAQ, W_CAKV, W_SAO, W_SAQKV, W_FC, W_PROJ };
+  const char* wside_env = getenv("B200_WGRAD_SIDE");
+  const bool wside = side != nullptr && wside_env != nullptr && atoi(wside_env) != 0;
+  bool wpend[b200_engine::W_SITES] = {};
   // every return path below goes through join_side (a captured graph must not be left forked)
   auto join_side = [&](void) {
     if (side && side_used) {
       cudaEventRecord(e->bias_join, side);
       cudaStreamWaitEvent(s, e->bias_join, 0);
       side_used = false;
+      for (auto& w : wpend) w = false;
     }
+  };
+  auto wwait = [&](int site_id) {
+    if (wpend[site_id]) {
+      cudaStreamWaitEvent(s, e->wdone[site_id], 0);
+      wpend[site_id] = false;
+    }
+  };
+  auto wgrad = [&](int site_id, const bf16* dy, int64_t lddy, const bf16* x, int64_t ldx, float* dW, float* db, int Mr,
+                   int N_out, int K_in) -> int {
+    if (!wside) return linear_wgrad(dy, lddy, x, ldx, dW, db, Mr, N_out, K_in, s, side, e->bias_fork, &side_used);
+    wpend[site_id] = true;
+    return linear_wgrad(dy, lddy, x, ldx, dW, db, Mr, N_out, K_in, s, side, e->bias_fork, &side_used, e->wdone[site_id]);
   };
   struct Joiner { decltype(join_side)& j; ~Joiner() { j(); } } joiner{join_side};
   // Joins: (1) before a gradient-bucket event is recorded (data-parallel runs consume the bucket's bias gradients
@@ -457,7 +487,7 @@ int run_backward(b200_engine* e, bool have_dlogits, float* dmemory, void* const*
     NvtxRange nvtx_part("b200.decoder.backward.lm_head");
     if (need_dmemp) B200_CHECK_CUDA(cudaMemsetAsync(pl.dmemp, 0, static_cast<size_t>(Ms) * E * sizeof(float), s));
     // --- LM head
-    RC(linear_wgrad(pl.dlogits, V, pl.x_final, E, e->gf + e->fc_w, e->gf + e->fc_b, M, V, E, s, side, e->bias_fork, &side_used));
+    RC(wgrad(W_FC, pl.dlogits, V, pl.x_final, E, e->gf + e->fc_w, e->gf + e->fc_b, M, V, E));
     RC(linear_dgrad(pl.dlogits, V, e->ph + e->fc_w, V, E, dx, E, M, nullptr, 0, nullptr, 0, s));
     mark();
   }
@@ -477,23 +507,29 @@ int run_backward(b200_engine* e, bool have_dlogits, float* dmemory, void* const*
     // of its bias sum).  Without dropout the two coincide and dz* alias dy*.
     bf16* dy3 = spare1;
     bf16* dz3 = dropping ? pl.dxd : dy3;
+    // (wside waits: the buffer a kernel is about to overwrite may still be read by a wgrad on the side stream -- the
+    // previous layer's for the per-site buffers, this layer's for the rotating dx buffers; pl.dxd carries all three dz
+    // of a layer when dropout is on)
+    if (dropping) wwait(W_SAO);
     RC(layernorm_bwd(dx, a.y3, e->pf + o.n3_w, a.mean3, a.rstd3, dy3, g + o.n3_w, g + o.n3_b, g + o.l2_b, M, E, s,
                      dropping ? dz3 : nullptr, site(1 + 6 * l + 5)));
     // FFN (linear2's bias gradient = column sums of dz3, produced by the LayerNorm backward above)
-    RC(linear_wgrad(dz3, E, a.h, F, g + o.l2_w, nullptr, M, E, F, s));
+    RC(wgrad(W_L2, dz3, E, a.h, F, g + o.l2_w, nullptr, M, E, F));
     // h = dropout(relu(.)) is positive exactly where the unit is active AND kept
-    join_side();
+    if (wside) wwait(W_L1); else join_side();
     RC(linear_dgrad(dz3, E, e->ph + o.l2_w, E, F, pl.dh, F, M, nullptr, 0, a.h, F, s, keep_scale));
-    RC(linear_wgrad(pl.dh, F, a.x2, E, g + o.l1_w, g + o.l1_b, M, F, E, s, side, e->bias_fork, &side_used));
+    RC(wgrad(W_L1, pl.dh, F, a.x2, E, g + o.l1_w, g + o.l1_b, M, F, E));
     bf16* dx2 = spare2;
+    wwait(W_SAO);            // dz1 of the previous layer lives in spare2
     RC(linear_dgrad(pl.dh, F, e->ph + o.l1_w, F, E, dx2, E, M, dy3, E, nullptr, 0, s));
     // LN2
     bf16* dy2 = dx;   // dx (grad of layer output) is dead now
     bf16* dz2 = dropping ? pl.dxd : dy2;      // dz3 is dead (its last reader, the FFN dgrad above, is ordered before)
+    if (dropping) wwait(W_L2);
     RC(layernorm_bwd(dx2, a.y2, e->pf + o.n2_w, a.mean2, a.rstd2, dy2, g + o.n2_w, g + o.n2_b, g + o.ca_ob, M, E, s,
                      dropping ? dz2 : nullptr, site(1 + 6 * l + 3)));
     // cross-attention
-    RC(linear_wgrad(dz2, E, a.attn_c, E, g + o.ca_ow, nullptr, M, E, E, s));
+    RC(wgrad(W_CAO, dz2, E, a.attn_c, E, g + o.ca_ow, nullptr, M, E, E));
     RC(linear_dgrad(dz2, E, e->ph + o.ca_ow, E, E, pl.dattn, E, M, nullptr, 0, nullptr, 0, s));
     AttnArgs ca;
     ca.q = a.qc; ca.q_bs = static_cast<long long>(T) * E; ca.q_ts = E;
@@ -506,9 +542,11 @@ int run_backward(b200_engine* e, bool have_dlogits, float* dmemory, void* const*
     cg.d_o = pl.dattn; cg.do_bs = static_cast<long long>(T) * E; cg.do_ts = E;
     cg.dq = pl.dqc; cg.dq_bs = static_cast<long long>(T) * E; cg.dq_ts = E;
     cg.dk = pl.dkv; cg.dv = pl.dkv + E; cg.dk_bs = cg.dv_bs = static_cast<long long>(S) * 2 * E; cg.dk_ts = cg.dv_ts = 2 * E;
+    wwait(W_CAQ);
+    wwait(W_CAKV);           // the previous layer's readers of pl.dqc / pl.dkv
     RC(attn_bwd(ca, cg, s));
-    RC(linear_wgrad(pl.dqc, E, a.x1, E, g + o.ca_w, g + o.ca_b, M, E, E, s, side, e->bias_fork, &side_used));
-    RC(linear_wgrad(pl.dkv, 2 * E, pl.memp, E, g + o.ca_w + static_cast<int64_t>(E) * E, g + o.ca_b + E, Ms, 2 * E, E, s, side, e->bias_fork, &side_used));
+    RC(wgrad(W_CAQ, pl.dqc, E, a.x1, E, g + o.ca_w, g + o.ca_b, M, E, E));
+    RC(wgrad(W_CAKV, pl.dkv, 2 * E, pl.memp, E, g + o.ca_w + static_cast<int64_t>(E) * E, g + o.ca_b + E, Ms, 2 * E, E));
     if (need_dmemp) {
       GemmProblem gp;
       gp.M = Ms; gp.N = E; gp.K = 2 * E;
@@ -517,14 +555,16 @@ int run_backward(b200_engine* e, bool have_dlogits, float* dmemory, void* const*
       RC(gemm_launch(gp, s));
     }
     bf16* dx1 = spare1;   // dy3 is dead
+    wwait(W_L2);             // ... once this layer's linear2 wgrad has read it
     RC(linear_dgrad(pl.dqc, E, e->ph + o.ca_w, E, E, dx1, E, M, dy2, E, nullptr, 0, s));
     // LN1
     bf16* dy1 = spare2;   // dx2 is dead
     bf16* dz1 = dropping ? pl.dxd : dy1;      // dz2 is dead
+    if (dropping) wwait(W_CAO);
     RC(layernorm_bwd(dx1, a.y1, e->pf + o.n1_w, a.mean1, a.rstd1, dy1, g + o.n1_w, g + o.n1_b, g + o.sa_ob, M, E, s,
                      dropping ? dz1 : nullptr, site(1 + 6 * l + 1)));
     // self-attention
-    RC(linear_wgrad(dz1, E, a.attn_o, E, g + o.sa_ow, nullptr, M, E, E, s));
+    RC(wgrad(W_SAO, dz1, E, a.attn_o, E, g + o.sa_ow, nullptr, M, E, E));
     RC(linear_dgrad(dz1, E, e->ph + o.sa_ow, E, E, pl.dattn, E, M, nullptr, 0, nullptr, 0, s));
     AttnArgs sa;
     sa.q = a.qkv; sa.k = a.qkv + E; sa.v = a.qkv + 2 * E;
@@ -537,9 +577,11 @@ int run_backward(b200_engine* e, bool have_dlogits, float* dmemory, void* const*
     sg.d_o = pl.dattn; sg.do_bs = static_cast<long long>(T) * E; sg.do_ts = E;
     sg.dq = pl.dqkv; sg.dk = pl.dqkv + E; sg.dv = pl.dqkv + 2 * E;
     sg.dq_bs = sg.dk_bs = sg.dv_bs = static_cast<long long>(T) * 3 * E; sg.dq_ts = sg.dk_ts = sg.dv_ts = 3 * E;
+    wwait(W_SAQKV);          // the previous layer's reader of pl.dqkv
     RC(attn_bwd(sa, sg, s));
-    RC(linear_wgrad(pl.dqkv, 3 * E, pl.xs[l], E, g + o.sa_w, g + o.sa_b, M, 3 * E, E, s, side, e->bias_fork, &side_used));
+    RC(wgrad(W_SAQKV, pl.dqkv, 3 * E, pl.xs[l], E, g + o.sa_w, g + o.sa_b, M, 3 * E, E));
     bf16* dx_in = dx;     // dy2 is dead
+    wwait(W_CAO);            // ... once this layer's cross out-projection wgrad has read it
     RC(linear_dgrad(pl.dqkv, 3 * E, e->ph + o.sa_w, 3 * E, E, dx_in, E, M, dy1, E, nullptr, 0, s));
     dx = dx_in;
     mark();
@@ -549,7 +591,7 @@ int run_backward(b200_engine* e, bool have_dlogits, float* dmemory, void* const*
   else RC(embed_bwd(e->last_tokens, dx, e->gf + e->emb, B, T, E, V, c.pad_idx, sqrtf(static_cast<float>(E)), s, site(0)));
   if (pl.mem_dim != E) {
     RC(cast_f32_to_bf16(pl.dmemp, pl.dmemp16, static_cast<long long>(Ms) * E, s));
-    RC(linear_wgrad(pl.dmemp16, E, pl.mem16, pl.mem_dim, e->gf + e->proj_w, e->gf + e->proj_b, Ms, E, pl.mem_dim, s, side, e->bias_fork, &side_used));
+    RC(wgrad(W_PROJ, pl.dmemp16, E, pl.mem16, pl.mem_dim, e->gf + e->proj_w, e->gf + e->proj_b, Ms, E, pl.mem_dim));
   } else if (dmemory) {
     B200_CHECK_CUDA(cudaMemcpyAsync(dmemory, pl.dmemp, static_cast<size_t>(Ms) * E * sizeof(float), cudaMemcpyDeviceToDevice, s));
   }
@@ -978,6 +1020,7 @@ void b200_engine_destroy(b200_engine* e) {
     if (e->bias_stream) cudaStreamDestroy(e->bias_stream);
     if (e->bias_fork) cudaEventDestroy(e->bias_fork);
     if (e->bias_join) cudaEventDestroy(e->bias_join);
+    for (auto w : e->wdone) if (w) cudaEventDestroy(w);
   }
   delete e;
 }
@@ -1017,6 +1060,7 @@ int b200_engine_bind(b200_engine* e, float* params_f32, void* params_bf16, float
     if (!e->bias_stream) B200_CHECK_CUDA(cudaStreamCreateWithFlags(&e->bias_stream, cudaStreamNonBlocking));
     if (!e->bias_fork) B200_CHECK_CUDA(cudaEventCreateWithFlags(&e->bias_fork, cudaEventDisableTiming));
     if (!e->bias_join) B200_CHECK_CUDA(cudaEventCreateWithFlags(&e->bias_join, cudaEventDisableTiming));
+    for (auto& w : e->wdone) if (!w) B200_CHECK_CUDA(cudaEventCreateWithFlags(&w, cudaEventDisableTiming));
     if (dev >= 0 && dev != cur) cudaSetDevice(cur);
   }
   return 0;
