@@ -26,7 +26,8 @@ namespace b200 {
 static constexpr int BLOCK_M = 128;
 static constexpr int BLOCK_K = 64;  // 64 bf16 = one 128-byte swizzle row
 static constexpr int UMMA_K = 16;
-static constexpr int NUM_THREADS = 256;
+static constexpr int NUM_THREADS = 256;      // warps 0-3: TMA producer, MMA issuer, TMEM allocator, (idle); 4-7: epilogue group 0
+static constexpr int MAX_THREADS = 384;      // + warps 8-11: epilogue group 1 (storing epilogues, B200_GEMM_EPI_GROUPS)
 static constexpr int ACC_STAGES = 2;
 
 struct GemmDev {
@@ -51,7 +52,8 @@ struct GemmDev {
 static constexpr int SLAB_BYTES = BLOCK_M * 128;   // epilogue staging slab: 128 rows x 128 B (64 bf16 / 32 fp32 columns)
 
 // Dynamic shared memory (1024-byte aligned base, at most MAX_SMEM):
-//   [stages x (A tile | B tile)] [2 output slabs] [2 aux slabs, only when a residual / mask is fused]
+//   [stages x (A tile | B tile)] [2 output slabs; 4 when a residual / mask is fused: the tile's slabs land there and are
+//   rewritten in place]
 //   [2 bias tiles] [barriers].  The stage count is whatever fits: 6 (5 with aux) for the 256-wide pair tile.
 static constexpr int MAX_SMEM = 227 * 1024;
 static constexpr int MAX_STAGES = 8;
@@ -82,7 +84,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
 //         128 x 256 x 64 MACs: the L2 -> SM operand stream (measured bound of the CL = 1 kernel,
 //         ~38 B/cycle/SM) shrinks by a third and the tensor core reads B from shared memory once per pair.
 template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, int CL>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(MAX_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_aux,
                     const GemmDev p) {
@@ -99,11 +101,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tmem_full = empty_bar + MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + ACC_STAGES;
-  uint64_t* aux_full = tmem_empty + ACC_STAGES;      // [2] residual / mask slabs landed
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(aux_full + 2);
+  uint64_t* aux_full = tmem_empty + ACC_STAGES;      // [4] residual / mask slabs landed
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(aux_full + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // Epilogue groups of 128 threads (1 or 2, from the launch's block size).  With two, group g owns the slabs of parity g
+  // and the staging / residual buffer g: per tile each group converts half of the columns, which is what brings the
+  // epilogue of a K = 768 product (~5.5 us per 256 x 256 tile with one group) under the tile's MMA time (4.6 us).
+  const int EG = (static_cast<int>(blockDim.x) - 128) >> 7;
   const uint32_t cta_rank = (CL > 1) ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
 
@@ -120,9 +126,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     for (int i = 0; i < ACC_STAGES; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128 * CL);   // every epilogue thread of the pair arrives on the leader's
-      mbar_init(&aux_full[i], 1);
+      mbar_init(&tmem_empty[i], 128 * EG * CL);   // every epilogue thread of the pair arrives on the leader's
     }
+    for (int i = 0; i < 4; ++i) mbar_init(&aux_full[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -252,11 +258,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // 128 B, double-buffered, prefetched two slabs ahead); results are staged in 128-byte-swizzled
     // shared memory and written with TMA stores (or TMA reduce-add for split-K / accumulation),
     // which also clips the M and N tails.
-    const int ew = warp - 4;                      // TMEM lane quarter this warp may read
-    const int et = static_cast<int>(threadIdx.x) - 128;   // 0..127
-    const bool elected = et == 0;
+    const int ew = warp & 3;                      // TMEM lane quarter this warp may read
+    const int grp = (warp - 4) >> 2;              // epilogue group
+    const int eall = static_cast<int>(threadIdx.x) - 128;     // index among all epilogue threads
+    const int et = eall - (grp << 7);             // 0..127 = accumulator row of the tile
+    const bool elected = et == 0;                 // one per group
+    const uint32_t bar_free = 2u + 2u * grp, bar_staged = 3u + 2u * grp;
+    // Staging slabs.  Without a fused residual / mask: two, alternating.  With one: four = the whole tile; its residual /
+    // mask slabs are all requested at the top of the tile (64 KB in flight per CTA while the accumulator is still being
+    // computed), land in the staging slabs, and each thread rewrites its own row in place before the TMA store.  (A
+    // two-slab prefetch tied to the staging pace left every slab's load latency exposed: +38 % on the FFN dgrad.)
     uint8_t* sC = smem + epi_offset;
-    uint8_t* sR = sC + 2 * SLAB_BYTES;              // present only when a residual / mask is fused
     float* sBias = reinterpret_cast<float*>(sC + (has_aux_smem ? 4 : 2) * SLAB_BYTES);
     constexpr bool STORES = (EPI == EPI_STD || EPI == EPI_CE_BWD);
     const bool out_f32 = (EPI == EPI_STD) && p.d_fp32;
@@ -265,7 +277,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const bool has_aux = (EPI == EPI_STD) && p.aux_mode != 0;
     const uint32_t sw = static_cast<uint32_t>(et & 7);          // 128-byte swizzle phase of this row
     int acc = 0, tile_par = 0;
-    uint32_t acc_phase = 0, aux_phase[2] = {0u, 0u};
+    uint32_t acc_phase = 0, aux_phase = 0u;      // aux_phase: one parity bit per slab barrier
     for (int w = w_begin; w < total_work; w += w_stride) {
       const int split = w % p.split_k;
       const int tile = w / p.split_k;
@@ -278,18 +290,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const bool tile_live = m0 < p.M;             // ghost tiles of an odd pair do nothing but drain TMEM
 
       float* bias_s = sBias + tile_par * BLOCK_N;
-      for (int i = et; i < BLOCK_N; i += 128)
+      for (int i = eall; i < BLOCK_N; i += 128 * EG)
         bias_s[i] = (p.bias != nullptr && split == 0 && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
-      if (has_aux && elected && tile_live) {
-#pragma unroll
-        for (int sl = 0; sl < 2; ++sl) {
-          if (sl < nslabs && n0 + sl * 64 < p.N) {
-            mbar_arrive_expect_tx(&aux_full[sl], SLAB_BYTES);
-            tma_load_2d(sR + sl * SLAB_BYTES, &tmap_aux, &aux_full[sl], n0 + sl * 64, m0);
+      if (has_aux && elected) {
+        bulk_wait_read<0>();                       // this group's stores of the previous tile have read their slabs
+        if (tile_live) {
+          for (int sl = grp; sl < nslabs; sl += EG) {
+            if (n0 + sl * 64 < p.N) {
+              mbar_arrive_expect_tx(&aux_full[sl], SLAB_BYTES);
+              tma_load_2d(sC + sl * SLAB_BYTES, &tmap_aux, &aux_full[sl], n0 + sl * 64, m0);
+            }
           }
         }
       }
-      named_barrier_sync(1, 128);                  // bias tile visible to all epilogue threads
+      named_barrier_sync(1, 128 * EG);             // bias tile visible to all epilogue threads
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -315,13 +329,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
 
 #pragma unroll 1
-      for (int slab = 0; slab < nslabs; ++slab) {
-        const int b = slab & 1;
+      for (int slab = grp; slab < nslabs; slab += EG) {
+        const int b = has_aux ? slab : (slab & 1);      // (slab & 1 == grp with two groups: nslabs is even)
         const int scol0 = n0 + slab * slab_cols;
         const bool slab_live = tile_live && scol0 < p.N && p.act != 99;   // warp-uniform (act 99: diagnostic, mainloop only)
         uint8_t* sCb = sC + b * SLAB_BYTES;
-        const uint8_t* sRb = sR + b * SLAB_BYTES;
-        if constexpr (STORES) named_barrier_sync(2, 128);   // the TMA store that last read sC[b] has drained (see below)
+        const uint8_t* sRb = sCb;                 // fused residual / mask: landed in the staging slab itself
+        if constexpr (STORES) {
+          if (!has_aux) named_barrier_sync(bar_free, 128);   // the TMA store that last read sC[b] has drained (see below)
+        }
 
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -331,7 +347,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           uint32_t r[32];
           tmem_ld_32x32(t_row + c * 32, r);       // warp-collective: executed by all lanes
           tmem_ld_wait();
-          if (slab == nslabs - 1 && (half == 1 || out_f32)) {
+          if (slab + EG >= nslabs && (half == 1 || out_f32)) {
             // last TMEM read of this tile is complete: hand the accumulator stage back to the MMA thread
             tc_fence_before();
             if constexpr (CL == 1) mbar_arrive(&tmem_empty[acc]);
@@ -364,8 +380,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
             if (has_aux) {
               if (half == 0) {                    // slab b of the aux tile has landed
-                mbar_wait(&aux_full[b], aux_phase[b]);
-                aux_phase[b] ^= 1u;
+                mbar_wait(&aux_full[b], (aux_phase >> b) & 1u);
+                aux_phase ^= 1u << b;
               }
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
@@ -452,17 +468,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
         if constexpr (STORES) {
           fence_proxy_async();                     // staging writes -> visible to the TMA engine
-          named_barrier_sync(3, 128);              // whole slab staged; everyone is done reading sR[b]
+          named_barrier_sync(bar_staged, 128);     // whole slab staged; everyone is done reading sR[b]
           if (elected) {
             if (slab_live) {
               if (EPI == EPI_STD && p.accumulate) tma_reduce_add_2d(&tmap_d, sCb, scol0, m0);
               else tma_store_2d(&tmap_d, sCb, scol0, m0 + split * p.part_rows);
             }
             bulk_commit();
-            bulk_wait_read<1>();                   // the store issued from the OTHER buffer has finished reading it
-            if (has_aux && tile_live && slab + 2 < nslabs && n0 + (slab + 2) * 64 < p.N) {
-              mbar_arrive_expect_tx(&aux_full[b], SLAB_BYTES);
-              tma_load_2d(sR + b * SLAB_BYTES, &tmap_aux, &aux_full[b], n0 + (slab + 2) * 64, m0);
+            // one group: the store issued from the OTHER buffer has finished reading it (this thread alternates buffers);
+            // two groups: this group's only buffer is staged again next, so its store must have read it
+            // fused residual / mask: every slab of the tile has its own buffer, drained at the top of the next tile
+            if (!has_aux) {
+              if (EG == 1) bulk_wait_read<1>();
+              else bulk_wait_read<0>();
             }
           }
         }
@@ -596,7 +614,11 @@ static int launch_instance(const CUtensorMap& ta, const CUtensorMap& tb, const C
   }
   const bool prof = gemm_profile_enabled();
   if (prof) gemm_profile_record(stream, true, 2.0 * d.M * static_cast<double>(d.N) * d.K);
-  B200_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(NUM_THREADS), smem, stream, !prof, CL, ta, tb, td, tx, d));
+  // storing epilogues run with two epilogue groups (B200_GEMM_EPI_GROUPS=1: one); the per-row reductions of the LM-head
+  // statistics / argmax epilogues walk all columns of a row in one thread and keep one
+  static const int epi_groups = getenv("B200_GEMM_EPI_GROUPS") ? atoi(getenv("B200_GEMM_EPI_GROUPS")) : 2;
+  const int threads = ((EPI == EPI_STD || EPI == EPI_CE_BWD) && epi_groups >= 2) ? MAX_THREADS : NUM_THREADS;
+  B200_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(threads), smem, stream, !prof, CL, ta, tb, td, tx, d));
   if (prof) gemm_profile_record(stream, false, 0.0);
   note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
