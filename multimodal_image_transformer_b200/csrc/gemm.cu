@@ -750,7 +750,9 @@ int gemm_launch(const GemmProblem& q, cudaStream_t stream, int* n_tiles_out) {
 
   const long long work = static_cast<long long>((d.num_m_tiles + cl - 1) / cl) * d.num_n_tiles * d.split_k;
   long long slots = sms / cl;
-  if (g_grid_cap > 0 && g_grid_cap / cl >= 1 && g_grid_cap / cl < slots) slots = g_grid_cap / cl;
+  static const int env_cap = getenv("B200_GEMM_GRID_CAP") ? atoi(getenv("B200_GEMM_GRID_CAP")) : 0;    // experiments (tools/gemm_variants.py)
+  const int cap = g_grid_cap > 0 ? g_grid_cap : env_cap;
+  if (cap > 0 && cap / cl >= 1 && cap / cl < slots) slots = cap / cl;
   const int grid = static_cast<int>(work < slots ? work : slots) * cl;
 
 #define B200_GEMM_CASE(BN, AMN, BMN, EP)                                                  \
